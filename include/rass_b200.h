@@ -1,0 +1,149 @@
+/*
+ * rass_b200.h -- C ABI of the B200-native retrieval engine that stands in for the
+ * OpenSearch server behind RASSEngine's OpenSearchIndexer.
+ *
+ * Every entry point replaces work the reference sends over HTTP to OpenSearch 2.11.1
+ * (file:line are relative to the reference repo, NeuralRevenant/RASSEngine):
+ *
+ *   rass_create / rass_destroy      client.indices.create(index, body)          app/main.py:576 (vector field :563-572)
+ *   rass_append / rass_overwrite    helpers.bulk(client, actions) "_op_type":"index" (insert-or-overwrite by _id)
+ *                                                                               app/main.py:1237,1269,1279 (actions :1258-1264)
+ *   rass_tombstone                  overwrite of an _id whose new doc has no embedding (same bulk call)
+ *   rass_count                      client.count(index)                         app/main.py:1475-1476
+ *   rass_search_knn                 client.search(body={"query":{"knn":{"embedding":{"vector","k"}}}})
+ *                                                                               app/main.py:1538-1553
+ *   rass_bm25_build                 Lucene inverted index built by the same bulk calls (text field `unstructuredText`,
+ *                                   mapping app/main.py:555-556)
+ *   rass_search_hybrid              client.search(body={"query":{"bool":{"should":[multi_match, multi_match, knn]}}})
+ *                                                                               app/main.py:1574-1609
+ *   rass_merge_topk_dev             the OpenSearch coordinator's per-shard top-k merge (number_of_shards, app/main.py:357)
+ *
+ * Conventions: C linkage, plain pointers and sizes, no exceptions cross the boundary.  Every function returns an
+ * int status (0 = ok, negative = RASS_E_*); rass_last_error(h) gives the message for the last failure on that
+ * handle.  The caller owns every input and output buffer; inputs may be freed on return.  One call at a time per
+ * handle.  The engine owns device memory, pinned staging and streams.  Row ids are engine-assigned, dense and
+ * append-ordered, so "row ascending" is the tie-break Lucene's doc-id order gives.
+ *
+ * There is no CPU fallback: every compute entry point fails with RASS_E_CUDA when no sm_100 device is present.
+ */
+#ifndef RASS_B200_H
+#define RASS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RASS_ABI_VERSION 1
+
+typedef struct rass_engine rass_engine;
+
+enum {
+  RASS_OK = 0,
+  RASS_E_INVALID = -1,
+  RASS_E_OOM = -2,
+  RASS_E_CUDA = -3,
+  RASS_E_NCCL = -4,
+  RASS_E_NOTFOUND = -5,
+  RASS_E_UNSUPPORTED = -6
+};
+
+enum { RASS_METRIC_COSINE = 0, RASS_METRIC_L2 = 1 };
+
+/* rass_create flags */
+enum {
+  RASS_KEEP_FP32 = 1u,  /* resident fp32 matrix + bf16 shadow (default when flags == 0)               */
+  RASS_BF16_ONLY = 2u   /* bf16 corpus: the bf16 values ARE the data (BASELINE config 5, 100M rows)  */
+};
+
+/* rass_search_* path selection (rass_set_option RASS_OPT_PATH) */
+enum {
+  RASS_PATH_AUTO = 0,    /* B <= 2: streaming GEMV+select; B >= 3: tcgen05 tiles                      */
+  RASS_PATH_STREAM = 1,  /* force the CUDA-core streaming scan (passes of <= 2 queries)                */
+  RASS_PATH_UMMA = 2,    /* force the TMA + tcgen05 scan (passes of <= 64 queries)                     */
+  RASS_PATH_EXACT = 3    /* force the fp64 full scan (the certificate-failure fallback), for tests     */
+};
+
+enum {
+  RASS_OPT_PATH = 1,
+  RASS_OPT_STREAM = 2    /* value = cudaStream_t to enqueue on (0 = engine-owned stream)               */
+};
+
+typedef struct rass_stats {
+  double scan_ms;        /* device time of the scan kernels of the last search (CUDA events)           */
+  double finish_ms;      /* device time of merge + exact rerank (+ fallback)                           */
+  double total_ms;       /* device time first kernel -> last kernel                                    */
+  int64_t rows_scanned;  /* live + tombstoned rows each pass streams                                   */
+  int64_t bytes_streamed;/* algorithmic bytes of the scan passes (rows * dim_pad * sizeof(elem) * passes) */
+  int32_t n_queries;
+  int32_t n_certified;   /* queries whose bf16 candidate set was proven to contain the exact top-k     */
+  int32_t n_fallback;    /* queries re-scanned exactly in fp64                                         */
+  int32_t path;          /* RASS_PATH_* actually used                                                  */
+  int32_t passes;        /* corpus passes of the scan                                                  */
+  int32_t launches;      /* kernels launched by this call                                              */
+  int32_t max_candidates;/* largest rerank candidate set                                               */
+  int32_t reserved;
+} rass_stats;
+
+const char* rass_version(void);
+const char* rass_last_error(const rass_engine* h);  /* h may be NULL: last create failure */
+
+/* dim: embedding dimension (<= 1024; padded to a multiple of 256 on device).  device: CUDA ordinal.
+ * capacity_rows: initial reservation (grows by doubling). */
+int rass_create(int dim, int metric, int device, int64_t capacity_rows, uint32_t flags, rass_engine** out);
+int rass_destroy(rass_engine* h);
+int rass_set_option(rass_engine* h, int opt, int64_t value);
+/* global row id of local row 0 (row-sharded corpora); search outputs carry base + local row */
+int rass_set_row_base(rass_engine* h, int64_t base);
+
+/* rows: [n, dim] row-major fp32, host (pageable or pinned).  *out_first_row = local row of rows[0]. */
+int rass_append(rass_engine* h, const float* rows_host, int64_t n, int64_t* out_first_row);
+/* same, source already in device memory of this engine's device */
+int rass_append_dev(rass_engine* h, const float* rows_dev, int64_t n, int64_t* out_first_row);
+int rass_overwrite(rass_engine* h, int64_t row, const float* v_host);
+int rass_tombstone(rass_engine* h, int64_t row);
+int rass_count(const rass_engine* h, int64_t* out_live_rows);
+int rass_rows(const rass_engine* h, int64_t* out_total_rows);
+/* stored values (fp32, or the bf16 values widened when RASS_BF16_ONLY) back to the host: [n, dim] */
+int rass_read_rows(rass_engine* h, int64_t first_row, int64_t n, float* out_host);
+
+/* Exact top-k.  q: [B, dim] fp32 (need not be normalised).  out_rows: [B, k] (base + local row, -1 = no hit),
+ * out_scores: [B, k] fp32 = 1/(2 - cos) (cosine) or 1/(1 + d^2) (L2).  out_keys (nullable): [B, k] fp64 cos / d^2.
+ * Ranking is (fp64-accumulated key, row ascending).  stats nullable. */
+int rass_search_knn(rass_engine* h, const float* q_host, int B, int k,
+                    int64_t* out_rows, float* out_scores, double* out_keys, rass_stats* stats);
+/* device-pointer flavour: q_dev and outputs in device memory; enqueued on the engine stream and synchronised */
+int rass_search_knn_dev(rass_engine* h, const float* q_dev, int B, int k,
+                        int64_t* out_rows_dev, float* out_scores_dev, double* out_keys_dev, rass_stats* stats);
+
+/* Merge G per-shard top-k lists (what each rank all-gathers) into the global top-k, (key desc, row asc).
+ * keys_dev: [G, B, k] fp64, rows_dev: [G, B, k] int64 (-1 = empty).  Outputs [B, k], device memory. */
+int rass_merge_topk_dev(rass_engine* h, const double* keys_dev, const int64_t* rows_dev, int G, int B, int k,
+                        int64_t* out_rows_dev, float* out_scores_dev, double* out_keys_dev);
+
+/* CSR postings of the text field: indptr[V+1], doc[nnz] (local rows, ascending per term), tf[nnz], doclen[N]
+ * (token count per row).  Statistics (docCount, sumTotalTermFreq, df) are taken from these arrays unless the
+ * global_* overrides are given (row-sharded corpora share global statistics so scores are shard-invariant). */
+int rass_bm25_build(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
+                    const uint32_t* doclen, int64_t V, int64_t N,
+                    int64_t global_doc_count, int64_t global_sum_ttf, const int64_t* global_df);
+
+/* bool.should boosted sum: S(d) = w_text * BM25(q, d) + w_knn * [d in kNN_k(q)] * knn_score(q, d), top-k by
+ * (S desc, row asc) over rows matching at least one clause.  qterm_indptr[B+1] / qterms: term ids per query
+ * (duplicates count twice; ids outside [0, V) are ignored).  q_host may be NULL (text-only) and qterm_indptr may
+ * be NULL (vector-only). */
+int rass_search_hybrid(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr,
+                       const int32_t* qterms, float w_text, float w_knn, int k,
+                       int64_t* out_rows, float* out_scores, rass_stats* stats);
+
+int rass_sync(rass_engine* h);
+
+/* Debug only (no reference counterpart): raw tensor-core dot products bf16(q_hat) . bf16(x) of B <= 64 queries
+ * against every row, out_host [rows, 64] fp32.  Used by the tests to check the TMA/tcgen05 descriptors. */
+int rass_debug_umma_scores(rass_engine* h, const float* q_host, int B, float* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RASS_B200_H */

@@ -1,0 +1,64 @@
+"""Builds librass_b200.so (the C-ABI shared library) in-tree with nvcc for sm_100a.
+
+    python -m rassengine_b200.build [--force] [--verbose]
+
+The library links cudart statically and resolves the one driver entry point it needs
+(cuTensorMapEncodeTiled) at run time, so it loads on a machine without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = ["engine.cu", "store.cu", "scan_stream.cu", "scan_umma.cu", "finish.cu", "bm25.cu"]
+LIB = os.path.join(HERE, "librass_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+         "--expt-relaxed-constexpr"]
+
+
+def _deps():
+    out = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
+                                                      os.path.join(HERE, "..", "include", "rass_b200.h"), __file__]
+    return out
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in _deps())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    for s in SOURCES:
+        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    failed = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            sys.stderr.write(f"--- {s}\n{out}\n")
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

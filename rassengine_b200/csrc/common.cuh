@@ -1,0 +1,311 @@
+// Shared declarations for the engine: handle layout, error plumbing, the per-warp top-list used by the selects.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/rass_b200.h"
+
+#define RASS_WARPS_PER_CTA 8
+#define RASS_MAX_K 128
+#define RASS_CAND_MAX 2048     // rerank candidate cap per query
+#define RASS_GROUP_Q 64        // queries finished per finish launch (= queries per tcgen05 pass)
+#define RASS_STREAM_SEG 32     // pool entries per (warp, query) segment of the streaming scan
+#define RASS_UMMA_SEG 256      // pool entries per (CTA, query) segment of the tcgen05 scan
+#define RASS_UMMA_KEEP 32      // entries a tcgen05 segment keeps at a compaction
+#define RASS_EXACT_NQ 4        // queries per pass of the fp64 scan
+#define RASS_FINISH_THREADS 1024
+
+struct Bm25State {
+  int64_t V = 0, N = 0, nnz = 0;
+  int64_t* indptr = nullptr;     // device [V+1]
+  int32_t* doc = nullptr;        // device [nnz]
+  uint16_t* tf = nullptr;        // device [nnz]
+  uint8_t* norm = nullptr;       // device [N]  SmallFloat byte4 of the doc length
+  float* inv_dev = nullptr;      // device [256] 1 / (k1 * ((1-b) + b * len/avgdl))
+  double* acc = nullptr;         // device [N] per-query accumulator (kept zeroed between queries)
+  uint32_t* touched = nullptr;   // device [touched_cap] rows with acc != 0 for the running query
+  int64_t touched_cap = 0;
+  int64_t acc_rows = 0;
+  int* touched_n = nullptr;      // device counter
+  float avgdl = 0.f;
+  int64_t doc_count = 0;
+  std::vector<int64_t> indptr_host;
+  std::vector<float> idf_host;   // (float) ln(1 + (docCount - df + .5) / (df + .5))
+};
+
+// device-resident scalars the kernels update / read without a host round trip
+struct DevScalars {
+  float rho_x;        // max over rows of ||x - bf16(x)|| / ||x||
+  float max_xnorm;    // max over rows of ||x||
+  int flagged_n;      // queries that failed the certificate in the running search
+  int max_cand;       // largest rerank candidate set in the running search
+  int n_certified;
+  int pad[3];
+};
+
+struct rass_engine {
+  int dim = 0, dim_pad = 0, metric = 0, device = 0;
+  uint32_t flags = 0;
+  int num_sms = 0;
+  int path = RASS_PATH_AUTO;
+  int64_t cap = 0, n_rows = 0, n_live = 0, row_base = 0;
+  float* x32 = nullptr;             // [cap, dim_pad] fp32 (null when BF16_ONLY)
+  __nv_bfloat16* x16 = nullptr;     // [cap, dim_pad] bf16 shadow / corpus
+  double* norm64 = nullptr;         // [cap] ||x|| accumulated in fp64 from the stored values
+  float* sa = nullptr;              // [cap] scan scale:  cosine 1/||x|| (0 for zero rows), L2 1
+  float* sb = nullptr;              // [cap] scan offset: cosine 0, L2 -0.5||x||^2; -inf = tombstone
+  DevScalars* scal = nullptr;       // device
+  DevScalars* scal_host = nullptr;  // pinned mirror
+  cudaStream_t stream = nullptr, user_stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  float* stage[2] = {nullptr, nullptr};  // pinned host staging
+  size_t stage_bytes = 0;
+  float* dev_stage = nullptr;            // device staging (BF16_ONLY appends, dim != dim_pad appends)
+  size_t dev_stage_bytes = 0;
+  // query workspace (grows on demand)
+  int q_cap = 0;
+  float* q_raw = nullptr;           // [q_cap, dim_pad] fp32 as given (zero padded)
+  float* q_hat = nullptr;           // [q_cap, dim_pad] fp32 scan query (unit for cosine)
+  __nv_bfloat16* q16 = nullptr;     // [q_cap rounded to 64, dim_pad]
+  double* q_norm = nullptr;         // [q_cap]
+  float* q_rho = nullptr;           // [q_cap] ||q_hat - bf16(q_hat)|| / ||q_hat||
+  // candidate pool of one query group (RASS_GROUP_Q queries)
+  size_t pool_entries = 0;          // per query
+  float* pool_key = nullptr;
+  uint32_t* pool_row = nullptr;
+  size_t pool_segs = 0;             // per query
+  float* pool_thr = nullptr;
+  int* pool_cnt = nullptr;
+  // exact (fp64) lists
+  size_t xlist_entries = 0;
+  double* xlist_key = nullptr;
+  uint32_t* xlist_row = nullptr;
+  int* flagged = nullptr;           // device [q_cap]: ids of queries that failed the certificate
+  int* flagged_host = nullptr;      // pinned [q_cap]
+  int64_t* out_rows = nullptr;      // device result staging for the host-pointer API
+  float* out_scores = nullptr;
+  double* out_keys = nullptr;
+  size_t out_cap = 0;
+  int64_t* out_rows_host = nullptr; // pinned
+  float* out_scores_host = nullptr;
+  double* out_keys_host = nullptr;
+  float* q_stage_host = nullptr;    // pinned query staging
+  float* q_stage_dev = nullptr;
+  size_t q_stage_cap = 0;
+  std::vector<uint8_t> dead;        // host mirror of the tombstones
+  std::vector<cudaEvent_t> ev_pool; // per-group scan timing
+  void* tmap_x = nullptr;           // host copy of the CUtensorMap over x16 (rebuilt on growth)
+  void* tmap_q = nullptr;
+  int64_t tmap_rows = -1;
+  const void* tmap_base = nullptr;
+  const void* tmap_qbase = nullptr;
+  Bm25State bm25;
+  std::string err;
+};
+
+extern thread_local std::string g_create_error;
+
+int rass_fail(rass_engine* h, int code, const char* fmt, ...);
+
+#define CUDA_TRY(h, call)                                                                         \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return rass_fail((h), e_ == cudaErrorMemoryAllocation ? RASS_E_OOM : RASS_E_CUDA,           \
+                       "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static inline cudaStream_t eng_stream(const rass_engine* h) { return h->user_stream ? h->user_stream : h->stream; }
+
+// fp32 accumulation allowance of a length-d dot product with |x||q| <= 1 (gamma_d, doubled for the tensor
+// pipe's unspecified summation order)
+static inline float acc_allowance(int dim_pad) { return (float)dim_pad * 1.1920929e-7f; }
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float bf16lo(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
+
+template <typename K>
+__device__ __forceinline__ K neg_inf();
+template <>
+__device__ __forceinline__ float neg_inf<float>() { return __int_as_float(0xff800000); }
+template <>
+__device__ __forceinline__ double neg_inf<double>() { return __longlong_as_double(0xfff0000000000000ULL); }
+
+template <typename K>
+__device__ __forceinline__ bool entry_better(K ka, uint32_t ra, K kb, uint32_t rb) {
+  return ka > kb || (ka == kb && ra < rb);
+}
+
+__device__ __forceinline__ float shfl_xor_t(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double shfl_xor_t(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ float shfl_t(float v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+__device__ __forceinline__ double shfl_t(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+// Per-warp running top-(32*M) list.  Lane l owns slots key[0..M), row[0..M).  (thr_key, thr_row) is the
+// worst kept entry, uniform across the warp.  An entry is better when its key is larger, or equal with a
+// smaller row -- the (score desc, row asc) order of the oracle.  All methods must be called by the
+// full warp with warp-uniform arguments.
+template <typename K, int M>
+struct WarpTop {
+  K key[M];
+  uint32_t row[M];
+  K thr_key;
+  uint32_t thr_row;
+
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < M; ++i) { key[i] = neg_inf<K>(); row[i] = 0xffffffffu; }
+    thr_key = neg_inf<K>();
+    thr_row = 0xffffffffu;
+  }
+
+  // hot-path test for streams that arrive in ascending row order: equal keys can never displace
+  __device__ __forceinline__ bool admits_ascending(K k) const { return k > thr_key; }
+
+  __device__ __noinline__ void insert(K k, uint32_t r) {
+    if (!entry_better<K>(k, r, thr_key, thr_row)) return;
+    const int lane = threadIdx.x & 31;
+    // locate the worst entry: first lane (then first slot) that holds (thr_key, thr_row)
+    int slot = -1;
+#pragma unroll
+    for (int i = M - 1; i >= 0; --i)
+      if (key[i] == thr_key && row[i] == thr_row) slot = i;
+    unsigned holders = __ballot_sync(0xffffffffu, slot >= 0);
+    int owner = __ffs(holders) - 1;
+    if (lane == owner) {
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+        if (i == slot) { key[i] = k; row[i] = r; }
+    }
+    // recompute the worst entry
+    K wk = key[0];
+    uint32_t wr = row[0];
+#pragma unroll
+    for (int i = 1; i < M; ++i)
+      if (entry_better<K>(wk, wr, key[i], row[i])) { wk = key[i]; wr = row[i]; }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      K ok = shfl_xor_t(wk, m);
+      uint32_t orow = __shfl_xor_sync(0xffffffffu, wr, m);
+      if (entry_better<K>(wk, wr, ok, orow)) { wk = ok; wr = orow; }
+    }
+    thr_key = wk;
+    thr_row = wr;
+  }
+};
+
+// The exact key of (row, query): fp64 accumulation of the stored values, the definition the oracle uses
+// (oracle/knn.py cos64 / l2sq64).  Called by a full warp; the result is uniform across the warp.
+//   cosine: dot64 / (||x||_64 * ||q||_64), 0 when either norm is 0        (larger is better)
+//   L2    : -(sum (x - q)^2)                                              (larger is better)
+// qs: the raw fp32 query in shared memory, zero padded to dim_pad.
+template <bool BF16_ROWS>
+__device__ __forceinline__ double exact_key_warp(const float* __restrict__ x32, const __nv_bfloat16* __restrict__ x16,
+                                                 const double* __restrict__ norm64, uint32_t row, const float* qs,
+                                                 double qnorm, int dim_pad, int metric) {
+  const int lane = threadIdx.x & 31;
+  double acc = 0.0;
+  if (BF16_ROWS) {
+    const uint4* p = reinterpret_cast<const uint4*>(x16 + (size_t)row * dim_pad);
+    for (int j = lane; j < dim_pad / 8; j += 32) {
+      uint4 v = __ldg(p + j);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      const float* qq = qs + j * 8;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        double a = (double)bf16lo(w[e]), b = (double)bf16hi(w[e]);
+        double q0 = (double)qq[2 * e], q1 = (double)qq[2 * e + 1];
+        if (metric == RASS_METRIC_COSINE) {
+          acc = fma(a, q0, acc);
+          acc = fma(b, q1, acc);
+        } else {
+          double d0 = a - q0, d1 = b - q1;
+          acc = fma(d0, d0, acc);
+          acc = fma(d1, d1, acc);
+        }
+      }
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(x32 + (size_t)row * dim_pad);
+    for (int j = lane; j < dim_pad / 4; j += 32) {
+      float4 v = __ldg(p + j);
+      const float4 q = *reinterpret_cast<const float4*>(qs + j * 4);
+      if (metric == RASS_METRIC_COSINE) {
+        acc = fma((double)v.x, (double)q.x, acc);
+        acc = fma((double)v.y, (double)q.y, acc);
+        acc = fma((double)v.z, (double)q.z, acc);
+        acc = fma((double)v.w, (double)q.w, acc);
+      } else {
+        double d0 = (double)v.x - (double)q.x, d1 = (double)v.y - (double)q.y;
+        double d2 = (double)v.z - (double)q.z, d3 = (double)v.w - (double)q.w;
+        acc = fma(d0, d0, acc);
+        acc = fma(d1, d1, acc);
+        acc = fma(d2, d2, acc);
+        acc = fma(d3, d3, acc);
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if (metric == RASS_METRIC_COSINE) {
+    double den = norm64[row] * qnorm;
+    return den > 0.0 ? acc / den : 0.0;
+  }
+  return -acc;
+}
+
+__device__ __forceinline__ float score_from_key(double key, int metric) {
+  // OpenSearch k-NN score translation: cosinesimil 1/(2 - cos); l2 1/(1 + d^2)
+  return metric == RASS_METRIC_COSINE ? (float)(1.0 / (2.0 - key)) : (float)(1.0 / (1.0 - key));
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers (defined in the .cu files)
+// ---------------------------------------------------------------------------------------------
+int launch_store_convert(rass_engine* h, const float* src_dev, int64_t src_stride, int64_t first_row, int64_t n,
+                         cudaStream_t st);
+int launch_query_prep(rass_engine* h, const float* q_dev, int B, cudaStream_t st);
+// streaming scan of queries [q0, q0+nq) (nq = 1 or 2); their pool slots are q - g0
+int launch_scan_stream(rass_engine* h, int q0, int nq, int g0, cudaStream_t st);
+int scan_stream_segs(const rass_engine* h);
+// tcgen05 scan of queries [q0, q0+nq) (nq <= 64) into pool slots 0..nq
+int launch_scan_umma(rass_engine* h, int q0, int nq, cudaStream_t st);
+int scan_umma_segs(const rass_engine* h);
+int umma_selftest(rass_engine* h, int n_rows_tile, float* out_host, cudaStream_t st);
+// merge the pool of queries [g0, g0+ng), rerank in fp64, emit top-k, flag uncertified queries
+int launch_finish(rass_engine* h, int g0, int ng, int k, int n_segs, int seg_size, bool has_cnt, bool q_is_bf16,
+                  int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st);
+// fp64 scan of the listed queries (qids host array, n_q of them)
+int launch_exact(rass_engine* h, int k, const int* qids_host, int n_q, int64_t* out_rows, float* out_scores,
+                 double* out_keys, cudaStream_t st, int* launches);
+int launch_merge_topk(rass_engine* h, const double* keys, const int64_t* rows, int G, int B, int k,
+                      int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st);
+int ensure_query_workspace(rass_engine* h, int B);
+int ensure_pool(rass_engine* h, size_t entries_per_query, size_t segs_per_query);
+int ensure_xlist_workspace(rass_engine* h, size_t entries);
+int ensure_out_workspace(rass_engine* h, size_t n);

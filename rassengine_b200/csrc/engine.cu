@@ -1,0 +1,594 @@
+// Engine handle, vector store management and the search orchestration behind the C ABI (include/rass_b200.h).
+//
+// The store is what OpenSearch keeps for the `embedding` knn_vector field (reference app/main.py:563-572):
+// here a device-resident fp32 matrix + bf16 shadow + per-row norms, filled by `bulk index` through pinned,
+// double-buffered async copies (reference app/main.py:1247-1269).
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+thread_local std::string g_create_error;
+
+int rass_fail(rass_engine* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+extern "C" const char* rass_version(void) { return "rass-b200 0.1 (abi 1, sm_100a)"; }
+
+extern "C" const char* rass_last_error(const rass_engine* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+#define CHECK_HANDLE(h)                    \
+  do {                                     \
+    if (!(h)) return RASS_E_INVALID;       \
+    cudaSetDevice((h)->device);            \
+  } while (0)
+
+template <typename T>
+static int dev_realloc(rass_engine* h, T** p, size_t old_n, size_t new_n, cudaStream_t st) {
+  T* np = nullptr;
+  CUDA_TRY(h, cudaMalloc(&np, new_n * sizeof(T)));
+  if (*p && old_n) CUDA_TRY(h, cudaMemcpyAsync(np, *p, old_n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+  if (*p) {
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    cudaFree(*p);
+  }
+  *p = np;
+  return RASS_OK;
+}
+
+static int ensure_capacity(rass_engine* h, int64_t rows) {
+  if (rows <= h->cap) return RASS_OK;
+  int64_t ncap = std::max<int64_t>(rows, std::max<int64_t>(h->cap * 2, 1024));
+  if (ncap > 0xfffffff0LL) return rass_fail(h, RASS_E_INVALID, "a shard holds at most 2^32-16 rows");
+  cudaStream_t st = eng_stream(h);
+  const size_t o = (size_t)h->n_rows, n = (size_t)ncap, d = (size_t)h->dim_pad;
+  int rc;
+  if (!(h->flags & RASS_BF16_ONLY))
+    if ((rc = dev_realloc(h, &h->x32, o * d, n * d, st))) return rc;
+  if ((rc = dev_realloc(h, &h->x16, o * d, n * d, st))) return rc;
+  if ((rc = dev_realloc(h, &h->norm64, o, n, st))) return rc;
+  if ((rc = dev_realloc(h, &h->sa, o, n, st))) return rc;
+  if ((rc = dev_realloc(h, &h->sb, o, n, st))) return rc;
+  h->cap = ncap;
+  return RASS_OK;
+}
+
+extern "C" int rass_create(int dim, int metric, int device, int64_t capacity_rows, uint32_t flags,
+                           rass_engine** out) {
+  if (!out) return rass_fail(nullptr, RASS_E_INVALID, "out is null");
+  *out = nullptr;
+  if (dim < 1 || dim > 1024) return rass_fail(nullptr, RASS_E_INVALID, "dim must be in [1, 1024], got %d", dim);
+  if (metric != RASS_METRIC_COSINE && metric != RASS_METRIC_L2)
+    return rass_fail(nullptr, RASS_E_INVALID, "unknown metric %d", metric);
+  if ((flags & RASS_KEEP_FP32) && (flags & RASS_BF16_ONLY))
+    return rass_fail(nullptr, RASS_E_INVALID, "RASS_KEEP_FP32 and RASS_BF16_ONLY are exclusive");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return rass_fail(nullptr, RASS_E_CUDA, "no CUDA device (%s); this engine has no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n_dev) return rass_fail(nullptr, RASS_E_INVALID, "device %d out of range", device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+    return rass_fail(nullptr, RASS_E_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return rass_fail(nullptr, RASS_E_CUDA, "device %d is sm_%d%d; this engine is built for sm_100a only", device,
+                     prop.major, prop.minor);
+  rass_engine* h = new rass_engine();
+  h->dim = dim;
+  h->dim_pad = (dim + 255) / 256 * 256;
+  h->metric = metric;
+  h->device = device;
+  h->flags = flags ? flags : RASS_KEEP_FP32;
+  h->num_sms = prop.multiProcessorCount;
+  auto bail = [&](int code) {
+    g_create_error = h->err;
+    rass_destroy(h);
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(RASS_E_CUDA); }
+#define CREATE_TRY(call)                                                                            \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      h->err = std::string(#call) + " failed: " + cudaGetErrorString(e_);                           \
+      return bail(e_ == cudaErrorMemoryAllocation ? RASS_E_OOM : RASS_E_CUDA);                      \
+    }                                                                                               \
+  } while (0)
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; ++i) CREATE_TRY(cudaEventCreate(&h->ev[i]));
+  for (int i = 0; i < 2; ++i) CREATE_TRY(cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming));
+  h->stage_bytes = (size_t)32 << 20;
+  for (int i = 0; i < 2; ++i) CREATE_TRY(cudaMallocHost(&h->stage[i], h->stage_bytes));
+  CREATE_TRY(cudaMalloc(&h->scal, sizeof(DevScalars)));
+  CREATE_TRY(cudaMemset(h->scal, 0, sizeof(DevScalars)));
+  CREATE_TRY(cudaMallocHost(&h->scal_host, sizeof(DevScalars)));
+  memset(h->scal_host, 0, sizeof(DevScalars));
+#undef CREATE_TRY
+  if (capacity_rows > 0) {
+    int rc = ensure_capacity(h, capacity_rows);
+    if (rc) return bail(rc);
+  }
+  *out = h;
+  return RASS_OK;
+}
+
+extern "C" int rass_destroy(rass_engine* h) {
+  if (!h) return RASS_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  cudaFree(h->x32); cudaFree(h->x16); cudaFree(h->norm64); cudaFree(h->sa); cudaFree(h->sb);
+  cudaFree(h->scal); cudaFreeHost(h->scal_host);
+  cudaFree(h->dev_stage);
+  cudaFree(h->q_raw); cudaFree(h->q_hat); cudaFree(h->q16); cudaFree(h->q_norm); cudaFree(h->q_rho);
+  cudaFree(h->pool_key); cudaFree(h->pool_row); cudaFree(h->pool_thr); cudaFree(h->pool_cnt);
+  cudaFree(h->xlist_key); cudaFree(h->xlist_row);
+  cudaFree(h->flagged); cudaFreeHost(h->flagged_host);
+  cudaFree(h->out_rows); cudaFree(h->out_scores); cudaFree(h->out_keys);
+  cudaFreeHost(h->out_rows_host); cudaFreeHost(h->out_scores_host); cudaFreeHost(h->out_keys_host);
+  cudaFreeHost(h->q_stage_host);
+  cudaFree(h->q_stage_dev);
+  for (cudaEvent_t e : h->ev_pool) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) { cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
+  for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  Bm25State& b = h->bm25;
+  cudaFree(b.indptr); cudaFree(b.doc); cudaFree(b.tf); cudaFree(b.norm); cudaFree(b.inv_dev); cudaFree(b.acc);
+  cudaFree(b.touched); cudaFree(b.touched_n);
+  free(h->tmap_x); free(h->tmap_q);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+  return RASS_OK;
+}
+
+extern "C" int rass_set_option(rass_engine* h, int opt, int64_t value) {
+  CHECK_HANDLE(h);
+  switch (opt) {
+    case RASS_OPT_PATH:
+      if (value < RASS_PATH_AUTO || value > RASS_PATH_EXACT) return rass_fail(h, RASS_E_INVALID, "bad path %lld", (long long)value);
+      h->path = (int)value;
+      return RASS_OK;
+    case RASS_OPT_STREAM:
+      h->user_stream = reinterpret_cast<cudaStream_t>(value);
+      return RASS_OK;
+    default:
+      return rass_fail(h, RASS_E_INVALID, "unknown option %d", opt);
+  }
+}
+
+extern "C" int rass_set_row_base(rass_engine* h, int64_t base) {
+  CHECK_HANDLE(h);
+  h->row_base = base;
+  return RASS_OK;
+}
+
+extern "C" int rass_count(const rass_engine* h, int64_t* out) {
+  if (!h || !out) return RASS_E_INVALID;
+  *out = h->n_live;
+  return RASS_OK;
+}
+
+extern "C" int rass_rows(const rass_engine* h, int64_t* out) {
+  if (!h || !out) return RASS_E_INVALID;
+  *out = h->n_rows;
+  return RASS_OK;
+}
+
+extern "C" int rass_sync(rass_engine* h) {
+  CHECK_HANDLE(h);
+  CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+  return RASS_OK;
+}
+
+static int ensure_dev_stage(rass_engine* h, size_t bytes) {
+  if (bytes <= h->dev_stage_bytes) return RASS_OK;
+  CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+  cudaFree(h->dev_stage);
+  h->dev_stage = nullptr;
+  h->dev_stage_bytes = 0;
+  CUDA_TRY(h, cudaMalloc(&h->dev_stage, bytes));
+  h->dev_stage_bytes = bytes;
+  return RASS_OK;
+}
+
+static bool direct_fp32(const rass_engine* h) { return !(h->flags & RASS_BF16_ONLY) && h->dim == h->dim_pad; }
+
+// rows already on the device: [n, dim] fp32
+static int append_from_device(rass_engine* h, const float* rows_dev, int64_t first, int64_t n, cudaStream_t st) {
+  if (direct_fp32(h)) {
+    float* dst = h->x32 + (size_t)first * h->dim_pad;
+    if (rows_dev != dst)
+      CUDA_TRY(h, cudaMemcpyAsync(dst, rows_dev, (size_t)n * h->dim * 4, cudaMemcpyDeviceToDevice, st));
+    return launch_store_convert(h, dst, h->dim_pad, first, n, st);
+  }
+  return launch_store_convert(h, rows_dev, h->dim, first, n, st);
+}
+
+extern "C" int rass_append_dev(rass_engine* h, const float* rows_dev, int64_t n, int64_t* out_first_row) {
+  CHECK_HANDLE(h);
+  if (n < 0 || (n > 0 && !rows_dev)) return rass_fail(h, RASS_E_INVALID, "bad rows");
+  int rc = ensure_capacity(h, h->n_rows + n);
+  if (rc) return rc;
+  cudaStream_t st = eng_stream(h);
+  const int64_t first = h->n_rows;
+  if ((rc = append_from_device(h, rows_dev, first, n, st))) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  h->n_rows += n;
+  h->n_live += n;
+  h->dead.resize((size_t)h->n_rows, 0);
+  if (out_first_row) *out_first_row = first;
+  return RASS_OK;
+}
+
+// host rows -> device rows [first, first+n) through the pinned double buffer
+static int upload_rows(rass_engine* h, const float* rows_host, int64_t first, int64_t n, cudaStream_t st) {
+  const size_t row_bytes = (size_t)h->dim * 4;
+  cudaPointerAttributes attr;
+  bool pinned = cudaPointerGetAttributes(&attr, rows_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const int64_t chunk = std::max<int64_t>(1, (int64_t)(h->stage_bytes / row_bytes));
+  int rc;
+  if (!direct_fp32(h) && (rc = ensure_dev_stage(h, (size_t)std::min<int64_t>(chunk, n) * row_bytes))) return rc;
+  int buf = 0;
+  for (int64_t off = 0; off < n; off += chunk, buf ^= 1) {
+    const int64_t m = std::min<int64_t>(chunk, n - off);
+    const float* src = rows_host + (size_t)off * h->dim;
+    if (!pinned) {
+      CUDA_TRY(h, cudaEventSynchronize(h->stage_ev[buf]));
+      memcpy(h->stage[buf], src, (size_t)m * row_bytes);
+      src = h->stage[buf];
+    }
+    float* dst = direct_fp32(h) ? h->x32 + (size_t)(first + off) * h->dim_pad : h->dev_stage;
+    CUDA_TRY(h, cudaMemcpyAsync(dst, src, (size_t)m * row_bytes, cudaMemcpyHostToDevice, st));
+    if (!pinned) CUDA_TRY(h, cudaEventRecord(h->stage_ev[buf], st));
+    if ((rc = launch_store_convert(h, dst, direct_fp32(h) ? h->dim_pad : h->dim, first + off, m, st))) return rc;
+  }
+  return RASS_OK;
+}
+
+extern "C" int rass_append(rass_engine* h, const float* rows_host, int64_t n, int64_t* out_first_row) {
+  CHECK_HANDLE(h);
+  if (n < 0 || (n > 0 && !rows_host)) return rass_fail(h, RASS_E_INVALID, "bad rows");
+  int rc = ensure_capacity(h, h->n_rows + n);
+  if (rc) return rc;
+  cudaStream_t st = eng_stream(h);
+  const int64_t first = h->n_rows;
+  if ((rc = upload_rows(h, rows_host, first, n, st))) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  h->n_rows += n;
+  h->n_live += n;
+  h->dead.resize((size_t)h->n_rows, 0);
+  if (out_first_row) *out_first_row = first;
+  return RASS_OK;
+}
+
+extern "C" int rass_overwrite(rass_engine* h, int64_t row, const float* v_host) {
+  CHECK_HANDLE(h);
+  if (row < 0 || row >= h->n_rows || !v_host) return rass_fail(h, RASS_E_NOTFOUND, "row %lld out of range", (long long)row);
+  cudaStream_t st = eng_stream(h);
+  int rc = upload_rows(h, v_host, row, 1, st);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  if (h->dead[(size_t)row]) { h->dead[(size_t)row] = 0; h->n_live++; }
+  return RASS_OK;
+}
+
+extern "C" int rass_tombstone(rass_engine* h, int64_t row) {
+  CHECK_HANDLE(h);
+  if (row < 0 || row >= h->n_rows) return rass_fail(h, RASS_E_NOTFOUND, "row %lld out of range", (long long)row);
+  if (h->dead[(size_t)row]) return RASS_OK;
+  cudaStream_t st = eng_stream(h);
+  const uint32_t ninf = 0xff800000u;
+  CUDA_TRY(h, cudaMemcpyAsync(h->sb + row, &ninf, 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  h->dead[(size_t)row] = 1;
+  h->n_live--;
+  return RASS_OK;
+}
+
+__global__ void widen_rows_kernel(const __nv_bfloat16* __restrict__ x16, int dim, int dim_pad, int64_t first,
+                                  int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * dim) return;
+  const int64_t r = i / dim;
+  const int c = (int)(i % dim);
+  out[i] = __bfloat162float(x16[(size_t)(first + r) * dim_pad + c]);
+}
+
+extern "C" int rass_read_rows(rass_engine* h, int64_t first_row, int64_t n, float* out_host) {
+  CHECK_HANDLE(h);
+  if (first_row < 0 || n < 0 || first_row + n > h->n_rows || (n && !out_host))
+    return rass_fail(h, RASS_E_NOTFOUND, "rows [%lld, +%lld) out of range", (long long)first_row, (long long)n);
+  if (n == 0) return RASS_OK;
+  cudaStream_t st = eng_stream(h);
+  if (!(h->flags & RASS_BF16_ONLY)) {
+    CUDA_TRY(h, cudaMemcpy2DAsync(out_host, (size_t)h->dim * 4, h->x32 + (size_t)first_row * h->dim_pad,
+                                  (size_t)h->dim_pad * 4, (size_t)h->dim * 4, (size_t)n, cudaMemcpyDeviceToHost, st));
+  } else {
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t)64 << 20) / (h->dim * 4));
+    int rc = ensure_dev_stage(h, (size_t)std::min(chunk, n) * h->dim * 4);
+    if (rc) return rc;
+    for (int64_t off = 0; off < n; off += chunk) {
+      const int64_t m = std::min(chunk, n - off);
+      const int64_t tot = m * h->dim;
+      widen_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->x16, h->dim, h->dim_pad, first_row + off, m,
+                                                                       h->dev_stage);
+      CUDA_TRY(h, cudaGetLastError());
+      CUDA_TRY(h, cudaMemcpyAsync(out_host + (size_t)off * h->dim, h->dev_stage, (size_t)tot * 4,
+                                  cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return RASS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspaces
+// ---------------------------------------------------------------------------------------------
+#define REALLOC_DEV(h, p, n)                                    \
+  do {                                                          \
+    cudaFree(p);                                                \
+    (p) = nullptr;                                              \
+    CUDA_TRY(h, cudaMalloc(&(p), (n) * sizeof(*(p))));          \
+  } while (0)
+#define REALLOC_HOST(h, p, n)                                   \
+  do {                                                          \
+    cudaFreeHost(p);                                            \
+    (p) = nullptr;                                              \
+    CUDA_TRY(h, cudaMallocHost(&(p), (n) * sizeof(*(p))));      \
+  } while (0)
+
+int ensure_query_workspace(rass_engine* h, int B) {
+  if (B <= h->q_cap) return RASS_OK;
+  CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+  const size_t cap = (size_t)(B + RASS_GROUP_Q - 1) / RASS_GROUP_Q * RASS_GROUP_Q, d = (size_t)h->dim_pad;
+  REALLOC_DEV(h, h->q_raw, cap * d);
+  REALLOC_DEV(h, h->q_hat, cap * d);
+  REALLOC_DEV(h, h->q16, cap * d);
+  REALLOC_DEV(h, h->q_norm, cap);
+  REALLOC_DEV(h, h->q_rho, cap);
+  REALLOC_DEV(h, h->flagged, cap);
+  REALLOC_HOST(h, h->flagged_host, cap);
+  h->q_cap = (int)cap;
+  h->tmap_qbase = nullptr;
+  return RASS_OK;
+}
+
+int ensure_pool(rass_engine* h, size_t entries_per_query, size_t segs_per_query) {
+  if (entries_per_query > h->pool_entries) {
+    CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+    REALLOC_DEV(h, h->pool_key, entries_per_query * RASS_GROUP_Q);
+    REALLOC_DEV(h, h->pool_row, entries_per_query * RASS_GROUP_Q);
+    h->pool_entries = entries_per_query;
+  }
+  if (segs_per_query > h->pool_segs) {
+    CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+    REALLOC_DEV(h, h->pool_thr, segs_per_query * RASS_GROUP_Q);
+    REALLOC_DEV(h, h->pool_cnt, segs_per_query * RASS_GROUP_Q);
+    h->pool_segs = segs_per_query;
+  }
+  return RASS_OK;
+}
+
+int ensure_xlist_workspace(rass_engine* h, size_t entries) {
+  if (entries <= h->xlist_entries) return RASS_OK;
+  CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+  REALLOC_DEV(h, h->xlist_key, entries * RASS_EXACT_NQ);
+  REALLOC_DEV(h, h->xlist_row, entries * RASS_EXACT_NQ);
+  h->xlist_entries = entries;
+  return RASS_OK;
+}
+
+int ensure_out_workspace(rass_engine* h, size_t n) {
+  if (n <= h->out_cap) return RASS_OK;
+  CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+  REALLOC_DEV(h, h->out_rows, n);
+  REALLOC_DEV(h, h->out_scores, n);
+  REALLOC_DEV(h, h->out_keys, n);
+  REALLOC_HOST(h, h->out_rows_host, n);
+  REALLOC_HOST(h, h->out_scores_host, n);
+  REALLOC_HOST(h, h->out_keys_host, n);
+  h->out_cap = n;
+  return RASS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------------------------
+__global__ void fill_empty_kernel(int64_t* rows, float* scores, double* keys, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rows[i] = -1;
+  scores[i] = 0.f;
+  if (keys) keys[i] = 0.0;
+}
+
+static int resolve_path(const rass_engine* h, int B) {
+  if (h->path != RASS_PATH_AUTO) return h->path;
+  return B <= 2 ? RASS_PATH_STREAM : RASS_PATH_UMMA;
+}
+
+static cudaEvent_t get_event(rass_engine* h, size_t i) {
+  while (h->ev_pool.size() <= i) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[i];
+}
+
+// q_dev: [B, dim] fp32 on this device; outputs on this device.  Synchronises the stream before returning.
+int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
+                double* out_keys, rass_stats* stats) {
+  if (B < 1) return rass_fail(h, RASS_E_INVALID, "B must be >= 1");
+  if (k < 1 || k > RASS_MAX_K) return rass_fail(h, RASS_E_INVALID, "k must be in [1, %d], got %d", RASS_MAX_K, k);
+  cudaStream_t st = eng_stream(h);
+  int rc;
+  if ((rc = ensure_query_workspace(h, B))) return rc;
+  rass_stats s;
+  memset(&s, 0, sizeof(s));
+  s.n_queries = B;
+  s.rows_scanned = h->n_rows;
+  const size_t n_out = (size_t)B * k;
+  if (h->n_rows == 0) {
+    fill_empty_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(out_rows, out_scores, out_keys, n_out);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    s.n_certified = B;
+    s.launches = 1;
+    if (stats) *stats = s;
+    return RASS_OK;
+  }
+  const int path = resolve_path(h, B);
+  s.path = path;
+  // reset the per-search device counters (keeps rho_x / max_xnorm)
+  CUDA_TRY(h, cudaMemsetAsync(&h->scal->flagged_n, 0, sizeof(int) * 3, st));
+  CUDA_TRY(h, cudaEventRecord(h->ev[0], st));
+  if ((rc = launch_query_prep(h, q_dev, B, st))) return rc;
+  s.launches = 1;
+  size_t n_ev = 0;
+  if (path == RASS_PATH_EXACT) {
+    for (int i = 0; i < B; ++i) h->flagged_host[i] = i;
+    CUDA_TRY(h, cudaEventRecord(h->ev[1], st));
+    if ((rc = launch_exact(h, k, h->flagged_host, B, out_rows, out_scores, out_keys, st, &s.launches))) return rc;
+    s.n_fallback = B;
+    s.passes = (B + RASS_EXACT_NQ - 1) / RASS_EXACT_NQ;
+    s.bytes_streamed = (int64_t)s.passes * h->n_rows * h->dim_pad * ((h->flags & RASS_BF16_ONLY) ? 2 : 4);
+  } else {
+    const bool umma = path == RASS_PATH_UMMA;
+    const int n_segs = umma ? scan_umma_segs(h) : scan_stream_segs(h);
+    const int seg = umma ? RASS_UMMA_SEG : RASS_STREAM_SEG;
+    if ((rc = ensure_pool(h, (size_t)n_segs * seg, (size_t)n_segs))) return rc;
+    for (int g0 = 0; g0 < B; g0 += RASS_GROUP_Q) {
+      const int ng = std::min(RASS_GROUP_Q, B - g0);
+      CUDA_TRY(h, cudaEventRecord(get_event(h, n_ev++), st));
+      if (umma) {
+        if ((rc = launch_scan_umma(h, g0, ng, st))) return rc;
+        s.launches += 2;
+        s.passes += 1;
+      } else {
+        for (int q0 = g0; q0 < g0 + ng; q0 += 2) {
+          if ((rc = launch_scan_stream(h, q0, std::min(2, g0 + ng - q0), g0, st))) return rc;
+          s.launches += 1;
+          s.passes += 1;
+        }
+      }
+      CUDA_TRY(h, cudaEventRecord(get_event(h, n_ev++), st));
+      if ((rc = launch_finish(h, g0, ng, k, n_segs, seg, umma, umma, out_rows, out_scores, out_keys, st))) return rc;
+      s.launches += 1;
+    }
+    s.bytes_streamed = (int64_t)s.passes * h->n_rows * h->dim_pad * 2;
+    CUDA_TRY(h, cudaEventRecord(h->ev[1], st));
+    CUDA_TRY(h, cudaMemcpyAsync(h->scal_host, h->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    const int nf = h->scal_host->flagged_n;
+    s.n_certified = h->scal_host->n_certified;
+    s.max_candidates = h->scal_host->max_cand;
+    if (nf > 0) {
+      CUDA_TRY(h, cudaMemcpyAsync(h->flagged_host, h->flagged, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(h, cudaStreamSynchronize(st));
+      std::sort(h->flagged_host, h->flagged_host + nf);
+      if ((rc = launch_exact(h, k, h->flagged_host, nf, out_rows, out_scores, out_keys, st, &s.launches))) return rc;
+      s.n_fallback = nf;
+    }
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev[2], st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]));
+  s.total_ms = ms;
+  double scan = 0.0;
+  for (size_t i = 0; i + 1 < n_ev; i += 2) {
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
+    scan += ms;
+  }
+  s.scan_ms = scan;
+  s.finish_ms = s.total_ms - scan;
+  if (stats) *stats = s;
+  return RASS_OK;
+}
+
+extern "C" int rass_search_knn_dev(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows_dev,
+                                   float* out_scores_dev, double* out_keys_dev, rass_stats* stats) {
+  CHECK_HANDLE(h);
+  if (!q_dev || !out_rows_dev || !out_scores_dev) return rass_fail(h, RASS_E_INVALID, "null buffer");
+  return search_core(h, q_dev, B, k, out_rows_dev, out_scores_dev, out_keys_dev, stats);
+}
+
+int stage_queries(rass_engine* h, const float* q_host, int B, float** q_dev_out) {
+  const size_t n = (size_t)B * h->dim;
+  if (n > h->q_stage_cap) {
+    CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+    REALLOC_HOST(h, h->q_stage_host, n);
+    cudaFree(h->q_stage_dev);
+    h->q_stage_dev = nullptr;
+    CUDA_TRY(h, cudaMalloc(&h->q_stage_dev, n * 4));
+    h->q_stage_cap = n;
+  }
+  memcpy(h->q_stage_host, q_host, n * 4);
+  CUDA_TRY(h, cudaMemcpyAsync(h->q_stage_dev, h->q_stage_host, n * 4, cudaMemcpyHostToDevice, eng_stream(h)));
+  *q_dev_out = h->q_stage_dev;
+  return RASS_OK;
+}
+
+extern "C" int rass_search_knn(rass_engine* h, const float* q_host, int B, int k, int64_t* out_rows,
+                               float* out_scores, double* out_keys, rass_stats* stats) {
+  CHECK_HANDLE(h);
+  if (!q_host || !out_rows || !out_scores) return rass_fail(h, RASS_E_INVALID, "null buffer");
+  if (B < 1) return rass_fail(h, RASS_E_INVALID, "B must be >= 1");
+  if (k < 1 || k > RASS_MAX_K) return rass_fail(h, RASS_E_INVALID, "k must be in [1, %d], got %d", RASS_MAX_K, k);
+  int rc;
+  float* q_dev = nullptr;
+  if ((rc = stage_queries(h, q_host, B, &q_dev))) return rc;
+  const size_t n_out = (size_t)B * k;
+  if ((rc = ensure_out_workspace(h, n_out))) return rc;
+  if ((rc = search_core(h, q_dev, B, k, h->out_rows, h->out_scores, out_keys ? h->out_keys : nullptr, stats)))
+    return rc;
+  cudaStream_t st = eng_stream(h);
+  CUDA_TRY(h, cudaMemcpyAsync(h->out_rows_host, h->out_rows, n_out * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaMemcpyAsync(h->out_scores_host, h->out_scores, n_out * 4, cudaMemcpyDeviceToHost, st));
+  if (out_keys) CUDA_TRY(h, cudaMemcpyAsync(h->out_keys_host, h->out_keys, n_out * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  memcpy(out_rows, h->out_rows_host, n_out * 8);
+  memcpy(out_scores, h->out_scores_host, n_out * 4);
+  if (out_keys) memcpy(out_keys, h->out_keys_host, n_out * 8);
+  return RASS_OK;
+}
+
+extern "C" int rass_merge_topk_dev(rass_engine* h, const double* keys_dev, const int64_t* rows_dev, int G, int B,
+                                   int k, int64_t* out_rows_dev, float* out_scores_dev, double* out_keys_dev) {
+  CHECK_HANDLE(h);
+  if (!keys_dev || !rows_dev || !out_rows_dev || !out_scores_dev || G < 1 || B < 1 || k < 1)
+    return rass_fail(h, RASS_E_INVALID, "bad merge arguments");
+  cudaStream_t st = eng_stream(h);
+  int rc = launch_merge_topk(h, keys_dev, rows_dev, G, B, k, out_rows_dev, out_scores_dev, out_keys_dev, st);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return RASS_OK;
+}
+
+// Debug entry (not part of the reference surface): raw tcgen05 dot products of <= 64 queries against every row,
+// out_host [n_rows, 64].  Lets the tests check the TMA/UMMA descriptors in isolation.
+extern "C" int rass_debug_umma_scores(rass_engine* h, const float* q_host, int B, float* out_host) {
+  CHECK_HANDLE(h);
+  if (!q_host || !out_host || B < 1 || B > RASS_GROUP_Q) return rass_fail(h, RASS_E_INVALID, "bad arguments");
+  if (h->n_rows == 0) return RASS_OK;
+  int rc;
+  float* q_dev = nullptr;
+  if ((rc = ensure_query_workspace(h, B))) return rc;
+  if ((rc = stage_queries(h, q_host, B, &q_dev))) return rc;
+  cudaStream_t st = eng_stream(h);
+  if ((rc = launch_query_prep(h, q_dev, B, st))) return rc;
+  return umma_selftest(h, 0, out_host, st);
+}

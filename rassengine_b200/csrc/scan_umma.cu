@@ -1,0 +1,424 @@
+// Batched kNN scan on the 5th-generation tensor cores: up to 64 queries per corpus pass.
+//
+// Replaces the `knn` clause executor (reference app/main.py:1538-1542 -> OpenSearch k-NN plugin / nmslib HNSW)
+// when several queries share one pass over the bf16 shadow matrix.  For <= 64 queries the pass is still
+// HBM-bound (64 flop/byte against a ridge of ~210), but only the tensor pipe can keep up with the stream.
+//
+// One persistent CTA per SM.  A = a 128-row corpus tile (M = 128, K-major, 128B-swizzled, streamed by TMA in
+// 64-element k-blocks through a ring of smem stages), B = the 64 queries (N = 64, resident in smem for the
+// whole pass), D = 128 x 64 fp32 in TMEM, four accumulator stages so the epilogue of tile i overlaps the MMAs
+// of tiles i+1..i+3.  Warp 0 lane 0 issues TMA, warp 1 lane 0 issues tcgen05.mma, warp 2 owns the TMEM
+// allocation, warps 4-7 are the epilogue: thread = corpus row (TMEM lane), 64 scores per thread read with
+// tcgen05.ld; a score that beats the CTA's running per-query threshold is appended to that query's segment of
+// the candidate pool.  When a segment passes 128 entries it is compacted to its best 32 and the threshold
+// rises to the 32nd key; everything dropped or rejected is <= that threshold, which is the bound the
+// certificate in finish.cu needs.  The score matrix never reaches HBM.
+#include <cuda.h>
+
+#include "common.cuh"
+
+#define UMMA_ROWS 128
+#define UMMA_NQ 64
+#define UMMA_KBLK 64                       // bf16 elements per k-block (128 bytes: one swizzle row)
+#define UMMA_STAGE_BYTES (UMMA_ROWS * 128)  // 16 KB
+#define UMMA_QBLK_BYTES (UMMA_NQ * 128)     // 8 KB
+#define UMMA_STAGES 5
+#define UMMA_ACC 4                          // TMEM accumulator stages (64 columns each)
+#define UMMA_TMEM_COLS 256
+#define UMMA_THREADS 256
+#define UMMA_HIGH_WATER 128
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// A wait that cannot hang the device: a barrier that stays closed for ~2 s is a bug, so trap.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("rass scan_umma: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile whose rows are 128 bytes: 8-row groups are 1024 bytes apart (SBO),
+// LBO is the canonical 1 (x16 bytes), descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = 64, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((UMMA_NQ >> 3) << 17) | ((UMMA_ROWS >> 4) << 24);
+
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+struct UmmaSmem {
+  uint64_t full[UMMA_STAGES];
+  uint64_t empty[UMMA_STAGES];
+  uint64_t acc_full[UMMA_ACC];
+  uint64_t acc_empty[UMMA_ACC];
+  uint64_t q_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+  float thr[UMMA_NQ];
+  int cnt[UMMA_NQ];
+};
+
+}  // namespace
+
+__global__ void __launch_bounds__(UMMA_THREADS, 1)
+    scan_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_q,
+                     const float* __restrict__ sa, const float* __restrict__ sb, int64_t n_rows, int n_tiles,
+                     int k_blocks, int q_row0, float* __restrict__ pool_key, uint32_t* __restrict__ pool_row,
+                     float* __restrict__ pool_thr, int* __restrict__ pool_cnt, size_t pool_entries, int n_segs,
+                     float* __restrict__ dbg_out) {
+  extern __shared__ unsigned char smem_dyn[];
+  // 128B-swizzled tiles need 1024-byte alignment: [ Q: k_blocks * 8 KB ][ stages: UMMA_STAGES * 16 KB ][ UmmaSmem ]
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  unsigned char* q_smem = smem;
+  unsigned char* x_smem = smem + (size_t)k_blocks * UMMA_QBLK_BYTES;
+  UmmaSmem* ss = reinterpret_cast<UmmaSmem*>(x_smem + (size_t)UMMA_STAGES * UMMA_STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < UMMA_STAGES; ++i) { mbar_init(&ss->full[i], 1); mbar_init(&ss->empty[i], 1); }
+    for (int i = 0; i < UMMA_ACC; ++i) { mbar_init(&ss->acc_full[i], 1); mbar_init(&ss->acc_empty[i], 4); }
+    mbar_init(&ss->q_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (threadIdx.x < UMMA_NQ) {
+    ss->thr[threadIdx.x] = neg_inf<float>();
+    ss->cnt[threadIdx.x] = 0;
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ss->tmem_base)),
+                 "r"((uint32_t)UMMA_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ss->tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(&ss->q_full, (uint32_t)k_blocks * UMMA_QBLK_BYTES);
+      for (int kb = 0; kb < k_blocks; ++kb)
+        tma_load_2d(&map_q, &ss->q_full, q_smem + (size_t)kb * UMMA_QBLK_BYTES, kb * UMMA_KBLK, q_row0, kEvictLast);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cta; tile < n_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&ss->empty[stage], phase ^ 1);
+          mbar_expect_tx(&ss->full[stage], UMMA_STAGE_BYTES);
+          tma_load_2d(&map_x, &ss->full[stage], x_smem + (size_t)stage * UMMA_STAGE_BYTES, kb * UMMA_KBLK,
+                      tile * UMMA_ROWS, kEvictFirst);
+          if (++stage == UMMA_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait(&ss->q_full, 0);
+      tc_fence_after();
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t q_base = smem_u32(q_smem), x_base = smem_u32(x_smem);
+      for (int tile = cta; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(&ss->acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * UMMA_NQ;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&ss->full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = x_base + (uint32_t)stage * UMMA_STAGE_BYTES;
+          const uint32_t b_addr = q_base + (uint32_t)kb * UMMA_QBLK_BYTES;
+#pragma unroll
+          for (int k = 0; k < UMMA_KBLK / 16; ++k)
+            umma_bf16(d_tmem, smem_desc_sw128(a_addr + k * 32), smem_desc_sw128(b_addr + k * 32), kIdesc,
+                      (uint32_t)((kb | k) != 0));
+          umma_commit(&ss->empty[stage]);   // frees the smem stage once these MMAs have read it
+          if (++stage == UMMA_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&ss->acc_full[acc]);    // accumulator complete
+        if (++acc == UMMA_ACC) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: thread = corpus row =====
+    const int ew = warp - 4;                 // TMEM lane quadrant (warp % 4)
+    const int et = threadIdx.x - 128;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cta; tile < n_tiles; tile += gridDim.x) {
+      const int64_t row = (int64_t)tile * UMMA_ROWS + ew * 32 + lane;
+      float a = 0.f, b = neg_inf<float>();
+      if (row < n_rows) { a = __ldg(sa + row); b = __ldg(sb + row); }
+      mbar_wait(&ss->acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * UMMA_NQ;
+#pragma unroll
+      for (int c = 0; c < UMMA_NQ; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        if (dbg_out && row < n_rows) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dbg_out[(size_t)row * UMMA_NQ + c + j] = __uint_as_float(v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float score = fmaf(__uint_as_float(v[j]), a, b);
+          if (score > ss->thr[c + j]) {
+            const int pos = atomicAdd(&ss->cnt[c + j], 1);
+            if (pos < RASS_UMMA_SEG) {
+              const size_t o = (size_t)(c + j) * pool_entries + (size_t)cta * RASS_UMMA_SEG + pos;
+              pool_key[o] = score;
+              pool_row[o] = (uint32_t)row;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ss->acc_empty[acc]);
+      if (++acc == UMMA_ACC) { acc = 0; acc_phase ^= 1; }
+
+      // compaction: all 128 epilogue threads have finished this tile's appends
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int q = ew; q < UMMA_NQ; q += 4) {
+        const int n = min(ss->cnt[q], RASS_UMMA_SEG);
+        if (n <= UMMA_HIGH_WATER) continue;
+        const size_t base = (size_t)q * pool_entries + (size_t)cta * RASS_UMMA_SEG;
+        float key[RASS_UMMA_SEG / 32];
+        uint32_t rw[RASS_UMMA_SEG / 32];
+#pragma unroll
+        for (int i = 0; i < RASS_UMMA_SEG / 32; ++i) {
+          const int idx = i * 32 + lane;
+          key[i] = idx < n ? __ldcg(pool_key + base + idx) : neg_inf<float>();
+          rw[i] = idx < n ? __ldcg(pool_row + base + idx) : 0xffffffffu;
+        }
+        __syncwarp();
+        float last = neg_inf<float>();
+        for (int r = 0; r < RASS_UMMA_KEEP; ++r) {
+          // best remaining entry of this lane, then of the warp
+          float bk = key[0];
+          uint32_t br = rw[0];
+          int bi = 0;
+#pragma unroll
+          for (int i = 1; i < RASS_UMMA_SEG / 32; ++i)
+            if (entry_better<float>(key[i], rw[i], bk, br)) { bk = key[i]; br = rw[i]; bi = i; }
+          float wk = bk;
+          uint32_t wr = br;
+#pragma unroll
+          for (int m = 16; m >= 1; m >>= 1) {
+            const float ok = __shfl_xor_sync(0xffffffffu, wk, m);
+            const uint32_t orow = __shfl_xor_sync(0xffffffffu, wr, m);
+            if (entry_better<float>(ok, orow, wk, wr)) { wk = ok; wr = orow; }
+          }
+          if (bk == wk && br == wr) {   // rows are distinct, so exactly one lane owns the winner
+#pragma unroll
+            for (int i = 0; i < RASS_UMMA_SEG / 32; ++i)
+              if (i == bi) { key[i] = neg_inf<float>(); rw[i] = 0xffffffffu; }
+            pool_key[base + r] = wk;
+            pool_row[base + r] = wr;
+          }
+          last = wk;
+        }
+        __syncwarp();
+        if (lane == 0) { ss->cnt[q] = RASS_UMMA_KEEP; ss->thr[q] = last; }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    // publish the segment sizes and bounds
+    if (et < UMMA_NQ) {
+      pool_cnt[(size_t)et * n_segs + cta] = min(ss->cnt[et], RASS_UMMA_SEG);
+      pool_thr[(size_t)et * n_segs + cta] = ss->thr[et];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)UMMA_TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode(rass_engine* h) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+    rass_fail(h, RASS_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+static int encode_rows_map(rass_engine* h, CUtensorMap* map, const void* base, int64_t rows, int box_rows) {
+  EncodeTiledFn enc = get_encode(h);
+  if (!enc) return RASS_E_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)h->dim_pad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)h->dim_pad * 2};
+  cuuint32_t box[2] = {UMMA_KBLK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return rass_fail(h, RASS_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return RASS_OK;
+}
+
+static size_t umma_smem_bytes(const rass_engine* h) {
+  return (size_t)(h->dim_pad / UMMA_KBLK) * UMMA_QBLK_BYTES + (size_t)UMMA_STAGES * UMMA_STAGE_BYTES +
+         sizeof(UmmaSmem) + 1024;
+}
+
+int scan_umma_segs(const rass_engine* h) { return h->num_sms; }
+
+static int umma_launch(rass_engine* h, int q0, int64_t n_rows, float* dbg_out, cudaStream_t st) {
+  int rc;
+  if (!h->tmap_x) h->tmap_x = calloc(1, sizeof(CUtensorMap));
+  if (!h->tmap_q) h->tmap_q = calloc(1, sizeof(CUtensorMap));
+  // the map spans the whole reservation (>= 1024 rows); rows >= n_rows are masked in the epilogue
+  if (h->tmap_base != h->x16 || h->tmap_rows != h->cap) {
+    if ((rc = encode_rows_map(h, (CUtensorMap*)h->tmap_x, h->x16, h->cap, UMMA_ROWS))) return rc;
+    h->tmap_base = h->x16;
+    h->tmap_rows = h->cap;
+  }
+  if (h->tmap_qbase != h->q16) {
+    if ((rc = encode_rows_map(h, (CUtensorMap*)h->tmap_q, h->q16, h->q_cap, UMMA_NQ))) return rc;
+    h->tmap_qbase = h->q16;
+  }
+  const int n_tiles = (int)((n_rows + UMMA_ROWS - 1) / UMMA_ROWS);
+  const int grid = n_tiles < h->num_sms ? n_tiles : h->num_sms;
+  const size_t smem = umma_smem_bytes(h);
+  CUDA_TRY(h, cudaFuncSetAttribute(scan_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  scan_umma_kernel<<<grid, UMMA_THREADS, smem, st>>>(*(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q, h->sa, h->sb,
+                                                     n_rows, n_tiles, h->dim_pad / UMMA_KBLK, q0, h->pool_key,
+                                                     h->pool_row, h->pool_thr, h->pool_cnt, h->pool_entries,
+                                                     scan_umma_segs(h), dbg_out);
+  CUDA_TRY(h, cudaGetLastError());
+  // segments of CTAs that did not launch (fewer tiles than SMs) were cleared by the caller and read as empty
+  return RASS_OK;
+}
+
+__global__ void clear_segs_kernel(float* thr, int* cnt, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  thr[i] = neg_inf<float>();
+  cnt[i] = 0;
+}
+
+int launch_scan_umma(rass_engine* h, int q0, int nq, cudaStream_t st) {
+  (void)nq;
+  const size_t n = (size_t)scan_umma_segs(h) * RASS_GROUP_Q;
+  clear_segs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pool_thr, h->pool_cnt, n);
+  CUDA_TRY(h, cudaGetLastError());
+  return umma_launch(h, q0, h->n_rows, nullptr, st);
+}
+
+// Debug/self-test entry: raw tensor-core dot products of the first 64 prepared queries against every row.
+// out_host: [n_rows, 64] fp32.  Used by tests to localise descriptor/layout errors.
+int umma_selftest(rass_engine* h, int n_rows_unused, float* out_host, cudaStream_t st) {
+  (void)n_rows_unused;
+  float* dbg = nullptr;
+  const size_t n = (size_t)h->n_rows * UMMA_NQ;
+  CUDA_TRY(h, cudaMalloc(&dbg, n * 4));
+  CUDA_TRY(h, cudaMemsetAsync(dbg, 0, n * 4, st));
+  int rc = ensure_pool(h, (size_t)scan_umma_segs(h) * RASS_UMMA_SEG, (size_t)scan_umma_segs(h));
+  if (!rc) {
+    const size_t ns = (size_t)scan_umma_segs(h) * RASS_GROUP_Q;
+    clear_segs_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(h->pool_thr, h->pool_cnt, ns);
+    rc = umma_launch(h, 0, h->n_rows, dbg, st);
+  }
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(out_host, dbg, n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = rass_fail(h, RASS_E_CUDA, "umma selftest: %s", cudaGetErrorString(e));
+  }
+  cudaFree(dbg);
+  return rc;
+}

@@ -1,0 +1,171 @@
+"""Python handle over the C-ABI engine (include/rass_b200.h): numpy in / numpy out for the host-pointer calls,
+raw device pointers (e.g. ``torch.Tensor.data_ptr()``) for the ``*_dev`` calls."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import RassError, RassStats
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One device-resident shard of the vector store + its postings (rass_create ... rass_destroy)."""
+
+    def __init__(self, dim: int = 1024, metric: int = capi.METRIC_COSINE, device: int = 0, capacity_rows: int = 0,
+                 flags: int = 0):
+        self._lib = capi.lib()
+        self._h = C.c_void_p()
+        rc = self._lib.rass_create(dim, metric, device, capacity_rows, flags, C.byref(self._h))
+        if rc:
+            msg = self._lib.rass_last_error(None).decode()
+            self._h = None
+            raise RassError(rc, msg)
+        self.dim, self.metric, self.device, self.flags = dim, metric, device, flags or capi.KEEP_FP32
+        self.last_stats: dict = {}
+
+    # -- plumbing ---------------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc:
+            raise RassError(rc, self._lib.rass_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rass_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_path(self, path: int):
+        self._check(self._lib.rass_set_option(self._h, capi.OPT_PATH, path))
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.rass_set_option(self._h, capi.OPT_STREAM, cuda_stream))
+
+    def set_row_base(self, base: int):
+        self._check(self._lib.rass_set_row_base(self._h, base))
+
+    def sync(self):
+        self._check(self._lib.rass_sync(self._h))
+
+    # -- store ------------------------------------------------------------------------------------------
+    def append(self, rows: np.ndarray) -> int:
+        rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, self.dim)
+        first = C.c_int64(-1)
+        self._check(self._lib.rass_append(self._h, _ptr(rows), rows.shape[0], C.byref(first)))
+        return first.value
+
+    def append_dev(self, dev_ptr: int, n: int) -> int:
+        first = C.c_int64(-1)
+        self._check(self._lib.rass_append_dev(self._h, C.c_void_p(dev_ptr), n, C.byref(first)))
+        return first.value
+
+    def overwrite(self, row: int, v: np.ndarray):
+        v = np.ascontiguousarray(v, dtype=np.float32).reshape(self.dim)
+        self._check(self._lib.rass_overwrite(self._h, row, _ptr(v)))
+
+    def tombstone(self, row: int):
+        self._check(self._lib.rass_tombstone(self._h, row))
+
+    def count(self) -> int:
+        n = C.c_int64()
+        self._check(self._lib.rass_count(self._h, C.byref(n)))
+        return n.value
+
+    def rows(self) -> int:
+        n = C.c_int64()
+        self._check(self._lib.rass_rows(self._h, C.byref(n)))
+        return n.value
+
+    def read_rows(self, first: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.dim), dtype=np.float32)
+        self._check(self._lib.rass_read_rows(self._h, first, n, _ptr(out)))
+        return out
+
+    # -- search -----------------------------------------------------------------------------------------
+    def search_knn(self, q: np.ndarray, k: int, want_keys: bool = False):
+        """q: [B, dim] fp32 (host).  Returns rows int64 [B, k] (-1 = no hit), scores fp32 [B, k]
+        (and keys fp64 [B, k] = cos or squared distance when want_keys)."""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
+        B = q.shape[0]
+        rows = np.empty((B, k), dtype=np.int64)
+        scores = np.empty((B, k), dtype=np.float32)
+        keys = np.empty((B, k), dtype=np.float64) if want_keys else None
+        st = RassStats()
+        self._check(self._lib.rass_search_knn(self._h, _ptr(q), B, k, _ptr(rows), _ptr(scores),
+                                              _ptr(keys) if want_keys else None, C.byref(st)))
+        self.last_stats = st.as_dict()
+        return (rows, scores, keys) if want_keys else (rows, scores)
+
+    def search_knn_dev(self, q_ptr: int, B: int, k: int, rows_ptr: int, scores_ptr: int, keys_ptr: int = 0) -> dict:
+        st = RassStats()
+        self._check(self._lib.rass_search_knn_dev(self._h, C.c_void_p(q_ptr), B, k, C.c_void_p(rows_ptr),
+                                                  C.c_void_p(scores_ptr), C.c_void_p(keys_ptr) if keys_ptr else None,
+                                                  C.byref(st)))
+        self.last_stats = st.as_dict()
+        return self.last_stats
+
+    def merge_topk_dev(self, keys_ptr: int, rows_ptr: int, G: int, B: int, k: int, out_rows_ptr: int,
+                       out_scores_ptr: int, out_keys_ptr: int = 0):
+        self._check(self._lib.rass_merge_topk_dev(self._h, C.c_void_p(keys_ptr), C.c_void_p(rows_ptr), G, B, k,
+                                                  C.c_void_p(out_rows_ptr), C.c_void_p(out_scores_ptr),
+                                                  C.c_void_p(out_keys_ptr) if out_keys_ptr else None))
+
+    # -- text -------------------------------------------------------------------------------------------
+    def bm25_build(self, indptr, doc, tf, doclen, global_doc_count: int = 0, global_sum_ttf: int = 0,
+                   global_df=None):
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        doc = np.ascontiguousarray(doc, dtype=np.int32)
+        tf = np.ascontiguousarray(tf, dtype=np.uint16)
+        doclen = np.ascontiguousarray(doclen, dtype=np.uint32)
+        gdf = None if global_df is None else np.ascontiguousarray(global_df, dtype=np.int64)
+        self._check(self._lib.rass_bm25_build(self._h, _ptr(indptr), _ptr(doc), _ptr(tf), _ptr(doclen),
+                                              indptr.size - 1, doclen.size, global_doc_count, global_sum_ttf,
+                                              _ptr(gdf) if gdf is not None else None))
+
+    def search_hybrid(self, q, qterms, w_text: float, w_knn: float, k: int):
+        """q: [B, dim] fp32 or None (text only); qterms: list of B term-id lists or None (vector only)."""
+        if q is not None:
+            q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
+            B = q.shape[0]
+        else:
+            B = len(qterms)
+        indptr = terms = None
+        if qterms is not None:
+            if len(qterms) != B:
+                raise ValueError("qterms must hold one list per query")
+            indptr = np.zeros(B + 1, dtype=np.int32)
+            indptr[1:] = np.cumsum([len(t) for t in qterms])
+            terms = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int32) for t in qterms])
+                                         if indptr[-1] else np.zeros(1, dtype=np.int32), dtype=np.int32)
+        rows = np.empty((B, k), dtype=np.int64)
+        scores = np.empty((B, k), dtype=np.float32)
+        st = RassStats()
+        self._check(self._lib.rass_search_hybrid(self._h, _ptr(q) if q is not None else None, B,
+                                                 _ptr(indptr) if indptr is not None else None,
+                                                 _ptr(terms) if terms is not None else None,
+                                                 w_text, w_knn, k, _ptr(rows), _ptr(scores), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return rows, scores
+
+    def debug_umma_scores(self, q: np.ndarray) -> np.ndarray:
+        """Raw tensor-core dot products bf16(q_hat) . bf16(x) of up to 64 queries against every row: [rows, 64]."""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
+        out = np.zeros((self.rows(), 64), dtype=np.float32)
+        self._check(self._lib.rass_debug_umma_scores(self._h, _ptr(q), q.shape[0], _ptr(out)))
+        return out

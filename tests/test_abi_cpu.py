@@ -1,0 +1,54 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/rass_b200.h
+declares, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from rassengine_b200 import build, _capi
+    build.build()
+    return _capi.lib()
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "rass_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rass_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from rassengine_b200 import _capi
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in _capi.PROTOTYPES, f"{n} has no ctypes prototype"
+
+
+def test_version_and_no_cpu_fallback(lib):
+    import torch
+    assert b"sm_100a" in lib.rass_version()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = ctypes.c_void_p()
+    rc = lib.rass_create(1024, 0, 0, 0, 0, ctypes.byref(h))
+    assert rc == -3 and not h.value                    # RASS_E_CUDA
+    assert b"no CPU fallback" in lib.rass_last_error(None)
+    import rassengine_b200 as rb
+    with pytest.raises(rb.RassError):
+        rb.Engine(1024)
+
+
+def test_invalid_arguments_are_rejected_before_cuda(lib):
+    h = ctypes.c_void_p()
+    assert lib.rass_create(0, 0, 0, 0, 0, ctypes.byref(h)) == -1
+    assert lib.rass_create(2048, 0, 0, 0, 0, ctypes.byref(h)) == -1
+    assert lib.rass_create(1024, 7, 0, 0, 0, ctypes.byref(h)) == -1
+    assert lib.rass_create(1024, 0, 0, 0, 3, ctypes.byref(h)) == -1
+    assert lib.rass_count(None, None) == -1

@@ -1,0 +1,214 @@
+"""GPU parity: the CUDA kNN paths (through the C ABI) against the numpy oracle and the golden fixtures.
+
+Bar: ids bit-identical to the oracle (fp64-accumulated key, (key desc, row asc)); scores within 1e-5 relative
+(BASELINE.json north_star).  Runs on the B200 box only (-m gpu)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import knn, synth
+
+pytestmark = pytest.mark.gpu
+
+SCORE_RTOL = 1e-5
+
+
+def _engine(**kw):
+    import rassengine_b200 as rb
+    return rb.Engine(**kw)
+
+
+def _paths():
+    import rassengine_b200 as rb
+    return {"stream": rb.PATH_STREAM, "umma": rb.PATH_UMMA, "exact": rb.PATH_EXACT, "auto": rb.PATH_AUTO}
+
+
+def _load_case(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    meta = json.loads(str(g["meta"]))
+    X = synth.embeddings(meta["n"], meta["d"], synth.SEED_CORPUS)
+    if meta["dup_pairs"]:
+        synth.plant_duplicates(X, len(meta["dup_pairs"]))
+    Q = (synth.clustered_queries(X, meta["nq"]) if meta["clustered"]
+         else synth.embeddings(meta["nq"], meta["d"], synth.SEED_QUERIES))
+    return X, Q, meta, g
+
+
+def _check(rows, scores, want_rows, want_scores):
+    assert np.array_equal(rows, want_rows)
+    np.testing.assert_allclose(scores, want_scores, rtol=SCORE_RTOL, atol=0)
+
+
+TINY_X = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [1, 1, 0, 0], [1, 0, 0, 0],
+                   [0, 0, 0, 0], [-1, 0, 0, 0], [3, 4, 0, 0], [0, 0, 1, 0]], dtype=np.float32)
+TINY_Q = np.array([[2, 0, 0, 0]], dtype=np.float32)
+TINY_ORDER = [0, 3, 2, 6, 1, 4, 7, 5]
+TINY_SCORE = [1.0, 1.0, 1 / (2 - math.sqrt(0.5)), 1 / 1.4, 0.5, 0.5, 0.5, 1 / 3]
+
+
+@pytest.mark.parametrize("path", ["stream", "umma", "exact"])
+def test_tiny_hand_set(path):
+    """Duplicates, a zero row, unnormalised rows, k > rows (same literals as tests/test_oracle.py)."""
+    with _engine(dim=4) as e:
+        e.set_path(_paths()[path])
+        r0, s0 = e.search_knn(TINY_Q, 3)          # empty index -> no hits
+        assert (r0 == -1).all()
+        assert e.append(TINY_X) == 0
+        assert e.count() == 8
+        rows, scores = e.search_knn(TINY_Q, 8)
+        assert rows[0].tolist() == TINY_ORDER
+        np.testing.assert_allclose(scores[0], np.array(TINY_SCORE, dtype=np.float32), rtol=1e-6)
+        rows, _ = e.search_knn(TINY_Q, 3)
+        assert rows[0].tolist() == TINY_ORDER[:3]
+        rows, scores = e.search_knn(TINY_Q, 20)    # fewer rows than k: return what exists, pad with -1
+        assert rows[0, :8].tolist() == TINY_ORDER and (rows[0, 8:] == -1).all()
+        # tombstone + overwrite (bulk "index" = insert-or-overwrite by _id)
+        e.tombstone(0)
+        assert e.count() == 7
+        rows, _ = e.search_knn(TINY_Q, 3)
+        assert rows[0].tolist() == [3, 2, 6]
+        e.overwrite(0, np.array([5, 0, 0, 0], dtype=np.float32))
+        assert e.count() == 8
+        rows, _ = e.search_knn(TINY_Q, 2)
+        assert rows[0].tolist() == [0, 3]
+        np.testing.assert_array_equal(e.read_rows(6, 1)[0], TINY_X[6])
+
+
+@pytest.mark.parametrize("path", ["stream", "umma", "exact"])
+def test_tiny_l2(path):
+    import rassengine_b200 as rb
+    with _engine(dim=4, metric=rb.METRIC_L2) as e:
+        e.set_path(_paths()[path])
+        e.append(TINY_X)
+        rows, scores, keys = e.search_knn(TINY_Q, 3, want_keys=True)
+        assert rows[0].tolist() == [0, 3, 2]
+        np.testing.assert_allclose(keys[0], [1, 1, 2])
+        np.testing.assert_allclose(scores[0], [0.5, 0.5, 1 / 3], rtol=1e-6)
+
+
+@pytest.mark.parametrize("path", ["stream", "umma", "exact", "auto"])
+@pytest.mark.parametrize("name", ["knn_small", "knn_clustered_dups", "knn_small_k100"])
+def test_seeded_golden(golden_dir, name, path):
+    X, Q, meta, g = _load_case(golden_dir, name)
+    if path == "exact":
+        Q = Q[:8]
+    with _engine(dim=meta["d"]) as e:
+        e.set_path(_paths()[path])
+        # ragged appends exercise the staging path
+        e.append(X[:7])
+        e.append(X[7:12345])
+        e.append(X[12345:])
+        assert e.rows() == meta["n"]
+        rows, scores, keys = e.search_knn(Q, meta["k"], want_keys=True)
+        st = e.last_stats
+    nq = Q.shape[0]
+    _check(rows, scores, g["rows"][:nq].astype(np.int64), g["score"][:nq])
+    np.testing.assert_allclose(keys, g["cos"][:nq], rtol=0, atol=1e-12)
+    assert st["n_queries"] == nq
+    assert st["n_certified"] + st["n_fallback"] == nq
+
+
+def test_umma_raw_scores_match_bf16_math():
+    """The tcgen05 accumulators equal the fp32 dot products of the bf16-rounded operands (descriptor check)."""
+    import torch
+    n, d = 1000, 1024
+    X = synth.embeddings(n, d, 7)
+    Q = synth.embeddings(64, d, 8)
+    with _engine(dim=d) as e:
+        e.append(X)
+        got = e.debug_umma_scores(Q)
+    xb = torch.from_numpy(X).to(torch.bfloat16).to(torch.float64)
+    qn = Q / np.linalg.norm(Q.astype(np.float64), axis=1, keepdims=True)
+    qb = torch.from_numpy(qn.astype(np.float32)).to(torch.bfloat16).to(torch.float64)
+    want = (xb @ qb.T).numpy()
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("path", ["stream", "umma"])
+def test_cfg1_100k_golden(golden_dir, path):
+    """BASELINE.json configs[0]: 100k x 1024, 1k queries, exact cosine top-10 -- ids identical to the golden file."""
+    X, Q, meta, g = _load_case(golden_dir, "knn_cfg1")
+    nq = 1000 if path == "umma" else 64
+    with _engine(dim=meta["d"], capacity_rows=meta["n"]) as e:
+        e.set_path(_paths()[path])
+        e.append(X)
+        rows, scores = e.search_knn(Q[:nq], meta["k"])
+        st = e.last_stats
+    _check(rows, scores, g["rows"][:nq].astype(np.int64), g["score"][:nq])
+    assert st["n_fallback"] == 0, st
+
+
+@pytest.mark.parametrize("dim", [384, 768, 100])
+def test_other_dims(dim):
+    X = synth.embeddings(5000, dim, 3)
+    Q = synth.embeddings(9, dim, 4)
+    want_rows, _, want_scores = knn.knn_exact(X, Q, 10)
+    for path in ("stream", "umma"):
+        with _engine(dim=dim) as e:
+            e.set_path(_paths()[path])
+            e.append(X)
+            rows, scores = e.search_knn(Q, 10)
+        _check(rows, scores, want_rows, want_scores)
+
+
+def test_bf16_corpus_mode():
+    """BASELINE config 5 stores a bf16 corpus: the bf16 values are the data, the oracle sees them widened."""
+    import rassengine_b200 as rb
+    import torch
+    X = synth.embeddings(20000, 1024, 11)
+    Q = synth.embeddings(16, 1024, 12)
+    Xb = torch.from_numpy(X).to(torch.bfloat16).to(torch.float32).numpy()
+    want_rows, _, want_scores = knn.knn_exact(Xb, Q, 10)
+    for path in ("stream", "umma"):
+        with _engine(dim=1024, flags=rb.BF16_ONLY) as e:
+            e.set_path(_paths()[path])
+            e.append(X)
+            np.testing.assert_array_equal(e.read_rows(5, 3), Xb[5:8])
+            rows, scores = e.search_knn(Q, 10)
+        _check(rows, scores, want_rows, want_scores)
+
+
+def test_unnormalised_rows_and_l2_seeded():
+    import rassengine_b200 as rb
+    rng = np.random.default_rng(5)
+    X = (rng.standard_normal((8000, 256)) * rng.uniform(0.1, 5.0, size=(8000, 1))).astype(np.float32)
+    Q = rng.standard_normal((5, 256)).astype(np.float32)
+    for metric, om in ((rb.METRIC_COSINE, knn.COSINE), (rb.METRIC_L2, knn.L2)):
+        want_rows, _, want_scores = knn.knn_exact_full(X, Q, 10, metric=om)
+        for path in ("stream", "umma"):
+            with _engine(dim=256, metric=metric) as e:
+                e.set_path(_paths()[path])
+                e.append(X)
+                rows, scores = e.search_knn(Q, 10)
+            _check(rows, scores, want_rows, want_scores)
+
+
+def test_merge_topk_matches_single_shard():
+    """Row-sharded corpus: per-shard top-k merged on the device equals the single-engine answer."""
+    import torch
+    X = synth.embeddings(30000, 1024, 21)
+    Q = synth.embeddings(12, 1024, 22)
+    k, G = 10, 3
+    want_rows, want_key, want_scores = knn.knn_exact(X, Q, k)
+    bounds = [0, 9000, 21000, 30000]
+    keys, rows = [], []
+    engines = []
+    for g in range(G):
+        e = _engine(dim=1024)
+        e.set_row_base(bounds[g])
+        e.append(X[bounds[g]:bounds[g + 1]])
+        r, s, kk = e.search_knn(Q, k, want_keys=True)
+        keys.append(kk)
+        rows.append(r)
+        engines.append(e)
+    dk = torch.from_numpy(np.stack(keys)).cuda()
+    dr = torch.from_numpy(np.stack(rows)).cuda()
+    out_r = torch.empty((Q.shape[0], k), dtype=torch.int64, device="cuda")
+    out_s = torch.empty((Q.shape[0], k), dtype=torch.float32, device="cuda")
+    engines[0].merge_topk_dev(dk.data_ptr(), dr.data_ptr(), G, Q.shape[0], k, out_r.data_ptr(), out_s.data_ptr())
+    _check(out_r.cpu().numpy(), out_s.cpu().numpy(), want_rows, want_scores)
+    for e in engines:
+        e.close()
