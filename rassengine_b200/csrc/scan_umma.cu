@@ -10,9 +10,9 @@
 // of tiles i+1..i+3.  Warp 0 lane 0 issues TMA, warp 1 lane 0 issues tcgen05.mma, warp 2 owns the TMEM
 // allocation, warps 4-7 are the epilogue: thread = corpus row (TMEM lane), 64 scores per thread read with
 // tcgen05.ld; a score that beats the CTA's running per-query threshold is appended to that query's segment of
-// the candidate pool.  When a segment passes 128 entries it is compacted to its best 32 and the threshold
-// rises to the 32nd key; everything dropped or rejected is <= that threshold, which is the bound the
-// certificate in finish.cu needs.  The score matrix never reaches HBM.
+// the candidate pool.  When a segment passes 128 entries it is compacted: a warp bisects for a pivot with
+// 32..64 entries above it, keeps those and raises the threshold to the pivot; everything dropped or
+// rejected is <= that threshold, which is the bound the certificate in finish.cu needs.  The score matrix never reaches HBM.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -22,7 +22,7 @@
 #define UMMA_KBLK 64                       // bf16 elements per k-block (128 bytes: one swizzle row)
 #define UMMA_STAGE_BYTES (UMMA_ROWS * 128)  // 16 KB
 #define UMMA_QBLK_BYTES (UMMA_NQ * 128)     // 8 KB
-#define UMMA_STAGES 5
+#define UMMA_STAGES 6
 #define UMMA_ACC 4                          // TMEM accumulator stages (64 columns each)
 #define UMMA_TMEM_COLS 256
 #define UMMA_THREADS 256
@@ -98,6 +98,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// order-preserving float <-> uint32 maps (larger float <-> larger integer)
+__device__ __forceinline__ uint32_t ord32(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unord32(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
 
 // K-major, 128B-swizzled operand tile whose rows are 128 bytes: 8-row groups are 1024 bytes apart (SBO),
 // LBO is the canonical 1 (x16 bytes), descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
@@ -237,14 +246,30 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 16; ++j) dbg_out[(size_t)row * UMMA_NQ + c + j] = __uint_as_float(v[j]);
         }
+        float sc[16];
+        uint32_t m = 0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float score = fmaf(__uint_as_float(v[j]), a, b);
-          if (score > ss->thr[c + j]) {
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(&ss->thr[c + j4]);
+          const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sc[j4 + j] = fmaf(__uint_as_float(v[j4 + j]), a, b);
+            m |= (sc[j4 + j] > tt[j]) ? (1u << (j4 + j)) : 0u;
+          }
+        }
+        if (__any_sync(0xffffffffu, m != 0)) {
+          // each lane walks its own hits; lanes run their i-th append together
+          while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            float s = sc[0];
+#pragma unroll
+            for (int t = 1; t < 16; ++t) s = (j == t) ? sc[t] : s;
             const int pos = atomicAdd(&ss->cnt[c + j], 1);
             if (pos < RASS_UMMA_SEG) {
               const size_t o = (size_t)(c + j) * pool_entries + (size_t)cta * RASS_UMMA_SEG + pos;
-              pool_key[o] = score;
+              pool_key[o] = s;
               pool_row[o] = (uint32_t)row;
             }
           }
@@ -261,43 +286,55 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
         const int n = min(ss->cnt[q], RASS_UMMA_SEG);
         if (n <= UMMA_HIGH_WATER) continue;
         const size_t base = (size_t)q * pool_entries + (size_t)cta * RASS_UMMA_SEG;
-        float key[RASS_UMMA_SEG / 32];
-        uint32_t rw[RASS_UMMA_SEG / 32];
+        // keys as order-preserving integers; empty slots sort below everything
+        uint32_t ok[RASS_UMMA_SEG / 32], rw[RASS_UMMA_SEG / 32];
+        uint32_t kmin = 0xffffffffu, kmax = 0;
 #pragma unroll
         for (int i = 0; i < RASS_UMMA_SEG / 32; ++i) {
           const int idx = i * 32 + lane;
-          key[i] = idx < n ? __ldcg(pool_key + base + idx) : neg_inf<float>();
-          rw[i] = idx < n ? __ldcg(pool_row + base + idx) : 0xffffffffu;
+          ok[i] = 0;
+          rw[i] = 0xffffffffu;
+          if (idx < n) {
+            ok[i] = ord32(__ldcg(pool_key + base + idx));
+            rw[i] = __ldcg(pool_row + base + idx);
+            kmin = min(kmin, ok[i]);
+            kmax = max(kmax, ok[i]);
+          }
+        }
+        kmin = __reduce_min_sync(0xffffffffu, kmin);
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        // bisection for a pivot with RASS_UMMA_KEEP .. 2*RASS_UMMA_KEEP entries strictly above it.
+        // count(> lo) > 2*KEEP and count(> hi) < KEEP hold throughout; ties may make the band unreachable,
+        // in which case hi is used (fewer entries kept, the bound below still holds).
+        uint32_t lo = kmin - 1, hi = kmax, pivot = kmax;
+        bool found = false;
+        while (hi - lo > 1) {
+          const uint32_t mid = lo + ((hi - lo) >> 1);
+          int cgt = 0;
+#pragma unroll
+          for (int i = 0; i < RASS_UMMA_SEG / 32; ++i) cgt += ok[i] > mid;
+          cgt = __reduce_add_sync(0xffffffffu, cgt);
+          if (cgt > 2 * RASS_UMMA_KEEP) lo = mid;
+          else if (cgt < RASS_UMMA_KEEP) hi = mid;
+          else { pivot = mid; found = true; break; }
+        }
+        if (!found) pivot = hi;
+        __syncwarp();
+        int kept = 0;
+#pragma unroll
+        for (int i = 0; i < RASS_UMMA_SEG / 32; ++i) {
+          const bool keep = ok[i] > pivot;
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if (keep) {
+            const int pos = kept + __popc(bal & ((1u << lane) - 1));
+            pool_key[base + pos] = unord32(ok[i]);
+            pool_row[base + pos] = rw[i];
+          }
+          kept += __popc(bal);
         }
         __syncwarp();
-        float last = neg_inf<float>();
-        for (int r = 0; r < RASS_UMMA_KEEP; ++r) {
-          // best remaining entry of this lane, then of the warp
-          float bk = key[0];
-          uint32_t br = rw[0];
-          int bi = 0;
-#pragma unroll
-          for (int i = 1; i < RASS_UMMA_SEG / 32; ++i)
-            if (entry_better<float>(key[i], rw[i], bk, br)) { bk = key[i]; br = rw[i]; bi = i; }
-          float wk = bk;
-          uint32_t wr = br;
-#pragma unroll
-          for (int m = 16; m >= 1; m >>= 1) {
-            const float ok = __shfl_xor_sync(0xffffffffu, wk, m);
-            const uint32_t orow = __shfl_xor_sync(0xffffffffu, wr, m);
-            if (entry_better<float>(ok, orow, wk, wr)) { wk = ok; wr = orow; }
-          }
-          if (bk == wk && br == wr) {   // rows are distinct, so exactly one lane owns the winner
-#pragma unroll
-            for (int i = 0; i < RASS_UMMA_SEG / 32; ++i)
-              if (i == bi) { key[i] = neg_inf<float>(); rw[i] = 0xffffffffu; }
-            pool_key[base + r] = wk;
-            pool_row[base + r] = wr;
-          }
-          last = wk;
-        }
-        __syncwarp();
-        if (lane == 0) { ss->cnt[q] = RASS_UMMA_KEEP; ss->thr[q] = last; }
+        // everything dropped here, and every row rejected from now on, has key <= pivot
+        if (lane == 0) { ss->cnt[q] = kept; ss->thr[q] = unord32(pivot); }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
