@@ -118,9 +118,11 @@ int rass_search_knn_dev(rass_engine* h, const float* q_dev, int B, int k,
                         int64_t* out_rows_dev, float* out_scores_dev, double* out_keys_dev, rass_stats* stats);
 
 /* Merge G per-shard top-k lists (what each rank all-gathers) into the global top-k, (key desc, row asc).
- * keys_dev: [G, B, k] fp64, rows_dev: [G, B, k] int64 (-1 = empty).  Outputs [B, k], device memory. */
-int rass_merge_topk_dev(rass_engine* h, const double* keys_dev, const int64_t* rows_dev, int G, int B, int k,
-                        int64_t* out_rows_dev, float* out_scores_dev, double* out_keys_dev);
+ * keys_dev / rows_dev point at shard 0's [B, k] fp64 keys / int64 rows (-1 = empty); shard g's lists start
+ * shard_stride elements further (0 = B * k, i.e. dense [G, B, k]; 2 * B * k when each rank gathers one packed
+ * [2, B, k] buffer).  Outputs [B, k], device memory.  Enqueued on the engine stream, not synchronised. */
+int rass_merge_topk_dev(rass_engine* h, const double* keys_dev, const int64_t* rows_dev, int64_t shard_stride,
+                        int G, int B, int k, int64_t* out_rows_dev, float* out_scores_dev, double* out_keys_dev);
 
 /* CSR postings of the text field: indptr[V+1], doc[nnz] (local rows, ascending per term), tf[nnz], doclen[N]
  * (token count per row).  Statistics (docCount, sumTotalTermFreq, df) are taken from these arrays unless the

@@ -56,7 +56,7 @@ PROTOTYPES = {
     "rass_read_rows": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     "rass_search_knn": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.POINTER(RassStats)]),
     "rass_search_knn_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.POINTER(RassStats)]),
-    "rass_merge_topk_dev": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "rass_merge_topk_dev": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "rass_bm25_build": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
     "rass_search_hybrid": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_float, C.c_float, C.c_int, _P, _P,
                                      C.POINTER(RassStats)]),

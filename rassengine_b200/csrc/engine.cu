@@ -566,16 +566,17 @@ extern "C" int rass_search_knn(rass_engine* h, const float* q_host, int B, int k
   return RASS_OK;
 }
 
-extern "C" int rass_merge_topk_dev(rass_engine* h, const double* keys_dev, const int64_t* rows_dev, int G, int B,
-                                   int k, int64_t* out_rows_dev, float* out_scores_dev, double* out_keys_dev) {
+extern "C" int rass_merge_topk_dev(rass_engine* h, const double* keys_dev, const int64_t* rows_dev,
+                                   int64_t shard_stride, int G, int B, int k, int64_t* out_rows_dev,
+                                   float* out_scores_dev, double* out_keys_dev) {
   CHECK_HANDLE(h);
   if (!keys_dev || !rows_dev || !out_rows_dev || !out_scores_dev || G < 1 || B < 1 || k < 1)
     return rass_fail(h, RASS_E_INVALID, "bad merge arguments");
   cudaStream_t st = eng_stream(h);
-  int rc = launch_merge_topk(h, keys_dev, rows_dev, G, B, k, out_rows_dev, out_scores_dev, out_keys_dev, st);
+  int rc = launch_merge_topk(h, keys_dev, rows_dev, shard_stride, G, B, k, out_rows_dev, out_scores_dev,
+                             out_keys_dev, st);
   if (rc) return rc;
-  CUDA_TRY(h, cudaStreamSynchronize(st));
-  return RASS_OK;
+  return RASS_OK;   // enqueued on the engine stream; the caller synchronises (rass_sync) when it needs the result
 }
 
 // Debug entry (not part of the reference surface): raw tcgen05 dot products of <= 64 queries against every row,

@@ -435,7 +435,8 @@ int launch_select_raw(rass_engine* h, size_t entries, int k, int q, int64_t* out
 // shard merge: G per-shard top-k lists -> global top-k  (the OpenSearch coordinator's merge)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) merge_topk_kernel(const double* __restrict__ keys,
-                                                         const int64_t* __restrict__ rows, int G, int B, int k,
+                                                         const int64_t* __restrict__ rows, int64_t shard_stride,
+                                                         int G, int B, int k,
                                                          int metric, int64_t* __restrict__ out_rows,
                                                          float* __restrict__ out_scores,
                                                          double* __restrict__ out_keys) {
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const double* __restric
   const int q = blockIdx.x, n = G * k;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int g = i / k, j = i % k;
-    const size_t src = ((size_t)g * B + q) * k + j;
+    const size_t src = (size_t)g * shard_stride + (size_t)q * k + j;
     const double v = keys[src];
     sk[i] = metric == RASS_METRIC_COSINE ? v : -v;
     sr[i] = rows[src];
@@ -479,12 +480,14 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const double* __restric
   }
 }
 
-int launch_merge_topk(rass_engine* h, const double* keys, const int64_t* rows, int G, int B, int k,
-                      int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st) {
+int launch_merge_topk(rass_engine* h, const double* keys, const int64_t* rows, int64_t shard_stride, int G, int B,
+                      int k, int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st) {
+  if (shard_stride <= 0) shard_stride = (int64_t)B * k;
   const size_t smem = (size_t)G * k * 16;
   if (smem > 200 * 1024) return rass_fail(h, RASS_E_INVALID, "merge of %d lists of %d exceeds shared memory", G, k);
   CUDA_TRY(h, cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_topk_kernel<<<B, 256, smem, st>>>(keys, rows, G, B, k, h->metric, out_rows, out_scores, out_keys);
+  merge_topk_kernel<<<B, 256, smem, st>>>(keys, rows, shard_stride, G, B, k, h->metric, out_rows, out_scores,
+                                          out_keys);
   CUDA_TRY(h, cudaGetLastError());
   return RASS_OK;
 }

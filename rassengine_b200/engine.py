@@ -121,8 +121,10 @@ class Engine:
         return self.last_stats
 
     def merge_topk_dev(self, keys_ptr: int, rows_ptr: int, G: int, B: int, k: int, out_rows_ptr: int,
-                       out_scores_ptr: int, out_keys_ptr: int = 0):
-        self._check(self._lib.rass_merge_topk_dev(self._h, C.c_void_p(keys_ptr), C.c_void_p(rows_ptr), G, B, k,
+                       out_scores_ptr: int, out_keys_ptr: int = 0, shard_stride: int = 0):
+        """Enqueued on the engine stream; call sync() (or synchronise that stream) before reading the outputs."""
+        self._check(self._lib.rass_merge_topk_dev(self._h, C.c_void_p(keys_ptr), C.c_void_p(rows_ptr), shard_stride,
+                                                  G, B, k,
                                                   C.c_void_p(out_rows_ptr), C.c_void_p(out_scores_ptr),
                                                   C.c_void_p(out_keys_ptr) if out_keys_ptr else None))
 

@@ -1,0 +1,77 @@
+"""Row-sharded corpus across the GPUs of one NVSwitch box: one process per GPU, local exact top-k, ONE NCCL
+all-gather of k candidates per query, on-device merge.
+
+This is the B200 form of OpenSearch's ``number_of_shards`` + coordinator merge (reference app/main.py:357;
+SURVEY.md 8e): rank g of G owns rows [g * ceil(N / G), ...), searches them exactly, and contributes its [B, k]
+(fp64 key, int64 global row) lists.  The exact rerank happens before the gather, so only exact keys travel and
+the merged top-k is the top-k of the union, bit-identical to a single-shard search.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _capi as capi
+
+
+def shard_bounds(n_rows: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous row range [lo, hi) of `rank`."""
+    per = -(-n_rows // world)
+    lo = min(n_rows, rank * per)
+    return lo, min(n_rows, lo + per)
+
+
+class ShardedIndex:
+    def __init__(self, dim: int = 1024, metric: int = capi.METRIC_COSINE, flags: int = 0, capacity_rows: int = 0,
+                 device: int | None = None, group=None, engine=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dim = dim
+        if engine is None:
+            from .engine import Engine
+            if device is None:
+                device = torch.cuda.current_device()
+            engine = Engine(dim=dim, metric=metric, device=device, capacity_rows=capacity_rows, flags=flags)
+            # run on torch's current stream so NCCL and the engine's kernels are ordered by the stream
+            engine.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.engine = engine
+        self.merge_launches = 0
+
+    def set_row_base(self, base: int):
+        self.engine.set_row_base(base)
+
+    def append_dev(self, rows: torch.Tensor) -> int:
+        assert rows.dtype == torch.float32 and rows.is_contiguous() and rows.shape[1] == self.dim
+        return self.engine.append_dev(rows.data_ptr(), rows.shape[0])
+
+    def search_dev(self, q: torch.Tensor, k: int):
+        """q: [B, dim] fp32 on this rank's device (the same batch on every rank).  Returns (rows int64 [B, k] global
+        row ids, scores fp32 [B, k]) on the device, identical on every rank."""
+        B = q.shape[0]
+        dev = q.device
+        packed = torch.empty((2, B, k), dtype=torch.int64, device=dev)     # plane 0: fp64 key bits, plane 1: rows
+        scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+        self.engine.search_knn_dev(q.data_ptr(), B, k, packed[1].data_ptr(), scores.data_ptr(), packed[0].data_ptr())
+        if self.world == 1:
+            return packed[1], scores
+        gathered = torch.empty((self.world, 2, B, k), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, packed, group=self.group)      # the one collective of the path
+        out_rows = torch.empty((B, k), dtype=torch.int64, device=dev)
+        out_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+        plane = B * k * 8
+        self.engine.merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + plane, self.world, B, k,
+                                   out_rows.data_ptr(), out_scores.data_ptr(), 0, shard_stride=2 * B * k)
+        self.merge_launches += 1
+        return out_rows, out_scores
+
+    def search(self, q_host, k: int):
+        """Host-buffer flavour: q_host is a pinned or pageable [B, dim] fp32 tensor/array; results come back as
+        host numpy arrays (the end-to-end path bench.py times)."""
+        q = torch.as_tensor(q_host, dtype=torch.float32)
+        qd = q.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
+        rows, scores = self.search_dev(qd, k)
+        return rows.cpu().numpy(), scores.cpu().numpy()
+
+    def close(self):
+        self.engine.close()

@@ -209,6 +209,7 @@ def test_merge_topk_matches_single_shard():
     out_r = torch.empty((Q.shape[0], k), dtype=torch.int64, device="cuda")
     out_s = torch.empty((Q.shape[0], k), dtype=torch.float32, device="cuda")
     engines[0].merge_topk_dev(dk.data_ptr(), dr.data_ptr(), G, Q.shape[0], k, out_r.data_ptr(), out_s.data_ptr())
+    engines[0].sync()
     _check(out_r.cpu().numpy(), out_s.cpu().numpy(), want_rows, want_scores)
     for e in engines:
         e.close()
