@@ -16,6 +16,7 @@
  *                                   mapping app/main.py:555-556)
  *   rass_search_hybrid              client.search(body={"query":{"bool":{"should":[multi_match, multi_match, knn]}}})
  *                                                                               app/main.py:1574-1609
+ *   rass_set_row_filter             bool.filter [term patientId / doc_type] of the hybrid query               app/main.py:1599-1604
  *   rass_merge_topk_dev             the OpenSearch coordinator's per-shard top-k merge (number_of_shards, app/main.py:357)
  *
  * Conventions: C linkage, plain pointers and sizes, no exceptions cross the boundary.  Every function returns an
@@ -138,6 +139,10 @@ int rass_bm25_build(rass_engine* h, const int64_t* indptr, const int32_t* doc, c
 int rass_search_hybrid(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr,
                        const int32_t* qterms, float w_text, float w_knn, int k,
                        int64_t* out_rows, float* out_scores, rass_stats* stats);
+
+/* bool.filter of the following rass_search_hybrid calls (app/main.py:1599-1604) as a per-row pass mask:
+ * mask_host[n] bytes, 1 = the row satisfies the filter; rows >= n fail.  NULL clears the filter. */
+int rass_set_row_filter(rass_engine* h, const uint8_t* mask_host, int64_t n);
 
 int rass_sync(rass_engine* h);
 

@@ -60,6 +60,7 @@ PROTOTYPES = {
     "rass_bm25_build": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
     "rass_search_hybrid": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_float, C.c_float, C.c_int, _P, _P,
                                      C.POINTER(RassStats)]),
+    "rass_set_row_filter": (C.c_int, [_P, _P, C.c_int64]),
     "rass_sync": (C.c_int, [_P]),
     "rass_debug_umma_scores": (C.c_int, [_P, _P, C.c_int, _P]),
 }

@@ -1,0 +1,326 @@
+"""An `opensearchpy.OpenSearch`-shaped client whose "server" is the B200 engine in this process.
+
+It stands in for the module-global `os_client` of the reference (app/main.py:337-343; app/embedding_gen.py:121-133)
+and answers the calls the hot path makes on it:
+
+  client.indices.exists(index)                 app/main.py:352
+  client.indices.create(index=, body=)         app/main.py:576   (reads the knn_vector field: dimension, space_type)
+  client.count(index=)                         app/main.py:1475
+  client.info()                                app/embedding_gen.py:129
+  client.search(index=, body=, routing=)       app/main.py:1552, 1607
+  helpers.bulk(client, actions)                app/main.py:1237, 1269, 1279
+
+`_source` dicts and the `_id` <-> row map live on the host; vectors and postings live on the GPU.  Row ids are
+append-ordered, so the engine's "row ascending" tie-break equals Lucene's doc-id order.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import _capi as capi
+from .dsl import Plan, parse_search_body
+from .engine import Engine
+from .text import TextField
+
+TEXT_FIELD = "unstructuredText"      # the only analysed field chunk documents carry (app/main.py:1120-1130)
+FILTER_FIELDS = ("patientId", "doc_type", "resourceType", "doc_id")   # keyword fields the hot path filters on
+_SPACE = {"cosinesimil": capi.METRIC_COSINE, "l2": capi.METRIC_L2}
+
+
+class NotFoundError(KeyError):
+    """index_not_found_exception"""
+
+
+class RequestError(ValueError):
+    """resource_already_exists_exception / bad request"""
+
+
+class _Index:
+    def __init__(self, name: str, body: dict | None, device: int):
+        self.name = name
+        self.body = body or {}
+        self.device = device
+        props = self.body.get("mappings", {}).get("properties", {})
+        self.vector_field = None
+        self.dim = None
+        self.metric = capi.METRIC_COSINE
+        for fld, spec in props.items():
+            if isinstance(spec, dict) and spec.get("type") == "knn_vector":
+                self.vector_field = fld
+                self.dim = int(spec["dimension"])
+                space = spec.get("method", {}).get("space_type", "l2")
+                if space not in _SPACE:
+                    raise NotImplementedError(f"space_type {space!r}")
+                self.metric = _SPACE[space]
+        self.engine: Engine | None = None
+        self.sources: list[dict | None] = []     # row -> _source
+        self.ids: list[str | None] = []          # row -> _id
+        self.row_of: dict[str, int] = {}
+        self.text = TextField()
+        self.n_docs = 0
+        self.kw: dict[str, dict[object, list[int]]] = {f: {} for f in FILTER_FIELDS}   # field -> value -> rows
+
+    # -- engine ------------------------------------------------------------------------------------------
+    def _ensure_engine(self, dim: int | None = None) -> Engine:
+        if self.engine is None:
+            if self.dim is None:
+                self.dim = dim or 1024
+                self.vector_field = self.vector_field or "embedding"
+            self.engine = Engine(dim=self.dim, metric=self.metric, device=self.device)
+        return self.engine
+
+    def close(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
+
+    # -- indexing: "_op_type": "index" = insert or overwrite by _id --------------------------------------
+    def index_batch(self, docs: list[tuple[str, dict]]):
+        """docs: (_id, _source).  New ids are appended in one device call; known ids are overwritten in place."""
+        vf = self.vector_field or "embedding"
+        fresh: list[tuple[str, dict]] = []
+        seen: dict[str, int] = {}
+        for _id, src in docs:
+            if _id in self.row_of:
+                self._overwrite(self.row_of[_id], src)
+            elif _id in seen:
+                fresh[seen[_id]] = (_id, src)     # same id twice in one batch: last write wins
+            else:
+                seen[_id] = len(fresh)
+                fresh.append((_id, src))
+        if not fresh:
+            return
+        first_vec = next((s.get(vf) for _, s in fresh if s.get(vf) is not None), None)
+        eng = self._ensure_engine(len(first_vec) if first_vec is not None else None)
+        mat = np.zeros((len(fresh), self.dim), dtype=np.float32)
+        has = np.zeros(len(fresh), dtype=bool)
+        for i, (_, src) in enumerate(fresh):
+            v = src.get(vf)
+            if v is not None:
+                if len(v) != self.dim:
+                    raise RequestError(f"vector length {len(v)} != dimension {self.dim}")
+                mat[i] = v
+                has[i] = True
+        first = eng.append(mat)
+        for i, (_id, src) in enumerate(fresh):
+            row = first + i
+            if not has[i]:
+                eng.tombstone(row)               # no embedding: the row never matches a knn clause
+            self.sources.append(src)
+            self.ids.append(_id)
+            self.row_of[_id] = row
+            self.text.set_row(row, src.get(TEXT_FIELD))
+            self._kw_add(row, src)
+        self.n_docs += len(fresh)
+
+    def _overwrite(self, row: int, src: dict):
+        vf = self.vector_field or "embedding"
+        eng = self._ensure_engine()
+        v = src.get(vf)
+        if v is not None:
+            eng.overwrite(row, np.asarray(v, dtype=np.float32))
+        else:
+            eng.tombstone(row)
+        self._kw_remove(row, self.sources[row] or {})
+        self.sources[row] = src
+        self.text.set_row(row, src.get(TEXT_FIELD))
+        self._kw_add(row, src)
+
+    def _kw_add(self, row: int, src: dict):
+        for f in FILTER_FIELDS:
+            v = src.get(f)
+            if isinstance(v, (str, int, bool)):
+                self.kw[f].setdefault(v, []).append(row)
+
+    def _kw_remove(self, row: int, src: dict):
+        for f in FILTER_FIELDS:
+            v = src.get(f)
+            rows = self.kw[f].get(v) if isinstance(v, (str, int, bool)) else None
+            if rows and row in rows:
+                rows.remove(row)
+
+    def _filter_mask(self, filters) -> np.ndarray:
+        mask = np.ones(len(self.sources), dtype=np.uint8)
+        for f, v in filters:
+            m = np.zeros(len(self.sources), dtype=np.uint8)
+            if f in self.kw:
+                m[np.asarray(self.kw[f].get(v, []), dtype=np.int64)] = 1
+            else:
+                for r, src in enumerate(self.sources):
+                    if src is not None and src.get(f) == v:
+                        m[r] = 1
+            mask &= m
+        return mask
+
+    def _sync_text(self):
+        if self.text.dirty and self.engine is not None:
+            indptr, doc, tf, doclen = self.text.postings(len(self.sources))
+            self.engine.bm25_build(indptr, doc, tf, doclen)
+            self.text.dirty = False
+
+    # -- search ------------------------------------------------------------------------------------------
+    def _hit(self, row: int, score: float) -> dict:
+        return {"_index": self.name, "_id": self.ids[row], "_score": float(score), "_source": self.sources[row]}
+
+    def _passes(self, row: int, filters) -> bool:
+        src = self.sources[row] or {}
+        return all(src.get(f) == v for f, v in filters)
+
+    def search(self, plan: Plan) -> list[dict]:
+        if plan.size <= 0 or self.engine is None or not self.sources:
+            return []
+        eng = self.engine
+        if plan.kind == "match_all":
+            rows = [r for r in range(len(self.sources)) if self.sources[r] is not None][: plan.size]
+            return [self._hit(r, 1.0) for r in rows]
+        if plan.vector is not None and plan.knn_field != (self.vector_field or "embedding"):
+            raise RequestError(f"field {plan.knn_field!r} is not a knn_vector")
+        q = None
+        if plan.vector is not None:
+            q = np.asarray(plan.vector, dtype=np.float32).reshape(1, -1)
+            if q.shape[1] != self.dim:
+                raise RequestError(f"query vector length {q.shape[1]} != dimension {self.dim}")
+        if plan.kind == "knn":
+            k = min(max(plan.knn_k, 1), 128)
+            rows, scores = eng.search_knn(q, k)
+            # OpenSearch applies bool.filter to the k nearest neighbours of the nmslib engine (post-filter)
+            hits = [(int(r), float(s) * plan.knn_boost) for r, s in zip(rows[0], scores[0]) if r >= 0]
+            hits = [(r, s) for r, s in hits if self._passes(r, plan.filters)]
+            return [self._hit(r, s) for r, s in hits[: plan.size]]
+        # hybrid: bool.should boosted sum
+        k = min(max(plan.size, 1), 128)
+        w_text, qterms = 0.0, None
+        for clause in plan.text:
+            fb = dict(clause.fields).get(TEXT_FIELD)
+            if fb is None:
+                continue     # keyword-field clause: a whole-question string never equals a keyword value -> no match
+            self._sync_text()
+            qterms = [self.text.query_terms(clause.query)]
+            w_text = float(np.float32(clause.boost) * np.float32(fb))
+        if q is not None and min(max(plan.knn_k, 1), 128) != k:
+            raise NotImplementedError("knn k different from size in a hybrid query")
+        if q is None and qterms is None:
+            return []
+        # bool.filter: only rows that satisfy every term filter may score (device-side pass mask)
+        eng.set_row_filter(self._filter_mask(plan.filters) if plan.filters else None)
+        try:
+            rows, scores = eng.search_hybrid(q, qterms, w_text, plan.knn_boost, k)
+        finally:
+            if plan.filters:
+                eng.set_row_filter(None)
+        return [self._hit(int(r), float(s)) for r, s in zip(rows[0], scores[0]) if r >= 0][: plan.size]
+
+
+class IndicesClient:
+    def __init__(self, client: "B200Client"):
+        self._c = client
+
+    def exists(self, index: str, **_) -> bool:
+        return index in self._c._indices
+
+    def create(self, index: str, body: dict | None = None, **_) -> dict:
+        if index in self._c._indices:
+            raise RequestError(f"resource_already_exists_exception: index [{index}] already exists")
+        self._c._indices[index] = _Index(index, body, self._c.device)
+        return {"acknowledged": True, "shards_acknowledged": True, "index": index}
+
+    def delete(self, index: str, **_) -> dict:
+        idx = self._c._indices.pop(index, None)
+        if idx is None:
+            raise NotFoundError(f"index_not_found_exception: no such index [{index}]")
+        idx.close()
+        return {"acknowledged": True}
+
+    def refresh(self, index: str | None = None, **_) -> dict:
+        return {"_shards": {"total": 1, "successful": 1, "failed": 0}}
+
+
+class B200Client:
+    """Drop-in for `OpenSearch(hosts=[...], ...)`; connection arguments are accepted and ignored."""
+
+    def __init__(self, hosts=None, device: int = 0, **_ignored):
+        self.device = device
+        self._indices: dict[str, _Index] = {}
+        self.indices = IndicesClient(self)
+
+    def _get(self, index: str) -> _Index:
+        try:
+            return self._indices[index]
+        except KeyError:
+            raise NotFoundError(f"index_not_found_exception: no such index [{index}]") from None
+
+    def info(self, **_) -> dict:
+        ver = capi.lib().rass_version().decode()
+        return {"name": "rass-b200", "cluster_name": "rass-b200", "version": {"distribution": "rass-b200",
+                "number": "2.11.1", "build_type": ver}, "tagline": "The OpenSearch Project: https://opensearch.org/"}
+
+    def ping(self, **_) -> bool:
+        return True
+
+    def count(self, index: str | None = None, body=None, **_) -> dict:
+        n = self._get(index).n_docs if index else sum(i.n_docs for i in self._indices.values())
+        return {"count": n, "_shards": {"total": 1, "successful": 1, "skipped": 0, "failed": 0}}
+
+    def index(self, index: str, body: dict, id: str | None = None, routing=None, **_) -> dict:
+        idx = self._get(index)
+        _id = id if id is not None else f"auto-{len(idx.ids)}"
+        created = _id not in idx.row_of
+        idx.index_batch([(_id, body)])
+        return {"_index": index, "_id": _id, "result": "created" if created else "updated"}
+
+    def bulk_actions(self, actions) -> tuple[int, list]:
+        """helpers.bulk: consecutive actions for one index are ingested as one batch (one device append)."""
+        ok, errors = 0, []
+        run_index, run = None, []
+
+        def flush():
+            nonlocal ok, run
+            if not run:
+                return
+            try:
+                self._get(run_index).index_batch(run)
+                ok += len(run)
+            except Exception as e:  # per-batch error report, as helpers.bulk(raise_on_error=False) would give
+                errors.extend({"index": {"_index": run_index, "_id": i, "error": str(e)}} for i, _ in run)
+            run = []
+
+        for a in actions:
+            op = a.get("_op_type", "index")
+            if op != "index":
+                errors.append({op: {"_id": a.get("_id"), "error": "unsupported _op_type"}})
+                continue
+            name = a["_index"]
+            if name != run_index:
+                flush()
+                run_index = name
+            src = a.get("_source")
+            if src is None:
+                src = {k: v for k, v in a.items() if not k.startswith("_")}
+            _id = a.get("_id")
+            if _id is None:
+                _id = f"auto-{len(self._get(name).ids) + len(run)}"
+            run.append((str(_id), src))
+        flush()
+        return ok, errors
+
+    def search(self, index: str | None = None, body: dict | None = None, routing=None, **_) -> dict:
+        t0 = time.perf_counter()
+        idx = self._get(index)
+        plan = parse_search_body(body or {})
+        hits = idx.search(plan)
+        return {"took": int((time.perf_counter() - t0) * 1e3), "timed_out": False,
+                "_shards": {"total": 1, "successful": 1, "skipped": 0, "failed": 0},
+                "hits": {"total": {"value": len(hits), "relation": "eq"},
+                         "max_score": max((h["_score"] for h in hits), default=None), "hits": hits}}
+
+    def close(self):
+        for idx in self._indices.values():
+            idx.close()
+        self._indices.clear()
+
+
+def bulk(client: B200Client, actions, **_) -> tuple[int, list]:
+    """opensearchpy.helpers.bulk(client, actions) -> (success_count, errors)   (app/main.py:1237)"""
+    return client.bulk_actions(actions)

@@ -117,7 +117,9 @@ __global__ void __launch_bounds__(256) bm25_accumulate_kernel(const __grid_const
                                                               const uint8_t* __restrict__ norm,
                                                               const float* __restrict__ inv,
                                                               const float* __restrict__ sb, int64_t n_rows,
-                                                              double* __restrict__ acc, uint32_t* __restrict__ touched,
+                                                              const uint8_t* __restrict__ row_filter,
+                                                              int64_t filter_rows, double* __restrict__ acc,
+                                                              uint32_t* __restrict__ touched,
                                                               int* __restrict__ touched_n) {
   __shared__ float s_inv[256];
   s_inv[threadIdx.x] = inv[threadIdx.x];
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(256) bm25_accumulate_kernel(const __grid_const
     while (i >= ta.cum[t + 1]) ++t;
     const int64_t p = ta.lo[t] + (i - ta.cum[t]);
     const uint32_t d = (uint32_t)__ldg(doc + p);
-    if ((int64_t)d < n_rows && sb[d] == neg_inf<float>()) continue;  // tombstoned row
+    if (row_filter && ((int64_t)d >= filter_rows || !row_filter[d])) continue;   // bool.filter
     const float w = ta.w[t];
     const float x = __fmul_rn((float)__ldg(tf + p), s_inv[norm[d]]);
     const float s = __fsub_rn(w, __fdiv_rn(w, __fadd_rn(1.0f, x)));
@@ -140,18 +142,18 @@ __global__ void __launch_bounds__(256) bm25_accumulate_kernel(const __grid_const
 
 // the knn clause: the k nearest rows of this query get float(w_knn * knn_score) added
 __global__ void fuse_knn_kernel(const int64_t* __restrict__ knn_rows, const float* __restrict__ knn_scores, int k,
-                                int64_t row_base, float w_knn, double* __restrict__ acc,
-                                uint32_t* __restrict__ touched, int* __restrict__ touched_n,
-                                uint8_t* __restrict__ knn_only) {
+                                int64_t row_base, float w_knn, const uint8_t* __restrict__ row_filter,
+                                int64_t filter_rows, double* __restrict__ acc, uint32_t* __restrict__ touched,
+                                int* __restrict__ touched_n) {
   const int j = threadIdx.x;
   if (j >= k) return;
   const int64_t r = knn_rows[j];
   if (r < 0) return;
   const uint32_t d = (uint32_t)(r - row_base);
+  if (row_filter && ((int64_t)d >= filter_rows || !row_filter[d])) return;   // bool.filter drops the neighbour
   const float c = __fmul_rn(w_knn, knn_scores[j]);
   const double old = atomicAdd(acc + d, (double)c);
   if (old == 0.0) touched[atomicAdd(touched_n, 1)] = d;
-  (void)knn_only;
 }
 
 // per-warp top lists over the touched rows; clears the accumulator behind itself
@@ -262,8 +264,9 @@ extern "C" int rass_search_hybrid(rass_engine* h, const float* q_host, int B, co
       const int64_t total = ta.cum[ta.n_terms];
       if (total > 0) {
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->num_sms * 16);
-        bm25_accumulate_kernel<<<blocks, 256, 0, st>>>(ta, b.doc, b.tf, b.norm, b.inv_dev, h->sb, h->n_rows, b.acc,
-                                                       b.touched, b.touched_n);
+        bm25_accumulate_kernel<<<blocks, 256, 0, st>>>(ta, b.doc, b.tf, b.norm, b.inv_dev, h->sb, h->n_rows,
+                                                       h->row_filter, h->row_filter_rows, b.acc, b.touched,
+                                                       b.touched_n);
         CUDA_TRY(h, cudaGetLastError());
         s.launches++;
         s.bytes_streamed += total * 6;
@@ -271,7 +274,8 @@ extern "C" int rass_search_hybrid(rass_engine* h, const float* q_host, int B, co
     }
     if (have_vec) {
       fuse_knn_kernel<<<1, RASS_MAX_K, 0, st>>>(knn_rows + (size_t)q * k, knn_scores + (size_t)q * k, k, h->row_base,
-                                                w_knn, b.acc, b.touched, b.touched_n, nullptr);
+                                                w_knn, h->row_filter, h->row_filter_rows, b.acc, b.touched,
+                                                b.touched_n);
       CUDA_TRY(h, cudaGetLastError());
       s.launches++;
     }

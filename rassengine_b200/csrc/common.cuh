@@ -104,6 +104,9 @@ struct rass_engine {
   int64_t tmap_rows = -1;
   const void* tmap_base = nullptr;
   const void* tmap_qbase = nullptr;
+  uint8_t* row_filter = nullptr;    // device [row_filter_rows] 1 = row passes the bool.filter of the running query
+  int64_t row_filter_rows = 0;
+  size_t row_filter_cap = 0;
   Bm25State bm25;
   std::string err;
 };

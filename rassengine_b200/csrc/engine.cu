@@ -139,6 +139,7 @@ extern "C" int rass_destroy(rass_engine* h) {
   cudaFreeHost(h->out_rows_host); cudaFreeHost(h->out_scores_host); cudaFreeHost(h->out_keys_host);
   cudaFreeHost(h->q_stage_host);
   cudaFree(h->q_stage_dev);
+  cudaFree(h->row_filter);
   for (cudaEvent_t e : h->ev_pool) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) { cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -532,6 +533,7 @@ int stage_queries(rass_engine* h, const float* q_host, int B, float** q_dev_out)
     CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
     REALLOC_HOST(h, h->q_stage_host, n);
     cudaFree(h->q_stage_dev);
+  cudaFree(h->row_filter);
     h->q_stage_dev = nullptr;
     CUDA_TRY(h, cudaMalloc(&h->q_stage_dev, n * 4));
     h->q_stage_cap = n;
@@ -577,6 +579,33 @@ extern "C" int rass_merge_topk_dev(rass_engine* h, const double* keys_dev, const
                              out_keys_dev, st);
   if (rc) return rc;
   return RASS_OK;   // enqueued on the engine stream; the caller synchronises (rass_sync) when it needs the result
+}
+
+// bool.filter of the next hybrid queries as a per-row pass mask (NULL clears it)
+extern "C" int rass_set_row_filter(rass_engine* h, const uint8_t* mask_host, int64_t n) {
+  CHECK_HANDLE(h);
+  cudaStream_t st = eng_stream(h);
+  if (!mask_host) {
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    cudaFree(h->row_filter);
+    h->row_filter = nullptr;
+    h->row_filter_rows = 0;
+    h->row_filter_cap = 0;
+    return RASS_OK;
+  }
+  if (n < 0) return rass_fail(h, RASS_E_INVALID, "bad filter length");
+  if ((size_t)n > h->row_filter_cap || !h->row_filter) {
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    cudaFree(h->row_filter);
+    h->row_filter = nullptr;
+    const size_t cap = std::max<size_t>((size_t)n, 1024) * 2;
+    CUDA_TRY(h, cudaMalloc(&h->row_filter, cap));
+    h->row_filter_cap = cap;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->row_filter, mask_host, (size_t)n, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  h->row_filter_rows = n;
+  return RASS_OK;
 }
 
 // Debug entry (not part of the reference surface): raw tcgen05 dot products of <= 64 queries against every row,

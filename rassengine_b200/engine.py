@@ -140,6 +140,14 @@ class Engine:
                                               indptr.size - 1, doclen.size, global_doc_count, global_sum_ttf,
                                               _ptr(gdf) if gdf is not None else None))
 
+    def set_row_filter(self, mask):
+        """mask: uint8/bool [rows] (1 = passes the query's bool.filter) or None to clear."""
+        if mask is None:
+            self._check(self._lib.rass_set_row_filter(self._h, None, 0))
+            return
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        self._check(self._lib.rass_set_row_filter(self._h, _ptr(m), m.size))
+
     def search_hybrid(self, q, qterms, w_text: float, w_knn: float, k: int):
         """q: [B, dim] fp32 or None (text only); qterms: list of B term-id lists or None (vector only)."""
         if q is not None:

@@ -1,0 +1,189 @@
+"""B200Indexer: the reference's `OpenSearchIndexer` surface (app/main.py:1395-2150) for the retrieval hot path, plus
+`ensure_index_exists` (app/main.py:350-579) and the vector half of `store_fhir_docs_in_opensearch`
+(app/main.py:1211-1282).  Same method names, argument meaning, return shape ([( _source, _score )]) and error
+behaviour (errors are logged and become `[]`), so `ask()` can construct it in place of OpenSearchIndexer.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .client import B200Client, bulk
+
+logger = logging.getLogger("rassengine_b200")
+
+EMBED_DIM = int(os.getenv("EMBED_DIM", "1024"))          # app/main.py:80
+TOP_K = int(os.getenv("TOP_K", "3"))                     # app/main.py:88
+BATCH_SIZE = int(os.getenv("BATCH_SIZE", "64"))          # app/main.py:78
+SHARD_COUNT = int(os.getenv("SHARD_COUNT", "1"))         # app/main.py:89
+REPLICA_COUNT = int(os.getenv("REPLICA_COUNT", "0"))     # app/main.py:90
+OPENSEARCH_INDEX_NAME = os.getenv("OPENSEARCH_INDEX_NAME", "rass-index")
+
+
+def get_index_name(user_id: str) -> str:
+    return f"{OPENSEARCH_INDEX_NAME}-{user_id}"          # app/main.py:346-347
+
+
+def index_body(dim: int = EMBED_DIM) -> dict:
+    """The parts of the reference mapping the engine acts on: index.knn, shard counts and the knn_vector field
+    (app/main.py:354-360, 563-572); chunk documents add doc_id/doc_type/patientId/unstructuredText."""
+    return {
+        "settings": {"index": {"knn": True, "number_of_shards": SHARD_COUNT, "number_of_replicas": REPLICA_COUNT}},
+        "mappings": {"properties": {
+            "doc_id": {"type": "keyword"}, "doc_type": {"type": "keyword"}, "patientId": {"type": "keyword"},
+            "resourceType": {"type": "keyword"}, "unstructuredText": {"type": "text"},
+            "embedding": {"type": "knn_vector", "dimension": dim,
+                          "method": {"name": "hnsw", "engine": "nmslib", "space_type": "cosinesimil",
+                                     "parameters": {"m": 48, "ef_construction": 400}}},
+        }},
+    }
+
+
+def ensure_index_exists(client, index_name: str, body: dict | None = None) -> None:
+    """Idempotent create; errors are printed and swallowed like the reference (app/main.py:578-579)."""
+    if not client:
+        return
+    try:
+        if not client.indices.exists(index_name):
+            client.indices.create(index=index_name, body=body or index_body())
+    except Exception as exc:
+        print(f"[ERROR] ensure_index_exists: {exc}")
+
+
+def store_chunks(client, index_name: str, docs: List[Dict], embeddings: np.ndarray) -> Tuple[int, list]:
+    """Vector half of store_fhir_docs_in_opensearch (app/main.py:1247-1279): L2-normalise in fp32 exactly as the
+    reference does, attach the embedding, bulk-index in flushes of BATCH_SIZE with `_id = doc_id`."""
+    if not client or not docs:
+        return 0, []
+    ensure_index_exists(client, index_name)
+    embeddings = np.asarray(embeddings, dtype=np.float32)
+    norms = np.linalg.norm(embeddings, axis=1, keepdims=True)
+    embeddings = embeddings / (norms + 1e-9)
+    ok, errors, actions = 0, [], []
+    for i, doc in enumerate(docs):
+        d = dict(doc)
+        d["embedding"] = embeddings[i].tolist()
+        actions.append({"_op_type": "index", "_index": index_name, "_id": d["doc_id"], "_source": d,
+                        "_routing": d.get("patientId")})
+        if len(actions) >= BATCH_SIZE:
+            s, e = bulk(client, actions)
+            ok, actions = ok + s, []
+            errors.extend(e)
+    if actions:
+        s, e = bulk(client, actions)
+        ok += s
+        errors.extend(e)
+    if errors:
+        logger.error("bulk index errors: %s", errors[:3])
+    return ok, errors
+
+
+class B200Indexer:
+    text_fields = ["unstructuredText^3"]      # the analysed field chunk documents carry (app/main.py:1403-1404)
+    keyword_fields: list[str] = []
+
+    def __init__(self, client: B200Client, index_name: str):
+        self.client = client
+        self.index_name = index_name
+
+    # -- app/main.py:1470-1478 ------------------------------------------------------------------------
+    def has_any_data(self) -> bool:
+        if not self.client:
+            return False
+        try:
+            return self.client.count(index=self.index_name)["count"] > 0
+        except Exception:
+            return False
+
+    @staticmethod
+    def _unit_vector(query_emb: np.ndarray) -> list:
+        norms = np.linalg.norm(query_emb, axis=1, keepdims=True)      # app/main.py:1536-1537
+        return (query_emb / (norms + 1e-9))[0].tolist()
+
+    @staticmethod
+    def _filters(filter_clause, patient_id):
+        out = []
+        if filter_clause:
+            out.append(filter_clause)
+        if patient_id:
+            out.append({"term": {"patientId": patient_id}})
+        return out
+
+    def _run(self, body: dict, patient_id, what: str) -> List[Tuple[Dict, float]]:
+        try:
+            resp = self.client.search(index=self.index_name, body=body, routing=patient_id)
+            return [(hit["_source"], float(hit["_score"])) for hit in resp["hits"]["hits"]]
+        except Exception as e:
+            logger.error(f"{what} error: {e}")
+            return []
+
+    # -- app/main.py:1527-1560 ------------------------------------------------------------------------
+    def semantic_search(self, query_emb: np.ndarray, k: int = TOP_K, filter_clause: Optional[Dict] = None,
+                        patient_id: Optional[str] = None, query: Optional[str] = None) -> List[Tuple[Dict, float]]:
+        """`query` is accepted and ignored: ask() passes it to every embedding-taking method (app/main.py:2879-2885)."""
+        if query_emb.size == 0:
+            return []
+        body = {"size": k, "query": {"knn": {"embedding": {"vector": self._unit_vector(query_emb), "k": k}}},
+                "terminate_after": k}
+        flt = self._filters(filter_clause, patient_id)
+        if flt:
+            body["query"] = {"bool": {"must": [body["query"]], "filter": flt}}
+        return self._run(body, patient_id, "Semantic search")
+
+    # -- app/main.py:1562-1615 ------------------------------------------------------------------------
+    def _hybrid_body(self, query: str, query_emb: np.ndarray, k: int, w_text: float, w_kw: float, w_knn: float,
+                     filter_clause, patient_id) -> dict:
+        should = [
+            {"multi_match": {"query": query, "fields": self.text_fields, "type": "best_fields", "operator": "or",
+                             "fuzziness": "AUTO", "boost": w_text}},
+            {"multi_match": {"query": query, "fields": self.keyword_fields, "type": "best_fields", "operator": "or",
+                             "boost": w_kw}},
+            {"knn": {"embedding": {"vector": self._unit_vector(query_emb), "k": k, "boost": w_knn}}},
+        ]
+        bool_query = {"should": should, "minimum_should_match": 1}
+        flt = self._filters(filter_clause, patient_id)
+        if flt:
+            bool_query["filter"] = flt
+        return {"size": k, "query": {"bool": bool_query}, "terminate_after": k}
+
+    def hybrid_search(self, query: str, query_emb: np.ndarray, k: int = TOP_K, filter_clause: Optional[Dict] = None,
+                      patient_id: Optional[str] = None) -> List[Tuple[Dict, float]]:
+        if not query.strip() or query_emb.size == 0:
+            return []
+        body = self._hybrid_body(query, query_emb, k, 1.5, 1.0, 2.0, filter_clause, patient_id)
+        return self._run(body, patient_id, "Hybrid search")
+
+    # -- app/main.py:1969-2027 (same clause shape, boosts 1.0 / 0.5 / 1.5; the malformed date clause is dropped) -
+    def multi_intent_search(self, query: str, query_emb: np.ndarray, k: int = TOP_K,
+                            filter_clause: Optional[Dict] = None, patient_id: Optional[str] = None):
+        if not query.strip() or query_emb.size == 0:
+            return []
+        body = self._hybrid_body(query, query_emb, k, 1.0, 0.5, 1.5, filter_clause, patient_id)
+        return self._run(body, patient_id, "Multi-intent search")
+
+    # -- the north-star core: search(query_emb, query_text, top_k) -> _id/_score hits --------------------
+    def search(self, query_emb: np.ndarray, query_text: Optional[str] = None, top_k: int = TOP_K) -> List[Dict]:
+        query_emb = np.asarray(query_emb, dtype=np.float32).reshape(1, -1)
+        if query_text and query_text.strip():
+            body = self._hybrid_body(query_text, query_emb, top_k, 1.5, 1.0, 2.0, None, None)
+        else:
+            body = {"size": top_k,
+                    "query": {"knn": {"embedding": {"vector": self._unit_vector(query_emb), "k": top_k}}}}
+        try:
+            return self.client.search(index=self.index_name, body=body)["hits"]["hits"]
+        except Exception as e:
+            logger.error(f"search error: {e}")
+            return []
+
+    # keyword-only family (phrase / range / aggs / collapse DSL): outside the hot path -> no results, never raise
+    def _unsupported(self, *_, **__):
+        return []
+
+    exact_match_search = structured_search = hybrid_structured_search = comparison_search = _unsupported
+    temporal_search = explanatory_search = entity_specific_search = document_fetch_search = _unsupported
+
+    def aggregate_search(self, *_, **__):
+        return {}

@@ -21,14 +21,33 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> tuple[int, int]:
     return lo, min(n_rows, lo + per)
 
 
+class _DeviceOps:
+    """Tensor-level view of the raw-pointer engine calls (the seam the gloo tests replace with a CPU double)."""
+
+    def __init__(self, engine):
+        self.engine = engine
+
+    def search(self, q, k, packed, scores):
+        """packed: int64 [2, B, k] -- plane 0 receives the fp64 key bits, plane 1 the global rows."""
+        self.engine.search_knn_dev(q.data_ptr(), q.shape[0], k, packed[1].data_ptr(), scores.data_ptr(),
+                                   packed[0].data_ptr())
+        return self.engine.last_stats
+
+    def merge(self, gathered, world, B, k, out_rows, out_scores):
+        """gathered: int64 [world * 2, B, k] = every rank's packed buffer, in rank order."""
+        plane = B * k * 8
+        self.engine.merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + plane, world, B, k,
+                                   out_rows.data_ptr(), out_scores.data_ptr(), 0, shard_stride=2 * B * k)
+
+
 class ShardedIndex:
     def __init__(self, dim: int = 1024, metric: int = capi.METRIC_COSINE, flags: int = 0, capacity_rows: int = 0,
-                 device: int | None = None, group=None, engine=None):
+                 device: int | None = None, group=None, engine=None, ops=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.dim = dim
-        if engine is None:
+        if engine is None and ops is None:
             from .engine import Engine
             if device is None:
                 device = torch.cuda.current_device()
@@ -36,6 +55,7 @@ class ShardedIndex:
             # run on torch's current stream so NCCL and the engine's kernels are ordered by the stream
             engine.set_stream(torch.cuda.current_stream().cuda_stream)
         self.engine = engine
+        self.ops = ops if ops is not None else _DeviceOps(engine)
         self.merge_launches = 0
 
     def set_row_base(self, base: int):
@@ -52,16 +72,14 @@ class ShardedIndex:
         dev = q.device
         packed = torch.empty((2, B, k), dtype=torch.int64, device=dev)     # plane 0: fp64 key bits, plane 1: rows
         scores = torch.empty((B, k), dtype=torch.float32, device=dev)
-        self.engine.search_knn_dev(q.data_ptr(), B, k, packed[1].data_ptr(), scores.data_ptr(), packed[0].data_ptr())
+        self.ops.search(q, k, packed, scores)
         if self.world == 1:
             return packed[1], scores
-        gathered = torch.empty((self.world, 2, B, k), dtype=torch.int64, device=dev)
+        gathered = torch.empty((self.world * 2, B, k), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(gathered, packed, group=self.group)      # the one collective of the path
         out_rows = torch.empty((B, k), dtype=torch.int64, device=dev)
         out_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
-        plane = B * k * 8
-        self.engine.merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + plane, self.world, B, k,
-                                   out_rows.data_ptr(), out_scores.data_ptr(), 0, shard_stride=2 * B * k)
+        self.ops.merge(gathered, self.world, B, k, out_rows, out_scores)
         self.merge_launches += 1
         return out_rows, out_scores
 
@@ -74,4 +92,5 @@ class ShardedIndex:
         return rows.cpu().numpy(), scores.cpu().numpy()
 
     def close(self):
-        self.engine.close()
+        if self.engine is not None:
+            self.engine.close()

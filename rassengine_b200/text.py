@@ -1,0 +1,73 @@
+"""Host side of the text clause: analysis and the inverted index handed to rass_bm25_build.
+
+The reference maps `unstructuredText` as {"type": "text"} with the default (standard) analyzer
+(app/main.py:555-556): word segmentation + lower-casing, no stop words.  For ASCII text that is "lower-case, split
+on runs of non-alphanumerics", which is what `analyze` does; the reference's own chunker splits on whitespace
+(app/main.py:2160-2170).  Postings are CSR (term -> ascending doc rows with term frequencies) plus a token count per
+row, the layout the device BM25 kernel walks.
+"""
+from __future__ import annotations
+
+import re
+
+import numpy as np
+
+_WORD = re.compile(r"[a-z0-9]+")
+
+
+def analyze(text: str) -> list[str]:
+    return _WORD.findall(text.lower()) if text else []
+
+
+class TextField:
+    """Growing term dictionary + per-row token-id arrays for one analysed field."""
+
+    def __init__(self):
+        self.vocab: dict[str, int] = {}
+        self.row_terms: dict[int, np.ndarray] = {}   # row -> int32 term ids (with repeats)
+        self.dirty = True
+
+    def set_row(self, row: int, text: str | None):
+        toks = analyze(text) if text else []
+        if not toks:
+            if self.row_terms.pop(row, None) is not None:
+                self.dirty = True
+            return
+        v = self.vocab
+        ids = np.fromiter((v.setdefault(t, len(v)) for t in toks), dtype=np.int32, count=len(toks))
+        self.row_terms[row] = ids
+        self.dirty = True
+
+    def set_row_ids(self, row: int, ids: np.ndarray):
+        """Pre-tokenised input (synthetic corpora): term ids must be < declare_vocab()."""
+        self.row_terms[row] = np.asarray(ids, dtype=np.int32)
+        self.dirty = True
+
+    def query_terms(self, text: str) -> list[int]:
+        """Term ids of the query tokens; unknown tokens map to -1 (the kernel ignores them)."""
+        return [self.vocab.get(t, -1) for t in analyze(text)]
+
+    def postings(self, n_rows: int):
+        """CSR over the current rows: indptr int64 [V+1], doc int32 [nnz] ascending per term, tf uint16 [nnz],
+        doclen uint32 [n_rows]."""
+        V = len(self.vocab)
+        doclen = np.zeros(n_rows, dtype=np.uint32)
+        if not self.row_terms:
+            return np.zeros(V + 1, dtype=np.int64), np.zeros(0, np.int32), np.zeros(0, np.uint16), doclen
+        rows = np.fromiter(self.row_terms.keys(), dtype=np.int64, count=len(self.row_terms))
+        lens = np.fromiter((a.size for a in self.row_terms.values()), dtype=np.int64, count=rows.size)
+        doclen[rows] = lens
+        terms = np.concatenate(list(self.row_terms.values())).astype(np.int64)
+        V = max(V, int(terms.max()) + 1)
+        docs = np.repeat(rows, lens)
+        return csr_from_pairs(terms, docs, V, n_rows) + (doclen,)
+
+
+def csr_from_pairs(terms: np.ndarray, docs: np.ndarray, V: int, n_rows: int):
+    key = terms * np.int64(n_rows) + docs
+    uniq, counts = np.unique(key, return_counts=True)
+    t_of = uniq // n_rows
+    d_of = (uniq - t_of * n_rows).astype(np.int32)
+    indptr = np.zeros(V + 1, dtype=np.int64)
+    np.add.at(indptr, t_of + 1, 1)
+    return np.cumsum(indptr), d_of, np.minimum(counts, 65535).astype(np.uint16)

@@ -1,0 +1,205 @@
+"""GPU parity of the BM25 + fusion kernels and of the OpenSearch-shaped boundary (client shim + B200Indexer)
+against the numpy oracle.  Bar: ranked ids identical, fused float32 scores bit-identical (integer/byte work and
+individually-rounded float ops), kNN scores within 1e-5 relative."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bm25, fusion, knn, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(**kw):
+    import rassengine_b200 as rb
+    return rb.Engine(**kw)
+
+
+def test_bm25_micro_golden_scores(golden_dir):
+    """tests/golden/bm25_micro.json (hand-checkable, incl. a 45-token doc quantised to 44) through the kernel."""
+    g = json.load(open(os.path.join(golden_dir, "bm25_micro.json")))
+    idx = bm25.BM25Index.from_token_ids(g["docs"], g["vocab"])
+    n = len(g["docs"])
+    with _engine(dim=4) as e:
+        e.append(np.eye(4, dtype=np.float32)[np.arange(n) % 4])
+        e.bm25_build(idx.indptr, idx.doc, idx.tf, idx.doclen)
+        for c in g["cases"]:
+            rows, scores = e.search_hybrid(None, [c["qterms"]], c["boost"], 0.0, n)
+            want = {d: s for d, s in enumerate(c["scores"]) if s > 0}
+            got = {int(r): float(s) for r, s in zip(rows[0], scores[0]) if r >= 0}
+            assert got == want
+            order = sorted(want, key=lambda d: (-want[d], d))
+            assert [int(r) for r in rows[0] if r >= 0] == order
+
+
+def _text_case(n_docs=6000, vocab=1500, dim=256, nq=24):
+    indptr, doc, tf, doclen = synth.text_corpus(n_docs, vocab=vocab, seed=11, median_len=60, max_len=300)
+    idx = bm25.BM25Index(indptr, doc, tf, doclen)
+    X = synth.embeddings(n_docs, dim, 31)
+    Q = synth.embeddings(nq, dim, 32)
+    qterms = synth.text_queries(nq, vocab=vocab, seed=12)
+    qterms[0] = qterms[0] + [qterms[0][0]]          # a duplicated query token counts twice
+    qterms[1] = qterms[1] + [vocab + 5, -1]         # unknown tokens are ignored
+    return idx, X, Q, qterms
+
+
+@pytest.mark.parametrize("k", [10, 100])
+def test_hybrid_matches_oracle(k):
+    idx, X, Q, qterms = _text_case()
+    knn_rows, _, knn_scores = knn.knn_exact(X, Q, k)
+    with _engine(dim=X.shape[1]) as e:
+        e.append(X)
+        e.bm25_build(idx.indptr, idx.doc, idx.tf, idx.doclen)
+        rows, scores = e.search_hybrid(Q, qterms, 4.5, 2.0, k)
+        for b in range(Q.shape[0]):
+            qt = [t for t in qterms[b] if 0 <= t < idx.vocab]
+            want_rows, want_scores = fusion.hybrid(idx, qt, knn_rows[b], knn_scores[b], 4.5, 2.0, k)
+            assert rows[b, :len(want_rows)].tolist() == want_rows.tolist(), b
+            np.testing.assert_allclose(scores[b, :len(want_rows)], want_scores, rtol=2e-6)
+        # text only and vector only degenerate forms
+        rows_t, scores_t = e.search_hybrid(None, qterms[:4], 4.5, 2.0, k)
+        for b in range(4):
+            qt = [t for t in qterms[b] if 0 <= t < idx.vocab]
+            wr, ws = bm25.topk(idx.score(qt, boost=4.5), k)
+            assert rows_t[b, :len(wr)].tolist() == wr.tolist()
+            assert scores_t[b, :len(wr)].tolist() == ws.tolist()       # bit-identical float32
+        rows_v, scores_v = e.search_hybrid(Q[:4], None, 4.5, 2.0, k)
+        assert np.array_equal(rows_v, knn_rows[:4])
+        np.testing.assert_allclose(scores_v, np.float32(2.0) * knn_scores[:4], rtol=1e-5)
+
+
+def test_hybrid_row_filter_matches_oracle_alive_mask():
+    idx, X, Q, qterms = _text_case(n_docs=3000, nq=6)
+    k = 10
+    knn_rows, _, knn_scores = knn.knn_exact(X, Q, k)
+    alive = (np.arange(3000) % 3 != 0)
+    with _engine(dim=X.shape[1]) as e:
+        e.append(X)
+        e.bm25_build(idx.indptr, idx.doc, idx.tf, idx.doclen)
+        e.set_row_filter(alive)
+        rows, scores = e.search_hybrid(Q, qterms, 4.5, 2.0, k)
+        e.set_row_filter(None)
+        rows_all, _ = e.search_hybrid(Q, qterms, 4.5, 2.0, k)
+    for b in range(Q.shape[0]):
+        qt = [t for t in qterms[b] if 0 <= t < idx.vocab]
+        wr, ws = fusion.hybrid(idx, qt, knn_rows[b], knn_scores[b], 4.5, 2.0, k, alive=alive)
+        assert rows[b, :len(wr)].tolist() == wr.tolist()
+        np.testing.assert_allclose(scores[b, :len(wr)], ws, rtol=2e-6)
+        wr2, _ = fusion.hybrid(idx, qt, knn_rows[b], knn_scores[b], 4.5, 2.0, k)
+        assert rows_all[b, :len(wr2)].tolist() == wr2.tolist()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the drop-in boundary: client shim + B200Indexer, driven the way main.py / embedding_gen.py drive OpenSearch
+# ---------------------------------------------------------------------------------------------------------
+def _chunk_docs(n_docs=1500, vocab=400, dim=64):
+    indptr, doc, tf, doclen = synth.text_corpus(n_docs, vocab=vocab, seed=5, median_len=40, max_len=120)
+    texts = synth.docs_as_text(indptr, doc, tf, n_docs)
+    raw = np.random.default_rng(9).standard_normal((n_docs, dim)).astype(np.float32) * 3.0   # NOT unit: store normalises
+    docs = [{"doc_id": f"txt-note-{i}", "doc_type": "unstructured", "resourceType": "DocumentReference",
+             "file_path": f"/data/p{i % 7}.txt", "file_type": "txt", "patientId": f"pat-{i % 7}",
+             "unstructuredText": texts[i]} for i in range(n_docs)]
+    return docs, raw, (indptr, doc, tf, doclen)
+
+
+def test_indexer_surface_end_to_end():
+    from rassengine_b200.client import B200Client
+    from rassengine_b200 import indexer as ix
+    docs, raw, (indptr, doc, tf, doclen) = _chunk_docs()
+    dim = raw.shape[1]
+    client = B200Client(hosts=[{"host": "localhost", "port": 9200}], http_compress=True, use_ssl=False)
+    name = ix.get_index_name("user-1")
+    ix.ensure_index_exists(client, name, ix.index_body(dim))
+    ix.ensure_index_exists(client, name, ix.index_body(dim))            # idempotent
+    assert client.indices.exists(name)
+    idxr = ix.B200Indexer(client, name)
+    assert not idxr.has_any_data()
+    ok, errors = ix.store_chunks(client, name, docs, raw)
+    assert ok == len(docs) and not errors
+    assert idxr.has_any_data() and client.count(index=name)["count"] == len(docs)
+    assert "version" in client.info()
+
+    X = knn.normalize_rows(raw).astype(np.float32)                      # what the store normalises to
+    # the JSON round trip of the reference sends python floats: the stored rows are float32(list(X))
+    rng = np.random.default_rng(3)
+    q_emb = rng.standard_normal((1, dim)).astype(np.float32)
+    q_unit = (q_emb / (np.linalg.norm(q_emb, axis=1, keepdims=True) + 1e-9)).astype(np.float32)
+    k = 5
+    want_rows, _, want_scores = knn.knn_exact(X, q_unit, k)
+
+    hits = idxr.semantic_search(q_emb, k=k, query="ignored like ask() passes it")
+    assert [h[0]["doc_id"] for h in hits] == [docs[r]["doc_id"] for r in want_rows[0]]
+    np.testing.assert_allclose([h[1] for h in hits], want_scores[0], rtol=1e-5)
+    assert len(hits[0][0]["embedding"]) == dim                          # _source comes back whole
+
+    # hybrid: 4.5 * BM25(unstructuredText) + 2.0 * knn, boosted sum, no normalisation (app/main.py:1574-1598)
+    bm = bm25.BM25Index(indptr, doc, tf, doclen)
+    qtext = " ".join(synth.token(t) for t in (3, 17, 3, 250)) + " unknownword"
+    qterms = [3, 17, 3, 250]
+    wr, ws = fusion.hybrid(bm, qterms, want_rows[0], want_scores[0], 4.5, 2.0, k)
+    hits = idxr.hybrid_search(qtext, q_emb, k=k)
+    assert [h[0]["doc_id"] for h in hits] == [docs[r]["doc_id"] for r in wr]
+    np.testing.assert_allclose([h[1] for h in hits], ws, rtol=2e-6)
+    # north-star core
+    core = idxr.search(q_emb, qtext, top_k=k)
+    assert [h["_id"] for h in core] == [docs[r]["doc_id"] for r in wr] and all("_score" in h for h in core)
+    # multi-intent: same shape, boosts 1.0*3 / 1.5
+    wr3, ws3 = fusion.hybrid(bm, qterms, want_rows[0], want_scores[0], 3.0, 1.5, k)
+    hits = idxr.multi_intent_search(qtext, q_emb, k=k)
+    assert [h[0]["doc_id"] for h in hits] == [docs[r]["doc_id"] for r in wr3]
+
+    # patient filter: post-filter on the k nearest for knn (nmslib semantics), pre-filter mask for hybrid
+    pid = "pat-3"
+    hits = idxr.semantic_search(q_emb, k=k, patient_id=pid)
+    assert [h[0]["doc_id"] for h in hits] == [docs[r]["doc_id"] for r in want_rows[0] if docs[r]["patientId"] == pid]
+    alive = np.array([d["patientId"] == pid for d in docs])
+    wrf, wsf = fusion.hybrid(bm, qterms, want_rows[0], want_scores[0], 4.5, 2.0, k, alive=alive)
+    hits = idxr.hybrid_search(qtext, q_emb, k=k, patient_id=pid)
+    assert [h[0]["doc_id"] for h in hits] == [docs[r]["doc_id"] for r in wrf]
+    assert all(h[0]["patientId"] == pid for h in hits)
+
+    # bulk "index" on an existing _id overwrites in place (same row, new vector and text)
+    from rassengine_b200.client import bulk
+    new = dict(docs[int(want_rows[0][0])])
+    new["unstructuredText"] = "replaced text"
+    new["embedding"] = (-X[int(want_rows[0][0])]).tolist()
+    s, e = bulk(client, [{"_op_type": "index", "_index": name, "_id": new["doc_id"], "_source": new}])
+    assert (s, e) == (1, []) and client.count(index=name)["count"] == len(docs)
+    hits = idxr.semantic_search(q_emb, k=k)
+    assert new["doc_id"] not in [h[0]["doc_id"] for h in hits]
+
+    # error conventions: empty inputs short-circuit, unsupported DSL / unknown index never raise out of the indexer
+    assert idxr.semantic_search(np.zeros((0, dim), dtype=np.float32)) == []
+    assert idxr.hybrid_search("   ", q_emb) == []
+    assert ix.B200Indexer(client, "no-such-index").semantic_search(q_emb) == []
+    assert idxr.semantic_search(q_emb, k=k, filter_clause=[{"text": "x", "label": "Y"}]) == []   # ask()'s NER list
+    assert idxr.exact_match_search("x") == [] and idxr.aggregate_search("x") == {}
+    with pytest.raises(NotImplementedError):
+        client.search(index=name, body={"size": 3, "query": {"match_phrase": {"unstructuredText": "x"}}})
+    client.close()
+
+
+def test_opensearchpy_shim_import(monkeypatch):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.syspath_prepend(os.path.join(root, "rassengine_b200", "shim"))
+    sys.modules.pop("opensearchpy", None)
+    from opensearchpy import OpenSearch, RequestsHttpConnection
+    from opensearchpy.helpers import bulk
+    c = OpenSearch(hosts=[{"host": "localhost", "port": 9200}], http_compress=True, use_ssl=False,
+                   verify_certs=False, connection_class=RequestsHttpConnection)
+    c.indices.create(index="i", body={"settings": {"index": {"knn": True}}, "mappings": {"properties": {
+        "embedding": {"type": "knn_vector", "dimension": 8, "method": {"name": "hnsw", "engine": "nmslib",
+                                                                         "space_type": "cosinesimil"}}}}})
+    vecs = np.eye(8, dtype=np.float32)
+    ok, err = bulk(c, [{"_op_type": "index", "_index": "i", "_id": f"d{i}", "_source": {"doc_id": f"d{i}",
+                        "embedding": vecs[i].tolist()}, "_routing": "p"} for i in range(8)])
+    assert ok == 8 and not err
+    resp = c.search(index="i", body={"size": 2, "query": {"knn": {"embedding": {"vector": vecs[5].tolist(), "k": 2}}},
+                                     "terminate_after": 2}, routing="p")
+    assert [h["_id"] for h in resp["hits"]["hits"]] == ["d5", "d0"]
+    assert resp["hits"]["hits"][0]["_score"] == pytest.approx(1.0) and resp["hits"]["hits"][1]["_score"] == pytest.approx(0.5)
+    c.close()
+    sys.modules.pop("opensearchpy", None)

@@ -1,0 +1,159 @@
+"""CPU tests of the host side: DSL parsing of the exact bodies the reference emits, the text index, the client's
+bookkeeping and error conventions, and the sharded search control flow over gloo (world size 2)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import bm25, knn, synth
+from rassengine_b200 import dsl, text
+from rassengine_b200.sharded import shard_bounds
+
+
+def test_parse_knn_bodies_as_the_reference_builds_them():
+    vec = [0.1] * 1024
+    body = {"size": 3, "query": {"knn": {"embedding": {"vector": vec, "k": 3}}}, "terminate_after": 3}   # main.py:1538-1542
+    p = dsl.parse_search_body(body)
+    assert (p.kind, p.size, p.knn_k, p.knn_boost, p.knn_field) == ("knn", 3, 3, 1.0, "embedding") and p.vector is vec
+    wrapped = {"size": 3, "terminate_after": 3, "query": {"bool": {"must": [body["query"]],
+               "filter": [{"term": {"patientId": "p-1"}}]}}}                                             # main.py:1543-1550
+    p = dsl.parse_search_body(wrapped)
+    assert p.kind == "knn" and p.filters == [("patientId", "p-1")]
+
+
+def test_parse_hybrid_body_as_the_reference_builds_it():
+    fields = ["unstructuredText^3", "patientName^3", "conditionNote^2", "observationValue"]
+    kw = ["patientGender^3", "encounterStatus"]
+    body = {"size": 10, "terminate_after": 10, "query": {"bool": {"should": [
+        {"multi_match": {"query": "what is diabetes", "fields": fields, "type": "best_fields", "operator": "or",
+                         "fuzziness": "AUTO", "boost": 1.5}},
+        {"multi_match": {"query": "what is diabetes", "fields": kw, "type": "best_fields", "operator": "or", "boost": 1.0}},
+        {"knn": {"embedding": {"vector": [0.0] * 8, "k": 10, "boost": 2.0}}}],
+        "minimum_should_match": 1}}}                                                                      # main.py:1574-1605
+    p = dsl.parse_search_body(body)
+    assert p.kind == "hybrid" and p.knn_boost == 2.0 and p.knn_k == 10
+    assert p.text[0].boost == 1.5 and dict(p.text[0].fields)["unstructuredText"] == 3.0
+    assert dict(p.text[0].fields)["observationValue"] == 1.0 and p.text[1].boost == 1.0
+
+
+@pytest.mark.parametrize("body", [
+    {"size": 3, "query": {"match_phrase": {"unstructuredText": "x"}}},
+    {"size": 0, "aggs": {"a": {"terms": {"field": "resourceType"}}}},
+    {"size": 3, "query": {"bool": {"must": [{"multi_match": {"query": "x", "fields": ["a"], "type": "phrase_prefix"}}]}}},
+    {"size": 3, "query": {"bool": {"filter": [{"range": {"patientDOB": {"gte": "2000"}}}], "should": [
+        {"knn": {"embedding": {"vector": [0.0], "k": 3}}}]}}},
+    {"size": 3, "sort": [{"encounterStart": "desc"}], "query": {"match_all": {}}},
+])
+def test_unsupported_dsl_raises_not_implemented(body):
+    with pytest.raises(NotImplementedError):
+        dsl.parse_search_body(body)
+
+
+def test_text_field_postings_equal_oracle_index():
+    indptr, doc, tf, doclen = synth.text_corpus(400, vocab=120, seed=3, median_len=30, max_len=90)
+    texts = synth.docs_as_text(indptr, doc, tf, 400)
+    f = text.TextField()
+    for r, t in enumerate(texts):
+        f.set_row(r, t)
+    ip, d, t_, dl = f.postings(400)
+    # vocabulary ids are assigned in first-seen order: compare per token through the dictionary
+    ref = bm25.BM25Index(indptr, doc, tf, doclen)
+    assert np.array_equal(dl, doclen)
+    for term_id in range(0, 120, 7):
+        tid = f.vocab.get(synth.token(term_id))
+        lo, hi = indptr[term_id], indptr[term_id + 1]
+        if tid is None:
+            assert lo == hi
+            continue
+        assert np.array_equal(d[ip[tid]:ip[tid + 1]], doc[lo:hi]) and np.array_equal(t_[ip[tid]:ip[tid + 1]], tf[lo:hi])
+    assert text.analyze("Hello, World-2 FOO_bar") == ["hello", "world", "2", "foo", "bar"]
+    assert f.query_terms("t00003 nope")[1] == -1
+    f.set_row(5, None)
+    assert f.postings(400)[3][5] == 0 and ref.doclen[5] > 0
+
+
+def test_client_without_gpu_follows_error_conventions():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from rassengine_b200.client import B200Client, bulk, NotFoundError
+    from rassengine_b200 import indexer as ix
+    c = B200Client(hosts=[{"host": "x", "port": 1}])
+    ix.ensure_index_exists(c, "idx", ix.index_body(8))
+    assert c.indices.exists("idx") and c.count(index="idx")["count"] == 0
+    with pytest.raises(NotFoundError):
+        c.count(index="nope")
+    # no device: the bulk call reports per-doc errors instead of raising (helpers.bulk style), searches give []
+    ok, errors = bulk(c, [{"_op_type": "index", "_index": "idx", "_id": "a", "_source": {"embedding": [0.0] * 8}}])
+    assert ok == 0 and len(errors) == 1 and "no CPU fallback" in errors[0]["index"]["error"]
+    idxr = ix.B200Indexer(c, "idx")
+    assert idxr.semantic_search(np.ones((1, 8), dtype=np.float32), k=3) == []
+    assert not idxr.has_any_data()
+
+
+def test_shard_bounds_cover_rows_once():
+    for n, g in ((10_000_000, 8), (100_000_000, 4), (7, 3), (5, 8)):
+        spans = [shard_bounds(n, g, r) for r in range(g)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+# ---- world_size-2 gloo run of the sharded search control flow with a CPU test double for the engine ----------
+_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO"])
+from oracle import knn, synth
+from rassengine_b200.sharded import ShardedIndex, shard_bounds
+
+class OracleOps:                          # CPU test double for the device ops: answers from the oracle
+    def __init__(self, X, base): self.X, self.base = X, base
+    def search(self, q, k, packed, scores):
+        r, key, s = knn.knn_exact(self.X, q.numpy(), k)
+        packed[1].copy_(torch.from_numpy(r + self.base)); scores.copy_(torch.from_numpy(s))
+        packed[0].copy_(torch.from_numpy(key).view(torch.int64))
+    def merge(self, gathered, world, B, k, out_rows, out_scores):
+        g = gathered.view(world, 2, B, k)
+        keys = g[:, 0].contiguous().view(torch.float64).numpy(); rows = g[:, 1].numpy()
+        for b in range(B):
+            kk = keys[:, b].reshape(-1); rr = rows[:, b].reshape(-1)
+            order = np.lexsort((rr, -kk))[:k]
+            out_rows[b] = torch.from_numpy(rr[order])
+            out_scores[b] = torch.from_numpy((1 / (2 - kk[order])).astype(np.float32))
+
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{os.environ['PORT']}", rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+X = synth.embeddings(4000, 64, 1); Q = torch.from_numpy(synth.embeddings(5, 64, 2)); k = 7
+lo, hi = shard_bounds(4000, 2, rank)
+idx = ShardedIndex(dim=64, ops=OracleOps(X[lo:hi], lo))
+assert idx.world == 2 and idx.rank == rank
+rows, scores = idx.search_dev(Q, k)      # the product's control flow: local search -> ONE all_gather -> merge
+want_rows, _, want_scores = knn.knn_exact(X, Q.numpy(), k)
+assert np.array_equal(rows.numpy(), want_rows), (rank, rows, want_rows)
+np.testing.assert_allclose(scores.numpy(), want_scores, rtol=1e-6)
+assert idx.merge_launches == 1
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_sharded_search_two_ranks_gloo(tmp_path):
+    import socket
+    import subprocess
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), PORT=str(port), REPO=root, OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out
+        assert "ok" in out
