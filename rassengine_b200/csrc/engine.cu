@@ -533,7 +533,6 @@ int stage_queries(rass_engine* h, const float* q_host, int B, float** q_dev_out)
     CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
     REALLOC_HOST(h, h->q_stage_host, n);
     cudaFree(h->q_stage_dev);
-  cudaFree(h->row_filter);
     h->q_stage_dev = nullptr;
     CUDA_TRY(h, cudaMalloc(&h->q_stage_dev, n * 4));
     h->q_stage_cap = n;
