@@ -68,7 +68,8 @@ enum {
 
 enum {
   RASS_OPT_PATH = 1,
-  RASS_OPT_STREAM = 2    /* value = cudaStream_t to enqueue on (0 = engine-owned stream)               */
+  RASS_OPT_STREAM = 2    /* value = cudaStream_t to enqueue on (0 = the legacy default stream, which is what
+                            torch's default stream is); -1 = back to the engine-owned stream           */
 };
 
 typedef struct rass_stats {

@@ -61,6 +61,7 @@ struct rass_engine {
   DevScalars* scal = nullptr;       // device
   DevScalars* scal_host = nullptr;  // pinned mirror
   cudaStream_t stream = nullptr, user_stream = nullptr, copy_stream = nullptr;
+  bool has_user_stream = false;     // user_stream may legitimately be 0 (the legacy default stream)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   float* stage[2] = {nullptr, nullptr};  // pinned host staging
@@ -123,7 +124,7 @@ int rass_fail(rass_engine* h, int code, const char* fmt, ...);
                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-static inline cudaStream_t eng_stream(const rass_engine* h) { return h->user_stream ? h->user_stream : h->stream; }
+static inline cudaStream_t eng_stream(const rass_engine* h) { return h->has_user_stream ? h->user_stream : h->stream; }
 
 // fp32 accumulation allowance of a length-d dot product with |x||q| <= 1 (gamma_d, doubled for the tensor
 // pipe's unspecified summation order)

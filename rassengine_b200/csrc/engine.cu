@@ -161,7 +161,13 @@ extern "C" int rass_set_option(rass_engine* h, int opt, int64_t value) {
       h->path = (int)value;
       return RASS_OK;
     case RASS_OPT_STREAM:
-      h->user_stream = reinterpret_cast<cudaStream_t>(value);
+      if (value == -1) {
+        h->has_user_stream = false;
+        h->user_stream = nullptr;
+      } else {
+        h->has_user_stream = true;
+        h->user_stream = reinterpret_cast<cudaStream_t>(value);
+      }
       return RASS_OK;
     default:
       return rass_fail(h, RASS_E_INVALID, "unknown option %d", opt);
