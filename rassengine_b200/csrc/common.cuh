@@ -13,7 +13,7 @@
 #define RASS_MAX_K 128
 #define RASS_CAND_MAX 2048     // rerank candidate cap per query
 #define RASS_GROUP_Q 64        // queries finished per finish launch (= queries per tcgen05 pass)
-#define RASS_STREAM_SEG 32     // pool entries per (warp, query) segment of the streaming scan
+#define RASS_STREAM_SEG 64     // pool entries per (CTA, query) segment of the streaming scan (32..64 kept)
 #define RASS_UMMA_SEG 256      // pool entries per (CTA, query) segment of the tcgen05 scan
 #define RASS_UMMA_KEEP 32      // entries a tcgen05 segment keeps at a compaction
 #define RASS_EXACT_NQ 4        // queries per pass of the fp64 scan
@@ -167,6 +167,67 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
   return v;
+}
+
+// order-preserving float <-> uint32 maps (larger float <-> larger integer); 0 is below every float
+__device__ __forceinline__ uint32_t ord32(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unord32(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// Warp-cooperative compaction of up to 32*E (ordered key, row) entries held E per lane (ok == 0: empty slot).
+// Bisects for a pivot with keep .. 2*keep entries strictly above it, writes those entries densely to
+// out_key/out_row and returns their count; every entry not written has key <= unord32(pivot).  Ties can make the
+// band unreachable; then the upper end is used (fewer entries kept, the bound still holds).
+template <int E>
+__device__ __forceinline__ int warp_compact(const uint32_t (&ok)[E], const uint32_t (&rw)[E], int keep,
+                                            float* out_key, uint32_t* out_row, uint32_t& pivot) {
+  const int lane = threadIdx.x & 31;
+  uint32_t kmin = 0xffffffffu, kmax = 0;
+#pragma unroll
+  for (int i = 0; i < E; ++i)
+    if (ok[i]) { kmin = min(kmin, ok[i]); kmax = max(kmax, ok[i]); }
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  // invariant: count(> lo) > 2*keep (or lo is below everything), count(> hi) < keep
+  uint32_t lo = kmin - 1, hi = kmax;
+  pivot = kmax;
+  int total = 0;
+#pragma unroll
+  for (int i = 0; i < E; ++i) total += ok[i] != 0;
+  total = __reduce_add_sync(0xffffffffu, total);
+  if (total <= 2 * keep) {
+    pivot = 0x007fffffu;        // ord32(-inf): nothing needs to go, every real entry is above it
+  } else {
+    bool found = false;
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      int cgt = 0;
+#pragma unroll
+      for (int i = 0; i < E; ++i) cgt += ok[i] > mid;
+      cgt = __reduce_add_sync(0xffffffffu, cgt);
+      if (cgt > 2 * keep) lo = mid;
+      else if (cgt < keep) hi = mid;
+      else { pivot = mid; found = true; break; }
+    }
+    if (!found) pivot = hi;
+  }
+  int kept = 0;
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    const bool k = ok[i] > pivot;
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    if (k) {
+      const int pos = kept + __popc(bal & ((1u << lane) - 1));
+      out_key[pos] = unord32(ok[i]);
+      out_row[pos] = rw[i];
+    }
+    kept += __popc(bal);
+  }
+  return kept;
 }
 
 // Per-warp running top-(32*M) list.  Lane l owns slots key[0..M), row[0..M).  (thr_key, thr_row) is the

@@ -492,7 +492,7 @@ int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_r
         }
       }
       CUDA_TRY(h, cudaEventRecord(get_event(h, n_ev++), st));
-      if ((rc = launch_finish(h, g0, ng, k, n_segs, seg, umma, umma, out_rows, out_scores, out_keys, st))) return rc;
+      if ((rc = launch_finish(h, g0, ng, k, n_segs, seg, true, umma, out_rows, out_scores, out_keys, st))) return rc;
       s.launches += 1;
     }
     s.bytes_streamed = (int64_t)s.passes * h->n_rows * h->dim_pad * 2;

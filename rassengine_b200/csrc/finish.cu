@@ -46,10 +46,9 @@ __global__ void __launch_bounds__(RASS_FINISH_THREADS, 1) finish_kernel(FinishAr
   float* qs = reinterpret_cast<float*>(smem_raw);                          // [dim_pad]
   double* ckey = reinterpret_cast<double*>(qs + a.dim_pad);                // [RASS_CAND_MAX]
   uint32_t* crow = reinterpret_cast<uint32_t*>(ckey + RASS_CAND_MAX);      // [RASS_CAND_MAX]
-  float* tmax = reinterpret_cast<float*>(crow + RASS_CAND_MAX);            // [RASS_FINISH_THREADS]
   __shared__ float s_red[32];
   __shared__ int s_redi[32];
-  __shared__ float s_t, s_bprime;
+  __shared__ float s_t;
   __shared__ int s_valid, s_ncand, s_have;
   __shared__ double s_sk;
 
@@ -58,21 +57,22 @@ __global__ void __launch_bounds__(RASS_FINISH_THREADS, 1) finish_kernel(FinishAr
   const int q = a.g0 + slot;            // query id within the search
   const float* pk = a.pool_key + (size_t)slot * a.pool_entries;
   const uint32_t* pr = a.pool_row + (size_t)slot * a.pool_entries;
-  const int total = a.n_segs * a.seg_size;
 
   for (int j = tid; j < a.dim_pad; j += blockDim.x) qs[j] = a.q_raw[(size_t)q * a.dim_pad + j];
   if (tid == 0) { s_ncand = 0; s_have = 0; }
 
-  // phase 1: per-thread maximum of the valid entries, t = max segment bound, number of valid entries
+  // phase 1: per-thread maximum of the valid entries (warp per segment, lanes over its entries),
+  // t = max segment bound, number of valid entries
   float mx = neg_inf<float>();
   int nvalid = 0;
-  for (int i = tid; i < total; i += blockDim.x) {
-    bool ok;
-    if (a.pool_cnt) ok = (i % a.seg_size) < a.pool_cnt[(size_t)slot * a.n_segs + i / a.seg_size];
-    else ok = pr[i] != 0xffffffffu;
-    if (ok) {
-      ++nvalid;
-      mx = fmaxf(mx, pk[i]);
+  for (int sgm = warp; sgm < a.n_segs; sgm += RASS_FINISH_THREADS / 32) {
+    const int cnt = a.pool_cnt ? min(a.pool_cnt[(size_t)slot * a.n_segs + sgm], a.seg_size) : a.seg_size;
+    for (int i = lane; i < cnt; i += 32) {
+      const size_t o = (size_t)sgm * a.seg_size + i;
+      if (a.pool_cnt || pr[o] != 0xffffffffu) {
+        ++nvalid;
+        mx = fmaxf(mx, pk[o]);
+      }
     }
   }
   float t = neg_inf<float>();
@@ -83,7 +83,6 @@ __global__ void __launch_bounds__(RASS_FINISH_THREADS, 1) finish_kernel(FinishAr
     nvalid += __shfl_xor_sync(0xffffffffu, nvalid, m);
   }
   if (lane == 0) { s_red[warp] = t; s_redi[warp] = nvalid; }
-  tmax[tid] = mx;
   __syncthreads();
   if (warp == 0) {
     float tt = s_red[lane];
@@ -93,23 +92,22 @@ __global__ void __launch_bounds__(RASS_FINISH_THREADS, 1) finish_kernel(FinishAr
       tt = fmaxf(tt, __shfl_xor_sync(0xffffffffu, tt, m));
       nv += __shfl_xor_sync(0xffffffffu, nv, m);
     }
-    if (lane == 0) { s_t = tt; s_valid = nv; s_bprime = neg_inf<float>(); }
+    if (lane == 0) { s_t = tt; s_valid = nv; }
   }
-  __syncthreads();
 
-  // phase 2: b' = k-th largest per-thread maximum (k distinct entries are >= it)
+  // phase 2: b' = k-th largest per-thread maximum (k distinct entries are >= it): MSB-first radix descent on the
+  // order-preserving integer image, one __syncthreads_count per bit.  Threads without an entry hold 0.
+  float bprime;
   {
-    int better = 0;
-    const bool mine = mx > neg_inf<float>();
-    if (mine) {
-      for (int j = 0; j < RASS_FINISH_THREADS; ++j) {
-        float o = tmax[j];
-        better += (o > mx) || (o == mx && j < tid);
-      }
-      if (better == a.k - 1) s_bprime = mx;
+    const uint32_t mine = mx > neg_inf<float>() ? ord32(mx) : 0u;
+    uint32_t prefix = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = prefix | (1u << bit);
+      if (__syncthreads_count(mine >= cand) >= a.k) prefix = cand;
     }
+    bprime = prefix > 0x007fffffu ? unord32(prefix) : neg_inf<float>();   // fewer than k holders -> take everything
   }
-  __syncthreads();
 
   float eps;
   {
@@ -122,16 +120,17 @@ __global__ void __launch_bounds__(RASS_FINISH_THREADS, 1) finish_kernel(FinishAr
     }
     eps = e * 1.0001f;
   }
-  const float cutoff = s_bprime - 2.f * eps;   // -inf when fewer than k threads hold an entry
+  const float cutoff = bprime - 2.f * eps;   // -inf when fewer than k threads hold an entry
 
   // phase 3: collect the candidates
-  for (int i = tid; i < total; i += blockDim.x) {
-    bool ok;
-    if (a.pool_cnt) ok = (i % a.seg_size) < a.pool_cnt[(size_t)slot * a.n_segs + i / a.seg_size];
-    else ok = pr[i] != 0xffffffffu;
-    if (ok && pk[i] >= cutoff) {
-      int pos = atomicAdd(&s_ncand, 1);
-      if (pos < RASS_CAND_MAX) crow[pos] = pr[i];
+  for (int sgm = warp; sgm < a.n_segs; sgm += RASS_FINISH_THREADS / 32) {
+    const int cnt = a.pool_cnt ? min(a.pool_cnt[(size_t)slot * a.n_segs + sgm], a.seg_size) : a.seg_size;
+    for (int i = lane; i < cnt; i += 32) {
+      const size_t o = (size_t)sgm * a.seg_size + i;
+      if ((a.pool_cnt || pr[o] != 0xffffffffu) && pk[o] >= cutoff) {
+        int pos = atomicAdd(&s_ncand, 1);
+        if (pos < RASS_CAND_MAX) crow[pos] = pr[o];
+      }
     }
   }
   __syncthreads();
@@ -197,7 +196,7 @@ __global__ void __launch_bounds__(RASS_FINISH_THREADS, 1) finish_kernel(FinishAr
 }
 
 static size_t finish_smem(int dim_pad) {
-  return (size_t)dim_pad * 4 + RASS_CAND_MAX * 12 + RASS_FINISH_THREADS * 4;
+  return (size_t)dim_pad * 4 + RASS_CAND_MAX * 12;
 }
 
 int launch_finish(rass_engine* h, int g0, int ng, int k, int n_segs, int seg_size, bool has_cnt, bool q_is_bf16,

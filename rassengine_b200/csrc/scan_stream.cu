@@ -15,8 +15,8 @@ template <int NQ, int VEC>
 __global__ void __launch_bounds__(RASS_WARPS_PER_CTA * 32, 2)
     scan_stream_kernel(const uint4* __restrict__ x16, const float* __restrict__ sa, const float* __restrict__ sb,
                        const float* __restrict__ q_hat, int64_t n_rows, float* __restrict__ pool_key,
-                       uint32_t* __restrict__ pool_row, float* __restrict__ pool_thr, int slot0, int n_segs,
-                       size_t pool_entries) {
+                       uint32_t* __restrict__ pool_row, float* __restrict__ pool_thr, int* __restrict__ pool_cnt,
+                       int slot0, int n_segs, size_t pool_entries) {
   constexpr int R = 4 / NQ;             // rows per group
   constexpr int ROW_U4 = VEC * 32;      // uint4 per row
   const int lane = threadIdx.x & 31;
@@ -103,18 +103,42 @@ __global__ void __launch_bounds__(RASS_WARPS_PER_CTA * 32, 2)
     }
   }
 
+  // CTA-level merge: the 8 warp lists of a query (256 entries) are compacted to the best 32..64 by warp qi.
+  // The segment bound covers what the merge drops (<= pivot) and what every warp dropped (<= its threshold).
+  __shared__ float s_key[NQ][RASS_WARPS_PER_CTA * 32];
+  __shared__ uint32_t s_row[NQ][RASS_WARPS_PER_CTA * 32];
+  __shared__ float s_thr[NQ][RASS_WARPS_PER_CTA];
 #pragma unroll
   for (int qi = 0; qi < NQ; ++qi) {
-    const size_t base = (size_t)(slot0 + qi) * pool_entries + (size_t)gw * RASS_STREAM_SEG;
-    pool_key[base + lane] = top[qi].key[0];
-    pool_row[base + lane] = top[qi].row[0];
-    if (lane == 0) pool_thr[(size_t)(slot0 + qi) * n_segs + gw] = top[qi].thr_key;
+    s_key[qi][warp * 32 + lane] = top[qi].key[0];
+    s_row[qi][warp * 32 + lane] = top[qi].row[0];
+    if (lane == 0) s_thr[qi][warp] = top[qi].thr_key;
+  }
+  __syncthreads();
+  if (warp < NQ) {
+    const int qi = warp;
+    uint32_t ok[RASS_WARPS_PER_CTA], rw[RASS_WARPS_PER_CTA];
+#pragma unroll
+    for (int i = 0; i < RASS_WARPS_PER_CTA; ++i) {
+      rw[i] = s_row[qi][i * 32 + lane];
+      ok[i] = rw[i] != 0xffffffffu ? ord32(s_key[qi][i * 32 + lane]) : 0u;
+    }
+    const size_t base = (size_t)(slot0 + qi) * pool_entries + (size_t)blockIdx.x * RASS_STREAM_SEG;
+    uint32_t pivot;
+    const int kept = warp_compact<RASS_WARPS_PER_CTA>(ok, rw, RASS_STREAM_SEG / 2, pool_key + base, pool_row + base, pivot);
+    if (lane == 0) {
+      float bound = unord32(pivot);   // -inf when the merge dropped nothing
+#pragma unroll
+      for (int w = 0; w < RASS_WARPS_PER_CTA; ++w) bound = fmaxf(bound, s_thr[qi][w]);
+      pool_thr[(size_t)(slot0 + qi) * n_segs + blockIdx.x] = bound;
+      pool_cnt[(size_t)(slot0 + qi) * n_segs + blockIdx.x] = kept;
+    }
   }
 }
 
 static int stream_ctas(const rass_engine* h) { return h->num_sms * 2; }
 
-int scan_stream_segs(const rass_engine* h) { return stream_ctas(h) * RASS_WARPS_PER_CTA; }
+int scan_stream_segs(const rass_engine* h) { return stream_ctas(h); }
 
 template <int NQ>
 static int launch_vec(rass_engine* h, int q0, int slot0, cudaStream_t st) {
@@ -124,8 +148,8 @@ static int launch_vec(rass_engine* h, int q0, int slot0, cudaStream_t st) {
   const float* qh = h->q_hat + (size_t)q0 * h->dim_pad;
 #define RASS_LAUNCH(V)                                                                                          \
   scan_stream_kernel<NQ, V><<<grid, RASS_WARPS_PER_CTA * 32, 0, st>>>(x, h->sa, h->sb, qh, h->n_rows, h->pool_key, \
-                                                                      h->pool_row, h->pool_thr, slot0, n_segs,  \
-                                                                      h->pool_entries)
+                                                                      h->pool_row, h->pool_thr, h->pool_cnt, slot0, \
+                                                                      n_segs, h->pool_entries)
   switch (h->dim_pad / 256) {
     case 1: RASS_LAUNCH(1); break;
     case 2: RASS_LAUNCH(2); break;

@@ -99,15 +99,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// order-preserving float <-> uint32 maps (larger float <-> larger integer)
-__device__ __forceinline__ uint32_t ord32(float f) {
-  const uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float unord32(uint32_t o) {
-  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
-}
-
 // K-major, 128B-swizzled operand tile whose rows are 128 bytes: 8-row groups are 1024 bytes apart (SBO),
 // LBO is the canonical 1 (x16 bytes), descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
@@ -286,52 +277,17 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
         const int n = min(ss->cnt[q], RASS_UMMA_SEG);
         if (n <= UMMA_HIGH_WATER) continue;
         const size_t base = (size_t)q * pool_entries + (size_t)cta * RASS_UMMA_SEG;
-        // keys as order-preserving integers; empty slots sort below everything
+        // keys as order-preserving integers; empty slots are 0
         uint32_t ok[RASS_UMMA_SEG / 32], rw[RASS_UMMA_SEG / 32];
-        uint32_t kmin = 0xffffffffu, kmax = 0;
 #pragma unroll
         for (int i = 0; i < RASS_UMMA_SEG / 32; ++i) {
           const int idx = i * 32 + lane;
-          ok[i] = 0;
-          rw[i] = 0xffffffffu;
-          if (idx < n) {
-            ok[i] = ord32(__ldcg(pool_key + base + idx));
-            rw[i] = __ldcg(pool_row + base + idx);
-            kmin = min(kmin, ok[i]);
-            kmax = max(kmax, ok[i]);
-          }
+          ok[i] = idx < n ? ord32(__ldcg(pool_key + base + idx)) : 0u;
+          rw[i] = idx < n ? __ldcg(pool_row + base + idx) : 0xffffffffu;
         }
-        kmin = __reduce_min_sync(0xffffffffu, kmin);
-        kmax = __reduce_max_sync(0xffffffffu, kmax);
-        // bisection for a pivot with RASS_UMMA_KEEP .. 2*RASS_UMMA_KEEP entries strictly above it.
-        // count(> lo) > 2*KEEP and count(> hi) < KEEP hold throughout; ties may make the band unreachable,
-        // in which case hi is used (fewer entries kept, the bound below still holds).
-        uint32_t lo = kmin - 1, hi = kmax, pivot = kmax;
-        bool found = false;
-        while (hi - lo > 1) {
-          const uint32_t mid = lo + ((hi - lo) >> 1);
-          int cgt = 0;
-#pragma unroll
-          for (int i = 0; i < RASS_UMMA_SEG / 32; ++i) cgt += ok[i] > mid;
-          cgt = __reduce_add_sync(0xffffffffu, cgt);
-          if (cgt > 2 * RASS_UMMA_KEEP) lo = mid;
-          else if (cgt < RASS_UMMA_KEEP) hi = mid;
-          else { pivot = mid; found = true; break; }
-        }
-        if (!found) pivot = hi;
         __syncwarp();
-        int kept = 0;
-#pragma unroll
-        for (int i = 0; i < RASS_UMMA_SEG / 32; ++i) {
-          const bool keep = ok[i] > pivot;
-          const unsigned bal = __ballot_sync(0xffffffffu, keep);
-          if (keep) {
-            const int pos = kept + __popc(bal & ((1u << lane) - 1));
-            pool_key[base + pos] = unord32(ok[i]);
-            pool_row[base + pos] = rw[i];
-          }
-          kept += __popc(bal);
-        }
+        uint32_t pivot;
+        const int kept = warp_compact<RASS_UMMA_SEG / 32>(ok, rw, RASS_UMMA_KEEP, pool_key + base, pool_row + base, pivot);
         __syncwarp();
         // everything dropped here, and every row rejected from now on, has key <= pivot
         if (lane == 0) { ss->cnt[q] = kept; ss->thr[q] = unord32(pivot); }
