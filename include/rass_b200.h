@@ -60,10 +60,12 @@ enum {
 
 /* rass_search_* path selection (rass_set_option RASS_OPT_PATH) */
 enum {
-  RASS_PATH_AUTO = 0,    /* B <= 2: streaming GEMV+select; B >= 3: tcgen05 tiles                      */
+  RASS_PATH_AUTO = 0,    /* B <= 2: streaming GEMV+select; B <= 128: tcgen05 tiles, 64 queries per pass;
+                            larger: CTA-pair tcgen05 contraction, 256 queries per pass                */
   RASS_PATH_STREAM = 1,  /* force the CUDA-core streaming scan (passes of <= 2 queries)                */
   RASS_PATH_UMMA = 2,    /* force the TMA + tcgen05 scan (passes of <= 64 queries)                     */
-  RASS_PATH_EXACT = 3    /* force the fp64 full scan (the certificate-failure fallback), for tests     */
+  RASS_PATH_EXACT = 3,   /* force the fp64 full scan (the certificate-failure fallback), for tests     */
+  RASS_PATH_GEMM = 4     /* force the CTA-pair (cta_group::2) tcgen05 scan (groups of 256 queries)     */
 };
 
 enum {
@@ -150,6 +152,8 @@ int rass_sync(rass_engine* h);
 /* Debug only (no reference counterpart): raw tensor-core dot products bf16(q_hat) . bf16(x) of B <= 64 queries
  * against every row, out_host [rows, 64] fp32.  Used by the tests to check the TMA/tcgen05 descriptors. */
 int rass_debug_umma_scores(rass_engine* h, const float* q_host, int B, float* out_host);
+/* same for the CTA-pair kernel: B <= 256 queries, out_host [rows, 256] fp32 */
+int rass_debug_gemm_scores(rass_engine* h, const float* q_host, int B, float* out_host);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@
 #define RASS_MAX_K 128
 #define RASS_CAND_MAX 2048     // rerank candidate cap per query
 #define RASS_GROUP_Q 64        // queries finished per finish launch (= queries per tcgen05 pass)
+#define RASS_QPAD 256          // the query workspace is zero padded to a multiple of this (one scan_gemm group)
 #define RASS_STREAM_SEG 64     // pool entries per (CTA, query) segment of the streaming scan (32..64 kept)
 #define RASS_UMMA_SEG 256      // pool entries per (CTA, query) segment of the tcgen05 scan
 #define RASS_UMMA_KEEP 32      // entries a tcgen05 segment keeps at a compaction
@@ -76,10 +77,12 @@ struct rass_engine {
   double* q_norm = nullptr;         // [q_cap]
   float* q_rho = nullptr;           // [q_cap] ||q_hat - bf16(q_hat)|| / ||q_hat||
   // candidate pool of one query group (RASS_GROUP_Q queries)
-  size_t pool_entries = 0;          // per query
+  size_t pool_entries = 0;          // per query: stride of the running search
+  size_t pool_alloc_entries = 0;    // allocated, in entries
   float* pool_key = nullptr;
   uint32_t* pool_row = nullptr;
-  size_t pool_segs = 0;             // per query
+  size_t pool_segs = 0;             // per query: stride of the running search
+  size_t pool_alloc_segs = 0;       // allocated, in segments
   float* pool_thr = nullptr;
   int* pool_cnt = nullptr;
   // exact (fp64) lists
@@ -101,7 +104,9 @@ struct rass_engine {
   std::vector<uint8_t> dead;        // host mirror of the tombstones
   std::vector<cudaEvent_t> ev_pool; // per-group scan timing
   void* tmap_x = nullptr;           // host copy of the CUtensorMap over x16 (rebuilt on growth)
-  void* tmap_q = nullptr;
+  void* tmap_q = nullptr;           // queries, 64-row boxes (scan_umma)
+  void* tmap_q2 = nullptr;          // queries, 128-row boxes (scan_gemm: one CTA's half of a 256-query group)
+  const void* tmap_q2base = nullptr;
   int64_t tmap_rows = -1;
   const void* tmap_base = nullptr;
   const void* tmap_qbase = nullptr;
@@ -362,6 +367,12 @@ int scan_stream_segs(const rass_engine* h);
 int launch_scan_umma(rass_engine* h, int q0, int nq, cudaStream_t st);
 int scan_umma_segs(const rass_engine* h);
 int umma_selftest(rass_engine* h, int n_rows_tile, float* out_host, cudaStream_t st);
+// CTA-pair tcgen05 scan of all B prepared queries (groups of 256) into pool slots 0..B
+int launch_scan_gemm(rass_engine* h, int B, cudaStream_t st);
+int scan_gemm_segs(const rass_engine* h, int B);
+int gemm_selftest(rass_engine* h, int B, float* out_host, cudaStream_t st);
+// CUtensorMap over a [rows, dim_pad] bf16 matrix: boxes of box_rows x 64 elements, 128B swizzle
+int encode_rows_map(rass_engine* h, void* map, const void* base, int64_t rows, int box_rows);
 // merge the pool of queries [g0, g0+ng), rerank in fp64, emit top-k, flag uncertified queries
 int launch_finish(rass_engine* h, int g0, int ng, int k, int n_segs, int seg_size, bool has_cnt, bool q_is_bf16,
                   int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st);
@@ -371,6 +382,6 @@ int launch_exact(rass_engine* h, int k, const int* qids_host, int n_q, int64_t* 
 int launch_merge_topk(rass_engine* h, const double* keys, const int64_t* rows, int64_t shard_stride, int G, int B,
                       int k, int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st);
 int ensure_query_workspace(rass_engine* h, int B);
-int ensure_pool(rass_engine* h, size_t entries_per_query, size_t segs_per_query);
+int ensure_pool(rass_engine* h, size_t entries_per_query, size_t segs_per_query, size_t n_queries = RASS_GROUP_Q);
 int ensure_xlist_workspace(rass_engine* h, size_t entries);
 int ensure_out_workspace(rass_engine* h, size_t n);

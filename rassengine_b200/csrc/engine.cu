@@ -146,7 +146,7 @@ extern "C" int rass_destroy(rass_engine* h) {
   Bm25State& b = h->bm25;
   cudaFree(b.indptr); cudaFree(b.doc); cudaFree(b.tf); cudaFree(b.norm); cudaFree(b.inv_dev); cudaFree(b.acc);
   cudaFree(b.touched); cudaFree(b.touched_n);
-  free(h->tmap_x); free(h->tmap_q);
+  free(h->tmap_x); free(h->tmap_q); free(h->tmap_q2);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -157,7 +157,7 @@ extern "C" int rass_set_option(rass_engine* h, int opt, int64_t value) {
   CHECK_HANDLE(h);
   switch (opt) {
     case RASS_OPT_PATH:
-      if (value < RASS_PATH_AUTO || value > RASS_PATH_EXACT) return rass_fail(h, RASS_E_INVALID, "bad path %lld", (long long)value);
+      if (value < RASS_PATH_AUTO || value > RASS_PATH_GEMM) return rass_fail(h, RASS_E_INVALID, "bad path %lld", (long long)value);
       h->path = (int)value;
       return RASS_OK;
     case RASS_OPT_STREAM:
@@ -359,7 +359,7 @@ extern "C" int rass_read_rows(rass_engine* h, int64_t first_row, int64_t n, floa
 int ensure_query_workspace(rass_engine* h, int B) {
   if (B <= h->q_cap) return RASS_OK;
   CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
-  const size_t cap = (size_t)(B + RASS_GROUP_Q - 1) / RASS_GROUP_Q * RASS_GROUP_Q, d = (size_t)h->dim_pad;
+  const size_t cap = (size_t)(B + RASS_QPAD - 1) / RASS_QPAD * RASS_QPAD, d = (size_t)h->dim_pad;
   REALLOC_DEV(h, h->q_raw, cap * d);
   REALLOC_DEV(h, h->q_hat, cap * d);
   REALLOC_DEV(h, h->q16, cap * d);
@@ -369,22 +369,28 @@ int ensure_query_workspace(rass_engine* h, int B) {
   REALLOC_HOST(h, h->flagged_host, cap);
   h->q_cap = (int)cap;
   h->tmap_qbase = nullptr;
+  h->tmap_q2base = nullptr;
   return RASS_OK;
 }
 
-int ensure_pool(rass_engine* h, size_t entries_per_query, size_t segs_per_query) {
-  if (entries_per_query > h->pool_entries) {
+int ensure_pool(rass_engine* h, size_t entries_per_query, size_t segs_per_query, size_t n_queries) {
+  const size_t need_e = entries_per_query * n_queries, need_s = segs_per_query * n_queries;
+  if (need_e > h->pool_alloc_entries) {
     CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
-    REALLOC_DEV(h, h->pool_key, entries_per_query * RASS_GROUP_Q);
-    REALLOC_DEV(h, h->pool_row, entries_per_query * RASS_GROUP_Q);
-    h->pool_entries = entries_per_query;
+    h->pool_alloc_entries = 0;
+    REALLOC_DEV(h, h->pool_key, need_e);
+    REALLOC_DEV(h, h->pool_row, need_e);
+    h->pool_alloc_entries = need_e;
   }
-  if (segs_per_query > h->pool_segs) {
+  if (need_s > h->pool_alloc_segs) {
     CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
-    REALLOC_DEV(h, h->pool_thr, segs_per_query * RASS_GROUP_Q);
-    REALLOC_DEV(h, h->pool_cnt, segs_per_query * RASS_GROUP_Q);
-    h->pool_segs = segs_per_query;
+    h->pool_alloc_segs = 0;
+    REALLOC_DEV(h, h->pool_thr, need_s);
+    REALLOC_DEV(h, h->pool_cnt, need_s);
+    h->pool_alloc_segs = need_s;
   }
+  h->pool_entries = entries_per_query;
+  h->pool_segs = segs_per_query;
   return RASS_OK;
 }
 
@@ -423,7 +429,7 @@ __global__ void fill_empty_kernel(int64_t* rows, float* scores, double* keys, si
 
 static int resolve_path(const rass_engine* h, int B) {
   if (h->path != RASS_PATH_AUTO) return h->path;
-  return B <= 2 ? RASS_PATH_STREAM : RASS_PATH_UMMA;
+  return B <= 2 ? RASS_PATH_STREAM : (B <= 2 * RASS_GROUP_Q ? RASS_PATH_UMMA : RASS_PATH_GEMM);
 }
 
 static cudaEvent_t get_event(rass_engine* h, size_t i) {
@@ -472,6 +478,17 @@ int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_r
     s.n_fallback = B;
     s.passes = (B + RASS_EXACT_NQ - 1) / RASS_EXACT_NQ;
     s.bytes_streamed = (int64_t)s.passes * h->n_rows * h->dim_pad * ((h->flags & RASS_BF16_ONLY) ? 2 : 4);
+  } else if (path == RASS_PATH_GEMM) {
+    const int n_segs = scan_gemm_segs(h, B);
+    if ((rc = ensure_pool(h, (size_t)n_segs * RASS_UMMA_SEG, (size_t)n_segs, (size_t)B))) return rc;
+    CUDA_TRY(h, cudaEventRecord(get_event(h, n_ev++), st));
+    if ((rc = launch_scan_gemm(h, B, st))) return rc;
+    CUDA_TRY(h, cudaEventRecord(get_event(h, n_ev++), st));
+    if ((rc = launch_finish(h, 0, B, k, n_segs, RASS_UMMA_SEG, true, true, out_rows, out_scores, out_keys, st)))
+      return rc;
+    s.launches += 3;
+    s.passes = (B + 255) / 256;
+    s.bytes_streamed = (int64_t)s.passes * h->n_rows * h->dim_pad * 2;
   } else {
     const bool umma = path == RASS_PATH_UMMA;
     const int n_segs = umma ? scan_umma_segs(h) : scan_stream_segs(h);
@@ -496,6 +513,8 @@ int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_r
       s.launches += 1;
     }
     s.bytes_streamed = (int64_t)s.passes * h->n_rows * h->dim_pad * 2;
+  }
+  if (path != RASS_PATH_EXACT) {
     CUDA_TRY(h, cudaEventRecord(h->ev[1], st));
     CUDA_TRY(h, cudaMemcpyAsync(h->scal_host, h->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
@@ -615,6 +634,19 @@ extern "C" int rass_set_row_filter(rass_engine* h, const uint8_t* mask_host, int
 
 // Debug entry (not part of the reference surface): raw tcgen05 dot products of <= 64 queries against every row,
 // out_host [n_rows, 64].  Lets the tests check the TMA/UMMA descriptors in isolation.
+extern "C" int rass_debug_gemm_scores(rass_engine* h, const float* q_host, int B, float* out_host) {
+  CHECK_HANDLE(h);
+  if (!q_host || !out_host || B < 1 || B > RASS_QPAD) return rass_fail(h, RASS_E_INVALID, "bad arguments");
+  if (h->n_rows == 0) return RASS_OK;
+  int rc;
+  float* q_dev = nullptr;
+  if ((rc = ensure_query_workspace(h, B))) return rc;
+  if ((rc = stage_queries(h, q_host, B, &q_dev))) return rc;
+  cudaStream_t st = eng_stream(h);
+  if ((rc = launch_query_prep(h, q_dev, B, st))) return rc;
+  return gemm_selftest(h, B, out_host, st);
+}
+
 extern "C" int rass_debug_umma_scores(rass_engine* h, const float* q_host, int B, float* out_host) {
   CHECK_HANDLE(h);
   if (!q_host || !out_host || B < 1 || B > RASS_GROUP_Q) return rass_fail(h, RASS_E_INVALID, "bad arguments");

@@ -1,0 +1,339 @@
+// Large-batch kNN scan: the dense Q . X^T contraction on CTA pairs of the 5th-generation tensor cores.
+//
+// Replaces the `knn` clause executor (reference app/main.py:1538-1542 -> OpenSearch k-NN plugin / nmslib HNSW)
+// when hundreds of queries share the corpus (BASELINE configs[2] batch 8192 top-100, configs[4] batch 1024).
+// At 256 queries per pass the scan is tensor-bound (256 flop per corpus byte against a ridge of ~210), so the
+// design goal is MMA issue without gaps and no score matrix in HBM.
+//
+// Work item = (corpus chunk, group of 256 queries).  Items are dealt round-robin to the 74 CTA pairs in group-major
+// order, so the pairs that run at the same time sweep the SAME chunk for DIFFERENT query groups: the chunk comes
+// from HBM once and from the 126 MB L2 for the other groups.  Inside an item a pair walks the chunk in tiles of
+// 256 rows: tcgen05.mma cta_group::2, M = 256 (128 rows per CTA), N = 256 queries, K = 16 per instruction;
+// every CTA streams its own 128 corpus rows and its half of the query block (2 x 16 KB per 64-element k-block)
+// through a TMA ring whose full-barriers live in the leader CTA; the accumulator (128 lanes x 256 fp32 columns per
+// CTA, two stages = all 512 TMEM columns) is drained by four epilogue warps per CTA: thread = corpus row,
+// tcgen05.ld, score = acc * sa + sb, one compare against the per-query running threshold, and the survivors are
+// appended to the (item, CTA) segment of the candidate pool and compacted exactly as in scan_umma.cu.  The bound
+// each segment publishes (every row it dropped or rejected has key <= thr) is what the certificate in finish.cu needs.
+#include "tc_ptx.cuh"
+
+#define G2_ROWS 128                        // corpus rows per CTA per tile (256 per pair)
+#define G2_NQ 256                          // queries per group (MMA N)
+#define G2_KBLK 64                         // bf16 elements per k-block (128 bytes: one swizzle row)
+#define G2_A_BYTES (G2_ROWS * 128)         // 16 KB
+#define G2_B_BYTES ((G2_NQ / 2) * 128)     // 16 KB: this CTA's half of the query block
+#define G2_STAGE_BYTES (G2_A_BYTES + G2_B_BYTES)
+#define G2_STAGES 6
+#define G2_ACC 2                           // TMEM accumulator stages (256 columns each)
+#define G2_TMEM_COLS 512
+#define G2_THREADS 256
+#define G2_HIGH_WATER 128
+
+namespace {
+
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 256 (pair)
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((G2_NQ >> 3) << 17) | ((256u >> 4) << 24);
+
+struct GemmSmem {
+  uint64_t full[G2_STAGES];       // used in the leader CTA: both CTAs' TMA bytes of a stage have landed
+  uint64_t empty[G2_STAGES];      // per CTA: the pair's MMAs have read this stage
+  uint64_t acc_full[G2_ACC];      // per CTA: accumulator stage complete
+  uint64_t acc_empty[G2_ACC];     // used in the leader CTA: both CTAs' epilogues have drained the stage
+  uint32_t tmem_base;
+  uint32_t pad;
+  alignas(16) float thr[G2_NQ];
+  int cnt[G2_NQ];
+};
+
+struct GemmPlan {
+  int n_ptiles;          // 256-row pair tiles
+  int n_groups;          // query groups of 256
+  int n_chunks;          // corpus chunks
+  int tiles_per_chunk;   // pair tiles per chunk
+  int n_items;           // n_chunks * n_groups
+};
+
+}  // namespace
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+    scan_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_q,
+                     const float* __restrict__ sa, const float* __restrict__ sb, int64_t n_rows, GemmPlan plan,
+                     int k_blocks, int n_queries, float* __restrict__ pool_key, uint32_t* __restrict__ pool_row,
+                     float* __restrict__ pool_thr, int* __restrict__ pool_cnt, size_t pool_entries, int n_segs,
+                     float* __restrict__ dbg_out) {
+  extern __shared__ unsigned char smem_dyn[];
+  // 128B-swizzled tiles need 1024-byte alignment: [ stages: G2_STAGES * (A 16 KB | B 16 KB) ][ GemmSmem ]
+  // (the dynamic window starts at the same offset in both CTAs, so the pair's operand descriptors agree)
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  GemmSmem* ss = reinterpret_cast<GemmSmem*>(smem + (size_t)G2_STAGES * G2_STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < G2_STAGES; ++i) { mbar_init(&ss->full[i], 1); mbar_init(&ss->empty[i], 1); }
+    for (int i = 0; i < G2_ACC; ++i) { mbar_init(&ss->acc_full[i], 1); mbar_init(&ss->acc_empty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ss->tmem_base)),
+                 "r"((uint32_t)G2_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();       // the peer's barriers are initialised before anything of ours can reach them
+  tc_fence_after();
+  const uint32_t tmem_base = ss->tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own 128 corpus rows + own half of the query block per k-block =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = pair; w < plan.n_items; w += n_pairs) {
+        const int chunk = w / plan.n_groups, grp = w - chunk * plan.n_groups;
+        const int t0 = chunk * plan.tiles_per_chunk, t1 = min(t0 + plan.tiles_per_chunk, plan.n_ptiles);
+        const int q_row = grp * G2_NQ + (int)rank * (G2_NQ / 2);
+        for (int t = t0; t < t1; ++t) {
+          const int x_row = t * 2 * G2_ROWS + (int)rank * G2_ROWS;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(&ss->empty[stage], phase ^ 1);
+            const uint32_t bar = mapa_u32(smem_u32(&ss->full[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&ss->full[stage], 2 * G2_STAGE_BYTES);
+            unsigned char* dst = smem + (size_t)stage * G2_STAGE_BYTES;
+            tma_load_2d_pair(&map_x, bar, dst, kb * G2_KBLK, x_row, kEvictNormal);
+            tma_load_2d_pair(&map_q, bar, dst + G2_A_BYTES, kb * G2_KBLK, q_row, kEvictLast);
+            if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (lane == 0 && rank == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t s_base = smem_u32(smem);
+      for (int w = pair; w < plan.n_items; w += n_pairs) {
+        const int chunk = w / plan.n_groups;
+        const int t0 = chunk * plan.tiles_per_chunk, t1 = min(t0 + plan.tiles_per_chunk, plan.n_ptiles);
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&ss->acc_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * G2_NQ;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(&ss->full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = s_base + (uint32_t)stage * G2_STAGE_BYTES;
+            const uint32_t b_addr = a_addr + G2_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < G2_KBLK / 16; ++k)
+              umma_bf16_pair(d_tmem, smem_desc_sw128(a_addr + k * 32), smem_desc_sw128(b_addr + k * 32), kIdescPair,
+                             (uint32_t)((kb | k) != 0));
+            umma_commit_pair(&ss->empty[stage]);   // frees the stage in both CTAs once these MMAs have read it
+            if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_pair(&ss->acc_full[acc]);    // accumulator complete, both CTAs' epilogues
+          if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs): thread = corpus row =====
+    const int ew = warp - 4;                 // TMEM lane quadrant (warp % 4)
+    const int et = threadIdx.x - 128;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = pair; w < plan.n_items; w += n_pairs) {
+      const int chunk = w / plan.n_groups, grp = w - chunk * plan.n_groups;
+      const int t0 = chunk * plan.tiles_per_chunk, t1 = min(t0 + plan.tiles_per_chunk, plan.n_ptiles);
+      const int seg = chunk * 2 + (int)rank;
+      const int nq_here = min(G2_NQ, n_queries - grp * G2_NQ);
+      // fresh running state of this item's 256 queries; padding queries admit nothing
+      for (int q = et; q < G2_NQ; q += 128) {
+        ss->thr[q] = q < nq_here ? neg_inf<float>() : __int_as_float(0x7f800000);
+        ss->cnt[q] = 0;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const size_t slot0 = (size_t)grp * G2_NQ;
+      for (int t = t0; t < t1; ++t) {
+        const int64_t row = (int64_t)t * 2 * G2_ROWS + rank * G2_ROWS + ew * 32 + lane;
+        float a = 0.f, b = neg_inf<float>();
+        if (row < n_rows) { a = __ldg(sa + row); b = __ldg(sb + row); }
+        mbar_wait(&ss->acc_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * G2_NQ;
+#pragma unroll 1
+        for (int c = 0; c < G2_NQ; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c, v);
+          tmem_ld_wait();
+          if (dbg_out && grp == 0 && row < n_rows) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dbg_out[(size_t)row * G2_NQ + c + j] = __uint_as_float(v[j]);
+          }
+          uint32_t m = 0;
+#pragma unroll
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(&ss->thr[c + j4]);
+            const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float s = fmaf(__uint_as_float(v[j4 + j]), a, b);
+              v[j4 + j] = __float_as_uint(s);
+              m |= (s > tt[j]) ? (1u << (j4 + j)) : 0u;
+            }
+          }
+          // each lane walks its own hits
+          while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            uint32_t s = v[0];
+#pragma unroll
+            for (int u = 1; u < 32; ++u) s = (j == u) ? v[u] : s;
+            const int pos = atomicAdd(&ss->cnt[c + j], 1);
+            if (pos < RASS_UMMA_SEG) {
+              const size_t o = (slot0 + c + j) * pool_entries + (size_t)seg * RASS_UMMA_SEG + pos;
+              pool_key[o] = __uint_as_float(s);
+              pool_row[o] = (uint32_t)row;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ss->acc_empty[acc]), 0));
+        if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1; }
+
+        // compaction: all 128 epilogue threads of this CTA have finished the tile's appends
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+        for (int qb = 0; qb < G2_NQ; qb += 128) {
+          // warp ew owns queries q = ew (mod 4); lane l looks at q = qb + 4 l + ew
+          unsigned need = __ballot_sync(0xffffffffu, ss->cnt[qb + 4 * lane + ew] > G2_HIGH_WATER);
+          while (need) {
+            const int q = qb + 4 * (__ffs(need) - 1) + ew;
+            need &= need - 1;
+            const int n = min(ss->cnt[q], RASS_UMMA_SEG);
+            const size_t base = (slot0 + q) * pool_entries + (size_t)seg * RASS_UMMA_SEG;
+            uint32_t ok[RASS_UMMA_SEG / 32], rw[RASS_UMMA_SEG / 32];
+#pragma unroll
+            for (int i = 0; i < RASS_UMMA_SEG / 32; ++i) {
+              const int idx = i * 32 + lane;
+              ok[i] = idx < n ? ord32(__ldcg(pool_key + base + idx)) : 0u;
+              rw[i] = idx < n ? __ldcg(pool_row + base + idx) : 0xffffffffu;
+            }
+            __syncwarp();
+            uint32_t pivot;
+            const int kept =
+                warp_compact<RASS_UMMA_SEG / 32>(ok, rw, RASS_UMMA_KEEP, pool_key + base, pool_row + base, pivot);
+            __syncwarp();
+            // everything dropped here, and every row rejected from now on, has key <= pivot
+            if (lane == 0) { ss->cnt[q] = kept; ss->thr[q] = unord32(pivot); }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      // publish the segment sizes and bounds of this item
+      for (int q = et; q < nq_here; q += 128) {
+        pool_cnt[(slot0 + q) * n_segs + seg] = min(ss->cnt[q], RASS_UMMA_SEG);
+        pool_thr[(slot0 + q) * n_segs + seg] = ss->thr[q];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();       // neither CTA leaves (or frees TMEM) while the pair's MMAs / remote arrives are in flight
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G2_TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
+
+static GemmPlan make_plan(const rass_engine* h, int B, int n_pairs) {
+  GemmPlan p;
+  p.n_ptiles = (int)((h->n_rows + 2 * G2_ROWS - 1) / (2 * G2_ROWS));
+  p.n_groups = (B + G2_NQ - 1) / G2_NQ;
+  // items = chunks x groups is a multiple of the pair count, so every pair gets the same number of items
+  int chunks = n_pairs / gcd_int(n_pairs, p.n_groups);
+  if (chunks > p.n_ptiles) chunks = p.n_ptiles;
+  p.tiles_per_chunk = (p.n_ptiles + chunks - 1) / chunks;
+  p.n_chunks = (p.n_ptiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  p.n_items = p.n_chunks * p.n_groups;
+  return p;
+}
+
+static int gemm_pairs(const rass_engine* h) { return h->num_sms / 2; }
+
+int scan_gemm_segs(const rass_engine* h, int B) { return 2 * make_plan(h, B, gemm_pairs(h)).n_chunks; }
+
+static size_t gemm_smem_bytes() { return (size_t)G2_STAGES * G2_STAGE_BYTES + sizeof(GemmSmem) + 1024; }
+
+__global__ void clear_gemm_segs_kernel(float* thr, int* cnt, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  thr[i] = neg_inf<float>();
+  cnt[i] = 0;
+}
+
+static int gemm_launch(rass_engine* h, int B, float* dbg_out, cudaStream_t st) {
+  int rc;
+  if (!h->tmap_x) h->tmap_x = calloc(1, sizeof(CUtensorMap));
+  if (!h->tmap_q2) h->tmap_q2 = calloc(1, sizeof(CUtensorMap));
+  if (h->tmap_base != h->x16 || h->tmap_rows != h->cap) {
+    if ((rc = encode_rows_map(h, h->tmap_x, h->x16, h->cap, G2_ROWS))) return rc;
+    h->tmap_base = h->x16;
+    h->tmap_rows = h->cap;
+  }
+  if (h->tmap_q2base != h->q16) {
+    if ((rc = encode_rows_map(h, h->tmap_q2, h->q16, h->q_cap, G2_NQ / 2))) return rc;
+    h->tmap_q2base = h->q16;
+  }
+  const int n_pairs = gemm_pairs(h);
+  const GemmPlan plan = make_plan(h, B, n_pairs);
+  const int n_segs = scan_gemm_segs(h, B);
+  const size_t n = (size_t)n_segs * B;
+  clear_gemm_segs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pool_thr, h->pool_cnt, n);
+  CUDA_TRY(h, cudaGetLastError());
+  const int grid = 2 * (plan.n_items < n_pairs ? plan.n_items : n_pairs);
+  const size_t smem = gemm_smem_bytes();
+  CUDA_TRY(h, cudaFuncSetAttribute(scan_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  scan_gemm_kernel<<<grid, G2_THREADS, smem, st>>>(*(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q2, h->sa, h->sb,
+                                                   h->n_rows, plan, h->dim_pad / G2_KBLK, B, h->pool_key, h->pool_row,
+                                                   h->pool_thr, h->pool_cnt, h->pool_entries, n_segs, dbg_out);
+  CUDA_TRY(h, cudaGetLastError());
+  return RASS_OK;
+}
+
+// all B prepared queries (q16 rows [0, B), padded with zero rows to a multiple of 256) against the whole shard;
+// query q's candidates land in pool slot q
+int launch_scan_gemm(rass_engine* h, int B, cudaStream_t st) { return gemm_launch(h, B, nullptr, st); }
+
+// Debug/self-test entry: raw tensor-core dot products of the first 256 prepared queries against every row.
+// out_host: [n_rows, 256] fp32.
+int gemm_selftest(rass_engine* h, int B, float* out_host, cudaStream_t st) {
+  float* dbg = nullptr;
+  const size_t n = (size_t)h->n_rows * G2_NQ;
+  CUDA_TRY(h, cudaMalloc(&dbg, n * 4));
+  CUDA_TRY(h, cudaMemsetAsync(dbg, 0, n * 4, st));
+  const int n_segs = scan_gemm_segs(h, B);
+  int rc = ensure_pool(h, (size_t)n_segs * RASS_UMMA_SEG, (size_t)n_segs, B);
+  if (!rc) rc = gemm_launch(h, B, dbg, st);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(out_host, dbg, n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = rass_fail(h, RASS_E_CUDA, "gemm selftest: %s", cudaGetErrorString(e));
+  }
+  cudaFree(dbg);
+  return rc;
+}

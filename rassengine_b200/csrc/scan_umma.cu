@@ -13,9 +13,7 @@
 // the candidate pool.  When a segment passes 128 entries it is compacted: a warp bisects for a pivot with
 // 32..64 entries above it, keeps those and raises the threshold to the pivot; everything dropped or
 // rejected is <= that threshold, which is the bound the certificate in finish.cu needs.  The score matrix never reaches HBM.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_ptx.cuh"
 
 #define UMMA_ROWS 128
 #define UMMA_NQ 64
@@ -30,92 +28,8 @@
 
 namespace {
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// A wait that cannot hang the device: a barrier that stays closed for ~2 s is a bug, so trap.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("rass scan_umma: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
-                                            uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
-      : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile whose rows are 128 bytes: 8-row groups are 1024 bytes apart (SBO),
-// LBO is the canonical 1 (x16 bytes), descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = 64, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((UMMA_NQ >> 3) << 17) | ((UMMA_ROWS >> 4) << 24);
-
-constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
-constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
 struct UmmaSmem {
   uint64_t full[UMMA_STAGES];
@@ -330,7 +244,8 @@ static EncodeTiledFn get_encode(rass_engine* h) {
   return fn;
 }
 
-static int encode_rows_map(rass_engine* h, CUtensorMap* map, const void* base, int64_t rows, int box_rows) {
+int encode_rows_map(rass_engine* h, void* map_out, const void* base, int64_t rows, int box_rows) {
+  CUtensorMap* map = reinterpret_cast<CUtensorMap*>(map_out);
   EncodeTiledFn enc = get_encode(h);
   if (!enc) return RASS_E_CUDA;
   cuuint64_t dims[2] = {(cuuint64_t)h->dim_pad, (cuuint64_t)rows};

@@ -76,7 +76,7 @@ int launch_store_convert(rass_engine* h, const float* src_dev, int64_t src_strid
   return RASS_OK;
 }
 
-// one warp per query slot; slots >= B (up to the 64-multiple the tcgen05 pass reads) are zeroed
+// one warp per query slot; slots >= B (up to the 256-multiple the tcgen05 passes read) are zeroed
 __global__ void __launch_bounds__(128) query_prep_kernel(const float* __restrict__ q, int dim, int dim_pad, int metric,
                                                          int B, int B_pad, float* __restrict__ q_raw,
                                                          float* __restrict__ q_hat, __nv_bfloat16* __restrict__ q16,
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128) query_prep_kernel(const float* __restrict
 }
 
 int launch_query_prep(rass_engine* h, const float* q_dev, int B, cudaStream_t st) {
-  const int B_pad = (B + RASS_GROUP_Q - 1) / RASS_GROUP_Q * RASS_GROUP_Q;
+  const int B_pad = (B + RASS_QPAD - 1) / RASS_QPAD * RASS_QPAD;
   const int warps = 4;
   query_prep_kernel<<<(B_pad + warps - 1) / warps, warps * 32, 0, st>>>(q_dev, h->dim, h->dim_pad, h->metric, B, B_pad,
                                                                         h->q_raw, h->q_hat, h->q16, h->q_norm,

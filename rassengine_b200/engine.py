@@ -179,3 +179,10 @@ class Engine:
         out = np.zeros((self.rows(), 64), dtype=np.float32)
         self._check(self._lib.rass_debug_umma_scores(self._h, _ptr(q), q.shape[0], _ptr(out)))
         return out
+
+    def debug_gemm_scores(self, q: np.ndarray) -> np.ndarray:
+        """Same through the CTA-pair (cta_group::2) kernel: up to 256 queries, [rows, 256]."""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
+        out = np.zeros((self.rows(), 256), dtype=np.float32)
+        self._check(self._lib.rass_debug_gemm_scores(self._h, _ptr(q), q.shape[0], _ptr(out)))
+        return out

@@ -23,7 +23,8 @@ def _engine(**kw):
 
 def _paths():
     import rassengine_b200 as rb
-    return {"stream": rb.PATH_STREAM, "umma": rb.PATH_UMMA, "exact": rb.PATH_EXACT, "auto": rb.PATH_AUTO}
+    return {"stream": rb.PATH_STREAM, "umma": rb.PATH_UMMA, "exact": rb.PATH_EXACT, "auto": rb.PATH_AUTO,
+            "gemm": rb.PATH_GEMM}
 
 
 def _load_case(golden_dir, name):
@@ -49,7 +50,7 @@ TINY_ORDER = [0, 3, 2, 6, 1, 4, 7, 5]
 TINY_SCORE = [1.0, 1.0, 1 / (2 - math.sqrt(0.5)), 1 / 1.4, 0.5, 0.5, 0.5, 1 / 3]
 
 
-@pytest.mark.parametrize("path", ["stream", "umma", "exact"])
+@pytest.mark.parametrize("path", ["stream", "umma", "gemm", "exact"])
 def test_tiny_hand_set(path):
     """Duplicates, a zero row, unnormalised rows, k > rows (same literals as tests/test_oracle.py)."""
     with _engine(dim=4) as e:
@@ -77,7 +78,7 @@ def test_tiny_hand_set(path):
         np.testing.assert_array_equal(e.read_rows(6, 1)[0], TINY_X[6])
 
 
-@pytest.mark.parametrize("path", ["stream", "umma", "exact"])
+@pytest.mark.parametrize("path", ["stream", "umma", "gemm", "exact"])
 def test_tiny_l2(path):
     import rassengine_b200 as rb
     with _engine(dim=4, metric=rb.METRIC_L2) as e:
@@ -89,7 +90,7 @@ def test_tiny_l2(path):
         np.testing.assert_allclose(scores[0], [0.5, 0.5, 1 / 3], rtol=1e-6)
 
 
-@pytest.mark.parametrize("path", ["stream", "umma", "exact", "auto"])
+@pytest.mark.parametrize("path", ["stream", "umma", "gemm", "exact", "auto"])
 @pytest.mark.parametrize("name", ["knn_small", "knn_clustered_dups", "knn_small_k100"])
 def test_seeded_golden(golden_dir, name, path):
     X, Q, meta, g = _load_case(golden_dir, name)
@@ -127,11 +128,29 @@ def test_umma_raw_scores_match_bf16_math():
     np.testing.assert_allclose(got, want, rtol=0, atol=2e-5)
 
 
-@pytest.mark.parametrize("path", ["stream", "umma"])
+def test_gemm_raw_scores_match_bf16_math():
+    """Same check for the CTA-pair kernel (cta_group::2 descriptors, both CTAs' halves of the query block); 300 rows
+    leave the second CTA of the last tile partly out of range."""
+    import torch
+    n, d = 300 + 256 * 3, 1024
+    X = synth.embeddings(n, d, 9)
+    Q = synth.embeddings(200, d, 10)
+    with _engine(dim=d) as e:
+        e.append(X)
+        got = e.debug_gemm_scores(Q)
+    xb = torch.from_numpy(X).to(torch.bfloat16).to(torch.float64)
+    qn = Q / np.linalg.norm(Q.astype(np.float64), axis=1, keepdims=True)
+    qb = torch.from_numpy(qn.astype(np.float32)).to(torch.bfloat16).to(torch.float64)
+    want = (xb @ qb.T).numpy()
+    np.testing.assert_allclose(got[:, :200], want, rtol=0, atol=2e-5)
+    assert not got[:, 200:].any()
+
+
+@pytest.mark.parametrize("path", ["stream", "umma", "gemm"])
 def test_cfg1_100k_golden(golden_dir, path):
     """BASELINE.json configs[0]: 100k x 1024, 1k queries, exact cosine top-10 -- ids identical to the golden file."""
     X, Q, meta, g = _load_case(golden_dir, "knn_cfg1")
-    nq = 1000 if path == "umma" else 64
+    nq = 64 if path == "stream" else 1000
     with _engine(dim=meta["d"], capacity_rows=meta["n"]) as e:
         e.set_path(_paths()[path])
         e.append(X)
@@ -146,7 +165,7 @@ def test_other_dims(dim):
     X = synth.embeddings(5000, dim, 3)
     Q = synth.embeddings(9, dim, 4)
     want_rows, _, want_scores = knn.knn_exact(X, Q, 10)
-    for path in ("stream", "umma"):
+    for path in ("stream", "umma", "gemm"):
         with _engine(dim=dim) as e:
             e.set_path(_paths()[path])
             e.append(X)
@@ -162,7 +181,7 @@ def test_bf16_corpus_mode():
     Q = synth.embeddings(16, 1024, 12)
     Xb = torch.from_numpy(X).to(torch.bfloat16).to(torch.float32).numpy()
     want_rows, _, want_scores = knn.knn_exact(Xb, Q, 10)
-    for path in ("stream", "umma"):
+    for path in ("stream", "umma", "gemm"):
         with _engine(dim=1024, flags=rb.BF16_ONLY) as e:
             e.set_path(_paths()[path])
             e.append(X)
@@ -178,7 +197,7 @@ def test_unnormalised_rows_and_l2_seeded():
     Q = rng.standard_normal((5, 256)).astype(np.float32)
     for metric, om in ((rb.METRIC_COSINE, knn.COSINE), (rb.METRIC_L2, knn.L2)):
         want_rows, _, want_scores = knn.knn_exact_full(X, Q, 10, metric=om)
-        for path in ("stream", "umma"):
+        for path in ("stream", "umma", "gemm"):
             with _engine(dim=256, metric=metric) as e:
                 e.set_path(_paths()[path])
                 e.append(X)

@@ -25,7 +25,9 @@ for c0 in range(0, N, CH):
     e.append_dev(x.data_ptr(), m)
 print(f"fill {N} rows: {time.time() - t0:.1f}s", flush=True)
 gq = torch.Generator(device="cuda").manual_seed(5678)
-for path, B, k in (("stream", 1, 10), ("stream", 2, 10), ("umma", 64, 10), ("umma", 1, 10), ("umma", 64, 100), ("stream", 1, 100))[:(3 if NOEXACT else 6)]:
+CASES = (("stream", 1, 10), ("stream", 2, 10), ("umma", 64, 10), ("umma", 1, 10), ("umma", 64, 100), ("stream", 1, 100),
+         ("gemm", 256, 10), ("gemm", 1024, 10), ("gemm", 8192, 100), ("gemm", 200, 10))
+for path, B, k in CASES:
     if path not in which:
         continue
     e.set_path(getattr(rb, "PATH_" + path.upper()))
@@ -37,6 +39,13 @@ for path, B, k in (("stream", 1, 10), ("stream", 2, 10), ("umma", 64, 10), ("umm
     gbs = st["bytes_streamed"] / (st["scan_ms"] * 1e-3) / 1e9 if st["scan_ms"] else 0
     print(path, "B", B, "k", k, {kk: (round(v, 3) if isinstance(v, float) else v) for kk, v in st.items()},
           f"scan {gbs:.0f} GB/s  qps {B / (st['total_ms'] * 1e-3):.1f}", flush=True)
+    if path == "gemm":
+        # every query against the 64-per-pass tcgen05 path (both certified exact, so ids must be identical)
+        e.set_path(rb.PATH_UMMA)
+        rows3 = torch.empty((B, k), dtype=torch.int64, device="cuda")
+        st3 = e.search_knn_dev(q.data_ptr(), B, k, rows3.data_ptr(), sc.data_ptr())
+        print("   ids equal to the 64-per-pass path:", bool((rows == rows3).all()), "umma total ms", round(st3["total_ms"], 2),
+              "fallbacks", st3["n_fallback"], f"tensor {2.0 * B * N * D / (st['scan_ms'] * 1e-3) / 1e12:.0f} TFLOP/s", flush=True)
     if NOEXACT:
         continue
     # parity of the fast path against the fp64 scan on the device (ids must be identical)
