@@ -76,6 +76,7 @@ struct rass_engine {
   __nv_bfloat16* q16 = nullptr;     // [q_cap rounded to 64, dim_pad]
   double* q_norm = nullptr;         // [q_cap]
   float* q_rho = nullptr;           // [q_cap] ||q_hat - bf16(q_hat)|| / ||q_hat||
+  uint32_t* q_gthr = nullptr;       // [q_cap] scan_gemm: largest pivot any CTA has published for the query
   // candidate pool of one query group (RASS_GROUP_Q queries)
   size_t pool_entries = 0;          // per query: stride of the running search
   size_t pool_alloc_entries = 0;    // allocated, in entries

@@ -131,7 +131,7 @@ extern "C" int rass_destroy(rass_engine* h) {
   cudaFree(h->x32); cudaFree(h->x16); cudaFree(h->norm64); cudaFree(h->sa); cudaFree(h->sb);
   cudaFree(h->scal); cudaFreeHost(h->scal_host);
   cudaFree(h->dev_stage);
-  cudaFree(h->q_raw); cudaFree(h->q_hat); cudaFree(h->q16); cudaFree(h->q_norm); cudaFree(h->q_rho);
+  cudaFree(h->q_raw); cudaFree(h->q_hat); cudaFree(h->q16); cudaFree(h->q_norm); cudaFree(h->q_rho); cudaFree(h->q_gthr);
   cudaFree(h->pool_key); cudaFree(h->pool_row); cudaFree(h->pool_thr); cudaFree(h->pool_cnt);
   cudaFree(h->xlist_key); cudaFree(h->xlist_row);
   cudaFree(h->flagged); cudaFreeHost(h->flagged_host);
@@ -365,6 +365,7 @@ int ensure_query_workspace(rass_engine* h, int B) {
   REALLOC_DEV(h, h->q16, cap * d);
   REALLOC_DEV(h, h->q_norm, cap);
   REALLOC_DEV(h, h->q_rho, cap);
+  REALLOC_DEV(h, h->q_gthr, cap);
   REALLOC_DEV(h, h->flagged, cap);
   REALLOC_HOST(h, h->flagged_host, cap);
   h->q_cap = (int)cap;

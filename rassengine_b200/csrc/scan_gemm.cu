@@ -60,7 +60,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
                      const float* __restrict__ sa, const float* __restrict__ sb, int64_t n_rows, GemmPlan plan,
                      int k_blocks, int n_queries, float* __restrict__ pool_key, uint32_t* __restrict__ pool_row,
                      float* __restrict__ pool_thr, int* __restrict__ pool_cnt, size_t pool_entries, int n_segs,
-                     float* __restrict__ dbg_out) {
+                     uint32_t* __restrict__ gthr, float* __restrict__ dbg_out) {
   extern __shared__ unsigned char smem_dyn[];
   // 128B-swizzled tiles need 1024-byte alignment: [ stages: G2_STAGES * (A 16 KB | B 16 KB) ][ GemmSmem ]
   // (the dynamic window starts at the same offset in both CTAs, so the pair's operand descriptors agree)
@@ -155,7 +155,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
       const int nq_here = min(G2_NQ, n_queries - grp * G2_NQ);
       // fresh running state of this item's 256 queries; padding queries admit nothing
       for (int q = et; q < G2_NQ; q += 128) {
-        ss->thr[q] = q < nq_here ? neg_inf<float>() : __int_as_float(0x7f800000);
+        const uint32_t g = __ldcg(gthr + (size_t)grp * G2_NQ + q);
+        ss->thr[q] = q < nq_here ? (g > 0x007fffffu ? unord32(g) : neg_inf<float>()) : __int_as_float(0x7f800000);
         ss->cnt[q] = 0;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -164,6 +165,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
         const int64_t row = (int64_t)t * 2 * G2_ROWS + rank * G2_ROWS + ew * 32 + lane;
         float a = 0.f, b = neg_inf<float>();
         if (row < n_rows) { a = __ldg(sa + row); b = __ldg(sb + row); }
+        // the pivots other CTAs have published for this lane's two queries (used after the tile, latency hidden)
+        const uint32_t g0 = __ldcg(gthr + slot0 + 4 * lane + ew), g1 = __ldcg(gthr + slot0 + 128 + 4 * lane + ew);
         mbar_wait(&ss->acc_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * G2_NQ;
@@ -213,6 +216,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 #pragma unroll 1
         for (int qb = 0; qb < G2_NQ; qb += 128) {
           // warp ew owns queries q = ew (mod 4); lane l looks at q = qb + 4 l + ew
+          {
+            // a pivot any CTA found for this query bounds every row this segment rejects from now on as well:
+            // that CTA keeps >= 32 rows above it, and the certificate takes the maximum over segments anyway
+            const uint32_t g = qb ? g1 : g0;
+            const int q = qb + 4 * lane + ew;
+            if (g > 0x007fffffu) ss->thr[q] = fmaxf(ss->thr[q], unord32(g));
+          }
+          __syncwarp();
           unsigned need = __ballot_sync(0xffffffffu, ss->cnt[qb + 4 * lane + ew] > G2_HIGH_WATER);
           while (need) {
             const int q = qb + 4 * (__ffs(need) - 1) + ew;
@@ -232,7 +243,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
                 warp_compact<RASS_UMMA_SEG / 32>(ok, rw, RASS_UMMA_KEEP, pool_key + base, pool_row + base, pivot);
             __syncwarp();
             // everything dropped here, and every row rejected from now on, has key <= pivot
-            if (lane == 0) { ss->cnt[q] = kept; ss->thr[q] = unord32(pivot); }
+            if (lane == 0) {
+              ss->cnt[q] = kept;
+              ss->thr[q] = fmaxf(ss->thr[q], unord32(pivot));
+              atomicMax(gthr + slot0 + q, pivot);
+            }
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -305,12 +320,15 @@ static int gemm_launch(rass_engine* h, int B, float* dbg_out, cudaStream_t st) {
   const size_t n = (size_t)n_segs * B;
   clear_gemm_segs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pool_thr, h->pool_cnt, n);
   CUDA_TRY(h, cudaGetLastError());
+  // per-query bound shared between the CTAs (ordered-integer image of a float; 0 = nothing published yet)
+  CUDA_TRY(h, cudaMemsetAsync(h->q_gthr, 0, (size_t)h->q_cap * sizeof(uint32_t), st));
   const int grid = 2 * (plan.n_items < n_pairs ? plan.n_items : n_pairs);
   const size_t smem = gemm_smem_bytes();
   CUDA_TRY(h, cudaFuncSetAttribute(scan_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   scan_gemm_kernel<<<grid, G2_THREADS, smem, st>>>(*(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q2, h->sa, h->sb,
                                                    h->n_rows, plan, h->dim_pad / G2_KBLK, B, h->pool_key, h->pool_row,
-                                                   h->pool_thr, h->pool_cnt, h->pool_entries, n_segs, dbg_out);
+                                                   h->pool_thr, h->pool_cnt, h->pool_entries, n_segs, h->q_gthr,
+                                                   dbg_out);
   CUDA_TRY(h, cudaGetLastError());
   return RASS_OK;
 }

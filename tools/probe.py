@@ -27,6 +27,10 @@ print(f"fill {N} rows: {time.time() - t0:.1f}s", flush=True)
 gq = torch.Generator(device="cuda").manual_seed(5678)
 CASES = (("stream", 1, 10), ("stream", 2, 10), ("umma", 64, 10), ("umma", 1, 10), ("umma", 64, 100), ("stream", 1, 100),
          ("gemm", 256, 10), ("gemm", 1024, 10), ("gemm", 8192, 100), ("gemm", 200, 10))
+custom = [w.split(":") for w in which if ":" in w]      # e.g. gemm:1024:10
+if custom:
+    CASES = tuple((c[0], int(c[1]), int(c[2])) for c in custom)
+    which = [c[0] for c in custom]
 for path, B, k in CASES:
     if path not in which:
         continue
