@@ -1,8 +1,14 @@
 #!/usr/bin/env python
 """Headline benchmark: exact top-10 QPS over a 10M x 1024 corpus (BASELINE.json configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows R] [--batch B] [--k K]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg5]
+                    [--rows R] [--batch B] [--k K]
     torchrun --nproc-per-node N ... bench.py --gpus N ...          (one rank per GPU, NCCL)
+
+--workload selects the BASELINE.json configuration: cfg2 (default, the one the metric is quoted on: 10M x 1024,
+batch 64, top-10, HBM roofline), cfg3 (10M x 1024, batch 8192, top-100, tensor roofline) or cfg5 (100M x 1024
+bf16 corpus row-sharded over >= 2 GPUs, batch 1024, top-10, tensor roofline).  The default run also reports the
+batch-1, batch-1024 and batch-8192/top-100 regimes of the same corpus under `batch1` / `batched`.
 
 One step = one query batch (default 64 queries) answered exactly against the whole corpus.  The corpus is
 synthetic (seeded N(0,1) rows, L2-normalised as app/main.py:1250-1251 does), generated on the device and
@@ -42,25 +48,47 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows", type=int, default=10_000_000)
-    ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--k", type=int, default=10)
-    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--rows", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--cpu-sample-rows", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip the batch-1 / batched side measurements")
+    a = ap.parse_args()
+    rows, batch, k = {"cfg2": (10_000_000, 64, 10), "cfg3": (10_000_000, 8192, 100),
+                      "cfg5": (100_000_000, 1024, 10)}[a.workload]
+    a.rows = a.rows if a.rows is not None else rows
+    a.batch = a.batch if a.batch is not None else batch
+    a.k = a.k if a.k is not None else k
+    a.bf16_only = a.workload == "cfg5"
+    if a.cpu_sample_rows is None:
+        a.cpu_sample_rows = 1_000_000 if a.batch <= 64 else 100_000
+    return a
 
 
 def workload_name(a):
-    return (f"cfg2: exact cosine top-{a.k}, {a.rows} x {DIM} synthetic fp32 unit rows (bf16 scan shadow + fp64 rerank), "
-            f"query batch {a.batch}")
+    store = ("bf16 corpus (the bf16 values are the data)" if a.bf16_only
+             else "synthetic fp32 unit rows (bf16 scan shadow + fp64 rerank)")
+    return f"{a.workload}: exact cosine top-{a.k}, {a.rows} x {DIM} {store}, query batch {a.batch}"
+
+
+def scan_kernel_name(B):
+    if B <= 2:
+        return "scan_stream_kernel (128-bit streaming GEMV + warp select)"
+    if B <= 128:
+        return "scan_umma_kernel (TMA + tcgen05, 64 queries/pass)"
+    return "scan_gemm_kernel (TMA + tcgen05 cta_group::2, 256 queries/pass)"
 
 
 def peaks():
+    """(HBM GB/s, bf16 TFLOP/s sustained, source)"""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         j = json.load(open(p))
-        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(j["hbm_gbs"]), float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), \
+            "measured (MEASURED_PEAKS.json hbm_gbs / bf16_tflops_sustained)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -200,14 +228,14 @@ def run_ours(a):
     dev = torch.device("cuda", local)
 
     lo, hi = shard_bounds(a.rows, world, rank)
-    index = ShardedIndex(dim=DIM, capacity_rows=hi - lo)
+    index = ShardedIndex(dim=DIM, capacity_rows=hi - lo, flags=rb.BF16_ONLY if a.bf16_only else 0)
     index.set_row_base(lo)
     fill_shard(index, lo, hi)
     eng = index.engine
     B, k = a.batch, a.k
 
     gq = torch.Generator(device=dev).manual_seed(SEED_QUERIES)
-    n_batches = 8
+    n_batches = 8 if B <= 1024 else 2
     q_dev = [torch.randn((B, DIM), generator=gq, device=dev) for _ in range(n_batches)]
     q_host = [q.cpu().pin_memory() for q in q_dev]
 
@@ -284,7 +312,7 @@ def run_ours(a):
 
     # ---- batch-1 latency regime (same corpus), for the record ----
     b1 = None
-    if B != 1:
+    if B != 1 and a.workload == "cfg2" and not a.no_extras:
         q1 = [q[:1].contiguous() for q in q_dev]
         reset()
 
@@ -301,6 +329,31 @@ def run_ours(a):
         b1_scan = stats["scan_ms"] / max(1, stats["n"])
         b1 = {"qps": a.steps / (ms_b1 * 1e-3), "ms_per_query": ms_b1 / a.steps,
               "scan_gbs": (stats["bytes"] / max(1, stats["n"])) / (b1_scan * 1e-3) / 1e9 if b1_scan else None}
+    # ---- large-batch regimes of the same corpus (tensor-core contraction), for the record ----
+    batched = None
+    if a.workload == "cfg2" and not a.no_extras:
+        batched = {}
+        for name, Bx, kx, nsteps in (("batch1024_top10", 1024, 10, 10), ("batch8192_top100", 8192, 100, 3)):
+            qx = torch.randn((Bx, DIM), generator=gq, device=dev)
+            reset()
+
+            def step_x(i):
+                index.search_dev(qx, kx)
+                stats["scan_ms"] += eng.last_stats["scan_ms"]
+                stats["fallback"] += eng.last_stats["n_fallback"]
+                stats["n"] += 1
+
+            for i in range(3):
+                step_x(i)
+            reset()
+            ms_x, _, _ = timed(step_x, nsteps, 0)
+            scan_x = stats["scan_ms"] / max(1, stats["n"])
+            flops = 2.0 * Bx * (hi - lo) * DIM
+            batched[name] = {"qps": nsteps * Bx / (ms_x * 1e-3), "ms_per_batch": ms_x / nsteps, "k": kx,
+                             "scan_kernel": scan_kernel_name(Bx), "scan_ms": scan_x,
+                             "scan_tflops_per_gpu": flops / (scan_x * 1e-3) / 1e12 if scan_x else None,
+                             "certificate_fallbacks": int(stats["fallback"])}
+            del qx
     if sampler:
         sampler.stop()
 
@@ -309,14 +362,24 @@ def run_ours(a):
             dist.destroy_process_group()
         return
 
-    peak, peak_src = peaks()
-    achieved = bytes_per_step / (scan_ms_avg * 1e-3) / 1e9 if scan_ms_avg else 0.0
+    peak_hbm, peak_tf, peak_src = peaks()
+    tensor_bound = B > 128
+    if tensor_bound:
+        flops_per_step = 2.0 * B * (hi - lo) * DIM
+        achieved = flops_per_step / (scan_ms_avg * 1e-3) / 1e12 if scan_ms_avg else 0.0
+        peak = peak_tf
+    else:
+        achieved = bytes_per_step / (scan_ms_avg * 1e-3) / 1e9 if scan_ms_avg else 0.0
+        peak = peak_hbm
+    if batched:
+        for v in batched.values():
+            v["frac_of_tensor_peak"] = v["scan_tflops_per_gpu"] / peak_tf if v["scan_tflops_per_gpu"] else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
             t = json.load(open(tp))
-            traffic = t.get("dram_bytes_per_row", 0) * (hi - lo) or None
+            traffic = (t.get("dram_bytes_per_row", 0) * (hi - lo) or None) if not tensor_bound else None
         except Exception:
             traffic = None
     out = {
@@ -329,18 +392,22 @@ def run_ours(a):
                    else "single shard",
                    "l2": "inputs larger than L2: every step streams the whole bf16 shard "
                          f"({(hi - lo) * DIM * 2 / 1e9:.2f} GB per GPU)",
-                   "scan_kernel": "scan_umma_kernel (TMA + tcgen05, 64 queries/pass)" if B > 2
-                   else "scan_stream_kernel (128-bit streaming GEMV + warp select)"},
+                   "scan_kernel": scan_kernel_name(B)},
         "e2e": {"value": a.steps * B / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": B * DIM * 4,
                 "d2h_bytes_per_step": B * k * 12, "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "scan_umma_kernel" if B > 2 else "scan_stream_kernel",
-                     "algorithmic_bytes_per_launch": bytes_per_step, "kernel_ms": scan_ms_avg,
-                     "frac_of_nominal_8TBs": achieved / 8000.0},
+        "roofline": ({"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                      "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                      "kernel": "scan_gemm_kernel", "algorithmic_flops_per_launch": 2.0 * B * (hi - lo) * DIM,
+                      "kernel_ms": scan_ms_avg, "frac_of_nominal_2250TF": achieved / 2250.0} if tensor_bound else
+                     {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                      "kernel": "scan_umma_kernel" if B > 2 else "scan_stream_kernel",
+                      "algorithmic_bytes_per_launch": bytes_per_step, "kernel_ms": scan_ms_avg,
+                      "frac_of_nominal_8TBs": achieved / 8000.0}),
         "parity": {"fast_path_ids_equal_fp64_scan": parity_ok, "certificate_fallbacks_in_timed_region": int(fallback)},
         "batch1": b1,
+        "batched": batched,
         "clocks": clocks,
     }
     if not a.no_cpu_baseline and world == 1:
