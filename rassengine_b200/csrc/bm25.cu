@@ -34,6 +34,30 @@ static const int kNumFree = 24;  // 255 - longToInt4(Integer.MAX_VALUE)
 static uint8_t int_to_byte4(uint32_t i) { return (uint8_t)(i < (uint32_t)kNumFree ? i : kNumFree + long_to_int4((int64_t)i - kNumFree)); }
 static int64_t byte4_to_int(int b) { return b < kNumFree ? b : kNumFree + int4_to_long(b - kNumFree); }
 
+#define BM25_MAX_TERMS 64
+#define HYB_TILE 4096            // docs per tile: the fused clause sums of a tile live in shared memory (32 KB)
+#define HYB_THREADS 256
+#define HYB_TABLE_MIN_DF 512     // terms at least this frequent get a row of per-tile posting offsets
+
+// Per-tile posting offsets of the frequent terms, built once per rass_bm25_build:
+// tile_off[row * (n_tiles + 1) + t] = number of postings of the term whose doc is < t * HYB_TILE.
+__global__ void tile_offsets_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ doc,
+                                    const int32_t* __restrict__ table_terms, int n_table, int n_tiles,
+                                    uint32_t* __restrict__ tile_off) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_table * (n_tiles + 1)) return;
+  const int row = (int)(i / (n_tiles + 1)), t = (int)(i % (n_tiles + 1));
+  const int32_t term = table_terms[row];
+  const int64_t lo = indptr[term], hi = indptr[term + 1];
+  const int64_t bound = (int64_t)t * HYB_TILE;
+  int64_t a = lo, b = hi;                 // first posting with doc >= bound
+  while (a < b) {
+    const int64_t m = (a + b) >> 1;
+    if ((int64_t)doc[m] < bound) a = m + 1; else b = m;
+  }
+  tile_off[i] = (uint32_t)(a - lo);
+}
+
 template <typename T>
 static int upload(rass_engine* h, T** dst, const T* src, size_t n) {
   cudaFree(*dst);
@@ -86,114 +110,230 @@ extern "C" int rass_bm25_build(rass_engine* h, const int64_t* indptr, const int3
   if ((rc = upload(h, &b.tf, tf, (size_t)nnz))) return rc;
   if ((rc = upload(h, &b.norm, norm.data(), (size_t)N))) return rc;
   if ((rc = upload(h, &b.inv_dev, inv, (size_t)256))) return rc;
-  cudaFree(b.acc); b.acc = nullptr;
-  cudaFree(b.touched); b.touched = nullptr;
-  cudaFree(b.touched_n); b.touched_n = nullptr;
-  const size_t n_acc = (size_t)std::max<int64_t>(std::max<int64_t>(N, h->n_rows), 1);
-  CUDA_TRY(h, cudaMalloc(&b.acc, n_acc * sizeof(double)));
-  CUDA_TRY(h, cudaMemset(b.acc, 0, n_acc * sizeof(double)));
-  b.acc_rows = (int64_t)n_acc;
-  b.touched_cap = (int64_t)n_acc;
-  CUDA_TRY(h, cudaMalloc(&b.touched, n_acc * sizeof(uint32_t)));
-  CUDA_TRY(h, cudaMalloc(&b.touched_n, sizeof(int)));
-  CUDA_TRY(h, cudaMemset(b.touched_n, 0, sizeof(int)));
+  // per-tile posting offsets of the frequent terms (hybrid_tile_kernel jumps straight to a tile's postings)
+  b.n_tiles = (int)((std::max<int64_t>(N, 1) + HYB_TILE - 1) / HYB_TILE);
+  b.table_row_host.assign((size_t)V, -1);
+  std::vector<int32_t> table_terms;
+  for (int64_t t = 0; t < V; ++t)
+    if (indptr[t + 1] - indptr[t] >= HYB_TABLE_MIN_DF) {
+      b.table_row_host[(size_t)t] = (int32_t)table_terms.size();
+      table_terms.push_back((int32_t)t);
+    }
+  cudaFree(b.tile_off); b.tile_off = nullptr;
+  const size_t n_off = table_terms.size() * (size_t)(b.n_tiles + 1);
+  CUDA_TRY(h, cudaMalloc(&b.tile_off, std::max<size_t>(n_off, 1) * sizeof(uint32_t)));
+  if (n_off) {
+    int32_t* tt_dev = nullptr;
+    if ((rc = upload(h, &tt_dev, table_terms.data(), table_terms.size()))) return rc;
+    tile_offsets_kernel<<<(unsigned)((n_off + 255) / 256), 256>>>(b.indptr, b.doc, tt_dev, (int)table_terms.size(),
+                                                                  b.n_tiles, b.tile_off);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(tt_dev);
+    if (e != cudaSuccess) return rass_fail(h, RASS_E_CUDA, "tile_offsets_kernel: %s", cudaGetErrorString(e));
+  }
+  b.built = true;
   return RASS_OK;
 }
 
 // ---- kernels ------------------------------------------------------------------------------------------------
-#define BM25_MAX_TERMS 64
-
-struct TermArgs {
-  int n_terms;
-  int64_t lo[BM25_MAX_TERMS];      // first posting of the term
-  int64_t cum[BM25_MAX_TERMS + 1]; // prefix sum of posting counts
-  float w[BM25_MAX_TERMS];         // float(boost) * idf
+struct HybridArgs {
+  const int32_t* doc;
+  const uint16_t* tf;
+  const uint8_t* norm;
+  const float* inv;
+  const uint32_t* tile_off;
+  const int32_t* qt_indptr;      // [B + 1] into the per-term arrays below (terms without postings are dropped)
+  const int64_t* t_lo;           // first posting of the term
+  const uint32_t* t_len;         // document frequency
+  const float* t_w;              // float(clause boost) * idf
+  const int32_t* t_row;          // row of tile_off, -1 for rare terms
+  const int64_t* knn_rows;       // [B, k] or null
+  const float* knn_scores;
+  const uint8_t* row_filter;
+  int64_t filter_rows;
+  int64_t row_base, n_docs;
+  int n_tiles, table_tiles, k;   // tiles of this launch; tiles the offset table covers (docs known to the postings)
+  float w_knn;
+  double* xkey;                  // [B][n_tiles * k]
+  uint32_t* xrow;
 };
 
-// one thread per posting of the query's terms: s = w - w / (1 + tf * inv[norm[d]])  (float, each op rounded)
-__global__ void __launch_bounds__(256) bm25_accumulate_kernel(const __grid_constant__ TermArgs ta,
-                                                              const int32_t* __restrict__ doc,
-                                                              const uint16_t* __restrict__ tf,
-                                                              const uint8_t* __restrict__ norm,
-                                                              const float* __restrict__ inv,
-                                                              const float* __restrict__ sb, int64_t n_rows,
-                                                              const uint8_t* __restrict__ row_filter,
-                                                              int64_t filter_rows, double* __restrict__ acc,
-                                                              uint32_t* __restrict__ touched,
-                                                              int* __restrict__ touched_n) {
+// One CTA per (tile of 4096 docs, query): the whole bool.should of the reference for those docs.
+//   text clause : for every query term in order, s = w - w / (1 + tf * inv[norm[d]]) in float (each op rounded),
+//                 summed in double per doc -- a term's postings name a doc once, so plain shared-memory adds
+//                 between barriers are race free and the summation order is the oracle's; cast to float
+//   knn clause  : the k nearest rows get float(w_knn * knn_score) added in double
+//   bool.filter : rows failing the pass mask never match
+//   top-k       : 32-bit radix select over the tile's fused float scores, ties by row ascending
+// The tile's best k (score, row) go to the query's list; exact_select_kernel ranks n_tiles * k entries.
+__global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_constant__ HybridArgs a) {
+  __shared__ double acc[HYB_TILE];
   __shared__ float s_inv[256];
-  s_inv[threadIdx.x] = inv[threadIdx.x];
+  __shared__ int64_t s_lo[BM25_MAX_TERMS];
+  __shared__ uint32_t s_n[BM25_MAX_TERMS];
+  __shared__ float s_w[BM25_MAX_TERMS];
+  __shared__ __align__(16) int s_cnt[2][HYB_THREADS / 32];
+  __shared__ int s_nout, s_nmatch;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x, q = blockIdx.y;
+  const int64_t d0 = (int64_t)tile * HYB_TILE;
+  const int64_t d1 = min(d0 + HYB_TILE, a.n_docs);
+  for (int i = tid; i < HYB_TILE; i += HYB_THREADS) acc[i] = 0.0;
+  s_inv[tid] = a.inv ? a.inv[tid] : 0.f;
+  if (tid == 0) { s_nout = 0; s_nmatch = 0; }
   __syncthreads();
-  const int64_t total = ta.cum[ta.n_terms];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int t = 0;
-    while (i >= ta.cum[t + 1]) ++t;
-    const int64_t p = ta.lo[t] + (i - ta.cum[t]);
-    const uint32_t d = (uint32_t)__ldg(doc + p);
-    if (row_filter && ((int64_t)d >= filter_rows || !row_filter[d])) continue;   // bool.filter
-    const float w = ta.w[t];
-    const float x = __fmul_rn((float)__ldg(tf + p), s_inv[norm[d]]);
-    const float s = __fsub_rn(w, __fdiv_rn(w, __fadd_rn(1.0f, x)));
-    if (!(s > 0.f)) continue;   // a doc matches the clause only with a positive score (oracle: text > 0)
-    const double old = atomicAdd(acc + d, (double)s);
-    if (old == 0.0) touched[atomicAdd(touched_n, 1)] = d;
-  }
-}
 
-// the knn clause: the k nearest rows of this query get float(w_knn * knn_score) added
-__global__ void fuse_knn_kernel(const int64_t* __restrict__ knn_rows, const float* __restrict__ knn_scores, int k,
-                                int64_t row_base, float w_knn, const uint8_t* __restrict__ row_filter,
-                                int64_t filter_rows, double* __restrict__ acc, uint32_t* __restrict__ touched,
-                                int* __restrict__ touched_n) {
-  const int j = threadIdx.x;
-  if (j >= k) return;
-  const int64_t r = knn_rows[j];
-  if (r < 0) return;
-  const uint32_t d = (uint32_t)(r - row_base);
-  if (row_filter && ((int64_t)d >= filter_rows || !row_filter[d])) return;   // bool.filter drops the neighbour
-  const float c = __fmul_rn(w_knn, knn_scores[j]);
-  const double old = atomicAdd(acc + d, (double)c);
-  if (old == 0.0) touched[atomicAdd(touched_n, 1)] = d;
-}
-
-// per-warp top lists over the touched rows; clears the accumulator behind itself
-template <int M>
-__global__ void __launch_bounds__(RASS_WARPS_PER_CTA * 32) fuse_collect_kernel(
-    double* __restrict__ acc, const uint32_t* __restrict__ touched, const int* __restrict__ touched_n,
-    double* __restrict__ xkey, uint32_t* __restrict__ xrow) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gw = blockIdx.x * RASS_WARPS_PER_CTA + warp;
-  const int W = gridDim.x * RASS_WARPS_PER_CTA;
-  const int n = *touched_n;
-  WarpTop<double, M> top;
-  top.init();
-  for (int base = gw * 32; base < n; base += W * 32) {
-    const int i = base + lane;
-    double key = neg_inf<double>();
-    uint32_t d = 0xffffffffu;
-    if (i < n) {
-      d = touched[i];
-      key = (double)(float)acc[d];   // Lucene casts the summed clause scores to float
-      acc[d] = 0.0;
+  // ---- text clause ----
+  if (a.qt_indptr) {
+    const int j0 = a.qt_indptr[q], nt = a.qt_indptr[q + 1] - j0;
+    // posting range of every term inside this tile, fetched by one thread per term (one latency for all terms)
+    if (tid < nt) {
+      const int j = j0 + tid;
+      const int row = a.t_row[j];
+      uint32_t pa = 0, pb = a.t_len[j];
+      if (row >= 0) {
+        if (tile < a.table_tiles) {
+          const uint32_t* off = a.tile_off + (size_t)row * (a.table_tiles + 1) + tile;
+          pa = off[0];
+          pb = off[1];
+        } else {
+          pb = 0;      // rows appended after rass_bm25_build carry no postings
+        }
+      }
+      s_lo[tid] = a.t_lo[j] + pa;
+      s_n[tid] = pb - pa;
+      s_w[tid] = a.t_w[j];
     }
-    unsigned hit = __ballot_sync(0xffffffffu, i < n && entry_better<double>(key, d, top.thr_key, top.thr_row));
-    while (hit) {
-      const int src = __ffs(hit) - 1;
-      hit &= hit - 1;
-      top.insert(shfl_t(key, src), __shfl_sync(0xffffffffu, d, src));
+    __syncthreads();
+    for (int j = 0; j < nt; ++j) {
+      const int64_t lo = s_lo[j];
+      const uint32_t n = s_n[j];
+      const float w = s_w[j];
+      for (uint32_t p = tid; p < n; p += HYB_THREADS) {
+        const int64_t d = (int64_t)__ldg(a.doc + lo + p);
+        if (d < d0 || d >= d1) continue;                                             // rare terms scan their whole list
+        if (a.row_filter && (d >= a.filter_rows || !a.row_filter[d])) continue;       // bool.filter
+        const float x = __fmul_rn((float)__ldg(a.tf + lo + p), s_inv[a.norm[d]]);
+        const float s = __fsub_rn(w, __fdiv_rn(w, __fadd_rn(1.0f, x)));
+        if (s > 0.f) acc[d - d0] += (double)s;
+      }
+      __syncthreads();
+    }
+    // the clause score is a float; the bool sums clause scores in double
+    for (int i = tid; i < HYB_TILE; i += HYB_THREADS) acc[i] = (double)(float)acc[i];
+    __syncthreads();
+  }
+
+  // ---- knn clause ----
+  if (a.knn_rows && tid < a.k) {
+    const int64_t r = a.knn_rows[(size_t)q * a.k + tid];
+    if (r >= 0) {
+      const int64_t d = r - a.row_base;
+      if (d >= d0 && d < d1 && !(a.row_filter && (d >= a.filter_rows || !a.row_filter[d])))
+        acc[d - d0] += (double)__fmul_rn(a.w_knn, a.knn_scores[(size_t)q * a.k + tid]);
     }
   }
+  __syncthreads();
+
+  // ---- top-k of the tile: keys as order-preserving integers, 0 = no match ----
+  constexpr int PER = HYB_TILE / HYB_THREADS;
+  uint32_t key[PER];
+  int nm = 0;
 #pragma unroll
-  for (int s = 0; s < M; ++s) {
-    xkey[(size_t)gw * (32 * M) + s * 32 + lane] = top.key[s];
-    xrow[(size_t)gw * (32 * M) + s * 32 + lane] = top.row[s];
+  for (int i = 0; i < PER; ++i) {
+    const double v = acc[i * HYB_THREADS + tid];          // doc = d0 + i * HYB_THREADS + tid
+    key[i] = v != 0.0 ? ord32((float)v) : 0u;
+    nm += v != 0.0;
+  }
+  if (nm) atomicAdd(&s_nmatch, nm);
+  __syncthreads();
+  const int n_match = s_nmatch;
+  double* xk = a.xkey + ((size_t)q * a.n_tiles + tile) * a.k;
+  uint32_t* xr = a.xrow + ((size_t)q * a.n_tiles + tile) * a.k;
+  if (n_match <= a.k) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+      if (key[i]) {
+        const int pos = atomicAdd(&s_nout, 1);
+        xk[pos] = (double)unord32(key[i]);
+        xr[pos] = (uint32_t)(d0 + i * HYB_THREADS + tid);
+      }
+  } else {
+    // k-th largest key by most-significant-bit-first descent: prefix grows while >= k keys are >= it
+    int buf = 0;
+    auto block_count = [&](int c) {
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0) s_cnt[buf][warp] = c;
+      __syncthreads();
+      const int4 c0 = *reinterpret_cast<const int4*>(&s_cnt[buf][0]), c1 = *reinterpret_cast<const int4*>(&s_cnt[buf][4]);
+      buf ^= 1;       // the next count writes the other buffer, so one barrier per count is enough
+      return c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+    };
+    uint32_t prefix = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = prefix | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) c += key[i] >= cand;
+      if (block_count(c) >= a.k) prefix = cand;
+    }
+    int n_gt = 0, n_eq = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { n_gt += key[i] > prefix; n_eq += key[i] == prefix; }
+    const int need_eq = a.k - block_count(n_gt);      // entries equal to the k-th key to take, lowest rows first
+    const int tot_eq = block_count(n_eq);
+    const bool all_eq = tot_eq == need_eq;    // the usual case: the k-th key is unique in the tile
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+      if (key[i] > prefix || (all_eq && key[i] == prefix)) {
+        const int pos = atomicAdd(&s_nout, 1);
+        xk[pos] = (double)unord32(key[i]);
+        xr[pos] = (uint32_t)(d0 + i * HYB_THREADS + tid);
+      }
+    __syncthreads();
+    if (!all_eq && tid == 0) {
+      // equal scores at the cut: Lucene's doc-id tie-break keeps the lowest rows
+      int pos = s_nout, left = need_eq;
+      for (int i = 0; i < HYB_TILE && left > 0; ++i) {
+        const double v = acc[i];
+        if (v != 0.0 && ord32((float)v) == prefix) {
+          xk[pos] = (double)(float)v;
+          xr[pos] = (uint32_t)(d0 + i);
+          ++pos;
+          --left;
+        }
+      }
+      s_nout = pos;
+    }
+  }
+  __syncthreads();
+  for (int i = s_nout + tid; i < a.k; i += HYB_THREADS) {
+    xk[i] = neg_inf<double>();
+    xr[i] = 0xffffffffu;
   }
 }
 
-__global__ void reset_counter_kernel(int* p) { *p = 0; }
+int launch_select_batch(rass_engine* h, size_t entries, int B, int k, int64_t* out_rows, float* out_scores,
+                        cudaStream_t st);
 
-int launch_select_raw(rass_engine* h, size_t entries, int k, int q, int64_t* out_rows, float* out_scores,
-                      cudaStream_t st);
+static int ensure_hybrid_workspace(rass_engine* h, size_t n_terms_cap, int B) {
+  Bm25State& b = h->bm25;
+  if (n_terms_cap > b.qt_cap || (size_t)B + 1 > b.qt_q_cap) {
+    CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+    const size_t tc = std::max<size_t>(n_terms_cap * 2, 1024), qc = std::max<size_t>((size_t)B * 2 + 2, 256);
+    // one pinned + one device block: [t_lo i64 x tc][t_len u32 x tc][t_w f32 x tc][t_row i32 x tc][indptr i32 x qc]
+    const size_t bytes = tc * (8 + 4 + 4 + 4) + qc * 4;
+    cudaFreeHost(b.qt_host); b.qt_host = nullptr;
+    cudaFree(b.qt_dev); b.qt_dev = nullptr;
+    CUDA_TRY(h, cudaMallocHost(&b.qt_host, bytes));
+    CUDA_TRY(h, cudaMalloc(&b.qt_dev, bytes));
+    b.qt_cap = tc;
+    b.qt_q_cap = qc;
+    b.qt_bytes = bytes;
+  }
+  return RASS_OK;
+}
 
 extern "C" int rass_search_hybrid(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr,
                                   const int32_t* qterms, float w_text, float w_knn, int k, int64_t* out_rows,
@@ -204,27 +344,11 @@ extern "C" int rass_search_hybrid(rass_engine* h, const float* q_host, int B, co
   if (k < 1 || k > RASS_MAX_K) return rass_fail(h, RASS_E_INVALID, "k must be in [1, %d], got %d", RASS_MAX_K, k);
   if (!q_host && !qterm_indptr) return rass_fail(h, RASS_E_INVALID, "neither a vector nor a text clause");
   Bm25State& b = h->bm25;
-  if (qterm_indptr && (!b.acc || !qterms)) return rass_fail(h, RASS_E_INVALID, "text clause without rass_bm25_build");
+  if (qterm_indptr && (!b.built || !qterms)) return rass_fail(h, RASS_E_INVALID, "text clause without rass_bm25_build");
   cudaStream_t st = eng_stream(h);
   int rc;
   const size_t n_out = (size_t)B * k;
   if ((rc = ensure_out_workspace(h, 2 * n_out))) return rc;
-  // accumulator must cover the vector rows too
-  const int64_t need = std::max<int64_t>(std::max<int64_t>(b.N, h->n_rows), 1);
-  if (need > b.acc_rows) {
-    CUDA_TRY(h, cudaStreamSynchronize(st));
-    cudaFree(b.acc); b.acc = nullptr;
-    cudaFree(b.touched); b.touched = nullptr;
-    CUDA_TRY(h, cudaMalloc(&b.acc, (size_t)need * sizeof(double)));
-    CUDA_TRY(h, cudaMemset(b.acc, 0, (size_t)need * sizeof(double)));
-    CUDA_TRY(h, cudaMalloc(&b.touched, (size_t)need * sizeof(uint32_t)));
-    if (!b.touched_n) {
-      CUDA_TRY(h, cudaMalloc(&b.touched_n, sizeof(int)));
-      CUDA_TRY(h, cudaMemset(b.touched_n, 0, sizeof(int)));
-    }
-    b.acc_rows = need;
-    b.touched_cap = need;
-  }
   rass_stats s;
   memset(&s, 0, sizeof(s));
   s.n_queries = B;
@@ -237,56 +361,82 @@ extern "C" int rass_search_hybrid(rass_engine* h, const float* q_host, int B, co
     if ((rc = stage_queries(h, q_host, B, &q_dev))) return rc;
     if ((rc = search_core(h, q_dev, B, k, knn_rows, knn_scores, nullptr, &s))) return rc;
   }
-  // 2. per query: postings walk, knn contributions, top-k over the touched rows
-  const int M = k <= 32 ? 1 : 4;
-  const int grid_c = h->num_sms;
-  const size_t entries = (size_t)grid_c * RASS_WARPS_PER_CTA * 32 * M;
-  if ((rc = ensure_xlist_workspace(h, entries))) return rc;
-  cudaEvent_t e0 = h->ev[0], e1 = h->ev[3];
-  CUDA_TRY(h, cudaEventRecord(e0, st));
-  for (int q = 0; q < B; ++q) {
-    if (qterm_indptr) {
-      TermArgs ta;
-      memset(&ta, 0, sizeof(ta));
-      const float bo = w_text;
+  // 2. the query terms: posting ranges and float(boost) * idf weights, in query order
+  const bool have_text = qterm_indptr != nullptr;
+  size_t n_terms = 0;
+  if (have_text) {
+    if ((rc = ensure_hybrid_workspace(h, (size_t)(qterm_indptr[B] - qterm_indptr[0]), B))) return rc;
+    unsigned char* base = b.qt_host;
+    int64_t* t_lo = reinterpret_cast<int64_t*>(base);
+    uint32_t* t_len = reinterpret_cast<uint32_t*>(base + b.qt_cap * 8);
+    float* t_w = reinterpret_cast<float*>(base + b.qt_cap * 12);
+    int32_t* t_row = reinterpret_cast<int32_t*>(base + b.qt_cap * 16);
+    int32_t* indptr = reinterpret_cast<int32_t*>(base + b.qt_cap * 20);
+    const float bo = w_text;
+    for (int q = 0; q < B; ++q) {
+      indptr[q] = (int32_t)n_terms;
+      int in_query = 0;
       for (int32_t j = qterm_indptr[q]; j < qterm_indptr[q + 1]; ++j) {
         const int32_t t = qterms[j];
         if (t < 0 || t >= b.V) continue;
         const int64_t lo = b.indptr_host[(size_t)t], len = b.indptr_host[(size_t)t + 1] - lo;
         if (len == 0) continue;
-        if (ta.n_terms == BM25_MAX_TERMS) return rass_fail(h, RASS_E_INVALID, "more than %d query terms", BM25_MAX_TERMS);
-        ta.lo[ta.n_terms] = lo;
-        ta.cum[ta.n_terms + 1] = ta.cum[ta.n_terms] + len;
+        if (++in_query > BM25_MAX_TERMS) return rass_fail(h, RASS_E_INVALID, "more than %d query terms", BM25_MAX_TERMS);
+        t_lo[n_terms] = lo;
+        t_len[n_terms] = (uint32_t)len;
         volatile float w = bo * b.idf_host[(size_t)t];
-        ta.w[ta.n_terms] = w;
-        ++ta.n_terms;
-      }
-      const int64_t total = ta.cum[ta.n_terms];
-      if (total > 0) {
-        const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->num_sms * 16);
-        bm25_accumulate_kernel<<<blocks, 256, 0, st>>>(ta, b.doc, b.tf, b.norm, b.inv_dev, h->sb, h->n_rows,
-                                                       h->row_filter, h->row_filter_rows, b.acc, b.touched,
-                                                       b.touched_n);
-        CUDA_TRY(h, cudaGetLastError());
-        s.launches++;
-        s.bytes_streamed += total * 6;
+        t_w[n_terms] = w;
+        t_row[n_terms] = b.table_row_host[(size_t)t];
+        s.bytes_streamed += len * 6;
+        ++n_terms;
       }
     }
-    if (have_vec) {
-      fuse_knn_kernel<<<1, RASS_MAX_K, 0, st>>>(knn_rows + (size_t)q * k, knn_scores + (size_t)q * k, k, h->row_base,
-                                                w_knn, h->row_filter, h->row_filter_rows, b.acc, b.touched,
-                                                b.touched_n);
-      CUDA_TRY(h, cudaGetLastError());
-      s.launches++;
-    }
-    if (M == 1) fuse_collect_kernel<1><<<grid_c, RASS_WARPS_PER_CTA * 32, 0, st>>>(b.acc, b.touched, b.touched_n, h->xlist_key, h->xlist_row);
-    else fuse_collect_kernel<4><<<grid_c, RASS_WARPS_PER_CTA * 32, 0, st>>>(b.acc, b.touched, b.touched_n, h->xlist_key, h->xlist_row);
-    CUDA_TRY(h, cudaGetLastError());
-    if ((rc = launch_select_raw(h, entries, k, q, h->out_rows, h->out_scores, st))) return rc;
-    reset_counter_kernel<<<1, 1, 0, st>>>(b.touched_n);
-    CUDA_TRY(h, cudaGetLastError());
-    s.launches += 3;
+    indptr[B] = (int32_t)n_terms;
+    CUDA_TRY(h, cudaMemcpyAsync(b.qt_dev, b.qt_host, b.qt_bytes, cudaMemcpyHostToDevice, st));
   }
+  // 3. one fused kernel over (tile, query), then the per-query top-k of the tile lists
+  const int64_t n_docs = std::max<int64_t>(std::max<int64_t>(b.built ? b.N : 0, h->n_rows), 1);
+  const int n_tiles = (int)((n_docs + HYB_TILE - 1) / HYB_TILE);
+  const size_t entries = (size_t)n_tiles * k;
+  if ((rc = ensure_xlist_workspace(h, (entries * B + RASS_EXACT_NQ - 1) / RASS_EXACT_NQ))) return rc;
+  cudaEvent_t e0 = h->ev[0], e1 = h->ev[3];
+  CUDA_TRY(h, cudaEventRecord(e0, st));
+  HybridArgs a;
+  memset(&a, 0, sizeof(a));
+  a.doc = b.doc; a.tf = b.tf; a.norm = b.norm; a.inv = b.inv_dev; a.tile_off = b.tile_off;
+  if (have_text) {
+    unsigned char* base = b.qt_dev;
+    a.t_lo = reinterpret_cast<const int64_t*>(base);
+    a.t_len = reinterpret_cast<const uint32_t*>(base + b.qt_cap * 8);
+    a.t_w = reinterpret_cast<const float*>(base + b.qt_cap * 12);
+    a.t_row = reinterpret_cast<const int32_t*>(base + b.qt_cap * 16);
+    a.qt_indptr = reinterpret_cast<const int32_t*>(base + b.qt_cap * 20);
+  }
+  a.knn_rows = have_vec ? knn_rows : nullptr;
+  a.knn_scores = knn_scores;
+  a.row_filter = h->row_filter;
+  a.filter_rows = h->row_filter_rows;
+  a.row_base = h->row_base;
+  a.n_docs = n_docs;
+  a.n_tiles = n_tiles;
+  a.table_tiles = b.built ? b.n_tiles : 0;
+  a.k = k;
+  a.w_knn = w_knn;
+  a.xkey = h->xlist_key;
+  a.xrow = h->xlist_row;
+  for (int q0 = 0; q0 < B; q0 += 32768) {
+    const int nq = std::min(B - q0, 32768);
+    HybridArgs aq = a;
+    if (aq.qt_indptr) aq.qt_indptr += q0;
+    if (aq.knn_rows) { aq.knn_rows += (size_t)q0 * k; aq.knn_scores += (size_t)q0 * k; }
+    aq.xkey += (size_t)q0 * a.n_tiles * k;
+    aq.xrow += (size_t)q0 * a.n_tiles * k;
+    hybrid_tile_kernel<<<dim3((unsigned)a.n_tiles, (unsigned)nq), HYB_THREADS, 0, st>>>(aq);
+    CUDA_TRY(h, cudaGetLastError());
+    s.launches++;
+  }
+  if ((rc = launch_select_batch(h, (size_t)a.n_tiles * k, B, k, h->out_rows, h->out_scores, st))) return rc;
+  s.launches++;
   CUDA_TRY(h, cudaEventRecord(e1, st));
   CUDA_TRY(h, cudaMemcpyAsync(h->out_rows_host, h->out_rows, n_out * 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(h, cudaMemcpyAsync(h->out_scores_host, h->out_scores, n_out * 4, cudaMemcpyDeviceToHost, st));

@@ -21,17 +21,19 @@
 #define RASS_FINISH_THREADS 1024
 
 struct Bm25State {
+  bool built = false;
   int64_t V = 0, N = 0, nnz = 0;
   int64_t* indptr = nullptr;     // device [V+1]
   int32_t* doc = nullptr;        // device [nnz]
   uint16_t* tf = nullptr;        // device [nnz]
   uint8_t* norm = nullptr;       // device [N]  SmallFloat byte4 of the doc length
   float* inv_dev = nullptr;      // device [256] 1 / (k1 * ((1-b) + b * len/avgdl))
-  double* acc = nullptr;         // device [N] per-query accumulator (kept zeroed between queries)
-  uint32_t* touched = nullptr;   // device [touched_cap] rows with acc != 0 for the running query
-  int64_t touched_cap = 0;
-  int64_t acc_rows = 0;
-  int* touched_n = nullptr;      // device counter
+  int n_tiles = 0;               // tiles of 4096 docs
+  uint32_t* tile_off = nullptr;  // device [n_table][n_tiles + 1] postings of a frequent term before each tile
+  std::vector<int32_t> table_row_host;   // term -> row of tile_off, -1 for rare terms
+  unsigned char* qt_host = nullptr;      // pinned staging of the per-call query-term arrays
+  unsigned char* qt_dev = nullptr;
+  size_t qt_cap = 0, qt_q_cap = 0, qt_bytes = 0;
   float avgdl = 0.f;
   int64_t doc_count = 0;
   std::vector<int64_t> indptr_host;

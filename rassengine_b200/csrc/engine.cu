@@ -144,8 +144,8 @@ extern "C" int rass_destroy(rass_engine* h) {
   for (int i = 0; i < 2; ++i) { cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   Bm25State& b = h->bm25;
-  cudaFree(b.indptr); cudaFree(b.doc); cudaFree(b.tf); cudaFree(b.norm); cudaFree(b.inv_dev); cudaFree(b.acc);
-  cudaFree(b.touched); cudaFree(b.touched_n);
+  cudaFree(b.indptr); cudaFree(b.doc); cudaFree(b.tf); cudaFree(b.norm); cudaFree(b.inv_dev);
+  cudaFree(b.tile_off); cudaFree(b.qt_dev); cudaFreeHost(b.qt_host);
   free(h->tmap_x); free(h->tmap_q); free(h->tmap_q2);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(1024, 1) exact_select_kernel(const double* __r
   __shared__ double selk[RASS_MAX_K];
   __shared__ uint32_t selr[RASS_MAX_K];
   const int tid = threadIdx.x;
-  const int q = qids ? qids[blockIdx.x] : q_fixed;
+  const int q = qids ? qids[blockIdx.x] : q_fixed + (int)blockIdx.x;
   const double* key = xkey + (size_t)blockIdx.x * xlist_entries;
   const uint32_t* row = xrow + (size_t)blockIdx.x * xlist_entries;
 
@@ -337,14 +337,26 @@ __global__ void __launch_bounds__(1024, 1) exact_select_kernel(const double* __r
         atomicAdd(&hist[b], 1);
       }
       __syncthreads();
-      if (tid == 0) {
-        int rem = s_remaining, cum = 0, b = 255;
-        for (; b > 0; --b) {
-          if (cum + hist[b] >= rem) break;
-          cum += hist[b];
+      if (tid < 32) {
+        // highest bucket whose suffix count reaches the remaining rank: lane L owns buckets [8L, 8L + 8)
+        int loc[8], sum = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { loc[i] = hist[8 * tid + i]; sum += loc[i]; }
+        int suf = sum;
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1) {
+          const int o = __shfl_down_sync(0xffffffffu, suf, m);
+          if (tid + m < 32) suf += o;
         }
-        s_bucket = b;
-        s_remaining = rem - cum;
+        const int rem = s_remaining, above = suf - sum;
+        if (above < rem && rem <= above + sum) {
+          int cum = above;
+#pragma unroll
+          for (int i = 7; i >= 0; --i) {
+            if (cum + loc[i] >= rem) { s_bucket = 8 * tid + i; s_remaining = rem - cum; break; }
+            cum += loc[i];
+          }
+        }
       }
       __syncthreads();
       const int b = s_bucket;
@@ -421,10 +433,10 @@ int launch_exact(rass_engine* h, int k, const int* qids_host, int n_q, int64_t* 
   return RASS_OK;
 }
 
-// top-k of one query's fused (score, row) lists; the score is emitted as is (bm25.cu)
-int launch_select_raw(rass_engine* h, size_t entries, int k, int q, int64_t* out_rows, float* out_scores,
-                      cudaStream_t st) {
-  exact_select_kernel<<<1, 1024, 0, st>>>(h->xlist_key, h->xlist_row, entries, (int)entries, k, nullptr, q, 1,
+// top-k of B queries' fused (score, row) lists of `entries` entries each; the score is emitted as is (bm25.cu)
+int launch_select_batch(rass_engine* h, size_t entries, int B, int k, int64_t* out_rows, float* out_scores,
+                        cudaStream_t st) {
+  exact_select_kernel<<<B, 1024, 0, st>>>(h->xlist_key, h->xlist_row, entries, (int)entries, k, nullptr, 0, 1,
                                           h->metric, h->row_base, out_rows, out_scores, nullptr);
   CUDA_TRY(h, cudaGetLastError());
   return RASS_OK;

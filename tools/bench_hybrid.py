@@ -85,9 +85,11 @@ for b in range(NQ):
     res.append(e.search_hybrid(Q[b:b + 1], [qterms[b]], 4.5, 2.0, K))
     posting_bytes += e.last_stats["bytes_streamed"] - N * D * 2
 t_single = time.perf_counter() - t0
+e.search_hybrid(Q, qterms, 4.5, 2.0, K)          # sizes the batch workspaces
 t0 = time.perf_counter()
-rows_b, scores_b = e.search_hybrid(Q, qterms, 4.5, 2.0, K)
-t_batch = time.perf_counter() - t0
+for _ in range(3):
+    rows_b, scores_b = e.search_hybrid(Q, qterms, 4.5, 2.0, K)
+t_batch = (time.perf_counter() - t0) / 3
 st = e.last_stats
 t0 = time.perf_counter()
 for b in range(NQ):
