@@ -37,6 +37,7 @@ static int64_t byte4_to_int(int b) { return b < kNumFree ? b : kNumFree + int4_t
 #define BM25_MAX_TERMS 64
 #define HYB_TILE 4096            // docs per tile: the fused clause sums of a tile live in shared memory (32 KB)
 #define HYB_THREADS 256
+#define HYB_LIST 512             // keys that survive the tile's top-k pre-filter (2 per thread)
 #define HYB_TABLE_MIN_DF 512     // terms at least this frequent get a row of per-tile posting offsets
 
 // Per-tile posting offsets of the frequent terms, built once per rass_bm25_build:
@@ -173,14 +174,15 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
   __shared__ uint32_t s_n[BM25_MAX_TERMS];
   __shared__ float s_w[BM25_MAX_TERMS];
   __shared__ __align__(16) int s_cnt[2][HYB_THREADS / 32];
-  __shared__ int s_nout, s_nmatch;
+  __shared__ uint32_t s_list[HYB_LIST];
+  __shared__ int s_nout, s_nmatch, s_ns;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, q = blockIdx.y;
   const int64_t d0 = (int64_t)tile * HYB_TILE;
   const int64_t d1 = min(d0 + HYB_TILE, a.n_docs);
   for (int i = tid; i < HYB_TILE; i += HYB_THREADS) acc[i] = 0.0;
   s_inv[tid] = a.inv ? a.inv[tid] : 0.f;
-  if (tid == 0) { s_nout = 0; s_nmatch = 0; }
+  if (tid == 0) { s_nout = 0; s_nmatch = 0; s_ns = 0; }
   __syncthreads();
 
   // ---- text clause ----
@@ -219,9 +221,6 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
       }
       __syncthreads();
     }
-    // the clause score is a float; the bool sums clause scores in double
-    for (int i = tid; i < HYB_TILE; i += HYB_THREADS) acc[i] = (double)(float)acc[i];
-    __syncthreads();
   }
 
   // ---- knn clause ----
@@ -230,7 +229,9 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
     if (r >= 0) {
       const int64_t d = r - a.row_base;
       if (d >= d0 && d < d1 && !(a.row_filter && (d >= a.filter_rows || !a.row_filter[d])))
-        acc[d - d0] += (double)__fmul_rn(a.w_knn, a.knn_scores[(size_t)q * a.k + tid]);
+        // the text clause's score is a float; the bool sums the clause scores in double (and the final cast to
+        // float below is the identity for rows without a knn contribution)
+        acc[d - d0] = (double)(float)acc[d - d0] + (double)__fmul_rn(a.w_knn, a.knn_scores[(size_t)q * a.k + tid]);
     }
   }
   __syncthreads();
@@ -259,7 +260,28 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
         xr[pos] = (uint32_t)(d0 + i * HYB_THREADS + tid);
       }
   } else {
-    // k-th largest key by most-significant-bit-first descent: prefix grows while >= k keys are >= it
+    // Pre-filter: b' = k-th largest per-thread maximum is a lower bound of the tile's k-th largest key, so only
+    // keys >= b' (normally between k and 2k of them) enter the selection.
+    uint32_t mx = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) mx = max(mx, key[i]);
+    uint32_t bp = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = bp | (1u << bit);
+      if (__syncthreads_count(mx >= cand) >= a.k) bp = cand;
+    }
+    if (mx >= bp && mx) {
+#pragma unroll
+      for (int i = 0; i < PER; ++i)
+        if (key[i] && key[i] >= bp) {
+          const int pos = atomicAdd(&s_ns, 1);
+          if (pos < HYB_LIST) s_list[pos] = key[i];
+        }
+    }
+    __syncthreads();
+    const int ns = s_ns;
+    // k-th largest key by most-significant-bit-first descent: prefix grows while >= k entries are >= it
     int buf = 0;
     auto block_count = [&](int c) {
       c = __reduce_add_sync(0xffffffffu, c);
@@ -270,13 +292,22 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
       return c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
     };
     uint32_t prefix = 0;
+    if (ns <= HYB_LIST) {
+      const uint32_t e0 = tid < ns ? s_list[tid] : 0u, e1 = tid + HYB_THREADS < ns ? s_list[tid + HYB_THREADS] : 0u;
 #pragma unroll 1
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t cand = prefix | (1u << bit);
-      int c = 0;
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = prefix | (1u << bit);
+        if (block_count((e0 >= cand) + (e1 >= cand)) >= a.k) prefix = cand;
+      }
+    } else {
+#pragma unroll 1
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = prefix | (1u << bit);
+        int c = 0;
 #pragma unroll
-      for (int i = 0; i < PER; ++i) c += key[i] >= cand;
-      if (block_count(c) >= a.k) prefix = cand;
+        for (int i = 0; i < PER; ++i) c += key[i] >= cand;
+        if (block_count(c) >= a.k) prefix = cand;
+      }
     }
     int n_gt = 0, n_eq = 0;
 #pragma unroll
