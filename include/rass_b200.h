@@ -18,6 +18,7 @@
  *                                                                               app/main.py:1574-1609
  *   rass_set_row_filter             bool.filter [term patientId / doc_type] of the hybrid query               app/main.py:1599-1604
  *   rass_merge_topk_dev             the OpenSearch coordinator's per-shard top-k merge (number_of_shards, app/main.py:357)
+ *   rass_save / rass_load           the on-disk Lucene index of the OpenSearch container (docker-compose.yml:4-17)
  *
  * Conventions: C linkage, plain pointers and sizes, no exceptions cross the boundary.  Every function returns an
  * int status (0 = ok, negative = RASS_E_*); rass_last_error(h) gives the message for the last failure on that
@@ -70,8 +71,12 @@ enum {
 
 enum {
   RASS_OPT_PATH = 1,
-  RASS_OPT_STREAM = 2    /* value = cudaStream_t to enqueue on (0 = the legacy default stream, which is what
+  RASS_OPT_STREAM = 2,   /* value = cudaStream_t to enqueue on (0 = the legacy default stream, which is what
                             torch's default stream is); -1 = back to the engine-owned stream           */
+  RASS_OPT_KNN_PREFILTER = 3  /* 1: rass_search_knn honours rass_set_row_filter as an exact PRE-filter (top-k of
+                            the rows that pass); 0 (default): the filter only applies to rass_search_hybrid and
+                            the host post-filters the k nearest, which is what OpenSearch's nmslib engine does
+                            with bool.must[knn] + filter (app/main.py:1543-1550)                          */
 };
 
 typedef struct rass_stats {
@@ -148,6 +153,13 @@ int rass_search_hybrid(rass_engine* h, const float* q_host, int B, const int32_t
 int rass_set_row_filter(rass_engine* h, const uint8_t* mask_host, int64_t n);
 
 int rass_sync(rass_engine* h);
+
+/* Snapshot / restore of the vector store (the reference relies on the OpenSearch container's own Lucene index
+ * directory, docker-compose.yml:4-17).  rass_save writes header + tombstones + the stored values; rass_load fills an
+ * EMPTY engine of the same dim/metric/corpus type through the normal append path.  Postings are rebuilt by the
+ * caller (rass_bm25_build). */
+int rass_save(rass_engine* h, const char* path);
+int rass_load(rass_engine* h, const char* path);
 
 /* Debug only (no reference counterpart): raw tensor-core dot products bf16(q_hat) . bf16(x) of B <= 64 queries
  * against every row, out_host [rows, 64] fp32.  Used by the tests to check the TMA/tcgen05 descriptors. */

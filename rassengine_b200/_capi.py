@@ -19,7 +19,7 @@ ERR_NAMES = {-1: "RASS_E_INVALID", -2: "RASS_E_OOM", -3: "RASS_E_CUDA", -4: "RAS
 METRIC_COSINE, METRIC_L2 = 0, 1
 KEEP_FP32, BF16_ONLY = 1, 2
 PATH_AUTO, PATH_STREAM, PATH_UMMA, PATH_EXACT, PATH_GEMM = 0, 1, 2, 3, 4
-OPT_PATH, OPT_STREAM = 1, 2
+OPT_PATH, OPT_STREAM, OPT_KNN_PREFILTER = 1, 2, 3
 
 
 class RassStats(C.Structure):
@@ -62,6 +62,8 @@ PROTOTYPES = {
                                      C.POINTER(RassStats)]),
     "rass_set_row_filter": (C.c_int, [_P, _P, C.c_int64]),
     "rass_sync": (C.c_int, [_P]),
+    "rass_save": (C.c_int, [_P, C.c_char_p]),
+    "rass_load": (C.c_int, [_P, C.c_char_p]),
     "rass_debug_umma_scores": (C.c_int, [_P, _P, C.c_int, _P]),
     "rass_debug_gemm_scores": (C.c_int, [_P, _P, C.c_int, _P]),
 }

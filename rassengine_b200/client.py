@@ -15,12 +15,16 @@ append-ordered, so the engine's "row ascending" tie-break equals Lucene's doc-id
 """
 from __future__ import annotations
 
+import json
+import os
+import threading
 import time
 
 import numpy as np
 
 from . import _capi as capi
 from .dsl import Plan, parse_search_body
+from .batcher import MicroBatcher
 from .engine import Engine
 from .text import TextField
 
@@ -38,10 +42,11 @@ class RequestError(ValueError):
 
 
 class _Index:
-    def __init__(self, name: str, body: dict | None, device: int):
+    def __init__(self, name: str, body: dict | None, device: int, knn_filter: str = "post"):
         self.name = name
         self.body = body or {}
         self.device = device
+        self.knn_filter = knn_filter
         props = self.body.get("mappings", {}).get("properties", {})
         self.vector_field = None
         self.dim = None
@@ -55,7 +60,11 @@ class _Index:
                     raise NotImplementedError(f"space_type {space!r}")
                 self.metric = _SPACE[space]
         self.engine: Engine | None = None
-        self.sources: list[dict | None] = []     # row -> _source
+        self.lock = threading.RLock()            # the engine takes one call at a time per handle
+        self.batcher: MicroBatcher | None = None
+        self.batch_window_s: float | None = None
+        self.sources: list[dict | None] = []     # row -> _source WITHOUT the vector (it lives on the GPU)
+        self.has_vec: list[bool] = []            # row -> the document carried a vector
         self.ids: list[str | None] = []          # row -> _id
         self.row_of: dict[str, int] = {}
         self.text = TextField()
@@ -72,13 +81,39 @@ class _Index:
         return self.engine
 
     def close(self):
+        if self.batcher is not None:
+            self.batcher.close()
+            self.batcher = None
         if self.engine is not None:
             self.engine.close()
             self.engine = None
 
+    def _knn(self, q: np.ndarray, k: int):
+        """kNN of one query; coalesced with concurrent callers when the client was given a batch window."""
+        if self.batch_window_s is None:
+            with self.lock:
+                return self.engine.search_knn(q, k)
+        if self.batcher is None:
+            def locked(Q, kk):
+                with self.lock:
+                    return self.engine.search_knn(Q, kk)
+            self.batcher = MicroBatcher(locked, max_batch=64, max_wait_s=self.batch_window_s)
+        rows, scores = self.batcher.search(q, k)
+        return rows[None, :], scores[None, :]
+
+    def _strip(self, src: dict) -> dict:
+        vf = self.vector_field or "embedding"
+        return {k: v for k, v in src.items() if k != vf} if vf in src else src
+
     # -- indexing: "_op_type": "index" = insert or overwrite by _id --------------------------------------
     def index_batch(self, docs: list[tuple[str, dict]]):
-        """docs: (_id, _source).  New ids are appended in one device call; known ids are overwritten in place."""
+        """docs: (_id, _source).  New ids are appended in one device call; known ids are overwritten in place.
+        `_source[vector_field]` may be a list of floats (what the reference sends, app/main.py:1256) or a numpy row
+        (the fast ingest path: no .tolist() / JSON detour)."""
+        with self.lock:
+            self._index_batch_locked(docs)
+
+    def _index_batch_locked(self, docs: list[tuple[str, dict]]):
         vf = self.vector_field or "embedding"
         fresh: list[tuple[str, dict]] = []
         seen: dict[str, int] = {}
@@ -108,7 +143,8 @@ class _Index:
             row = first + i
             if not has[i]:
                 eng.tombstone(row)               # no embedding: the row never matches a knn clause
-            self.sources.append(src)
+            self.sources.append(self._strip(src))
+            self.has_vec.append(bool(has[i]))
             self.ids.append(_id)
             self.row_of[_id] = row
             self.text.set_row(row, src.get(TEXT_FIELD))
@@ -124,7 +160,8 @@ class _Index:
         else:
             eng.tombstone(row)
         self._kw_remove(row, self.sources[row] or {})
-        self.sources[row] = src
+        self.sources[row] = self._strip(src)
+        self.has_vec[row] = v is not None
         self.text.set_row(row, src.get(TEXT_FIELD))
         self._kw_add(row, src)
 
@@ -162,7 +199,14 @@ class _Index:
 
     # -- search ------------------------------------------------------------------------------------------
     def _hit(self, row: int, score: float) -> dict:
-        return {"_index": self.name, "_id": self.ids[row], "_score": float(score), "_source": self.sources[row]}
+        """_source comes back whole, like OpenSearch returns it: the vector is read back from the device store
+        (float32 -> python floats, the same doubles the reference's JSON round trip yields)."""
+        src = self.sources[row]
+        if src is not None and self.has_vec[row]:
+            src = dict(src)
+            with self.lock:
+                src[self.vector_field or "embedding"] = self.engine.read_rows(row, 1)[0].tolist()
+        return {"_index": self.name, "_id": self.ids[row], "_score": float(score), "_source": src}
 
     def _passes(self, row: int, filters) -> bool:
         src = self.sources[row] or {}
@@ -171,6 +215,12 @@ class _Index:
     def search(self, plan: Plan) -> list[dict]:
         if plan.size <= 0 or self.engine is None or not self.sources:
             return []
+        if plan.kind == "knn" and not (plan.filters and self.knn_filter == "pre"):
+            return self._search(plan)         # takes the lock per engine call, so concurrent callers can coalesce
+        with self.lock:
+            return self._search(plan)
+
+    def _search(self, plan: Plan) -> list[dict]:
         eng = self.engine
         if plan.kind == "match_all":
             rows = [r for r in range(len(self.sources)) if self.sources[r] is not None][: plan.size]
@@ -184,7 +234,19 @@ class _Index:
                 raise RequestError(f"query vector length {q.shape[1]} != dimension {self.dim}")
         if plan.kind == "knn":
             k = min(max(plan.knn_k, 1), 128)
-            rows, scores = eng.search_knn(q, k)
+            if plan.filters and self.knn_filter == "pre":
+                # exact filtered kNN: the scan itself skips rows failing the term filters, so the
+                # k best rows OF THE PATIENT come back instead of whichever of the global k nearest happen to pass
+                eng.set_row_filter(self._filter_mask(plan.filters))
+                eng.set_knn_prefilter(True)
+                try:
+                    rows, scores = eng.search_knn(q, k)
+                finally:
+                    eng.set_knn_prefilter(False)
+                    eng.set_row_filter(None)
+                hits = [(int(r), float(s) * plan.knn_boost) for r, s in zip(rows[0], scores[0]) if r >= 0]
+                return [self._hit(r, s) for r, s in hits[: plan.size]]
+            rows, scores = self._knn(q, k)
             # OpenSearch applies bool.filter to the k nearest neighbours of the nmslib engine (post-filter)
             hits = [(int(r), float(s) * plan.knn_boost) for r, s in zip(rows[0], scores[0]) if r >= 0]
             hits = [(r, s) for r, s in hits if self._passes(r, plan.filters)]
@@ -223,7 +285,9 @@ class IndicesClient:
     def create(self, index: str, body: dict | None = None, **_) -> dict:
         if index in self._c._indices:
             raise RequestError(f"resource_already_exists_exception: index [{index}] already exists")
-        self._c._indices[index] = _Index(index, body, self._c.device)
+        idx = _Index(index, body, self._c.device, self._c.knn_filter)
+        idx.batch_window_s = self._c.batch_window_s
+        self._c._indices[index] = idx
         return {"acknowledged": True, "shards_acknowledged": True, "index": index}
 
     def delete(self, index: str, **_) -> dict:
@@ -240,8 +304,16 @@ class IndicesClient:
 class B200Client:
     """Drop-in for `OpenSearch(hosts=[...], ...)`; connection arguments are accepted and ignored."""
 
-    def __init__(self, hosts=None, device: int = 0, **_ignored):
+    def __init__(self, hosts=None, device: int = 0, knn_filter: str = "post", batch_window_ms: float | None = None,
+                 **_ignored):
+        """knn_filter: "post" (default) applies bool.filter to the k nearest neighbours, as OpenSearch's nmslib engine
+        does; "pre" returns the exact top-k among the rows passing the filter (device-side pass mask in the scan)."""
+        if knn_filter not in ("post", "pre"):
+            raise ValueError("knn_filter must be 'post' or 'pre'")
         self.device = device
+        self.knn_filter = knn_filter
+        # batch_window_ms: concurrent knn searches (threads) wait up to this long to share one corpus pass
+        self.batch_window_s = None if batch_window_ms is None else batch_window_ms / 1e3
         self._indices: dict[str, _Index] = {}
         self.indices = IndicesClient(self)
 
@@ -319,6 +391,52 @@ class B200Client:
         for idx in self._indices.values():
             idx.close()
         self._indices.clear()
+
+    # -- snapshot / restore (the reference relies on the OpenSearch container keeping its index on disk) ------
+    def snapshot(self, directory: str) -> list[str]:
+        """Writes every index as <name>.vec (rass_save: stored rows + tombstones) and <name>.json (mapping, _ids and
+        vector-less _sources in row order).  Returns the index names written."""
+        os.makedirs(directory, exist_ok=True)
+        names = []
+        for name, idx in self._indices.items():
+            with idx.lock:
+                meta = {"name": name, "body": idx.body, "ids": idx.ids, "sources": idx.sources,
+                        "has_vec": idx.has_vec, "n_docs": idx.n_docs, "dim": idx.dim}
+                with open(os.path.join(directory, name + ".json"), "w") as f:
+                    json.dump(meta, f)
+                if idx.engine is not None:
+                    idx.engine.save(os.path.join(directory, name + ".vec"))
+            names.append(name)
+        return names
+
+    def restore(self, directory: str) -> list[str]:
+        """Loads every <name>.json / <name>.vec pair of `directory`; rows keep their ids, so results are identical
+        to the snapshotted client's.  The postings are rebuilt from the restored text on the first hybrid query."""
+        names = []
+        for fn in sorted(os.listdir(directory)):
+            if not fn.endswith(".json"):
+                continue
+            with open(os.path.join(directory, fn)) as f:
+                meta = json.load(f)
+            name = meta["name"]
+            if name in self._indices:
+                raise RequestError(f"resource_already_exists_exception: index [{name}] already exists")
+            idx = _Index(name, meta["body"], self.device, self.knn_filter)
+            idx.batch_window_s = self.batch_window_s
+            idx.ids, idx.sources, idx.has_vec = meta["ids"], meta["sources"], meta["has_vec"]
+            idx.n_docs = meta["n_docs"]
+            idx.row_of = {i: r for r, i in enumerate(idx.ids) if i is not None}
+            vec = os.path.join(directory, name + ".vec")
+            if os.path.exists(vec):
+                idx.dim = idx.dim or meta.get("dim")
+                idx._ensure_engine(idx.dim).load(vec)
+            for row, src in enumerate(idx.sources):
+                if src is not None:
+                    idx.text.set_row(row, src.get(TEXT_FIELD))
+                    idx._kw_add(row, src)
+            self._indices[name] = idx
+            names.append(name)
+        return names
 
 
 def bulk(client: B200Client, actions, **_) -> tuple[int, list]:

@@ -114,6 +114,11 @@ struct rass_engine {
   const void* tmap_base = nullptr;
   const void* tmap_qbase = nullptr;
   uint8_t* row_filter = nullptr;    // device [row_filter_rows] 1 = row passes the bool.filter of the running query
+  bool knn_prefilter = false;       // RASS_OPT_KNN_PREFILTER: rass_search_knn scans only rows passing row_filter
+  float* sb_filtered = nullptr;     // [cap] sb with -inf for rows failing the filter (built lazily)
+  int64_t sb_filtered_cap = 0;
+  bool sb_filtered_dirty = true;
+  const float* sb_scan = nullptr;   // the offset array the running search's scans read: sb or sb_filtered
   int64_t row_filter_rows = 0;
   size_t row_filter_cap = 0;
   Bm25State bm25;

@@ -140,6 +140,7 @@ extern "C" int rass_destroy(rass_engine* h) {
   cudaFreeHost(h->q_stage_host);
   cudaFree(h->q_stage_dev);
   cudaFree(h->row_filter);
+  cudaFree(h->sb_filtered);
   for (cudaEvent_t e : h->ev_pool) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) { cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -156,6 +157,9 @@ extern "C" int rass_destroy(rass_engine* h) {
 extern "C" int rass_set_option(rass_engine* h, int opt, int64_t value) {
   CHECK_HANDLE(h);
   switch (opt) {
+    case RASS_OPT_KNN_PREFILTER:
+      h->knn_prefilter = value != 0;
+      return RASS_OK;
     case RASS_OPT_PATH:
       if (value < RASS_PATH_AUTO || value > RASS_PATH_GEMM) return rass_fail(h, RASS_E_INVALID, "bad path %lld", (long long)value);
       h->path = (int)value;
@@ -298,6 +302,7 @@ extern "C" int rass_tombstone(rass_engine* h, int64_t row) {
   cudaStream_t st = eng_stream(h);
   const uint32_t ninf = 0xff800000u;
   CUDA_TRY(h, cudaMemcpyAsync(h->sb + row, &ninf, 4, cudaMemcpyHostToDevice, st));
+  h->sb_filtered_dirty = true;
   CUDA_TRY(h, cudaStreamSynchronize(st));
   h->dead[(size_t)row] = 1;
   h->n_live--;
@@ -338,6 +343,79 @@ extern "C" int rass_read_rows(rass_engine* h, int64_t first_row, int64_t n, floa
   }
   CUDA_TRY(h, cudaStreamSynchronize(st));
   return RASS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// snapshot / restore of the vector store (checkpoint/resume; 8f N3)
+// ---------------------------------------------------------------------------------------------
+struct SnapHeader {
+  char magic[8];          // "RASSB200"
+  uint32_t version, dim, metric, flags;
+  int64_t n_rows, n_live;
+};
+
+// File = header, tombstone bytes [n_rows], stored values [n_rows, dim] fp32 (the bf16 values widened for a bf16
+// corpus).  Restore re-ingests through the normal append path, so shadow, norms and bounds are rebuilt, not trusted.
+extern "C" int rass_save(rass_engine* h, const char* path) {
+  CHECK_HANDLE(h);
+  if (!path) return rass_fail(h, RASS_E_INVALID, "null path");
+  FILE* f = fopen(path, "wb");
+  if (!f) return rass_fail(h, RASS_E_INVALID, "cannot open %s for writing", path);
+  SnapHeader hd;
+  memset(&hd, 0, sizeof(hd));
+  memcpy(hd.magic, "RASSB200", 8);
+  hd.version = 1; hd.dim = (uint32_t)h->dim; hd.metric = (uint32_t)h->metric; hd.flags = h->flags;
+  hd.n_rows = h->n_rows; hd.n_live = h->n_live;
+  bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1;
+  if (ok && h->n_rows) ok = fwrite(h->dead.data(), 1, (size_t)h->n_rows, f) == (size_t)h->n_rows;
+  const int64_t chunk = std::max<int64_t>(1, (int64_t)(h->stage_bytes / ((size_t)h->dim * 4)));
+  int rc = RASS_OK;
+  for (int64_t off = 0; ok && off < h->n_rows; off += chunk) {
+    const int64_t m = std::min<int64_t>(chunk, h->n_rows - off);
+    if ((rc = rass_read_rows(h, off, m, h->stage[0]))) break;
+    ok = fwrite(h->stage[0], (size_t)h->dim * 4, (size_t)m, f) == (size_t)m;
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (rc) return rc;
+  if (!ok) return rass_fail(h, RASS_E_INVALID, "short write to %s", path);
+  return RASS_OK;
+}
+
+extern "C" int rass_load(rass_engine* h, const char* path) {
+  CHECK_HANDLE(h);
+  if (!path) return rass_fail(h, RASS_E_INVALID, "null path");
+  if (h->n_rows != 0) return rass_fail(h, RASS_E_INVALID, "rass_load needs an empty engine");
+  FILE* f = fopen(path, "rb");
+  if (!f) return rass_fail(h, RASS_E_NOTFOUND, "cannot open %s", path);
+  SnapHeader hd;
+  int rc = RASS_OK;
+  std::vector<uint8_t> dead;
+  if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "RASSB200", 8) != 0 || hd.version != 1) {
+    rc = rass_fail(h, RASS_E_INVALID, "%s is not a rass_b200 snapshot", path);
+  } else if ((int)hd.dim != h->dim || (int)hd.metric != h->metric ||
+             ((hd.flags ^ h->flags) & RASS_BF16_ONLY)) {
+    rc = rass_fail(h, RASS_E_INVALID, "snapshot is dim %u metric %u flags %u, engine is dim %d metric %d flags %u",
+                   hd.dim, hd.metric, hd.flags, h->dim, h->metric, h->flags);
+  } else {
+    dead.resize((size_t)hd.n_rows);
+    if (hd.n_rows && fread(dead.data(), 1, dead.size(), f) != dead.size())
+      rc = rass_fail(h, RASS_E_INVALID, "%s is truncated", path);
+  }
+  const int64_t chunk = std::max<int64_t>(1, (int64_t)(h->stage_bytes / ((size_t)h->dim * 4)));
+  std::vector<float> buf;
+  if (!rc) buf.resize((size_t)std::min<int64_t>(chunk, std::max<int64_t>(hd.n_rows, 1)) * h->dim);
+  for (int64_t off = 0; !rc && off < hd.n_rows; off += chunk) {
+    const int64_t m = std::min<int64_t>(chunk, hd.n_rows - off);
+    if (fread(buf.data(), (size_t)h->dim * 4, (size_t)m, f) != (size_t)m) {
+      rc = rass_fail(h, RASS_E_INVALID, "%s is truncated", path);
+      break;
+    }
+    rc = rass_append(h, buf.data(), m, nullptr);
+  }
+  fclose(f);
+  for (int64_t r = 0; !rc && r < hd.n_rows; ++r)
+    if (dead[(size_t)r]) rc = rass_tombstone(h, r);
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -428,6 +506,35 @@ __global__ void fill_empty_kernel(int64_t* rows, float* scores, double* keys, si
   if (keys) keys[i] = 0.0;
 }
 
+// sb with the bool.filter folded in: rows failing the pass mask read -inf, exactly like tombstones
+__global__ void fold_filter_kernel(const float* __restrict__ sb, const uint8_t* __restrict__ mask, int64_t mask_rows,
+                                   int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = (i < mask_rows && mask[i]) ? sb[i] : __int_as_float(0xff800000);
+}
+
+static int select_scan_offsets(rass_engine* h, cudaStream_t st) {
+  h->sb_scan = h->sb;
+  if (!h->knn_prefilter || !h->row_filter) return RASS_OK;
+  if (h->sb_filtered_cap < h->cap) {
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    cudaFree(h->sb_filtered);
+    h->sb_filtered = nullptr;
+    CUDA_TRY(h, cudaMalloc(&h->sb_filtered, (size_t)h->cap * sizeof(float)));
+    h->sb_filtered_cap = h->cap;
+    h->sb_filtered_dirty = true;
+  }
+  if (h->sb_filtered_dirty && h->n_rows > 0) {
+    fold_filter_kernel<<<(unsigned)((h->n_rows + 255) / 256), 256, 0, st>>>(h->sb, h->row_filter, h->row_filter_rows,
+                                                                           h->n_rows, h->sb_filtered);
+    CUDA_TRY(h, cudaGetLastError());
+    h->sb_filtered_dirty = false;
+  }
+  h->sb_scan = h->sb_filtered;
+  return RASS_OK;
+}
+
 static int resolve_path(const rass_engine* h, int B) {
   if (h->path != RASS_PATH_AUTO) return h->path;
   return B <= 2 ? RASS_PATH_STREAM : (B <= 2 * RASS_GROUP_Q ? RASS_PATH_UMMA : RASS_PATH_GEMM);
@@ -466,6 +573,7 @@ int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_r
   }
   const int path = resolve_path(h, B);
   s.path = path;
+  if ((rc = select_scan_offsets(h, st))) return rc;
   // reset the per-search device counters (keeps rho_x / max_xnorm)
   CUDA_TRY(h, cudaMemsetAsync(&h->scal->flagged_n, 0, sizeof(int) * 3, st));
   CUDA_TRY(h, cudaEventRecord(h->ev[0], st));
@@ -616,6 +724,7 @@ extern "C" int rass_set_row_filter(rass_engine* h, const uint8_t* mask_host, int
     h->row_filter = nullptr;
     h->row_filter_rows = 0;
     h->row_filter_cap = 0;
+    h->sb_filtered_dirty = true;
     return RASS_OK;
   }
   if (n < 0) return rass_fail(h, RASS_E_INVALID, "bad filter length");
@@ -630,6 +739,7 @@ extern "C" int rass_set_row_filter(rass_engine* h, const uint8_t* mask_host, int
   CUDA_TRY(h, cudaMemcpyAsync(h->row_filter, mask_host, (size_t)n, cudaMemcpyHostToDevice, st));
   CUDA_TRY(h, cudaStreamSynchronize(st));
   h->row_filter_rows = n;
+  h->sb_filtered_dirty = true;
   return RASS_OK;
 }
 
@@ -645,6 +755,7 @@ extern "C" int rass_debug_gemm_scores(rass_engine* h, const float* q_host, int B
   if ((rc = stage_queries(h, q_host, B, &q_dev))) return rc;
   cudaStream_t st = eng_stream(h);
   if ((rc = launch_query_prep(h, q_dev, B, st))) return rc;
+  if ((rc = select_scan_offsets(h, st))) return rc;
   return gemm_selftest(h, B, out_host, st);
 }
 
@@ -658,5 +769,6 @@ extern "C" int rass_debug_umma_scores(rass_engine* h, const float* q_host, int B
   if ((rc = stage_queries(h, q_host, B, &q_dev))) return rc;
   cudaStream_t st = eng_stream(h);
   if ((rc = launch_query_prep(h, q_dev, B, st))) return rc;
+  if ((rc = select_scan_offsets(h, st))) return rc;
   return umma_selftest(h, 0, out_host, st);
 }

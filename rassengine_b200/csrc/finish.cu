@@ -419,7 +419,7 @@ int launch_exact(rass_engine* h, int k, const int* qids_host, int n_q, int64_t* 
     const int nq = n_q - p < RASS_EXACT_NQ ? n_q - p : RASS_EXACT_NQ;
 #define RASS_EX(BF, MM)                                                                                           \
   exact_scan_kernel<BF, MM><<<grid, RASS_WARPS_PER_CTA * 32, smem, st>>>(                                         \
-      h->x32, h->x16, h->norm64, h->sb, h->q_raw, h->q_norm, qids_dev + p, nq, h->n_rows, h->dim_pad, h->metric, \
+      h->x32, h->x16, h->norm64, h->sb_scan, h->q_raw, h->q_norm, qids_dev + p, nq, h->n_rows, h->dim_pad, h->metric, \
       h->xlist_key, h->xlist_row, entries)
     if (bf) { if (M == 1) RASS_EX(true, 1); else RASS_EX(true, 4); }
     else    { if (M == 1) RASS_EX(false, 1); else RASS_EX(false, 4); }

@@ -334,7 +334,7 @@ static int gemm_launch(rass_engine* h, int B, float* dbg_out, cudaStream_t st) {
   static const int dbg_mode = getenv("RASS_GEMM_DEBUG_MODE") ? atoi(getenv("RASS_GEMM_DEBUG_MODE")) : 0;
   const size_t smem = gemm_smem_bytes();
   CUDA_TRY(h, cudaFuncSetAttribute(scan_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  scan_gemm_kernel<<<grid, G2_THREADS, smem, st>>>(*(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q2, h->sa, h->sb,
+  scan_gemm_kernel<<<grid, G2_THREADS, smem, st>>>(*(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q2, h->sa, h->sb_scan,
                                                    h->n_rows, plan, h->dim_pad / G2_KBLK, B, h->pool_key, h->pool_row,
                                                    h->pool_thr, h->pool_cnt, h->pool_entries, n_segs, h->q_gthr,
                                                    dbg_out, dbg_mode);

@@ -147,7 +147,7 @@ static int launch_vec(rass_engine* h, int q0, int slot0, cudaStream_t st) {
   const uint4* x = reinterpret_cast<const uint4*>(h->x16);
   const float* qh = h->q_hat + (size_t)q0 * h->dim_pad;
 #define RASS_LAUNCH(V)                                                                                          \
-  scan_stream_kernel<NQ, V><<<grid, RASS_WARPS_PER_CTA * 32, 0, st>>>(x, h->sa, h->sb, qh, h->n_rows, h->pool_key, \
+  scan_stream_kernel<NQ, V><<<grid, RASS_WARPS_PER_CTA * 32, 0, st>>>(x, h->sa, h->sb_scan, qh, h->n_rows, h->pool_key, \
                                                                       h->pool_row, h->pool_thr, h->pool_cnt, slot0, \
                                                                       n_segs, h->pool_entries)
   switch (h->dim_pad / 256) {

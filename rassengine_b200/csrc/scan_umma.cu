@@ -284,7 +284,7 @@ static int umma_launch(rass_engine* h, int q0, int64_t n_rows, float* dbg_out, c
   const int grid = n_tiles < h->num_sms ? n_tiles : h->num_sms;
   const size_t smem = umma_smem_bytes(h);
   CUDA_TRY(h, cudaFuncSetAttribute(scan_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  scan_umma_kernel<<<grid, UMMA_THREADS, smem, st>>>(*(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q, h->sa, h->sb,
+  scan_umma_kernel<<<grid, UMMA_THREADS, smem, st>>>(*(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q, h->sa, h->sb_scan,
                                                      n_rows, n_tiles, h->dim_pad / UMMA_KBLK, q0, h->pool_key,
                                                      h->pool_row, h->pool_thr, h->pool_cnt, h->pool_entries,
                                                      scan_umma_segs(h), dbg_out);

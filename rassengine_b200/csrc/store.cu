@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) store_convert_kernel(const float* __restr
 int launch_store_convert(rass_engine* h, const float* src_dev, int64_t src_stride, int64_t first_row, int64_t n,
                          cudaStream_t st) {
   if (n <= 0) return RASS_OK;
+  h->sb_filtered_dirty = true;
   const bool bf16_only = (h->flags & RASS_BF16_ONLY) != 0;
   const bool in_place = !bf16_only && src_dev == h->x32 + (size_t)first_row * h->dim_pad;
   const int warps = 8;

@@ -57,11 +57,23 @@ class Engine:
     def set_stream(self, cuda_stream: int):
         self._check(self._lib.rass_set_option(self._h, capi.OPT_STREAM, cuda_stream))
 
+    def set_knn_prefilter(self, on: bool):
+        """When on, search_knn returns the exact top-k of the rows passing set_row_filter (pre-filter)."""
+        self._check(self._lib.rass_set_option(self._h, capi.OPT_KNN_PREFILTER, 1 if on else 0))
+
     def set_row_base(self, base: int):
         self._check(self._lib.rass_set_row_base(self._h, base))
 
     def sync(self):
         self._check(self._lib.rass_sync(self._h))
+
+    def save(self, path: str):
+        """Snapshot of the stored rows + tombstones (rass_save)."""
+        self._check(self._lib.rass_save(self._h, path.encode()))
+
+    def load(self, path: str):
+        """Restore into an empty engine of the same dim / metric / corpus type (rass_load)."""
+        self._check(self._lib.rass_load(self._h, path.encode()))
 
     # -- store ------------------------------------------------------------------------------------------
     def append(self, rows: np.ndarray) -> int:

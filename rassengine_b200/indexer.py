@@ -53,22 +53,29 @@ def ensure_index_exists(client, index_name: str, body: dict | None = None) -> No
         print(f"[ERROR] ensure_index_exists: {exc}")
 
 
-def store_chunks(client, index_name: str, docs: List[Dict], embeddings: np.ndarray) -> Tuple[int, list]:
+def store_chunks(client, index_name: str, docs: List[Dict], embeddings: np.ndarray, as_lists: bool = True,
+                 flush: int | None = None) -> Tuple[int, list]:
     """Vector half of store_fhir_docs_in_opensearch (app/main.py:1247-1279): L2-normalise in fp32 exactly as the
-    reference does, attach the embedding, bulk-index in flushes of BATCH_SIZE with `_id = doc_id`."""
+    reference does, attach the embedding, bulk-index in flushes of BATCH_SIZE with `_id = doc_id`.
+
+    as_lists=True sends each vector as a python list, byte for byte what the reference does (`.tolist()`,
+    app/main.py:1256).  as_lists=False is the fast ingest path: the float32 rows go to the
+    engine as numpy views -- same stored values, no per-element python objects -- and `flush` may be raised far
+    above BATCH_SIZE because a flush is one pinned async copy, not an HTTP request."""
     if not client or not docs:
         return 0, []
     ensure_index_exists(client, index_name)
     embeddings = np.asarray(embeddings, dtype=np.float32)
     norms = np.linalg.norm(embeddings, axis=1, keepdims=True)
     embeddings = embeddings / (norms + 1e-9)
+    flush = flush or BATCH_SIZE
     ok, errors, actions = 0, [], []
     for i, doc in enumerate(docs):
         d = dict(doc)
-        d["embedding"] = embeddings[i].tolist()
+        d["embedding"] = embeddings[i].tolist() if as_lists else embeddings[i]
         actions.append({"_op_type": "index", "_index": index_name, "_id": d["doc_id"], "_source": d,
                         "_routing": d.get("patientId")})
-        if len(actions) >= BATCH_SIZE:
+        if len(actions) >= flush:
             s, e = bulk(client, actions)
             ok, actions = ok + s, []
             errors.extend(e)

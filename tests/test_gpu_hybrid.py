@@ -160,6 +160,16 @@ def test_indexer_surface_end_to_end():
     assert [h[0]["doc_id"] for h in hits] == [docs[r]["doc_id"] for r in wrf]
     assert all(h[0]["patientId"] == pid for h in hits)
 
+    # knn_filter="pre": the exact top-k AMONG the patient's rows (device pass mask inside the scan)
+    pre_client = B200Client(knn_filter="pre")
+    ix.ensure_index_exists(pre_client, name, ix.index_body(dim))
+    ix.store_chunks(pre_client, name, docs, raw)
+    wr_pre, _, ws_pre = knn.knn_exact(X, q_unit, k, alive=alive)
+    hits = ix.B200Indexer(pre_client, name).semantic_search(q_emb, k=k, patient_id=pid)
+    assert [h[0]["doc_id"] for h in hits] == [docs[r]["doc_id"] for r in wr_pre[0]]
+    np.testing.assert_allclose([h[1] for h in hits], ws_pre[0], rtol=1e-5)
+    pre_client.close()
+
     # bulk "index" on an existing _id overwrites in place (same row, new vector and text)
     from rassengine_b200.client import bulk
     new = dict(docs[int(want_rows[0][0])])

@@ -232,3 +232,33 @@ def test_merge_topk_matches_single_shard():
     _check(out_r.cpu().numpy(), out_s.cpu().numpy(), want_rows, want_scores)
     for e in engines:
         e.close()
+
+
+@pytest.mark.parametrize("path", ["stream", "umma", "gemm", "exact"])
+def test_prefiltered_knn_matches_oracle_alive_mask(path):
+    """bool.must[knn] + filter[term patientId] as an exact PRE-filter -- top-k of the rows that pass,
+    ids identical to the oracle restricted to those rows; includes a filter that leaves fewer than k rows."""
+    X = synth.embeddings(30000, 1024, 31)
+    Q = synth.embeddings(5, 1024, 32)
+    rng = np.random.default_rng(33)
+    patient = rng.integers(0, 40, size=X.shape[0])
+    with _engine(dim=1024) as e:
+        e.set_path(_paths()[path])
+        e.append(X)
+        e.tombstone(17)
+        e.set_knn_prefilter(True)
+        for mask in (patient == 3, patient < 20, np.arange(X.shape[0]) < 4):
+            alive = mask.copy()
+            alive[17] = False
+            want_rows, _, want_scores = knn.knn_exact(X, Q, 10, alive=alive)
+            e.set_row_filter(mask)
+            rows, scores = e.search_knn(Q, 10)
+            kk = want_rows.shape[1]
+            _check(rows[:, :kk], scores[:, :kk], want_rows, want_scores)
+            assert (rows[:, kk:] == -1).all()
+        e.set_row_filter(None)              # no filter: back to the whole corpus
+        alive = np.ones(X.shape[0], dtype=bool)
+        alive[17] = False
+        want_rows, _, want_scores = knn.knn_exact(X, Q, 10, alive=alive)
+        rows, scores = e.search_knn(Q, 10)
+        _check(rows, scores, want_rows, want_scores)
