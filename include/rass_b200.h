@@ -16,6 +16,9 @@
  *                                   mapping app/main.py:555-556)
  *   rass_search_hybrid              client.search(body={"query":{"bool":{"should":[multi_match, multi_match, knn]}}})
  *                                                                               app/main.py:1574-1609
+ *   rass_search_hybrid_weighted,    the same query with "fuzziness": "AUTO" on the text clause (FuzzyQuery rewrite)
+ *   rass_text_set_vocab,                                                        app/main.py:1577-1585
+ *   rass_fuzzy_expand
  *   rass_set_row_filter             bool.filter [term patientId / doc_type] of the hybrid query               app/main.py:1599-1604
  *   rass_merge_topk_dev             the OpenSearch coordinator's per-shard top-k merge (number_of_shards, app/main.py:357)
  *   rass_save / rass_load           the on-disk Lucene index of the OpenSearch container (docker-compose.yml:4-17)
@@ -147,6 +150,23 @@ int rass_bm25_build(rass_engine* h, const int64_t* indptr, const int32_t* doc, c
 int rass_search_hybrid(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr,
                        const int32_t* qterms, float w_text, float w_knn, int k,
                        int64_t* out_rows, float* out_scores, rass_stats* stats);
+
+/* Same with caller-supplied per-term weights qweights[nnz of qterms] = float(clause boost * field boost * term boost)
+ * * idf instead of w_text * idf(term): the boosted TermQuerys a `fuzziness: AUTO` token rewrites to
+ * (app/main.py:1577-1585) carry a similarity boost and blended statistics, which the host computes from
+ * rass_fuzzy_expand. */
+int rass_search_hybrid_weighted(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr,
+                                const int32_t* qterms, const float* qweights, float w_knn, int k,
+                                int64_t* out_rows, float* out_scores, rass_stats* stats);
+
+/* The term dictionary of the text field, terms back to back in blob, term t = blob[offsets[t] .. offsets[t+1])
+ * (ASCII: the analyzer emits [a-z0-9]+).  Needed only for rass_fuzzy_expand. */
+int rass_text_set_vocab(rass_engine* h, const char* blob, const int64_t* offsets, int64_t V);
+/* Lucene FuzzyQuery term enumeration on the device: every dictionary term within max_edits (0..2) of the token under
+ * the optimal-string-alignment distance (an adjacent swap is one edit).  *out_n = number of matches; the first
+ * min(*out_n, max_out) (term id, edits) pairs are written, in no particular order. */
+int rass_fuzzy_expand(rass_engine* h, const char* token, int token_len, int max_edits, int64_t max_out,
+                      int32_t* out_terms, int32_t* out_edits, int64_t* out_n);
 
 /* bool.filter of the following rass_search_hybrid calls (app/main.py:1599-1604) as a per-row pass mask:
  * mask_host[n] bytes, 1 = the row satisfies the filter; rows >= n fail.  NULL clears the filter. */

@@ -23,9 +23,10 @@ from .bm25 import BM25Index
 
 
 def hybrid(index: BM25Index, qterms, knn_rows: np.ndarray, knn_score32: np.ndarray,
-           w_text: float, w_knn: float, k: int, alive: np.ndarray | None = None):
-    """Returns rows[int64 <=k], score32[<=k]."""
-    text = index.score(qterms, boost=w_text)               # float32 dense
+           w_text: float, w_knn: float, k: int, alive: np.ndarray | None = None, text32: np.ndarray | None = None):
+    """Returns rows[int64 <=k], score32[<=k].  text32: the text clause's dense float32 score when it is not the plain
+    `or` of qterms (the fuzzy rewrite of oracle/fuzzy.py)."""
+    text = index.score(qterms, boost=w_text) if text32 is None else np.asarray(text32, dtype=np.float32)
     fused = text.astype(np.float64)
     matched = text > 0
     contrib = (np.float32(w_knn) * np.asarray(knn_score32, dtype=np.float32)).astype(np.float32)

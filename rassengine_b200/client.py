@@ -195,6 +195,7 @@ class _Index:
         if self.text.dirty and self.engine is not None:
             indptr, doc, tf, doclen = self.text.postings(len(self.sources))
             self.engine.bm25_build(indptr, doc, tf, doclen)
+            self.engine.set_vocab(self.text.terms_in_id_order())
             self.text.dirty = False
 
     # -- search ------------------------------------------------------------------------------------------
@@ -253,14 +254,18 @@ class _Index:
             return [self._hit(r, s) for r, s in hits[: plan.size]]
         # hybrid: bool.should boosted sum
         k = min(max(plan.size, 1), 128)
-        w_text, qterms = 0.0, None
+        w_text, qterms, qweights = 0.0, None, None
         for clause in plan.text:
             fb = dict(clause.fields).get(TEXT_FIELD)
             if fb is None:
                 continue     # keyword-field clause: a whole-question string never equals a keyword value -> no match
             self._sync_text()
-            qterms = [self.text.query_terms(clause.query)]
             w_text = float(np.float32(clause.boost) * np.float32(fb))
+            if clause.fuzziness == "AUTO":
+                ids, ws = self.text.fuzzy_weighted_terms(clause.query, w_text, eng.fuzzy_expand)
+                qterms, qweights = [ids], [ws]
+            else:
+                qterms = [self.text.query_terms(clause.query)]
         if q is not None and min(max(plan.knn_k, 1), 128) != k:
             raise NotImplementedError("knn k different from size in a hybrid query")
         if q is None and qterms is None:
@@ -268,7 +273,7 @@ class _Index:
         # bool.filter: only rows that satisfy every term filter may score (device-side pass mask)
         eng.set_row_filter(self._filter_mask(plan.filters) if plan.filters else None)
         try:
-            rows, scores = eng.search_hybrid(q, qterms, w_text, plan.knn_boost, k)
+            rows, scores = eng.search_hybrid(q, qterms, w_text, plan.knn_boost, k, qweights=qweights)
         finally:
             if plan.filters:
                 eng.set_row_filter(None)

@@ -34,7 +34,7 @@ static const int kNumFree = 24;  // 255 - longToInt4(Integer.MAX_VALUE)
 static uint8_t int_to_byte4(uint32_t i) { return (uint8_t)(i < (uint32_t)kNumFree ? i : kNumFree + long_to_int4((int64_t)i - kNumFree)); }
 static int64_t byte4_to_int(int b) { return b < kNumFree ? b : kNumFree + int4_to_long(b - kNumFree); }
 
-#define BM25_MAX_TERMS 64
+#define BM25_MAX_TERMS 1024      // term queries per query string: 12 tokens x <= 50 fuzzy expansions and then some
 #define HYB_TILE 4096            // docs per tile: the fused clause sums of a tile live in shared memory (32 KB)
 #define HYB_THREADS 256
 #define HYB_LIST 512             // keys that survive the tile's top-k pre-filter (2 per thread)
@@ -170,9 +170,9 @@ struct HybridArgs {
 __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_constant__ HybridArgs a) {
   __shared__ double acc[HYB_TILE];
   __shared__ float s_inv[256];
-  __shared__ int64_t s_lo[BM25_MAX_TERMS];
-  __shared__ uint32_t s_n[BM25_MAX_TERMS];
-  __shared__ float s_w[BM25_MAX_TERMS];
+  __shared__ int64_t s_lo[HYB_THREADS];
+  __shared__ uint32_t s_n[HYB_THREADS];
+  __shared__ float s_w[HYB_THREADS];
   __shared__ __align__(16) int s_cnt[2][HYB_THREADS / 32];
   __shared__ uint32_t s_list[HYB_LIST];
   __shared__ int s_nout, s_nmatch, s_ns;
@@ -187,39 +187,44 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
 
   // ---- text clause ----
   if (a.qt_indptr) {
-    const int j0 = a.qt_indptr[q], nt = a.qt_indptr[q + 1] - j0;
-    // posting range of every term inside this tile, fetched by one thread per term (one latency for all terms)
-    if (tid < nt) {
-      const int j = j0 + tid;
-      const int row = a.t_row[j];
-      uint32_t pa = 0, pb = a.t_len[j];
-      if (row >= 0) {
-        if (tile < a.table_tiles) {
-          const uint32_t* off = a.tile_off + (size_t)row * (a.table_tiles + 1) + tile;
-          pa = off[0];
-          pb = off[1];
-        } else {
-          pb = 0;      // rows appended after rass_bm25_build carry no postings
+    const int j_begin = a.qt_indptr[q], j_end = a.qt_indptr[q + 1];
+    for (int j0 = j_begin; j0 < j_end; j0 += HYB_THREADS) {
+      const int nt = min(HYB_THREADS, j_end - j0);
+      // posting range of every term inside this tile, fetched by one thread per term (one latency for all terms)
+      if (tid < nt) {
+        const int j = j0 + tid;
+        const int row = a.t_row[j];
+        uint32_t pa = 0, pb = a.t_len[j];
+        if (row >= 0) {
+          if (tile < a.table_tiles) {
+            const uint32_t* off = a.tile_off + (size_t)row * (a.table_tiles + 1) + tile;
+            pa = off[0];
+            pb = off[1];
+          } else {
+            pb = 0;      // rows appended after rass_bm25_build carry no postings
+          }
         }
-      }
-      s_lo[tid] = a.t_lo[j] + pa;
-      s_n[tid] = pb - pa;
-      s_w[tid] = a.t_w[j];
-    }
-    __syncthreads();
-    for (int j = 0; j < nt; ++j) {
-      const int64_t lo = s_lo[j];
-      const uint32_t n = s_n[j];
-      const float w = s_w[j];
-      for (uint32_t p = tid; p < n; p += HYB_THREADS) {
-        const int64_t d = (int64_t)__ldg(a.doc + lo + p);
-        if (d < d0 || d >= d1) continue;                                             // rare terms scan their whole list
-        if (a.row_filter && (d >= a.filter_rows || !a.row_filter[d])) continue;       // bool.filter
-        const float x = __fmul_rn((float)__ldg(a.tf + lo + p), s_inv[a.norm[d]]);
-        const float s = __fsub_rn(w, __fdiv_rn(w, __fadd_rn(1.0f, x)));
-        if (s > 0.f) acc[d - d0] += (double)s;
+        s_lo[tid] = a.t_lo[j] + pa;
+        s_n[tid] = pb - pa;
+        s_w[tid] = a.t_w[j];
       }
       __syncthreads();
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t n = s_n[j];
+        if (n == 0) continue;                 // uniform: nothing of this term in the tile, no barrier needed
+        const int64_t lo = s_lo[j];
+        const float w = s_w[j];
+        for (uint32_t p = tid; p < n; p += HYB_THREADS) {
+          const int64_t d = (int64_t)__ldg(a.doc + lo + p);
+          if (d < d0 || d >= d1) continue;                                             // rare terms scan their whole list
+          if (a.row_filter && (d >= a.filter_rows || !a.row_filter[d])) continue;       // bool.filter
+          const float x = __fmul_rn((float)__ldg(a.tf + lo + p), s_inv[a.norm[d]]);
+          const float s = __fsub_rn(w, __fdiv_rn(w, __fadd_rn(1.0f, x)));
+          if (s > 0.f) acc[d - d0] += (double)s;
+        }
+        __syncthreads();
+      }
+      __syncthreads();                        // the next chunk overwrites s_lo / s_n / s_w
     }
   }
 
@@ -366,9 +371,11 @@ static int ensure_hybrid_workspace(rass_engine* h, size_t n_terms_cap, int B) {
   return RASS_OK;
 }
 
-extern "C" int rass_search_hybrid(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr,
-                                  const int32_t* qterms, float w_text, float w_knn, int k, int64_t* out_rows,
-                                  float* out_scores, rass_stats* stats) {
+// qweights == null: weight of a term = float(w_text) * idf(term); otherwise the caller's per-term weights
+// (fuzzy expansions carry their own boost and blended idf)
+static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr, const int32_t* qterms,
+                       const float* qweights, float w_text, float w_knn, int k, int64_t* out_rows, float* out_scores,
+                       rass_stats* stats) {
   if (!h) return RASS_E_INVALID;
   cudaSetDevice(h->device);
   if (B < 1 || !out_rows || !out_scores) return rass_fail(h, RASS_E_INVALID, "bad arguments");
@@ -416,7 +423,7 @@ extern "C" int rass_search_hybrid(rass_engine* h, const float* q_host, int B, co
         t_lo[n_terms] = lo;
         t_len[n_terms] = (uint32_t)len;
         volatile float w = bo * b.idf_host[(size_t)t];
-        t_w[n_terms] = w;
+        t_w[n_terms] = qweights ? qweights[j] : w;
         t_row[n_terms] = b.table_row_host[(size_t)t];
         s.bytes_streamed += len * 6;
         ++n_terms;
@@ -479,5 +486,114 @@ extern "C" int rass_search_hybrid(rass_engine* h, const float* q_host, int B, co
   s.finish_ms += ms;
   s.total_ms += ms;
   if (stats) *stats = s;
+  return RASS_OK;
+}
+
+extern "C" int rass_search_hybrid(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr,
+                                  const int32_t* qterms, float w_text, float w_knn, int k, int64_t* out_rows,
+                                  float* out_scores, rass_stats* stats) {
+  return hybrid_core(h, q_host, B, qterm_indptr, qterms, nullptr, w_text, w_knn, k, out_rows, out_scores, stats);
+}
+
+extern "C" int rass_search_hybrid_weighted(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr,
+                                           const int32_t* qterms, const float* qweights, float w_knn, int k,
+                                           int64_t* out_rows, float* out_scores, rass_stats* stats) {
+  if (h && qterm_indptr && !qweights) return rass_fail(h, RASS_E_INVALID, "null weights");
+  return hybrid_core(h, q_host, B, qterm_indptr, qterms, qweights, 0.f, w_knn, k, out_rows, out_scores, stats);
+}
+
+// ---- fuzziness: AUTO -- edit-distance scan of the term dictionary -------------------------------------------
+#define FUZZY_MAX_TOKEN 64
+
+struct FuzzyToken {
+  int len;
+  unsigned char c[FUZZY_MAX_TOKEN];
+};
+
+// One thread per dictionary term: optimal-string-alignment distance (insert / delete / substitute / adjacent swap)
+// to the query token, cut off at max_edits; matches are appended to (out_terms, out_edits) in no particular order.
+__global__ void __launch_bounds__(256) fuzzy_scan_kernel(const unsigned char* __restrict__ blob,
+                                                         const int64_t* __restrict__ off, int64_t V,
+                                                         const __grid_constant__ FuzzyToken tok, int max_edits,
+                                                         int32_t* __restrict__ out_terms,
+                                                         int32_t* __restrict__ out_edits, int* __restrict__ out_n) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= V) return;
+  const int64_t o = off[t];
+  const int lt = (int)(off[t + 1] - o), m = tok.len;
+  if (lt == 0 || abs(lt - m) > max_edits) return;
+  const unsigned char* term = blob + o;
+  // rows of the DP over the token (columns 0..m); row i = prefix of the term of length i
+  unsigned char prev2[FUZZY_MAX_TOKEN + 1], prev[FUZZY_MAX_TOKEN + 1], cur[FUZZY_MAX_TOKEN + 1];
+  for (int j = 0; j <= m; ++j) prev[j] = (unsigned char)j;
+  for (int i = 1; i <= lt; ++i) {
+    const unsigned char ci = term[i - 1];
+    cur[0] = (unsigned char)min(i, 255);
+    int row_min = cur[0];
+    for (int j = 1; j <= m; ++j) {
+      const unsigned char cj = tok.c[j - 1];
+      int v = min(min(prev[j] + 1, cur[j - 1] + 1), prev[j - 1] + (ci != cj));
+      if (i > 1 && j > 1 && ci == tok.c[j - 2] && term[i - 2] == cj) v = min(v, prev2[j - 2] + 1);
+      cur[j] = (unsigned char)min(v, 255);
+      row_min = min(row_min, v);
+    }
+    if (row_min > max_edits) return;      // the distance can only grow from here
+    for (int j = 0; j <= m; ++j) { prev2[j] = prev[j]; prev[j] = cur[j]; }
+  }
+  const int ed = prev[m];
+  if (ed > max_edits) return;
+  const int pos = atomicAdd(out_n, 1);
+  out_terms[pos] = (int32_t)t;
+  out_edits[pos] = ed;
+}
+
+extern "C" int rass_text_set_vocab(rass_engine* h, const char* blob, const int64_t* offsets, int64_t V) {
+  if (!h) return RASS_E_INVALID;
+  cudaSetDevice(h->device);
+  if (V < 0 || !offsets || (offsets[V] > 0 && !blob)) return rass_fail(h, RASS_E_INVALID, "bad vocabulary");
+  Bm25State& b = h->bm25;
+  CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+  int rc;
+  if ((rc = upload(h, &b.vocab_blob, reinterpret_cast<const unsigned char*>(blob), (size_t)offsets[V]))) return rc;
+  if ((rc = upload(h, &b.vocab_off, offsets, (size_t)V + 1))) return rc;
+  cudaFree(b.fz_terms); b.fz_terms = nullptr;
+  cudaFree(b.fz_edits); b.fz_edits = nullptr;
+  CUDA_TRY(h, cudaMalloc(&b.fz_terms, std::max<size_t>((size_t)V, 1) * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc(&b.fz_edits, std::max<size_t>((size_t)V, 1) * sizeof(int32_t)));
+  if (!b.fz_n) CUDA_TRY(h, cudaMalloc(&b.fz_n, sizeof(int)));
+  b.vocab_V = V;
+  return RASS_OK;
+}
+
+extern "C" int rass_fuzzy_expand(rass_engine* h, const char* token, int token_len, int max_edits, int64_t max_out,
+                                 int32_t* out_terms, int32_t* out_edits, int64_t* out_n) {
+  if (!h) return RASS_E_INVALID;
+  cudaSetDevice(h->device);
+  Bm25State& b = h->bm25;
+  if (!token || token_len < 1 || max_edits < 0 || max_edits > 2 || !out_n || (max_out > 0 && (!out_terms || !out_edits)))
+    return rass_fail(h, RASS_E_INVALID, "bad arguments");
+  if (!b.vocab_off) return rass_fail(h, RASS_E_INVALID, "rass_fuzzy_expand before rass_text_set_vocab");
+  if (token_len > FUZZY_MAX_TOKEN) return rass_fail(h, RASS_E_INVALID, "token longer than %d bytes", FUZZY_MAX_TOKEN);
+  *out_n = 0;
+  if (b.vocab_V == 0) return RASS_OK;
+  FuzzyToken tok;
+  memset(&tok, 0, sizeof(tok));
+  tok.len = token_len;
+  memcpy(tok.c, token, (size_t)token_len);
+  cudaStream_t st = eng_stream(h);
+  CUDA_TRY(h, cudaMemsetAsync(b.fz_n, 0, sizeof(int), st));
+  fuzzy_scan_kernel<<<(unsigned)((b.vocab_V + 255) / 256), 256, 0, st>>>(b.vocab_blob, b.vocab_off, b.vocab_V, tok,
+                                                                        max_edits, b.fz_terms, b.fz_edits, b.fz_n);
+  CUDA_TRY(h, cudaGetLastError());
+  int n = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(&n, b.fz_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  *out_n = n;
+  const int64_t m = std::min<int64_t>(n, max_out);
+  if (m > 0) {
+    CUDA_TRY(h, cudaMemcpyAsync(out_terms, b.fz_terms, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(out_edits, b.fz_edits, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+  }
   return RASS_OK;
 }

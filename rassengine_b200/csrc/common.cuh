@@ -34,6 +34,12 @@ struct Bm25State {
   unsigned char* qt_host = nullptr;      // pinned staging of the per-call query-term arrays
   unsigned char* qt_dev = nullptr;
   size_t qt_cap = 0, qt_q_cap = 0, qt_bytes = 0;
+  unsigned char* vocab_blob = nullptr;   // device: the term dictionary, terms back to back (fuzziness: AUTO)
+  int64_t* vocab_off = nullptr;          // device [vocab_V + 1]
+  int64_t vocab_V = 0;
+  int32_t* fz_terms = nullptr;           // device [vocab_V] matches of the running fuzzy scan
+  int32_t* fz_edits = nullptr;
+  int* fz_n = nullptr;
   float avgdl = 0.f;
   int64_t doc_count = 0;
   std::vector<int64_t> indptr_host;

@@ -20,6 +20,7 @@ class TextClause:
     query: str
     fields: list[tuple[str, float]]      # (field name, field boost)
     boost: float = 1.0
+    fuzziness: str | None = None         # "AUTO" on the reference's text_fields clause (app/main.py:1583)
 
 
 @dataclass
@@ -105,8 +106,12 @@ def parse_search_body(body: dict) -> Plan:
             m = c["multi_match"]
             if m.get("type", "best_fields") != "best_fields" or m.get("operator", "or") != "or":
                 raise NotImplementedError("multi_match type/operator outside best_fields/or")
+            fz = m.get("fuzziness")
+            if fz is not None and str(fz).upper() not in ("AUTO", "0"):
+                raise NotImplementedError(f"fuzziness {fz!r} (the reference only sends AUTO)")
             plan.text.append(TextClause(str(m.get("query", "")), [_parse_field(f) for f in m.get("fields", [])],
-                                        float(m.get("boost", 1.0))))
+                                        float(m.get("boost", 1.0)),
+                                        "AUTO" if fz is not None and str(fz).upper() == "AUTO" else None))
         else:
             raise NotImplementedError(f"unsupported should clause: {list(c)}")
     return plan

@@ -160,8 +160,29 @@ class Engine:
         m = np.ascontiguousarray(mask, dtype=np.uint8)
         self._check(self._lib.rass_set_row_filter(self._h, _ptr(m), m.size))
 
-    def search_hybrid(self, q, qterms, w_text: float, w_knn: float, k: int):
-        """q: [B, dim] fp32 or None (text only); qterms: list of B term-id lists or None (vector only)."""
+    def set_vocab(self, terms: list[str]):
+        """The text field's term dictionary in term-id order (needed by fuzzy_expand)."""
+        enc = [t.encode("ascii", "replace") for t in terms]
+        off = np.zeros(len(enc) + 1, dtype=np.int64)
+        if enc:
+            off[1:] = np.cumsum([len(e) for e in enc])
+        self._check(self._lib.rass_text_set_vocab(self._h, b"".join(enc), _ptr(off), len(enc)))
+        self._vocab_size = len(enc)
+
+    def fuzzy_expand(self, token: str, max_edits: int):
+        """Dictionary terms within max_edits (optimal string alignment) of the token: (term ids, edits), unordered."""
+        n_cap = max(getattr(self, "_vocab_size", 0), 1)
+        terms = np.empty(n_cap, dtype=np.int32)
+        edits = np.empty(n_cap, dtype=np.int32)
+        n = C.c_int64(0)
+        tok = token.encode("ascii", "replace")
+        self._check(self._lib.rass_fuzzy_expand(self._h, tok, len(tok), max_edits, n_cap, _ptr(terms), _ptr(edits),
+                                                C.byref(n)))
+        return terms[: n.value].copy(), edits[: n.value].copy()
+
+    def search_hybrid(self, q, qterms, w_text: float, w_knn: float, k: int, qweights=None):
+        """q: [B, dim] fp32 or None (text only); qterms: list of B term-id lists or None (vector only); qweights:
+        optional list of B float32 lists, the weight of every term occurrence (replaces w_text * idf)."""
         if q is not None:
             q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
             B = q.shape[0]
@@ -178,6 +199,16 @@ class Engine:
         rows = np.empty((B, k), dtype=np.int64)
         scores = np.empty((B, k), dtype=np.float32)
         st = RassStats()
+        if qweights is not None and qterms is not None:
+            w = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float32) for x in qweights])
+                                     if indptr[-1] else np.zeros(1, dtype=np.float32), dtype=np.float32)
+            if w.size != max(int(indptr[-1]), 1):
+                raise ValueError("qweights must hold one weight per query term")
+            self._check(self._lib.rass_search_hybrid_weighted(self._h, _ptr(q) if q is not None else None, B,
+                                                              _ptr(indptr), _ptr(terms), _ptr(w), w_knn, k,
+                                                              _ptr(rows), _ptr(scores), C.byref(st)))
+            self.last_stats = st.as_dict()
+            return rows, scores
         self._check(self._lib.rass_search_hybrid(self._h, _ptr(q) if q is not None else None, B,
                                                  _ptr(indptr) if indptr is not None else None,
                                                  _ptr(terms) if terms is not None else None,

@@ -26,6 +26,8 @@ class TextField:
         self.vocab: dict[str, int] = {}
         self.row_terms: dict[int, np.ndarray] = {}   # row -> int32 term ids (with repeats)
         self.dirty = True
+        self.df = np.zeros(0, dtype=np.int64)        # document frequency per term, as of the last postings()
+        self.doc_count = 0                           # documents with at least one token, as of the last postings()
 
     def set_row(self, row: int, text: str | None):
         toks = analyze(text) if text else []
@@ -53,6 +55,7 @@ class TextField:
         V = len(self.vocab)
         doclen = np.zeros(n_rows, dtype=np.uint32)
         if not self.row_terms:
+            self.df, self.doc_count = np.zeros(V, dtype=np.int64), 0
             return np.zeros(V + 1, dtype=np.int64), np.zeros(0, np.int32), np.zeros(0, np.uint16), doclen
         rows = np.fromiter(self.row_terms.keys(), dtype=np.int64, count=len(self.row_terms))
         lens = np.fromiter((a.size for a in self.row_terms.values()), dtype=np.int64, count=rows.size)
@@ -60,7 +63,57 @@ class TextField:
         terms = np.concatenate(list(self.row_terms.values())).astype(np.int64)
         V = max(V, int(terms.max()) + 1)
         docs = np.repeat(rows, lens)
-        return csr_from_pairs(terms, docs, V, n_rows) + (doclen,)
+        indptr, d_of, tf = csr_from_pairs(terms, docs, V, n_rows)
+        self.df, self.doc_count = np.diff(indptr), int(np.count_nonzero(doclen))
+        return indptr, d_of, tf, doclen
+
+    def terms_in_id_order(self) -> list[str]:
+        out = [""] * len(self.vocab)
+        for t, i in self.vocab.items():
+            out[i] = t
+        return out
+
+    @staticmethod
+    def auto_max_edits(n_chars: int) -> int:
+        """fuzziness AUTO = AUTO:3,6: 0 edits below 3 characters, 1 for 3..5, 2 from 6 on."""
+        return 0 if n_chars <= 2 else (1 if n_chars <= 5 else 2)
+
+    def fuzzy_weighted_terms(self, text: str, boost: float, expand, max_expansions: int = 50):
+        """The boosted term queries `multi_match(..., fuzziness: AUTO)` rewrites a query string to (Lucene FuzzyQuery +
+        TopTermsBlendedFreqScoringRewrite, restated in oracle/fuzzy.py): for every token the <= 50 best dictionary
+        terms by (similarity boost desc, term asc), scored with the largest document frequency among them.
+        expand(token, max_edits) -> (term ids, edits) is the device dictionary scan.  Returns (term ids, float32
+        weights = float(boost * term boost) * idf)."""
+        import math
+        terms_by_id = None
+        ids: list[int] = []
+        ws: list[np.float32] = []
+        bo = np.float32(boost)
+        for tok in analyze(text):
+            me = self.auto_max_edits(len(tok))
+            if me == 0 or len(tok) > 64:
+                t = self.vocab.get(tok, -1)
+                cand = [(t, 0)] if t >= 0 else []
+            else:
+                tid, ed = expand(tok, me)
+                cand = list(zip(tid.tolist(), ed.tolist()))
+            cand = [(t, e) for t, e in cand if t < self.df.size and self.df[t] > 0]
+            if not cand:
+                continue
+            if terms_by_id is None:
+                terms_by_id = self.terms_in_id_order()
+            scored = []
+            for t, e in cand:
+                b = np.float32(1.0) if e == 0 else np.float32(1.0) - np.float32(e) / np.float32(min(len(terms_by_id[t]), len(tok)))
+                scored.append((t, np.float32(b)))
+            scored.sort(key=lambda x: (-float(x[1]), terms_by_id[x[0]]))
+            scored = scored[:max_expansions]
+            max_df = max(int(self.df[t]) for t, _ in scored)
+            idf = np.float32(math.log(1.0 + (self.doc_count - max_df + 0.5) / (max_df + 0.5)))
+            for t, b in scored:
+                ids.append(int(t))
+                ws.append(np.float32(np.float32(bo * b) * idf))
+        return ids, ws
 
 
 def csr_from_pairs(terms: np.ndarray, docs: np.ndarray, V: int, n_rows: int):

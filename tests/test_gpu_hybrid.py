@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle import bm25, fusion, knn, synth
+from oracle import bm25, fusion, fuzzy, knn, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -94,6 +94,56 @@ def test_hybrid_row_filter_matches_oracle_alive_mask():
 # ---------------------------------------------------------------------------------------------------------
 # the drop-in boundary: client shim + B200Indexer, driven the way main.py / embedding_gen.py drive OpenSearch
 # ---------------------------------------------------------------------------------------------------------
+WORDS = ("patient reports chest pain radiating to the left arm since yesterday evening denies fever cough nausea "
+         "history of hypertension diabetes mellitus type two metformin lisinopril aspirin daily allergic penicillin "
+         "blood pressure pulse oxygen saturation normal sinus rhythm troponin negative discharged follow up cardiology "
+         "paitent repotrs chets pian hypertention diabetis metforming asprin cardiolgy presure oxigen").split()
+
+
+def test_fuzzy_expand_matches_oracle_on_the_term_dictionary():
+    """rass_fuzzy_expand (device scan of the dictionary) against oracle/fuzzy.py: same terms, same edit counts,
+    for exact tokens, misspellings, transpositions, short tokens and tokens absent from the dictionary."""
+    vocab = sorted(set(WORDS)) + [synth.token(t) for t in range(0, 3000, 7)]
+    with _engine(dim=4) as e:
+        e.append(np.eye(4, dtype=np.float32))
+        e.set_vocab(vocab)
+        for tok in ["patient", "paitent", "chest", "chets", "pian", "to", "up", "aspirin", "metformin", "t00014",
+                    "t00700", "zzzzzzzz", "cardiology", "hypertension", "a" * 40]:
+            me = fuzzy.auto_max_edits(len(tok))
+            want = {}
+            for tid, term in enumerate(vocab):
+                if abs(len(term) - len(tok)) <= me:
+                    d = fuzzy.osa_distance(tok, term)
+                    if d <= me:
+                        want[tid] = d
+            tid, ed = e.fuzzy_expand(tok, me)
+            assert dict(zip(tid.tolist(), ed.tolist())) == want, tok
+
+
+def test_weighted_hybrid_matches_fuzzy_oracle():
+    """rass_search_hybrid_weighted with the fuzzy rewrite's (term, weight) lists: fused float32 scores bit-identical to
+    the oracle's, with and without the knn clause."""
+    idx, X, Q, _ = _text_case(n_docs=5000, vocab=1200, dim=256, nq=8)
+    vocab_terms = [synth.token(t) for t in range(idx.vocab)]
+    rng = np.random.default_rng(77)
+    k = 10
+    knn_rows, _, knn_scores = knn.knn_exact(X, Q, k)
+    with _engine(dim=256) as e:
+        e.append(X)
+        e.bm25_build(idx.indptr, idx.doc, idx.tf, idx.doclen)
+        for b in range(Q.shape[0]):
+            tokens = [synth.token(int(t)) for t in rng.integers(0, idx.vocab, size=4)]
+            ids, ws = fuzzy.weighted_terms(idx, vocab_terms, tokens, 4.5)
+            text32 = fuzzy.score(idx, ids, ws)
+            wr, wsc = fusion.hybrid(idx, None, knn_rows[b], knn_scores[b], 4.5, 2.0, k, text32=text32)
+            rows, scores = e.search_hybrid(Q[b:b + 1], [ids], 0.0, 2.0, k, qweights=[ws])
+            assert rows[0, :len(wr)].tolist() == wr.tolist()
+            np.testing.assert_allclose(scores[0, :len(wr)], wsc, rtol=2e-6, atol=0)
+            tr, ts = bm25.topk(text32, k)
+            rows, scores = e.search_hybrid(None, [ids], 0.0, 0.0, k, qweights=[ws])
+            assert rows[0].tolist() == tr.tolist() and scores[0].tolist() == ts.tolist()
+
+
 def _chunk_docs(n_docs=1500, vocab=400, dim=64):
     indptr, doc, tf, doclen = synth.text_corpus(n_docs, vocab=vocab, seed=5, median_len=40, max_len=120)
     texts = synth.docs_as_text(indptr, doc, tf, n_docs)
@@ -134,11 +184,20 @@ def test_indexer_surface_end_to_end():
     np.testing.assert_allclose([h[1] for h in hits], want_scores[0], rtol=1e-5)
     assert len(hits[0][0]["embedding"]) == dim                          # _source comes back whole
 
-    # hybrid: 4.5 * BM25(unstructuredText) + 2.0 * knn, boosted sum, no normalisation (app/main.py:1574-1598)
+    # hybrid: 4.5 * BM25(unstructuredText, fuzziness AUTO) + 2.0 * knn, boosted sum, no normalisation
+    # (app/main.py:1574-1598); the text clause is the fuzzy rewrite restated in oracle/fuzzy.py
     bm = bm25.BM25Index(indptr, doc, tf, doclen)
-    qtext = " ".join(synth.token(t) for t in (3, 17, 3, 250)) + " unknownword"
-    qterms = [3, 17, 3, 250]
-    wr, ws = fusion.hybrid(bm, qterms, want_rows[0], want_scores[0], 4.5, 2.0, k)
+    vocab_terms = [synth.token(t) for t in range(bm.vocab)]
+    qtext = " ".join(synth.token(t) for t in (3, 17, 3, 250)) + " unknownword zz"
+    qtokens = [synth.token(t) for t in (3, 17, 3, 250)] + ["unknownword", "zz"]
+
+    def fused(w_text, w_knn, alive=None):
+        ids, ws_ = fuzzy.weighted_terms(bm, vocab_terms, qtokens, w_text)
+        assert len(ids) > len(qtokens)               # the synthetic tokens do have neighbours within 2 edits
+        return fusion.hybrid(bm, None, want_rows[0], want_scores[0], w_text, w_knn, k, alive=alive,
+                             text32=fuzzy.score(bm, ids, ws_))
+
+    wr, ws = fused(4.5, 2.0)
     hits = idxr.hybrid_search(qtext, q_emb, k=k)
     assert [h[0]["doc_id"] for h in hits] == [docs[r]["doc_id"] for r in wr]
     np.testing.assert_allclose([h[1] for h in hits], ws, rtol=2e-6)
@@ -146,7 +205,7 @@ def test_indexer_surface_end_to_end():
     core = idxr.search(q_emb, qtext, top_k=k)
     assert [h["_id"] for h in core] == [docs[r]["doc_id"] for r in wr] and all("_score" in h for h in core)
     # multi-intent: same shape, boosts 1.0*3 / 1.5
-    wr3, ws3 = fusion.hybrid(bm, qterms, want_rows[0], want_scores[0], 3.0, 1.5, k)
+    wr3, ws3 = fused(3.0, 1.5)
     hits = idxr.multi_intent_search(qtext, q_emb, k=k)
     assert [h[0]["doc_id"] for h in hits] == [docs[r]["doc_id"] for r in wr3]
 
@@ -155,7 +214,7 @@ def test_indexer_surface_end_to_end():
     hits = idxr.semantic_search(q_emb, k=k, patient_id=pid)
     assert [h[0]["doc_id"] for h in hits] == [docs[r]["doc_id"] for r in want_rows[0] if docs[r]["patientId"] == pid]
     alive = np.array([d["patientId"] == pid for d in docs])
-    wrf, wsf = fusion.hybrid(bm, qterms, want_rows[0], want_scores[0], 4.5, 2.0, k, alive=alive)
+    wrf, wsf = fused(4.5, 2.0, alive=alive)
     hits = idxr.hybrid_search(qtext, q_emb, k=k, patient_id=pid)
     assert [h[0]["doc_id"] for h in hits] == [docs[r]["doc_id"] for r in wrf]
     assert all(h[0]["patientId"] == pid for h in hits)

@@ -158,3 +158,31 @@ def test_text_corpus_csr_is_consistent():
     texts = synth.docs_as_text(indptr, doc, tf, 2000)
     assert len(analyzer.analyze(texts[5])) == doclen[5]
     assert analyzer.analyze("Hello, World-2 FOO_bar") == ["hello", "world", "2", "foo", "bar"]
+
+
+def test_fuzzy_auto_restatement_known_answers():
+    """oracle/fuzzy.py: AUTO thresholds, optimal-string-alignment distances (a swap is one edit, no second edit of a
+    swapped pair), similarity boosts and the (boost desc, term asc) order of the expansion, blended idf."""
+    from oracle import bm25, fuzzy
+    assert [fuzzy.auto_max_edits(n) for n in (1, 2, 3, 5, 6, 12)] == [0, 0, 1, 1, 2, 2]
+    for a, b, d in (("abcd", "abdc", 1), ("ca", "abc", 3), ("kitten", "sitting", 3), ("", "abc", 3),
+                    ("flaw", "lawn", 2), ("paitent", "patient", 1), ("same", "same", 0)):
+        assert fuzzy.osa_distance(a, b) == d and fuzzy.osa_distance(b, a) == d
+    vocab = ["pain", "pian", "paid", "pains", "plain", "spain", "rain", "p", "pa", "panic"]
+    ex = fuzzy.expand(vocab, "pain")                      # 4 characters -> one edit
+    assert [vocab[t] for t, _, _ in ex] == ["pain", "paid", "pains", "pian", "plain", "rain", "spain"]
+    assert [e for _, e, _ in ex] == [0, 1, 1, 1, 1, 1, 1]
+    assert all(float(b) == 0.75 for _, e, b in ex if e == 1) and float(ex[0][2]) == 1.0
+    assert [vocab[t] for t, _, _ in fuzzy.expand(vocab, "pa")] == ["pa"]          # 2 characters -> exact only
+    assert fuzzy.expand(vocab, "zzzz") == []
+    assert len(fuzzy.expand([f"t{i:05d}" for i in range(2000)], "t00000")) == 50   # max_expansions
+    # blended statistics: every surviving term is scored with the idf of the most frequent one
+    docs = [[0, 1], [0], [0, 2], [1], [3]]
+    idx = bm25.BM25Index.from_token_ids(docs, 4)
+    ids, ws = fuzzy.weighted_terms(idx, ["pain", "pian", "paid", "zzzz"], ["pain"], 2.0)
+    assert ids == [0, 2, 1]                                                        # pain, then paid < pian at boost .75
+    idf = np.float32(np.log(1.0 + (5 - 3 + 0.5) / (3 + 0.5)))                      # df(pain) = 3 is the largest
+    np.testing.assert_array_equal(ws, np.array([np.float32(2.0) * idf, np.float32(1.5) * idf, np.float32(1.5) * idf],
+                                               dtype=np.float32))
+    dense = fuzzy.score(idx, ids, ws)
+    assert dense.shape == (5,) and dense[4] == 0 and (dense[:4] > 0).all()
