@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
                      const float* __restrict__ sa, const float* __restrict__ sb, int64_t n_rows, int n_tiles,
                      int k_blocks, int q_row0, float* __restrict__ pool_key, uint32_t* __restrict__ pool_row,
                      float* __restrict__ pool_thr, int* __restrict__ pool_cnt, size_t pool_entries, int n_segs,
-                     float* __restrict__ dbg_out) {
+                     uint32_t* __restrict__ gthr, float* __restrict__ dbg_out) {
   extern __shared__ unsigned char smem_dyn[];
   // 128B-swizzled tiles need 1024-byte alignment: [ Q: k_blocks * 8 KB ][ stages: UMMA_STAGES * 16 KB ][ UmmaSmem ]
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
       const int64_t row = (int64_t)tile * UMMA_ROWS + ew * 32 + lane;
       float a = 0.f, b = neg_inf<float>();
       if (row < n_rows) { a = __ldg(sa + row); b = __ldg(sb + row); }
+      // the largest pivot any CTA has published for the query this lane looks after (used after the tile)
+      const uint32_t g = lane < UMMA_NQ / 4 ? __ldcg(gthr + 4 * lane + ew) : 0u;
       mbar_wait(&ss->acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * UMMA_NQ;
@@ -187,6 +189,10 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
 
       // compaction: all 128 epilogue threads have finished this tile's appends
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      // warp ew owns queries q = ew (mod 4).  A pivot found by ANY CTA bounds what this CTA may reject as well: the
+      // certificate takes the maximum bound over segments, and this segment publishes the largest threshold it used.
+      if (g > 0x007fffffu) ss->thr[4 * lane + ew] = fmaxf(ss->thr[4 * lane + ew], unord32(g));
+      __syncwarp();
       for (int q = ew; q < UMMA_NQ; q += 4) {
         const int n = min(ss->cnt[q], RASS_UMMA_SEG);
         if (n <= UMMA_HIGH_WATER) continue;
@@ -204,7 +210,11 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
         const int kept = warp_compact<RASS_UMMA_SEG / 32>(ok, rw, RASS_UMMA_KEEP, pool_key + base, pool_row + base, pivot);
         __syncwarp();
         // everything dropped here, and every row rejected from now on, has key <= pivot
-        if (lane == 0) { ss->cnt[q] = kept; ss->thr[q] = unord32(pivot); }
+        if (lane == 0) {
+          ss->cnt[q] = kept;
+          ss->thr[q] = fmaxf(ss->thr[q], unord32(pivot));
+          atomicMax(gthr + q, pivot);
+        }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
@@ -282,12 +292,13 @@ static int umma_launch(rass_engine* h, int q0, int64_t n_rows, float* dbg_out, c
   }
   const int n_tiles = (int)((n_rows + UMMA_ROWS - 1) / UMMA_ROWS);
   const int grid = n_tiles < h->num_sms ? n_tiles : h->num_sms;
+  CUDA_TRY(h, cudaMemsetAsync(h->q_gthr + q0, 0, UMMA_NQ * sizeof(uint32_t), st));   // nothing published yet
   const size_t smem = umma_smem_bytes(h);
   CUDA_TRY(h, cudaFuncSetAttribute(scan_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   scan_umma_kernel<<<grid, UMMA_THREADS, smem, st>>>(*(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q, h->sa, h->sb_scan,
                                                      n_rows, n_tiles, h->dim_pad / UMMA_KBLK, q0, h->pool_key,
                                                      h->pool_row, h->pool_thr, h->pool_cnt, h->pool_entries,
-                                                     scan_umma_segs(h), dbg_out);
+                                                     scan_umma_segs(h), h->q_gthr + q0, dbg_out);
   CUDA_TRY(h, cudaGetLastError());
   // segments of CTAs that did not launch (fewer tiles than SMs) were cleared by the caller and read as empty
   return RASS_OK;
