@@ -76,7 +76,7 @@ def workload_name(a):
 def scan_kernel_name(B):
     if B <= 2:
         return "scan_stream_kernel (128-bit streaming GEMV + warp select)"
-    if B <= 128:
+    if B <= 64:
         return "scan_umma_kernel (TMA + tcgen05, 64 queries/pass)"
     return "scan_gemm_kernel (TMA + tcgen05 cta_group::2, 256 queries/pass)"
 
@@ -363,7 +363,7 @@ def run_ours(a):
         return
 
     peak_hbm, peak_tf, peak_src = peaks()
-    tensor_bound = B > 128
+    tensor_bound = B > 64
     if tensor_bound:
         flops_per_step = 2.0 * B * (hi - lo) * DIM
         achieved = flops_per_step / (scan_ms_avg * 1e-3) / 1e12 if scan_ms_avg else 0.0
