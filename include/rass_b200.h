@@ -143,6 +143,12 @@ int rass_bm25_build(rass_engine* h, const int64_t* indptr, const int32_t* doc, c
                     const uint32_t* doclen, int64_t V, int64_t N,
                     int64_t global_doc_count, int64_t global_sum_ttf, const int64_t* global_df);
 
+/* Several analysed fields in one CSR (structured FHIR documents share the index with the chunks, app/main.py:1223-1240):
+ * term t belongs to field term_field[t] (0 <= field < F <= 255); doclen is [F][N], the token count of the field in the
+ * row (0 = the row lacks the field).  docCount, avgdl and idf are per field, as Lucene keeps them. */
+int rass_bm25_build_fields(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
+                           const int32_t* term_field, const uint32_t* doclen, int64_t V, int64_t N, int F);
+
 /* bool.should boosted sum: S(d) = w_text * BM25(q, d) + w_knn * [d in kNN_k(q)] * knn_score(q, d), top-k by
  * (S desc, row asc) over rows matching at least one clause.  qterm_indptr[B+1] / qterms: term ids per query
  * (duplicates count twice; ids outside [0, V) are ignored).  q_host may be NULL (text-only) and qterm_indptr may
@@ -154,19 +160,25 @@ int rass_search_hybrid(rass_engine* h, const float* q_host, int B, const int32_t
 /* Same with caller-supplied per-term weights qweights[nnz of qterms] = float(clause boost * field boost * term boost)
  * * idf instead of w_text * idf(term): the boosted TermQuerys a `fuzziness: AUTO` token rewrites to
  * (app/main.py:1577-1585) carry a similarity boost and blended statistics, which the host computes from
- * rass_fuzzy_expand. */
+ * rass_fuzzy_expand.
+ *
+ * qflags (nullable) marks structure for multi-field / multi-clause queries (the reference's two multi_match clauses
+ * over 26 text and 24 keyword fields, app/main.py:1403-1456, 1576-1594): bit 0 = last term of its field group,
+ * bit 1 = last term of its clause.  A clause scores max over its field groups of the group's term sum (best_fields,
+ * tie_breaker 0; every group score is a float), the text part of S(d) is the sum over clauses (in double). */
 int rass_search_hybrid_weighted(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr,
-                                const int32_t* qterms, const float* qweights, float w_knn, int k,
-                                int64_t* out_rows, float* out_scores, rass_stats* stats);
+                                const int32_t* qterms, const float* qweights, const uint8_t* qflags, float w_knn,
+                                int k, int64_t* out_rows, float* out_scores, rass_stats* stats);
 
 /* The term dictionary of the text field, terms back to back in blob, term t = blob[offsets[t] .. offsets[t+1])
  * (ASCII: the analyzer emits [a-z0-9]+).  Needed only for rass_fuzzy_expand. */
 int rass_text_set_vocab(rass_engine* h, const char* blob, const int64_t* offsets, int64_t V);
 /* Lucene FuzzyQuery term enumeration on the device: every dictionary term within max_edits (0..2) of the token under
- * the optimal-string-alignment distance (an adjacent swap is one edit).  *out_n = number of matches; the first
+ * the optimal-string-alignment distance (an adjacent swap is one edit), among the terms [term_lo, term_hi) (one
+ * field's slice of the dictionary; term_hi < 0 = to the end).  *out_n = number of matches; the first
  * min(*out_n, max_out) (term id, edits) pairs are written, in no particular order. */
-int rass_fuzzy_expand(rass_engine* h, const char* token, int token_len, int max_edits, int64_t max_out,
-                      int32_t* out_terms, int32_t* out_edits, int64_t* out_n);
+int rass_fuzzy_expand(rass_engine* h, const char* token, int token_len, int max_edits, int64_t term_lo,
+                      int64_t term_hi, int64_t max_out, int32_t* out_terms, int32_t* out_edits, int64_t* out_n);
 
 /* bool.filter of the following rass_search_hybrid calls (app/main.py:1599-1604) as a per-row pass mask:
  * mask_host[n] bytes, 1 = the row satisfies the filter; rows >= n fail.  NULL clears the filter. */

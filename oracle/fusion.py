@@ -23,12 +23,18 @@ from .bm25 import BM25Index
 
 
 def hybrid(index: BM25Index, qterms, knn_rows: np.ndarray, knn_score32: np.ndarray,
-           w_text: float, w_knn: float, k: int, alive: np.ndarray | None = None, text32: np.ndarray | None = None):
+           w_text: float, w_knn: float, k: int, alive: np.ndarray | None = None, text32: np.ndarray | None = None,
+           text64: np.ndarray | None = None):
     """Returns rows[int64 <=k], score32[<=k].  text32: the text clause's dense float32 score when it is not the plain
-    `or` of qterms (the fuzzy rewrite of oracle/fuzzy.py)."""
-    text = index.score(qterms, boost=w_text) if text32 is None else np.asarray(text32, dtype=np.float32)
-    fused = text.astype(np.float64)
-    matched = text > 0
+    `or` of qterms (the fuzzy rewrite of oracle/fuzzy.py); text64: the double sum of several clauses' float scores
+    (oracle/multifield.py)."""
+    if text64 is not None:
+        fused = np.array(text64, dtype=np.float64)
+        matched = fused > 0
+    else:
+        text = index.score(qterms, boost=w_text) if text32 is None else np.asarray(text32, dtype=np.float32)
+        fused = text.astype(np.float64)
+        matched = text > 0
     contrib = (np.float32(w_knn) * np.asarray(knn_score32, dtype=np.float32)).astype(np.float32)
     for r, c in zip(np.asarray(knn_rows, dtype=np.int64), contrib):
         if r < 0:

@@ -26,7 +26,7 @@ from . import _capi as capi
 from .dsl import Plan, parse_search_body
 from .batcher import MicroBatcher
 from .engine import Engine
-from .text import TextField
+from .text import TextIndex
 
 TEXT_FIELD = "unstructuredText"      # the only analysed field chunk documents carry (app/main.py:1120-1130)
 FILTER_FIELDS = ("patientId", "doc_type", "resourceType", "doc_id")   # keyword fields the hot path filters on
@@ -67,7 +67,11 @@ class _Index:
         self.has_vec: list[bool] = []            # row -> the document carried a vector
         self.ids: list[str | None] = []          # row -> _id
         self.row_of: dict[str, int] = {}
-        self.text = TextField()
+        # analysed / keyword fields of the mapping (app/main.py:361-561); chunk documents only carry TEXT_FIELD
+        types = {f: spec["type"] for f, spec in props.items()
+                 if isinstance(spec, dict) and spec.get("type") in ("text", "keyword")}
+        types.setdefault(TEXT_FIELD, "text")
+        self.text = TextIndex(types)
         self.n_docs = 0
         self.kw: dict[str, dict[object, list[int]]] = {f: {} for f in FILTER_FIELDS}   # field -> value -> rows
 
@@ -147,7 +151,7 @@ class _Index:
             self.has_vec.append(bool(has[i]))
             self.ids.append(_id)
             self.row_of[_id] = row
-            self.text.set_row(row, src.get(TEXT_FIELD))
+            self.text.set_doc(row, src)
             self._kw_add(row, src)
         self.n_docs += len(fresh)
 
@@ -162,7 +166,7 @@ class _Index:
         self._kw_remove(row, self.sources[row] or {})
         self.sources[row] = self._strip(src)
         self.has_vec[row] = v is not None
-        self.text.set_row(row, src.get(TEXT_FIELD))
+        self.text.set_doc(row, src)
         self._kw_add(row, src)
 
     def _kw_add(self, row: int, src: dict):
@@ -193,8 +197,8 @@ class _Index:
 
     def _sync_text(self):
         if self.text.dirty and self.engine is not None:
-            indptr, doc, tf, doclen = self.text.postings(len(self.sources))
-            self.engine.bm25_build(indptr, doc, tf, doclen)
+            indptr, doc, tf, term_field, doclen = self.text.postings(len(self.sources))
+            self.engine.bm25_build_fields(indptr, doc, tf, term_field, doclen)
             self.engine.set_vocab(self.text.terms_in_id_order())
             self.text.dirty = False
 
@@ -254,18 +258,42 @@ class _Index:
             return [self._hit(r, s) for r, s in hits[: plan.size]]
         # hybrid: bool.should boosted sum
         k = min(max(plan.size, 1), 128)
-        w_text, qterms, qweights = 0.0, None, None
+        # text clauses: multi_match best_fields = max over the fields of the field's term sum (every declared field the
+        # index holds postings for), bool.should = sum over the clauses; term weights and structure marks go to the
+        # device as (term, weight, flag) lists (bit 0 = last term of a field group, bit 1 = last term of a clause)
+        ids, ws, flags = [], [], []
+        have_text = False
         for clause in plan.text:
-            fb = dict(clause.fields).get(TEXT_FIELD)
-            if fb is None:
-                continue     # keyword-field clause: a whole-question string never equals a keyword value -> no match
-            self._sync_text()
-            w_text = float(np.float32(clause.boost) * np.float32(fb))
-            if clause.fuzziness == "AUTO":
-                ids, ws = self.text.fuzzy_weighted_terms(clause.query, w_text, eng.fuzzy_expand)
-                qterms, qweights = [ids], [ws]
-            else:
-                qterms = [self.text.query_terms(clause.query)]
+            first_of_clause = len(ids)
+            for fname, fb in clause.fields:
+                fld = self.text.fields.get(fname)
+                if fld is None:
+                    continue     # no document carries the field: nothing can match
+                self._sync_text()
+                have_text = True
+                base = self.text.base[fname]
+                bo = float(np.float32(clause.boost) * np.float32(fb))
+                if self.text.types.get(fname) == "keyword":
+                    t_ids, t_ws = fld.exact_weighted_terms([clause.query], bo)      # the whole string is the term
+                elif clause.fuzziness == "AUTO":
+                    def expand(tok, me, base=base, n=len(fld.vocab)):
+                        t, e = eng.fuzzy_expand(tok, me, base, base + n)
+                        return t - base, e
+                    t_ids, t_ws = fld.fuzzy_weighted_terms(clause.query, bo, expand)
+                else:
+                    from .text import analyze
+                    t_ids, t_ws = fld.exact_weighted_terms(analyze(clause.query), bo)
+                if not t_ids:
+                    continue
+                ids.extend(base + t for t in t_ids)
+                ws.extend(t_ws)
+                flags.extend([0] * (len(t_ids) - 1) + [1])
+            if len(ids) > first_of_clause:
+                flags[-1] |= 2
+        qterms = [ids] if have_text else None
+        qweights = [ws] if have_text else None
+        qflags = [flags] if have_text else None
+        w_text = 0.0
         if q is not None and min(max(plan.knn_k, 1), 128) != k:
             raise NotImplementedError("knn k different from size in a hybrid query")
         if q is None and qterms is None:
@@ -273,7 +301,7 @@ class _Index:
         # bool.filter: only rows that satisfy every term filter may score (device-side pass mask)
         eng.set_row_filter(self._filter_mask(plan.filters) if plan.filters else None)
         try:
-            rows, scores = eng.search_hybrid(q, qterms, w_text, plan.knn_boost, k, qweights=qweights)
+            rows, scores = eng.search_hybrid(q, qterms, w_text, plan.knn_boost, k, qweights=qweights, qflags=qflags)
         finally:
             if plan.filters:
                 eng.set_row_filter(None)
@@ -437,7 +465,7 @@ class B200Client:
                 idx._ensure_engine(idx.dim).load(vec)
             for row, src in enumerate(idx.sources):
                 if src is not None:
-                    idx.text.set_row(row, src.get(TEXT_FIELD))
+                    idx.text.set_doc(row, src)
                     idx._kw_add(row, src)
             self._indices[name] = idx
             names.append(name)

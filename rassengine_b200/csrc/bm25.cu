@@ -68,49 +68,63 @@ static int upload(rass_engine* h, T** dst, const T* src, size_t n) {
   return RASS_OK;
 }
 
-extern "C" int rass_bm25_build(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
-                               const uint32_t* doclen, int64_t V, int64_t N, int64_t global_doc_count,
-                               int64_t global_sum_ttf, const int64_t* global_df) {
+// F analysed fields share one CSR: term t belongs to field term_field[t]; doclen is [F][N] (tokens of the field per
+// row, 0 = the row does not have the field).  Statistics (docCount, avgdl, idf) are per field, as in Lucene.
+static int bm25_build_impl(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
+                           const int32_t* term_field, const uint32_t* doclen, int64_t V, int64_t N, int F,
+                           int64_t global_doc_count, int64_t global_sum_ttf, const int64_t* global_df) {
   if (!h) return RASS_E_INVALID;
   cudaSetDevice(h->device);
-  if (V < 0 || N < 0 || !indptr || (N && !doclen)) return rass_fail(h, RASS_E_INVALID, "bad postings");
+  if (V < 0 || N < 0 || F < 1 || F > 255 || !indptr || (N && !doclen)) return rass_fail(h, RASS_E_INVALID, "bad postings");
   const int64_t nnz = indptr[V];
   if (nnz < 0 || (nnz && (!doc || !tf))) return rass_fail(h, RASS_E_INVALID, "bad postings");
   if (N > 0xfffffff0LL) return rass_fail(h, RASS_E_INVALID, "too many documents");
+  if (term_field)
+    for (int64_t t = 0; t < V; ++t)
+      if (term_field[t] < 0 || term_field[t] >= F) return rass_fail(h, RASS_E_INVALID, "term %lld: bad field", (long long)t);
   Bm25State& b = h->bm25;
-  b.V = V; b.N = N; b.nnz = nnz;
-  int64_t doc_count = 0, sum_ttf = 0;
-  std::vector<uint8_t> norm((size_t)N);
-  for (int64_t i = 0; i < N; ++i) {
-    doc_count += doclen[i] != 0;
-    sum_ttf += doclen[i];
-    norm[(size_t)i] = int_to_byte4(doclen[i]);
+  b.V = V; b.N = N; b.nnz = nnz; b.F = F;
+  std::vector<uint8_t> norm((size_t)N * F);
+  std::vector<float> inv((size_t)256 * F);
+  std::vector<int64_t> doc_count((size_t)F, 0);
+  const float k1 = 1.2f, bb = 0.75f, one = 1.0f;
+  for (int f = 0; f < F; ++f) {
+    int64_t dc = 0, sum_ttf = 0;
+    const uint32_t* dl = doclen + (size_t)f * N;
+    for (int64_t i = 0; i < N; ++i) {
+      dc += dl[i] != 0;
+      sum_ttf += dl[i];
+      norm[(size_t)f * N + i] = int_to_byte4(dl[i]);
+    }
+    if (F == 1 && global_doc_count > 0) { dc = global_doc_count; sum_ttf = global_sum_ttf; }
+    doc_count[(size_t)f] = dc;
+    const float avgdl = dc ? (float)((double)sum_ttf / (double)dc) : 0.f;
+    if (f == 0) { b.doc_count = dc; b.avgdl = avgdl; }
+    for (int i = 0; i < 256; ++i) {
+      if (!dc) { inv[(size_t)f * 256 + i] = 0.f; continue; }
+      volatile float t = bb * (float)byte4_to_int(i);   // volatile: every step rounds to float, no contraction
+      t = t / avgdl;
+      t = (one - bb) + t;
+      t = k1 * t;
+      inv[(size_t)f * 256 + i] = one / t;
+    }
   }
-  if (global_doc_count > 0) { doc_count = global_doc_count; sum_ttf = global_sum_ttf; }
-  b.doc_count = doc_count;
-  b.avgdl = doc_count ? (float)((double)sum_ttf / (double)doc_count) : 0.f;
   b.indptr_host.assign(indptr, indptr + V + 1);
   b.idf_host.resize((size_t)V);
+  b.term_field_host.assign((size_t)V, 0);
   for (int64_t t = 0; t < V; ++t) {
-    const int64_t df = global_df ? global_df[t] : indptr[t + 1] - indptr[t];
-    b.idf_host[(size_t)t] = (float)log(1.0 + ((double)doc_count - (double)df + 0.5) / ((double)df + 0.5));
-  }
-  float inv[256];
-  const float k1 = 1.2f, bb = 0.75f, one = 1.0f;
-  for (int i = 0; i < 256; ++i) {
-    if (!doc_count) { inv[i] = 0.f; continue; }
-    volatile float t = bb * (float)byte4_to_int(i);   // volatile: every step rounds to float, no contraction
-    t = t / b.avgdl;
-    t = (one - bb) + t;
-    t = k1 * t;
-    inv[i] = one / t;
+    const int f = term_field ? term_field[t] : 0;
+    b.term_field_host[(size_t)t] = (uint8_t)f;
+    const int64_t df = (F == 1 && global_df) ? global_df[t] : indptr[t + 1] - indptr[t];
+    const double dc = (double)doc_count[(size_t)f];
+    b.idf_host[(size_t)t] = (float)log(1.0 + (dc - (double)df + 0.5) / ((double)df + 0.5));
   }
   int rc;
   if ((rc = upload(h, &b.indptr, indptr, (size_t)V + 1))) return rc;
   if ((rc = upload(h, &b.doc, doc, (size_t)nnz))) return rc;
   if ((rc = upload(h, &b.tf, tf, (size_t)nnz))) return rc;
-  if ((rc = upload(h, &b.norm, norm.data(), (size_t)N))) return rc;
-  if ((rc = upload(h, &b.inv_dev, inv, (size_t)256))) return rc;
+  if ((rc = upload(h, &b.norm, norm.data(), norm.size()))) return rc;
+  if ((rc = upload(h, &b.inv_dev, inv.data(), inv.size()))) return rc;
   // per-tile posting offsets of the frequent terms (hybrid_tile_kernel jumps straight to a tile's postings)
   b.n_tiles = (int)((std::max<int64_t>(N, 1) + HYB_TILE - 1) / HYB_TILE);
   b.table_row_host.assign((size_t)V, -1);
@@ -136,6 +150,18 @@ extern "C" int rass_bm25_build(rass_engine* h, const int64_t* indptr, const int3
   return RASS_OK;
 }
 
+extern "C" int rass_bm25_build(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
+                               const uint32_t* doclen, int64_t V, int64_t N, int64_t global_doc_count,
+                               int64_t global_sum_ttf, const int64_t* global_df) {
+  return bm25_build_impl(h, indptr, doc, tf, nullptr, doclen, V, N, 1, global_doc_count, global_sum_ttf, global_df);
+}
+
+extern "C" int rass_bm25_build_fields(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
+                                      const int32_t* term_field, const uint32_t* doclen, int64_t V, int64_t N, int F) {
+  if (h && !term_field) return rass_fail(h, RASS_E_INVALID, "null term_field");
+  return bm25_build_impl(h, indptr, doc, tf, term_field, doclen, V, N, F, 0, 0, nullptr);
+}
+
 // ---- kernels ------------------------------------------------------------------------------------------------
 struct HybridArgs {
   const int32_t* doc;
@@ -148,11 +174,13 @@ struct HybridArgs {
   const uint32_t* t_len;         // document frequency
   const float* t_w;              // float(clause boost) * idf
   const int32_t* t_row;          // row of tile_off, -1 for rare terms
+  const uint8_t* t_field;        // field of the term (selects norm plane and inv table)
+  const uint8_t* t_flag;         // bit 0: last term of its field group (dis-max over fields), bit 1: last of its clause
   const int64_t* knn_rows;       // [B, k] or null
   const float* knn_scores;
   const uint8_t* row_filter;
   int64_t filter_rows;
-  int64_t row_base, n_docs;
+  int64_t row_base, n_docs, norm_rows;   // norm is [F][norm_rows]
   int n_tiles, table_tiles, k;   // tiles of this launch; tiles the offset table covers (docs known to the postings)
   float w_knn;
   double* xkey;                  // [B][n_tiles * k]
@@ -167,12 +195,21 @@ struct HybridArgs {
 //   bool.filter : rows failing the pass mask never match
 //   top-k       : 32-bit radix select over the tile's fused float scores, ties by row ascending
 // The tile's best k (score, row) go to the query's list; exact_select_kernel ranks n_tiles * k entries.
+// MULTI = false: one analysed field, one text clause (chunk-only indices): the clause sum stays in acc.
+// MULTI = true : several field groups / clauses: acc = running sum of the current field group, best = dis-max over
+//                the groups of the current clause (float, like every Lucene scorer's score()), total = sum over the
+//                finished clauses in double; dynamic shared memory holds total and best behind acc.
+template <bool MULTI>
 __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_constant__ HybridArgs a) {
-  __shared__ double acc[HYB_TILE];
+  extern __shared__ __align__(16) unsigned char hyb_smem[];
+  double* acc = reinterpret_cast<double*>(hyb_smem);                       // [HYB_TILE]
+  double* total = acc + (MULTI ? HYB_TILE : 0);                            // [HYB_TILE] (MULTI)
+  float* best = reinterpret_cast<float*>(total + HYB_TILE);               // [HYB_TILE] (MULTI)
   __shared__ float s_inv[256];
   __shared__ int64_t s_lo[HYB_THREADS];
   __shared__ uint32_t s_n[HYB_THREADS];
   __shared__ float s_w[HYB_THREADS];
+  __shared__ uint8_t s_field[HYB_THREADS], s_flag[HYB_THREADS];
   __shared__ __align__(16) int s_cnt[2][HYB_THREADS / 32];
   __shared__ uint32_t s_list[HYB_LIST];
   __shared__ int s_nout, s_nmatch, s_ns;
@@ -180,14 +217,19 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
   const int tile = blockIdx.x, q = blockIdx.y;
   const int64_t d0 = (int64_t)tile * HYB_TILE;
   const int64_t d1 = min(d0 + HYB_TILE, a.n_docs);
-  for (int i = tid; i < HYB_TILE; i += HYB_THREADS) acc[i] = 0.0;
-  s_inv[tid] = a.inv ? a.inv[tid] : 0.f;
+  for (int i = tid; i < HYB_TILE; i += HYB_THREADS) {
+    acc[i] = 0.0;
+    if (MULTI) { total[i] = 0.0; best[i] = 0.f; }
+  }
   if (tid == 0) { s_nout = 0; s_nmatch = 0; s_ns = 0; }
   __syncthreads();
 
-  // ---- text clause ----
+  // ---- text clauses ----
   if (a.qt_indptr) {
     const int j_begin = a.qt_indptr[q], j_end = a.qt_indptr[q + 1];
+    int cur_field = -1;
+    const uint8_t* norm_f = a.norm;
+    bool group_touched = false, clause_touched = false;     // uniform across the CTA
     for (int j0 = j_begin; j0 < j_end; j0 += HYB_THREADS) {
       const int nt = min(HYB_THREADS, j_end - j0);
       // posting range of every term inside this tile, fetched by one thread per term (one latency for all terms)
@@ -207,26 +249,58 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
         s_lo[tid] = a.t_lo[j] + pa;
         s_n[tid] = pb - pa;
         s_w[tid] = a.t_w[j];
+        s_field[tid] = a.t_field[j];
+        s_flag[tid] = a.t_flag[j];
       }
       __syncthreads();
       for (int j = 0; j < nt; ++j) {
         const uint32_t n = s_n[j];
-        if (n == 0) continue;                 // uniform: nothing of this term in the tile, no barrier needed
-        const int64_t lo = s_lo[j];
-        const float w = s_w[j];
-        for (uint32_t p = tid; p < n; p += HYB_THREADS) {
-          const int64_t d = (int64_t)__ldg(a.doc + lo + p);
-          if (d < d0 || d >= d1) continue;                                             // rare terms scan their whole list
-          if (a.row_filter && (d >= a.filter_rows || !a.row_filter[d])) continue;       // bool.filter
-          const float x = __fmul_rn((float)__ldg(a.tf + lo + p), s_inv[a.norm[d]]);
-          const float s = __fsub_rn(w, __fdiv_rn(w, __fadd_rn(1.0f, x)));
-          if (s > 0.f) acc[d - d0] += (double)s;
+        if (n != 0) {                         // uniform: a term without postings in the tile needs no barrier
+          const int field = s_field[j];
+          if (field != cur_field) {           // per-field length table and norm plane
+            s_inv[tid] = a.inv[field * 256 + tid];
+            norm_f = a.norm + (size_t)field * a.norm_rows;
+            cur_field = field;
+            __syncthreads();
+          }
+          const int64_t lo = s_lo[j];
+          const float w = s_w[j];
+          for (uint32_t p = tid; p < n; p += HYB_THREADS) {
+            const int64_t d = (int64_t)__ldg(a.doc + lo + p);
+            if (d < d0 || d >= d1) continue;                                             // rare terms scan their whole list
+            if (a.row_filter && (d >= a.filter_rows || !a.row_filter[d])) continue;       // bool.filter
+            const float x = __fmul_rn((float)__ldg(a.tf + lo + p), s_inv[norm_f[d]]);
+            const float s = __fsub_rn(w, __fdiv_rn(w, __fadd_rn(1.0f, x)));
+            if (s > 0.f) acc[d - d0] += (double)s;
+          }
+          group_touched = true;
+          __syncthreads();
         }
-        __syncthreads();
+        if (MULTI) {
+          const int flag = s_flag[j];
+          if ((flag & 1) && group_touched) {  // end of a field group: dis-max of the float field scores
+            for (int i = tid; i < HYB_TILE; i += HYB_THREADS) {
+              const double v = acc[i];
+              if (v != 0.0) { best[i] = fmaxf(best[i], (float)v); acc[i] = 0.0; }
+            }
+            group_touched = false;
+            clause_touched = true;
+            __syncthreads();
+          }
+          if ((flag & 2) && clause_touched) { // end of a clause: the bool sums clause scores in double
+            for (int i = tid; i < HYB_TILE; i += HYB_THREADS) {
+              const float v = best[i];
+              if (v != 0.f) { total[i] += (double)v; best[i] = 0.f; }
+            }
+            clause_touched = false;
+            __syncthreads();
+          }
+        }
       }
       __syncthreads();                        // the next chunk overwrites s_lo / s_n / s_w
     }
   }
+  double* fused = MULTI ? total : acc;
 
   // ---- knn clause ----
   if (a.knn_rows && tid < a.k) {
@@ -234,12 +308,14 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
     if (r >= 0) {
       const int64_t d = r - a.row_base;
       if (d >= d0 && d < d1 && !(a.row_filter && (d >= a.filter_rows || !a.row_filter[d])))
-        // the text clause's score is a float; the bool sums the clause scores in double (and the final cast to
-        // float below is the identity for rows without a knn contribution)
-        acc[d - d0] = (double)(float)acc[d - d0] + (double)__fmul_rn(a.w_knn, a.knn_scores[(size_t)q * a.k + tid]);
+        // a clause's score is a float; the bool sums the clause scores in double (and the final cast to float below
+        // is the identity for rows without a knn contribution)
+        fused[d - d0] = (MULTI ? fused[d - d0] : (double)(float)fused[d - d0]) +
+                        (double)__fmul_rn(a.w_knn, a.knn_scores[(size_t)q * a.k + tid]);
     }
   }
   __syncthreads();
+  acc = fused;
 
   // ---- top-k of the tile: keys as order-preserving integers, 0 = no match ----
   constexpr int PER = HYB_TILE / HYB_THREADS;
@@ -358,8 +434,9 @@ static int ensure_hybrid_workspace(rass_engine* h, size_t n_terms_cap, int B) {
   if (n_terms_cap > b.qt_cap || (size_t)B + 1 > b.qt_q_cap) {
     CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
     const size_t tc = std::max<size_t>(n_terms_cap * 2, 1024), qc = std::max<size_t>((size_t)B * 2 + 2, 256);
-    // one pinned + one device block: [t_lo i64 x tc][t_len u32 x tc][t_w f32 x tc][t_row i32 x tc][indptr i32 x qc]
-    const size_t bytes = tc * (8 + 4 + 4 + 4) + qc * 4;
+    // one pinned + one device block:
+    // [t_lo i64 x tc][t_len u32 x tc][t_w f32 x tc][t_row i32 x tc][indptr i32 x qc][t_field u8 x tc][t_flag u8 x tc]
+    const size_t bytes = tc * (8 + 4 + 4 + 4 + 1 + 1) + qc * 4;
     cudaFreeHost(b.qt_host); b.qt_host = nullptr;
     cudaFree(b.qt_dev); b.qt_dev = nullptr;
     CUDA_TRY(h, cudaMallocHost(&b.qt_host, bytes));
@@ -373,9 +450,11 @@ static int ensure_hybrid_workspace(rass_engine* h, size_t n_terms_cap, int B) {
 
 // qweights == null: weight of a term = float(w_text) * idf(term); otherwise the caller's per-term weights
 // (fuzzy expansions carry their own boost and blended idf)
+// qflags (nullable): per term, bit 0 = last term of its field group, bit 1 = last term of its clause; the clause score is
+// the maximum over its field groups (multi_match best_fields), the query's text score the sum over clauses.
 static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr, const int32_t* qterms,
-                       const float* qweights, float w_text, float w_knn, int k, int64_t* out_rows, float* out_scores,
-                       rass_stats* stats) {
+                       const float* qweights, const uint8_t* qflags, float w_text, float w_knn, int k,
+                       int64_t* out_rows, float* out_scores, rass_stats* stats) {
   if (!h) return RASS_E_INVALID;
   cudaSetDevice(h->device);
   if (B < 1 || !out_rows || !out_scores) return rass_fail(h, RASS_E_INVALID, "bad arguments");
@@ -402,6 +481,7 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
   // 2. the query terms: posting ranges and float(boost) * idf weights, in query order
   const bool have_text = qterm_indptr != nullptr;
   size_t n_terms = 0;
+  bool multi = false;
   if (have_text) {
     if ((rc = ensure_hybrid_workspace(h, (size_t)(qterm_indptr[B] - qterm_indptr[0]), B))) return rc;
     unsigned char* base = b.qt_host;
@@ -410,21 +490,34 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
     float* t_w = reinterpret_cast<float*>(base + b.qt_cap * 12);
     int32_t* t_row = reinterpret_cast<int32_t*>(base + b.qt_cap * 16);
     int32_t* indptr = reinterpret_cast<int32_t*>(base + b.qt_cap * 20);
+    uint8_t* t_field = base + b.qt_cap * 20 + b.qt_q_cap * 4;
+    uint8_t* t_flag = t_field + b.qt_cap;
     const float bo = w_text;
     for (int q = 0; q < B; ++q) {
       indptr[q] = (int32_t)n_terms;
       int in_query = 0;
       for (int32_t j = qterm_indptr[q]; j < qterm_indptr[q + 1]; ++j) {
         const int32_t t = qterms[j];
-        if (t < 0 || t >= b.V) continue;
-        const int64_t lo = b.indptr_host[(size_t)t], len = b.indptr_host[(size_t)t + 1] - lo;
-        if (len == 0) continue;
+        const uint8_t fl = qflags ? qflags[j] : 0;
+        const int64_t lo = (t < 0 || t >= b.V) ? 0 : b.indptr_host[(size_t)t];
+        const int64_t len = (t < 0 || t >= b.V) ? 0 : b.indptr_host[(size_t)t + 1] - lo;
+        if (len == 0) {
+          // a dropped term hands its group / clause end marks to the last kept term of the query
+          if (fl && in_query > 0) {
+            if ((fl & ~t_flag[n_terms - 1]) && j + 1 < qterm_indptr[q + 1]) multi = true;
+            t_flag[n_terms - 1] |= fl;
+          }
+          continue;
+        }
         if (++in_query > BM25_MAX_TERMS) return rass_fail(h, RASS_E_INVALID, "more than %d query terms", BM25_MAX_TERMS);
         t_lo[n_terms] = lo;
         t_len[n_terms] = (uint32_t)len;
         volatile float w = bo * b.idf_host[(size_t)t];
         t_w[n_terms] = qweights ? qweights[j] : w;
         t_row[n_terms] = b.table_row_host[(size_t)t];
+        t_field[n_terms] = b.term_field_host[(size_t)t];
+        t_flag[n_terms] = fl;
+        if (fl && j + 1 < qterm_indptr[q + 1]) multi = true;     // a group or clause ends before the query does
         s.bytes_streamed += len * 6;
         ++n_terms;
       }
@@ -449,7 +542,10 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
     a.t_w = reinterpret_cast<const float*>(base + b.qt_cap * 12);
     a.t_row = reinterpret_cast<const int32_t*>(base + b.qt_cap * 16);
     a.qt_indptr = reinterpret_cast<const int32_t*>(base + b.qt_cap * 20);
+    a.t_field = base + b.qt_cap * 20 + b.qt_q_cap * 4;
+    a.t_flag = a.t_field + b.qt_cap;
   }
+  a.norm_rows = b.N;
   a.knn_rows = have_vec ? knn_rows : nullptr;
   a.knn_scores = knn_scores;
   a.row_filter = h->row_filter;
@@ -462,6 +558,8 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
   a.w_knn = w_knn;
   a.xkey = h->xlist_key;
   a.xrow = h->xlist_row;
+  const size_t smem_single = (size_t)HYB_TILE * 8, smem_multi = (size_t)HYB_TILE * (8 + 8 + 4);
+  CUDA_TRY(h, cudaFuncSetAttribute(hybrid_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi));
   for (int q0 = 0; q0 < B; q0 += 32768) {
     const int nq = std::min(B - q0, 32768);
     HybridArgs aq = a;
@@ -469,7 +567,8 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
     if (aq.knn_rows) { aq.knn_rows += (size_t)q0 * k; aq.knn_scores += (size_t)q0 * k; }
     aq.xkey += (size_t)q0 * a.n_tiles * k;
     aq.xrow += (size_t)q0 * a.n_tiles * k;
-    hybrid_tile_kernel<<<dim3((unsigned)a.n_tiles, (unsigned)nq), HYB_THREADS, 0, st>>>(aq);
+    if (multi) hybrid_tile_kernel<true><<<dim3((unsigned)a.n_tiles, (unsigned)nq), HYB_THREADS, smem_multi, st>>>(aq);
+    else hybrid_tile_kernel<false><<<dim3((unsigned)a.n_tiles, (unsigned)nq), HYB_THREADS, smem_single, st>>>(aq);
     CUDA_TRY(h, cudaGetLastError());
     s.launches++;
   }
@@ -492,14 +591,17 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
 extern "C" int rass_search_hybrid(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr,
                                   const int32_t* qterms, float w_text, float w_knn, int k, int64_t* out_rows,
                                   float* out_scores, rass_stats* stats) {
-  return hybrid_core(h, q_host, B, qterm_indptr, qterms, nullptr, w_text, w_knn, k, out_rows, out_scores, stats);
+  return hybrid_core(h, q_host, B, qterm_indptr, qterms, nullptr, nullptr, w_text, w_knn, k, out_rows, out_scores,
+                     stats);
 }
 
 extern "C" int rass_search_hybrid_weighted(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr,
-                                           const int32_t* qterms, const float* qweights, float w_knn, int k,
-                                           int64_t* out_rows, float* out_scores, rass_stats* stats) {
+                                           const int32_t* qterms, const float* qweights, const uint8_t* qflags,
+                                           float w_knn, int k, int64_t* out_rows, float* out_scores,
+                                           rass_stats* stats) {
   if (h && qterm_indptr && !qweights) return rass_fail(h, RASS_E_INVALID, "null weights");
-  return hybrid_core(h, q_host, B, qterm_indptr, qterms, qweights, 0.f, w_knn, k, out_rows, out_scores, stats);
+  return hybrid_core(h, q_host, B, qterm_indptr, qterms, qweights, qflags, 0.f, w_knn, k, out_rows, out_scores,
+                     stats);
 }
 
 // ---- fuzziness: AUTO -- edit-distance scan of the term dictionary -------------------------------------------
@@ -513,11 +615,11 @@ struct FuzzyToken {
 // One thread per dictionary term: optimal-string-alignment distance (insert / delete / substitute / adjacent swap)
 // to the query token, cut off at max_edits; matches are appended to (out_terms, out_edits) in no particular order.
 __global__ void __launch_bounds__(256) fuzzy_scan_kernel(const unsigned char* __restrict__ blob,
-                                                         const int64_t* __restrict__ off, int64_t V,
+                                                         const int64_t* __restrict__ off, int64_t t_lo, int64_t V,
                                                          const __grid_constant__ FuzzyToken tok, int max_edits,
                                                          int32_t* __restrict__ out_terms,
                                                          int32_t* __restrict__ out_edits, int* __restrict__ out_n) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t t = t_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= V) return;
   const int64_t o = off[t];
   const int lt = (int)(off[t + 1] - o), m = tok.len;
@@ -565,8 +667,9 @@ extern "C" int rass_text_set_vocab(rass_engine* h, const char* blob, const int64
   return RASS_OK;
 }
 
-extern "C" int rass_fuzzy_expand(rass_engine* h, const char* token, int token_len, int max_edits, int64_t max_out,
-                                 int32_t* out_terms, int32_t* out_edits, int64_t* out_n) {
+extern "C" int rass_fuzzy_expand(rass_engine* h, const char* token, int token_len, int max_edits, int64_t term_lo,
+                                 int64_t term_hi, int64_t max_out, int32_t* out_terms, int32_t* out_edits,
+                                 int64_t* out_n) {
   if (!h) return RASS_E_INVALID;
   cudaSetDevice(h->device);
   Bm25State& b = h->bm25;
@@ -575,15 +678,17 @@ extern "C" int rass_fuzzy_expand(rass_engine* h, const char* token, int token_le
   if (!b.vocab_off) return rass_fail(h, RASS_E_INVALID, "rass_fuzzy_expand before rass_text_set_vocab");
   if (token_len > FUZZY_MAX_TOKEN) return rass_fail(h, RASS_E_INVALID, "token longer than %d bytes", FUZZY_MAX_TOKEN);
   *out_n = 0;
-  if (b.vocab_V == 0) return RASS_OK;
+  if (term_hi < 0 || term_hi > b.vocab_V) term_hi = b.vocab_V;
+  if (term_lo < 0) term_lo = 0;
+  if (term_lo >= term_hi) return RASS_OK;
   FuzzyToken tok;
   memset(&tok, 0, sizeof(tok));
   tok.len = token_len;
   memcpy(tok.c, token, (size_t)token_len);
   cudaStream_t st = eng_stream(h);
   CUDA_TRY(h, cudaMemsetAsync(b.fz_n, 0, sizeof(int), st));
-  fuzzy_scan_kernel<<<(unsigned)((b.vocab_V + 255) / 256), 256, 0, st>>>(b.vocab_blob, b.vocab_off, b.vocab_V, tok,
-                                                                        max_edits, b.fz_terms, b.fz_edits, b.fz_n);
+  fuzzy_scan_kernel<<<(unsigned)((term_hi - term_lo + 255) / 256), 256, 0, st>>>(
+      b.vocab_blob, b.vocab_off, term_lo, term_hi, tok, max_edits, b.fz_terms, b.fz_edits, b.fz_n);
   CUDA_TRY(h, cudaGetLastError());
   int n = 0;
   CUDA_TRY(h, cudaMemcpyAsync(&n, b.fz_n, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -23,11 +23,13 @@
 struct Bm25State {
   bool built = false;
   int64_t V = 0, N = 0, nnz = 0;
+  int F = 1;                     // analysed fields sharing the CSR
+  std::vector<uint8_t> term_field_host;  // term -> field
   int64_t* indptr = nullptr;     // device [V+1]
   int32_t* doc = nullptr;        // device [nnz]
   uint16_t* tf = nullptr;        // device [nnz]
-  uint8_t* norm = nullptr;       // device [N]  SmallFloat byte4 of the doc length
-  float* inv_dev = nullptr;      // device [256] 1 / (k1 * ((1-b) + b * len/avgdl))
+  uint8_t* norm = nullptr;       // device [F][N]  SmallFloat byte4 of the field length of the doc
+  float* inv_dev = nullptr;      // device [F][256] 1 / (k1 * ((1-b) + b * len/avgdl))
   int n_tiles = 0;               // tiles of 4096 docs
   uint32_t* tile_off = nullptr;  // device [n_table][n_tiles + 1] postings of a frequent term before each tile
   std::vector<int32_t> table_row_host;   // term -> row of tile_off, -1 for rare terms

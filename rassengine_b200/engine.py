@@ -152,6 +152,18 @@ class Engine:
                                               indptr.size - 1, doclen.size, global_doc_count, global_sum_ttf,
                                               _ptr(gdf) if gdf is not None else None))
 
+    def bm25_build_fields(self, indptr, doc, tf, term_field, doclen):
+        """Several analysed fields in one CSR: term_field int32 [V], doclen uint32 [F, N]."""
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        doc = np.ascontiguousarray(doc, dtype=np.int32)
+        tf = np.ascontiguousarray(tf, dtype=np.uint16)
+        term_field = np.ascontiguousarray(term_field, dtype=np.int32)
+        doclen = np.ascontiguousarray(doclen, dtype=np.uint32)
+        if doclen.ndim != 2 or term_field.size != indptr.size - 1:
+            raise ValueError("doclen must be [F, N] and term_field [V]")
+        self._check(self._lib.rass_bm25_build_fields(self._h, _ptr(indptr), _ptr(doc), _ptr(tf), _ptr(term_field),
+                                                     _ptr(doclen), indptr.size - 1, doclen.shape[1], doclen.shape[0]))
+
     def set_row_filter(self, mask):
         """mask: uint8/bool [rows] (1 = passes the query's bool.filter) or None to clear."""
         if mask is None:
@@ -169,20 +181,22 @@ class Engine:
         self._check(self._lib.rass_text_set_vocab(self._h, b"".join(enc), _ptr(off), len(enc)))
         self._vocab_size = len(enc)
 
-    def fuzzy_expand(self, token: str, max_edits: int):
-        """Dictionary terms within max_edits (optimal string alignment) of the token: (term ids, edits), unordered."""
+    def fuzzy_expand(self, token: str, max_edits: int, term_lo: int = 0, term_hi: int = -1):
+        """Dictionary terms of [term_lo, term_hi) within max_edits (optimal string alignment) of the token:
+        (term ids, edits), unordered."""
         n_cap = max(getattr(self, "_vocab_size", 0), 1)
         terms = np.empty(n_cap, dtype=np.int32)
         edits = np.empty(n_cap, dtype=np.int32)
         n = C.c_int64(0)
         tok = token.encode("ascii", "replace")
-        self._check(self._lib.rass_fuzzy_expand(self._h, tok, len(tok), max_edits, n_cap, _ptr(terms), _ptr(edits),
-                                                C.byref(n)))
+        self._check(self._lib.rass_fuzzy_expand(self._h, tok, len(tok), max_edits, term_lo, term_hi, n_cap,
+                                                _ptr(terms), _ptr(edits), C.byref(n)))
         return terms[: n.value].copy(), edits[: n.value].copy()
 
-    def search_hybrid(self, q, qterms, w_text: float, w_knn: float, k: int, qweights=None):
+    def search_hybrid(self, q, qterms, w_text: float, w_knn: float, k: int, qweights=None, qflags=None):
         """q: [B, dim] fp32 or None (text only); qterms: list of B term-id lists or None (vector only); qweights:
-        optional list of B float32 lists, the weight of every term occurrence (replaces w_text * idf)."""
+        optional list of B float32 lists, the weight of every term occurrence (replaces w_text * idf); qflags:
+        optional list of B uint8 lists (bit 0 = last term of its field group, bit 1 = last term of its clause)."""
         if q is not None:
             q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
             B = q.shape[0]
@@ -204,8 +218,15 @@ class Engine:
                                      if indptr[-1] else np.zeros(1, dtype=np.float32), dtype=np.float32)
             if w.size != max(int(indptr[-1]), 1):
                 raise ValueError("qweights must hold one weight per query term")
+            fl = None
+            if qflags is not None:
+                fl = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.uint8) for x in qflags])
+                                          if indptr[-1] else np.zeros(1, dtype=np.uint8), dtype=np.uint8)
+                if fl.size != w.size:
+                    raise ValueError("qflags must hold one byte per query term")
             self._check(self._lib.rass_search_hybrid_weighted(self._h, _ptr(q) if q is not None else None, B,
-                                                              _ptr(indptr), _ptr(terms), _ptr(w), w_knn, k,
+                                                              _ptr(indptr), _ptr(terms), _ptr(w),
+                                                              _ptr(fl) if fl is not None else None, w_knn, k,
                                                               _ptr(rows), _ptr(scores), C.byref(st)))
             self.last_stats = st.as_dict()
             return rows, scores

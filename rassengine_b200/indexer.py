@@ -27,19 +27,36 @@ def get_index_name(user_id: str) -> str:
     return f"{OPENSEARCH_INDEX_NAME}-{user_id}"          # app/main.py:346-347
 
 
+# The boosted field lists of OpenSearchIndexer.__init__ (app/main.py:1403-1456): interface data of the two multi_match
+# clauses.  Chunk documents only carry unstructuredText; structured FHIR documents carry the others.
+TEXT_FIELDS = [
+    "unstructuredText^3", "patientName^3", "patientAddress^3", "patientTelecom^3", "conditionCodeText^2",
+    "conditionNote^2", "observationCodeText", "observationValue", "observationReferenceRange", "observationNote^2",
+    "encounterType", "encounterReasonCode", "encounterLocation", "encounterNote", "medRequestMedicationDisplay",
+    "medRequestNote", "procedureCodeText", "procedureNote", "allergyCodeText", "allergyNote^2", "practitionerName^3",
+    "practitionerAddress", "practitionerTelecom", "organizationName^3", "organizationAddress", "organizationTelecom",
+]
+KEYWORD_FIELDS = [
+    "patientGender^3", "patientMaritalStatus^2", "patientLanguage^3", "conditionCategory^2", "conditionClinicalStatus",
+    "conditionVerificationStatus", "conditionSeverity", "observationUnit", "observationInterpretation",
+    "encounterStatus", "encounterClass", "encounterServiceProvider", "medRequestIntent", "medRequestStatus",
+    "medRequestPriority", "procedureStatus", "allergyClinicalStatus", "allergyVerificationStatus", "allergyType",
+    "allergyCategory", "allergyCriticality", "practitionerGender", "practitionerSpecialty", "organizationType",
+]
+
+
 def index_body(dim: int = EMBED_DIM) -> dict:
-    """The parts of the reference mapping the engine acts on: index.knn, shard counts and the knn_vector field
-    (app/main.py:354-360, 563-572); chunk documents add doc_id/doc_type/patientId/unstructuredText."""
-    return {
-        "settings": {"index": {"knn": True, "number_of_shards": SHARD_COUNT, "number_of_replicas": REPLICA_COUNT}},
-        "mappings": {"properties": {
-            "doc_id": {"type": "keyword"}, "doc_type": {"type": "keyword"}, "patientId": {"type": "keyword"},
-            "resourceType": {"type": "keyword"}, "unstructuredText": {"type": "text"},
-            "embedding": {"type": "knn_vector", "dimension": dim,
+    """The parts of the reference mapping the engine acts on (app/main.py:354-572): index.knn, shard counts, the
+    knn_vector field, and the type (text / keyword) of every field the two multi_match clauses search."""
+    props = {"doc_id": {"type": "keyword"}, "doc_type": {"type": "keyword"}, "patientId": {"type": "keyword"},
+             "resourceType": {"type": "keyword"}, "file_path": {"type": "keyword"}, "file_type": {"type": "keyword"}}
+    props.update({f.split("^")[0]: {"type": "text"} for f in TEXT_FIELDS})
+    props.update({f.split("^")[0]: {"type": "keyword"} for f in KEYWORD_FIELDS})
+    props["embedding"] = {"type": "knn_vector", "dimension": dim,
                           "method": {"name": "hnsw", "engine": "nmslib", "space_type": "cosinesimil",
-                                     "parameters": {"m": 48, "ef_construction": 400}}},
-        }},
-    }
+                                     "parameters": {"m": 48, "ef_construction": 400}}}
+    return {"settings": {"index": {"knn": True, "number_of_shards": SHARD_COUNT, "number_of_replicas": REPLICA_COUNT}},
+            "mappings": {"properties": props}}
 
 
 def ensure_index_exists(client, index_name: str, body: dict | None = None) -> None:
@@ -51,6 +68,21 @@ def ensure_index_exists(client, index_name: str, body: dict | None = None) -> No
             client.indices.create(index=index_name, body=body or index_body())
     except Exception as exc:
         print(f"[ERROR] ensure_index_exists: {exc}")
+
+
+def store_structured(client, index_name: str, docs: List[Dict]) -> Tuple[int, list]:
+    """Structured half of store_fhir_docs_in_opensearch (app/main.py:1222-1240): FHIR resource documents without a
+    vector, one bulk call, `_id = doc_id`.  They share the index with the chunks and match the text / keyword
+    clauses of the hybrid query through their own fields."""
+    if not client or not docs:
+        return 0, []
+    ensure_index_exists(client, index_name)
+    actions = [{"_op_type": "index", "_index": index_name, "_id": d["doc_id"], "_source": d,
+                "_routing": d.get("patientId")} for d in docs]
+    ok, errors = bulk(client, actions)
+    if errors:
+        logger.error("bulk index errors: %s", errors[:3])
+    return ok, errors
 
 
 def store_chunks(client, index_name: str, docs: List[Dict], embeddings: np.ndarray, as_lists: bool = True,
@@ -89,8 +121,8 @@ def store_chunks(client, index_name: str, docs: List[Dict], embeddings: np.ndarr
 
 
 class B200Indexer:
-    text_fields = ["unstructuredText^3"]      # the analysed field chunk documents carry (app/main.py:1403-1404)
-    keyword_fields: list[str] = []
+    text_fields = TEXT_FIELDS
+    keyword_fields = KEYWORD_FIELDS
 
     def __init__(self, client: B200Client, index_name: str):
         self.client = client

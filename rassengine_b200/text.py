@@ -30,7 +30,9 @@ class TextField:
         self.doc_count = 0                           # documents with at least one token, as of the last postings()
 
     def set_row(self, row: int, text: str | None):
-        toks = analyze(text) if text else []
+        self.set_row_tokens(row, analyze(text) if text else [])
+
+    def set_row_tokens(self, row: int, toks: list[str]):
         if not toks:
             if self.row_terms.pop(row, None) is not None:
                 self.dirty = True
@@ -78,7 +80,22 @@ class TextField:
         """fuzziness AUTO = AUTO:3,6: 0 edits below 3 characters, 1 for 3..5, 2 from 6 on."""
         return 0 if n_chars <= 2 else (1 if n_chars <= 5 else 2)
 
-    def fuzzy_weighted_terms(self, text: str, boost: float, expand, max_expansions: int = 50):
+    def exact_weighted_terms(self, tokens: list[str], boost: float):
+        """Plain term queries (no fuzziness): (term ids, float32 weights = float(boost) * idf), query order."""
+        import math
+        ids, ws = [], []
+        bo = np.float32(boost)
+        for tok in tokens:
+            t = self.vocab.get(tok, -1)
+            if t < 0 or t >= self.df.size or self.df[t] == 0:
+                continue
+            df = int(self.df[t])
+            idf = np.float32(math.log(1.0 + (self.doc_count - df + 0.5) / (df + 0.5)))
+            ids.append(int(t))
+            ws.append(np.float32(bo * idf))
+        return ids, ws
+
+    def fuzzy_weighted_terms(self, text, boost: float, expand, max_expansions: int = 50):
         """The boosted term queries `multi_match(..., fuzziness: AUTO)` rewrites a query string to (Lucene FuzzyQuery +
         TopTermsBlendedFreqScoringRewrite, restated in oracle/fuzzy.py): for every token the <= 50 best dictionary
         terms by (similarity boost desc, term asc), scored with the largest document frequency among them.
@@ -89,7 +106,7 @@ class TextField:
         ids: list[int] = []
         ws: list[np.float32] = []
         bo = np.float32(boost)
-        for tok in analyze(text):
+        for tok in (analyze(text) if isinstance(text, str) else text):
             me = self.auto_max_edits(len(tok))
             if me == 0 or len(tok) > 64:
                 t = self.vocab.get(tok, -1)
@@ -124,3 +141,79 @@ def csr_from_pairs(terms: np.ndarray, docs: np.ndarray, V: int, n_rows: int):
     indptr = np.zeros(V + 1, dtype=np.int64)
     np.add.at(indptr, t_of + 1, 1)
     return np.cumsum(indptr), d_of, np.minimum(counts, 65535).astype(np.uint16)
+
+
+class TextIndex:
+    """Every analysed (`text`) and `keyword` field of an index, sharing one CSR on the device: field f owns the global
+    term ids [base[f], base[f] + V_f).  A keyword field is a field whose "analyzer" emits the whole value as one token
+    (no lower-casing), which is how Lucene indexes it; its norms are omitted, i.e. every value counts as length 1."""
+
+    def __init__(self, field_types: dict[str, str]):
+        self.types = dict(field_types)            # field name -> "text" | "keyword"
+        self.fields: dict[str, TextField] = {}    # created when the first document carries the field
+        self.order: list[str] = []                # field id -> name
+        self.base: dict[str, int] = {}            # as of the last postings()
+        self.dirty = True
+
+    def field_id(self, name: str) -> int:
+        return self.order.index(name)
+
+    def tokens(self, name: str, value) -> list[str]:
+        values = value if isinstance(value, (list, tuple)) else [value]
+        out: list[str] = []
+        for v in values:
+            if v is None:
+                continue
+            if self.types.get(name) == "keyword":
+                out.append(str(v))
+            elif isinstance(v, str):
+                out.extend(analyze(v))
+        return out
+
+    def set_doc(self, row: int, src: dict | None):
+        """(Re)index one row: every declared field the document carries; fields it no longer carries are cleared."""
+        src = src or {}
+        for name in self.types:
+            toks = self.tokens(name, src[name]) if name in src else []
+            fld = self.fields.get(name)
+            if fld is None:
+                if not toks:
+                    continue
+                fld = self.fields[name] = TextField()
+                self.order.append(name)
+            before = fld.dirty
+            fld.dirty = False
+            fld.set_row_tokens(row, toks)
+            if fld.dirty:
+                self.dirty = True
+            fld.dirty = fld.dirty or before
+
+    def postings(self, n_rows: int):
+        """Combined CSR: indptr int64 [V+1], doc int32, tf uint16, term_field int32 [V], doclen uint32 [F, n_rows]."""
+        indptrs, docs, tfs, fields, lens = [], [], [], [], []
+        base = nnz = 0
+        self.base = {}
+        for fid, name in enumerate(self.order):
+            fld = self.fields[name]
+            ip, d, t, dl = fld.postings(n_rows)
+            if self.types.get(name) == "keyword":
+                dl = (dl > 0).astype(np.uint32)        # omitted norms: length 1 for every document that has a value
+            self.base[name] = base
+            indptrs.append(ip[:-1] + nnz)
+            nnz += d.size
+            docs.append(d)
+            tfs.append(t)
+            fields.append(np.full(ip.size - 1, fid, dtype=np.int32))
+            lens.append(dl)
+            base += ip.size - 1
+        if not self.order:
+            z = np.zeros
+            return z(1, np.int64), z(0, np.int32), z(0, np.uint16), z(0, np.int32), z((1, n_rows), np.uint32)
+        indptr = np.concatenate(indptrs + [np.array([nnz], dtype=np.int64)]).astype(np.int64)
+        return (indptr, np.concatenate(docs), np.concatenate(tfs), np.concatenate(fields), np.stack(lens))
+
+    def terms_in_id_order(self) -> list[str]:
+        out: list[str] = []
+        for name in self.order:
+            out.extend(self.fields[name].terms_in_id_order())
+        return out

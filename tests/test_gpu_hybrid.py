@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle import bm25, fusion, fuzzy, knn, synth
+from oracle import bm25, fusion, fuzzy, knn, multifield, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -272,3 +272,72 @@ def test_opensearchpy_shim_import(monkeypatch):
     assert resp["hits"]["hits"][0]["_score"] == pytest.approx(1.0) and resp["hits"]["hits"][1]["_score"] == pytest.approx(0.5)
     c.close()
     sys.modules.pop("opensearchpy", None)
+
+
+def test_mixed_index_multi_field_dismax_matches_oracle():
+    """structured FHIR documents share the index with the chunks (app/main.py:1223-1240); the hybrid
+    query's two multi_match clauses then score max-over-fields per clause and sum over clauses
+    (oracle/multifield.py).  Ranked ids identical, fused float32 scores bit-identical."""
+    from rassengine_b200.client import B200Client
+    from rassengine_b200 import indexer as ix
+    rng = np.random.default_rng(21)
+    names = ["john smith", "jon smyth", "maria garcia", "john garcia", "wei chen", "smith johnson"]
+    conds = ["chest pain", "type two diabetes mellitus", "essential hypertension", "chronic chest pain syndrome",
+             "acute bronchitis", "hypertensive heart disease"]
+    genders = ["male", "female", "other"]
+    n_struct, n_chunk, dim = 240, 600, 64
+    docs = []
+    for i in range(n_struct):
+        kind = i % 3
+        d = {"doc_id": f"res-{i}", "doc_type": "structured", "patientId": f"pat-{i % 9}"}
+        if kind == 0:
+            d.update(resourceType="Patient", patientName=names[int(rng.integers(len(names)))],
+                     patientGender=genders[int(rng.integers(3))], patientAddress=f"{int(rng.integers(1, 99))} main street")
+        elif kind == 1:
+            d.update(resourceType="Condition", conditionCodeText=conds[int(rng.integers(len(conds)))],
+                     conditionNote="patient reports " + conds[int(rng.integers(len(conds)))],
+                     conditionClinicalStatus=["active", "resolved"][int(rng.integers(2))])
+        else:
+            d.update(resourceType="Practitioner", practitionerName="dr " + names[int(rng.integers(len(names)))],
+                     practitionerGender=genders[int(rng.integers(3))])
+        docs.append(d)
+    words = ("patient john reports chest pain and hypertension denies diabetes smith male female follow up with dr "
+             "garcia regarding chronic pain medication metformin daily active resolved street").split()
+    chunk_raw = rng.standard_normal((n_chunk, dim)).astype(np.float32)
+    chunks = [{"doc_id": f"note-{i}", "doc_type": "unstructured", "patientId": f"pat-{i % 9}",
+               "unstructuredText": " ".join(words[int(j)] for j in rng.integers(0, len(words), size=int(rng.integers(5, 40))))}
+              for i in range(n_chunk)]
+    client = B200Client()
+    name = ix.get_index_name("mixed")
+    ix.ensure_index_exists(client, name, ix.index_body(dim))
+    assert ix.store_structured(client, name, docs[:100]) == (100, [])
+    assert ix.store_chunks(client, name, chunks, chunk_raw, as_lists=False, flush=256) == (n_chunk, [])
+    assert ix.store_structured(client, name, docs[100:]) == (n_struct - 100, [])
+    all_docs = docs[:100] + chunks + docs[100:]                      # row order = ingest order
+    types = {f.split("^")[0]: "text" for f in ix.TEXT_FIELDS}
+    types.update({f.split("^")[0]: "keyword" for f in ix.KEYWORD_FIELDS})
+    fields = multifield.build(all_docs, types)
+    assert {"unstructuredText", "patientName", "conditionCodeText", "conditionNote", "patientGender"} <= set(fields)
+    n = len(all_docs)
+    X = np.zeros((n, dim), dtype=np.float32)
+    alive = np.zeros(n, dtype=bool)
+    X[100:100 + n_chunk] = knn.normalize_rows(chunk_raw)
+    alive[100:100 + n_chunk] = True                                  # structured documents carry no vector
+    spec = lambda lst: [(f.split("^")[0], float(f.split("^")[1]) if "^" in f else 1.0) for f in lst]
+    idxr = ix.B200Indexer(client, name)
+    k = 8
+    for qtext in ("john smith chest pain", "male", "diabetes hypertention garcia", "active", "smyth"):
+        q_emb = rng.standard_normal((1, dim)).astype(np.float32)
+        q_unit = (q_emb / (np.linalg.norm(q_emb, axis=1, keepdims=True) + 1e-9)).astype(np.float32)
+        knn_rows, _, knn_scores = knn.knn_exact(X, q_unit, k, alive=alive)
+        for (w_t, w_kw, w_knn), call in (((1.5, 1.0, 2.0), idxr.hybrid_search), ((1.0, 0.5, 1.5), idxr.multi_intent_search)):
+            total = multifield.text_total(fields, [(qtext, spec(ix.TEXT_FIELDS), w_t, True),
+                                                   (qtext, spec(ix.KEYWORD_FIELDS), w_kw, False)], n)
+            wr, ws = fusion.hybrid(None, None, knn_rows[0], knn_scores[0], 0.0, w_knn, k, text64=total)
+            hits = call(qtext, q_emb, k=k)
+            assert [h[0]["doc_id"] for h in hits] == [all_docs[r]["doc_id"] for r in wr], qtext
+            np.testing.assert_allclose([h[1] for h in hits], ws, rtol=2e-6, atol=0)
+    # a structured document and a chunk both surface for a name query; a keyword value matches only as a whole string
+    hits = idxr.hybrid_search("john smith", rng.standard_normal((1, dim)).astype(np.float32), k=k)
+    assert {h[0]["doc_type"] for h in hits} == {"structured", "unstructured"} or len(hits) == k
+    client.close()
