@@ -28,6 +28,7 @@
 #define G2_TMEM_COLS 512
 #define G2_THREADS 256
 #define G2_HIGH_WATER 128
+#define G2_HIT_STRIDE 36                   // floats per epilogue thread in the hit staging area (36: STS.128 conflict-free)
 
 namespace {
 
@@ -199,17 +200,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
           }
           if (dbg_mode == 2) m = 0;
           // each lane walks its own hits
-          while (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            uint32_t s = v[0];
+          if (m) {
+            float* mine = ss->hit + (size_t)et * G2_HIT_STRIDE;
 #pragma unroll
-            for (int u = 1; u < 32; ++u) s = (j == u) ? v[u] : s;
-            const int pos = atomicAdd(&ss->cnt[c + j], 1);
-            if (pos < RASS_UMMA_SEG) {
-              const size_t o = (slot0 + c + j) * pool_entries + (size_t)seg * RASS_UMMA_SEG + pos;
-              pool_key[o] = __uint_as_float(s);
-              pool_row[o] = (uint32_t)row;
+            for (int u = 0; u < 32; u += 4)
+              *reinterpret_cast<uint4*>(mine + u) = make_uint4(v[u], v[u + 1], v[u + 2], v[u + 3]);
+            while (m) {
+              const int j = __ffs(m) - 1;
+              m &= m - 1;
+              const float s = mine[j];
+              const int pos = atomicAdd(&ss->cnt[c + j], 1);
+              if (pos < RASS_UMMA_SEG) {
+                const size_t o = (slot0 + c + j) * pool_entries + (size_t)seg * RASS_UMMA_SEG + pos;
+                pool_key[o] = s;
+                pool_row[o] = (uint32_t)row;
+              }
             }
           }
         }

@@ -28,14 +28,22 @@ gq = torch.Generator(device="cuda").manual_seed(5678)
 CASES = (("stream", 1, 10), ("stream", 2, 10), ("umma", 64, 10), ("umma", 1, 10), ("umma", 64, 100), ("stream", 1, 100),
          ("gemm", 256, 10), ("gemm", 1024, 10), ("gemm", 8192, 100), ("gemm", 200, 10))
 custom = [w.split(":") for w in which if ":" in w]      # e.g. gemm:1024:10
+CLUSTERED = set()
 if custom:
-    CASES = tuple((c[0], int(c[1]), int(c[2])) for c in custom)
+    CASES = tuple((c[0], int(c[1]), int(c[2])) for c in custom)     # a 4th field "c" = clustered queries
+    CLUSTERED = {(c[0], int(c[1]), int(c[2])) for c in custom if len(c) > 3 and c[3] == "c"}
     which = [c[0] for c in custom]
 for path, B, k in CASES:
     if path not in which:
         continue
     e.set_path(getattr(rb, "PATH_" + path.upper()))
     q = torch.randn((B, D), generator=gq, device="cuda")
+    if (path, B, k) in CLUSTERED:
+        # queries = stored rows + N(0, 0.05^2) noise per element (SURVEY.md 8d "clustered variant"): near-ties at the top
+        pick = torch.randint(0, N, (B,), generator=gq, device="cuda")
+        base = torch.from_numpy(e.read_rows(0, 1)).cuda()   # placeholder to keep dtype/device
+        rows_np = np.stack([e.read_rows(int(r), 1)[0] for r in pick.tolist()])
+        q = torch.from_numpy(rows_np).cuda() + 0.05 * torch.randn((B, D), generator=gq, device="cuda") / 32.0
     rows = torch.empty((B, k), dtype=torch.int64, device="cuda")
     sc = torch.empty((B, k), dtype=torch.float32, device="cuda")
     for it in range(5):
