@@ -63,7 +63,7 @@ def parse():
     a.k = a.k if a.k is not None else k
     a.bf16_only = a.workload == "cfg5"
     if a.cpu_sample_rows is None:
-        a.cpu_sample_rows = 1_000_000 if a.batch <= 64 else 100_000
+        a.cpu_sample_rows = 2_000_000 if a.batch <= 64 else 200_000
     return a
 
 
@@ -414,7 +414,7 @@ def run_ours(a):
         cores = os.cpu_count() or 1
         sample = min(a.cpu_sample_rows, a.rows)
         Xs = eng.read_rows(0, sample)            # the same rows the GPU scanned
-        qps, t = cpu_scan_qps(a, sample, B, repeats=2, X=Xs)
+        qps, t = cpu_scan_qps(a, sample, B, repeats=5, X=Xs)
         out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                                "sample": f"numpy fp32 sgemm + argpartition (oracle.knn.knn_fp32_baseline) over the "
                                          f"first {sample} of {a.rows} rows x {B} queries ({t:.2f} s), scaled "

@@ -57,6 +57,22 @@ class ShardedIndex:
         self.engine = engine
         self.ops = ops if ops is not None else _DeviceOps(engine)
         self.merge_launches = 0
+        self._bufs: dict = {}          # (B, k, device) -> work tensors, reused across calls (no allocator traffic)
+
+    def _buffers(self, B: int, k: int, dev):
+        key = (B, k, str(dev))
+        b = self._bufs.get(key)
+        if b is None:
+            if len(self._bufs) > 8:
+                self._bufs.clear()
+            b = {"packed": torch.empty((2, B, k), dtype=torch.int64, device=dev),
+                 "scores": torch.empty((B, k), dtype=torch.float32, device=dev)}
+            if self.world > 1:
+                b["gathered"] = torch.empty((self.world * 2, B, k), dtype=torch.int64, device=dev)
+                b["out_rows"] = torch.empty((B, k), dtype=torch.int64, device=dev)
+                b["out_scores"] = torch.empty((B, k), dtype=torch.float32, device=dev)
+            self._bufs[key] = b
+        return b
 
     def set_row_base(self, base: int):
         self.engine.set_row_base(base)
@@ -67,18 +83,17 @@ class ShardedIndex:
 
     def search_dev(self, q: torch.Tensor, k: int):
         """q: [B, dim] fp32 on this rank's device (the same batch on every rank).  Returns (rows int64 [B, k] global
-        row ids, scores fp32 [B, k]) on the device, identical on every rank."""
+        row ids, scores fp32 [B, k]) on the device, identical on every rank.  The returned tensors are work buffers
+        owned by the index: they are overwritten by the next call with the same (B, k) -- clone to keep them."""
         B = q.shape[0]
         dev = q.device
-        packed = torch.empty((2, B, k), dtype=torch.int64, device=dev)     # plane 0: fp64 key bits, plane 1: rows
-        scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+        b = self._buffers(B, k, dev)
+        packed, scores = b["packed"], b["scores"]                            # plane 0: fp64 key bits, plane 1: rows
         self.ops.search(q, k, packed, scores)
         if self.world == 1:
             return packed[1], scores
-        gathered = torch.empty((self.world * 2, B, k), dtype=torch.int64, device=dev)
+        gathered, out_rows, out_scores = b["gathered"], b["out_rows"], b["out_scores"]
         dist.all_gather_into_tensor(gathered, packed, group=self.group)      # the one collective of the path
-        out_rows = torch.empty((B, k), dtype=torch.int64, device=dev)
-        out_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
         self.ops.merge(gathered, self.world, B, k, out_rows, out_scores)
         self.merge_launches += 1
         return out_rows, out_scores
