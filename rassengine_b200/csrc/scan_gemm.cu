@@ -44,6 +44,9 @@ struct GemmSmem {
   uint32_t pad;
   alignas(16) float thr[G2_NQ];
   int cnt[G2_NQ];
+  // a thread that finds survivors among its 32 scores parks them here so the append loop can index them (registers
+  // cannot be indexed: the alternative is a 32-deep select chain per survivor)
+  alignas(16) float hit[128 * G2_HIT_STRIDE];
 };
 
 struct GemmPlan {
