@@ -292,7 +292,10 @@ static int umma_launch(rass_engine* h, int q0, int64_t n_rows, float* dbg_out, c
   }
   const int n_tiles = (int)((n_rows + UMMA_ROWS - 1) / UMMA_ROWS);
   const int grid = n_tiles < h->num_sms ? n_tiles : h->num_sms;
-  CUDA_TRY(h, cudaMemsetAsync(h->q_gthr + q0, 0, UMMA_NQ * sizeof(uint32_t), st));   // nothing published yet
+  // timing experiment only: keeping the previous search's pivots shows what a perfect threshold seed would save
+  static const bool keep_gthr = getenv("RASS_DEBUG_KEEP_GTHR") != nullptr;
+  if (!keep_gthr)
+    CUDA_TRY(h, cudaMemsetAsync(h->q_gthr + q0, 0, UMMA_NQ * sizeof(uint32_t), st));   // nothing published yet
   const size_t smem = umma_smem_bytes(h);
   CUDA_TRY(h, cudaFuncSetAttribute(scan_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   scan_umma_kernel<<<grid, UMMA_THREADS, smem, st>>>(*(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q, h->sa, h->sb_scan,

@@ -1,8 +1,9 @@
 """BASELINE.json configs[3]: hybrid BM25 multi_match + vector fusion over N synthetic FHIR-narrative-shaped chunks
 (~30k-term Zipf vocabulary), top-10.  Builds the corpus on the device, times rass_search_hybrid per query (the
-reference issues one hybrid query per /ask request) and checks ids/scores against the oracle at full size.
+reference issues one hybrid query per /ask request) and checks ids/scores against the oracle at full size -- which is
+why it lives under tests/: only tests may execute oracle/ (it is a script, not collected by pytest).
 
-    python tools/bench_hybrid.py [N_DOCS] [N_QUERIES]      -> one JSON line
+    python tests/cfg4_hybrid_bench.py [N_DOCS] [N_QUERIES]      -> one JSON line
 """
 import json
 import os

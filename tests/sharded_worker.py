@@ -1,5 +1,5 @@
 """torchrun worker: row-sharded search over NCCL equals the oracle (and therefore a single-shard search).
-    python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 --master-port P tools/check_sharded.py"""
+    python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 --master-port P tests/sharded_worker.py"""
 import os
 import sys
 

@@ -23,6 +23,6 @@ def test_sharded_search_equals_oracle_over_nccl():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={g}",
                           "--master-addr", "127.0.0.1", "--master-port", str(port),
-                          os.path.join(root, "tools", "check_sharded.py")], capture_output=True, text=True, timeout=600)
+                          os.path.join(root, "tests", "sharded_worker.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "identical to the oracle" in out.stdout

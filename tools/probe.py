@@ -46,7 +46,7 @@ for path, B, k in CASES:
         q = torch.from_numpy(rows_np).cuda() + 0.05 * torch.randn((B, D), generator=gq, device="cuda") / 32.0
     rows = torch.empty((B, k), dtype=torch.int64, device="cuda")
     sc = torch.empty((B, k), dtype=torch.float32, device="cuda")
-    for it in range(5):
+    for it in range(int(os.environ.get("PROBE_ITERS", "5"))):
         st = e.search_knn_dev(q.data_ptr(), B, k, rows.data_ptr(), sc.data_ptr())
     gbs = st["bytes_streamed"] / (st["scan_ms"] * 1e-3) / 1e9 if st["scan_ms"] else 0
     print(path, "B", B, "k", k, {kk: (round(v, 3) if isinstance(v, float) else v) for kk, v in st.items()},
