@@ -95,7 +95,8 @@ typedef struct rass_stats {
   int32_t passes;        /* corpus passes of the scan                                                  */
   int32_t launches;      /* kernels launched by this call                                              */
   int32_t max_candidates;/* largest rerank candidate set                                               */
-  int32_t reserved;
+  int32_t n_retried;     /* queries (k > 32) that failed the first certificate and were re-scanned with wider
+                            candidate segments before any fp64 fallback                                */
 } rass_stats;
 
 const char* rass_version(void);

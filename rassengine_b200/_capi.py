@@ -26,10 +26,10 @@ class RassStats(C.Structure):
     _fields_ = [("scan_ms", C.c_double), ("finish_ms", C.c_double), ("total_ms", C.c_double),
                 ("rows_scanned", C.c_int64), ("bytes_streamed", C.c_int64), ("n_queries", C.c_int32),
                 ("n_certified", C.c_int32), ("n_fallback", C.c_int32), ("path", C.c_int32), ("passes", C.c_int32),
-                ("launches", C.c_int32), ("max_candidates", C.c_int32), ("reserved", C.c_int32)]
+                ("launches", C.c_int32), ("max_candidates", C.c_int32), ("n_retried", C.c_int32)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 class RassError(RuntimeError):

@@ -15,8 +15,9 @@
 #define RASS_GROUP_Q 64        // queries finished per finish launch (= queries per tcgen05 pass)
 #define RASS_QPAD 256          // the query workspace is zero padded to a multiple of this (one scan_gemm group)
 #define RASS_STREAM_SEG 64     // pool entries per (CTA, query) segment of the streaming scan (32..64 kept)
-#define RASS_UMMA_SEG 256      // pool entries per (CTA, query) segment of the tcgen05 scan
-#define RASS_UMMA_KEEP 32      // entries a tcgen05 segment keeps at a compaction
+// pool entries per (CTA, query) segment of the tcgen05 scans: 256 (a compaction keeps 32..64) for k <= 32,
+// 512 (keeps 128..256) for larger k
+static inline int rass_tc_seg(int k) { return k > 32 ? 512 : 256; }
 #define RASS_EXACT_NQ 4        // queries per pass of the fp64 scan
 #define RASS_FINISH_THREADS 1024
 
@@ -121,6 +122,14 @@ struct rass_engine {
   int64_t tmap_rows = -1;
   const void* tmap_base = nullptr;
   const void* tmap_qbase = nullptr;
+  // second-chance pass (queries whose certificate failed at k > 32): ids, gathered queries, results
+  int* retry_ids = nullptr;
+  float* retry_q = nullptr;
+  int64_t* retry_rows = nullptr;
+  float* retry_scores = nullptr;
+  double* retry_keys = nullptr;
+  size_t retry_cap = 0;
+  int retry_k = 0;
   uint8_t* row_filter = nullptr;    // device [row_filter_rows] 1 = row passes the bool.filter of the running query
   bool knn_prefilter = false;       // RASS_OPT_KNN_PREFILTER: rass_search_knn scans only rows passing row_filter
   float* sb_filtered = nullptr;     // [cap] sb with -inf for rows failing the filter (built lazily)
@@ -380,11 +389,11 @@ int launch_query_prep(rass_engine* h, const float* q_dev, int B, cudaStream_t st
 int launch_scan_stream(rass_engine* h, int q0, int nq, int g0, cudaStream_t st);
 int scan_stream_segs(const rass_engine* h);
 // tcgen05 scan of queries [q0, q0+nq) (nq <= 64) into pool slots 0..nq
-int launch_scan_umma(rass_engine* h, int q0, int nq, cudaStream_t st);
+int launch_scan_umma(rass_engine* h, int q0, int nq, int seg, cudaStream_t st);
 int scan_umma_segs(const rass_engine* h);
 int umma_selftest(rass_engine* h, int n_rows_tile, float* out_host, cudaStream_t st);
 // CTA-pair tcgen05 scan of all B prepared queries (groups of 256) into pool slots 0..B
-int launch_scan_gemm(rass_engine* h, int B, cudaStream_t st);
+int launch_scan_gemm(rass_engine* h, int B, int seg, cudaStream_t st);
 int scan_gemm_segs(const rass_engine* h, int B);
 int gemm_selftest(rass_engine* h, int B, float* out_host, cudaStream_t st);
 // CUtensorMap over a [rows, dim_pad] bf16 matrix: boxes of box_rows x 64 elements, 128B swizzle

@@ -141,6 +141,7 @@ extern "C" int rass_destroy(rass_engine* h) {
   cudaFree(h->q_stage_dev);
   cudaFree(h->row_filter);
   cudaFree(h->sb_filtered);
+  cudaFree(h->retry_ids); cudaFree(h->retry_q); cudaFree(h->retry_rows); cudaFree(h->retry_scores); cudaFree(h->retry_keys);
   for (cudaEvent_t e : h->ev_pool) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) { cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -552,9 +553,40 @@ static cudaEvent_t get_event(rass_engine* h, size_t i) {
   return h->ev_pool[i];
 }
 
+// second-chance pass for queries whose certificate failed: gather them, search with 512-entry segments, scatter back
+__global__ void gather_queries_kernel(const float* __restrict__ q, const int* __restrict__ ids, int dim,
+                                      float* __restrict__ out) {
+  const float* src = q + (size_t)ids[blockIdx.x] * dim;
+  float* dst = out + (size_t)blockIdx.x * dim;
+  for (int j = threadIdx.x; j < dim; j += blockDim.x) dst[j] = src[j];
+}
+__global__ void scatter_results_kernel(const int* __restrict__ ids, int k, const int64_t* __restrict__ rows,
+                                       const float* __restrict__ scores, const double* __restrict__ keys,
+                                       int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
+                                       double* __restrict__ out_keys) {
+  const size_t src = (size_t)blockIdx.x * k, dst = (size_t)ids[blockIdx.x] * k;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    out_rows[dst + j] = rows[src + j];
+    out_scores[dst + j] = scores[src + j];
+    if (out_keys) out_keys[dst + j] = keys[src + j];
+  }
+}
+
+static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
+                            double* out_keys, rass_stats* stats, bool robust);
+
 // q_dev: [B, dim] fp32 on this device; outputs on this device.  Synchronises the stream before returning.
 int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
                 double* out_keys, rass_stats* stats) {
+  return search_core_impl(h, q_dev, B, k, out_rows, out_scores, out_keys, stats, false);
+}
+
+// robust = false: 256-entry segments (a compaction keeps 32..64 entries): fastest, and every pivot has >= 32 >= k
+// entries above it when k <= 32.  For k > 32 a cluster of near neighbours inside one segment can lift a pivot above
+// the k-th best; those queries fail their certificate and get a second pass with robust = true (512-entry segments,
+// >= 128 entries above every pivot) at tensor-core speed instead of the fp64 scan.
+static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
+                            double* out_keys, rass_stats* stats, bool robust) {
   if (B < 1) return rass_fail(h, RASS_E_INVALID, "B must be >= 1");
   if (k < 1 || k > RASS_MAX_K) return rass_fail(h, RASS_E_INVALID, "k must be in [1, %d], got %d", RASS_MAX_K, k);
   cudaStream_t st = eng_stream(h);
@@ -564,6 +596,7 @@ int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_r
   memset(&s, 0, sizeof(s));
   s.n_queries = B;
   s.rows_scanned = h->n_rows;
+  double retry_scan_ms = 0.0, retry_total_ms = 0.0, first_scan_ms = 0.0, first_total_ms = -1.0;
   const size_t n_out = (size_t)B * k;
   if (h->n_rows == 0) {
     fill_empty_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(out_rows, out_scores, out_keys, n_out);
@@ -574,7 +607,8 @@ int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_r
     if (stats) *stats = s;
     return RASS_OK;
   }
-  const int path = resolve_path(h, B);
+  int path = resolve_path(h, B);
+  if (robust && path == RASS_PATH_STREAM) path = RASS_PATH_UMMA;    // the streaming scan keeps 32 per warp only
   s.path = path;
   if ((rc = select_scan_offsets(h, st))) return rc;
   // reset the per-search device counters (keeps rho_x / max_xnorm)
@@ -592,11 +626,12 @@ int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_r
     s.bytes_streamed = (int64_t)s.passes * h->n_rows * h->dim_pad * ((h->flags & RASS_BF16_ONLY) ? 2 : 4);
   } else if (path == RASS_PATH_GEMM) {
     const int n_segs = scan_gemm_segs(h, B);
-    if ((rc = ensure_pool(h, (size_t)n_segs * RASS_UMMA_SEG, (size_t)n_segs, (size_t)B))) return rc;
+    const int seg = robust ? rass_tc_seg(k) : 256;
+    if ((rc = ensure_pool(h, (size_t)n_segs * seg, (size_t)n_segs, (size_t)B))) return rc;
     CUDA_TRY(h, cudaEventRecord(get_event(h, n_ev++), st));
-    if ((rc = launch_scan_gemm(h, B, st))) return rc;
+    if ((rc = launch_scan_gemm(h, B, seg, st))) return rc;
     CUDA_TRY(h, cudaEventRecord(get_event(h, n_ev++), st));
-    if ((rc = launch_finish(h, 0, B, k, n_segs, RASS_UMMA_SEG, true, true, out_rows, out_scores, out_keys, st)))
+    if ((rc = launch_finish(h, 0, B, k, n_segs, seg, true, true, out_rows, out_scores, out_keys, st)))
       return rc;
     s.launches += 3;
     s.passes = (B + 255) / 256;
@@ -604,13 +639,13 @@ int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_r
   } else {
     const bool umma = path == RASS_PATH_UMMA;
     const int n_segs = umma ? scan_umma_segs(h) : scan_stream_segs(h);
-    const int seg = umma ? RASS_UMMA_SEG : RASS_STREAM_SEG;
+    const int seg = umma ? (robust ? rass_tc_seg(k) : 256) : RASS_STREAM_SEG;
     if ((rc = ensure_pool(h, (size_t)n_segs * seg, (size_t)n_segs))) return rc;
     for (int g0 = 0; g0 < B; g0 += RASS_GROUP_Q) {
       const int ng = std::min(RASS_GROUP_Q, B - g0);
       CUDA_TRY(h, cudaEventRecord(get_event(h, n_ev++), st));
       if (umma) {
-        if ((rc = launch_scan_umma(h, g0, ng, st))) return rc;
+        if ((rc = launch_scan_umma(h, g0, ng, seg, st))) return rc;
         s.launches += 2;
         s.passes += 1;
       } else {
@@ -637,22 +672,74 @@ int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_r
       CUDA_TRY(h, cudaMemcpyAsync(h->flagged_host, h->flagged, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(h, cudaStreamSynchronize(st));
       std::sort(h->flagged_host, h->flagged_host + nf);
-      if ((rc = launch_exact(h, k, h->flagged_host, nf, out_rows, out_scores, out_keys, st, &s.launches))) return rc;
-      s.n_fallback = nf;
+      const bool second_chance = !robust && k > 32 && rass_tc_seg(k) != 256;
+      if (second_chance) {
+        // the recursive search also reuses the timing events: keep this pass's times
+        float pre = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&pre, h->ev[0], h->ev[1]));
+        for (size_t i = 0; i + 1 < n_ev; i += 2) {
+          float ms1 = 0.f;
+          CUDA_TRY(h, cudaEventElapsedTime(&ms1, h->ev_pool[i], h->ev_pool[i + 1]));
+          first_scan_ms += ms1;
+        }
+        n_ev = 0;
+        first_total_ms = pre;
+        // the recursive search reuses every workspace of this one, so stage ids, queries and results on the side
+        if ((size_t)nf > h->retry_cap || k > h->retry_k) {
+          const size_t cap = std::max<size_t>((size_t)nf * 2, 256);
+          const int kk = std::max(k, h->retry_k);
+          cudaFree(h->retry_ids); cudaFree(h->retry_q); cudaFree(h->retry_rows); cudaFree(h->retry_scores);
+          cudaFree(h->retry_keys);
+          h->retry_ids = nullptr; h->retry_q = nullptr; h->retry_rows = nullptr; h->retry_scores = nullptr;
+          h->retry_keys = nullptr;
+          h->retry_cap = 0;
+          CUDA_TRY(h, cudaMalloc(&h->retry_ids, cap * sizeof(int)));
+          CUDA_TRY(h, cudaMalloc(&h->retry_q, cap * h->dim * sizeof(float)));
+          CUDA_TRY(h, cudaMalloc(&h->retry_rows, cap * kk * sizeof(int64_t)));
+          CUDA_TRY(h, cudaMalloc(&h->retry_scores, cap * kk * sizeof(float)));
+          CUDA_TRY(h, cudaMalloc(&h->retry_keys, cap * kk * sizeof(double)));
+          h->retry_cap = cap;
+          h->retry_k = kk;
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(h->retry_ids, h->flagged_host, (size_t)nf * sizeof(int), cudaMemcpyHostToDevice, st));
+        gather_queries_kernel<<<nf, 256, 0, st>>>(q_dev, h->retry_ids, h->dim, h->retry_q);
+        CUDA_TRY(h, cudaGetLastError());
+        rass_stats s2;
+        if ((rc = search_core_impl(h, h->retry_q, nf, k, h->retry_rows, h->retry_scores, h->retry_keys, &s2, true)))
+          return rc;
+        scatter_results_kernel<<<nf, 128, 0, st>>>(h->retry_ids, k, h->retry_rows, h->retry_scores, h->retry_keys,
+                                                   out_rows, out_scores, out_keys);
+        CUDA_TRY(h, cudaGetLastError());
+        s.n_certified += s2.n_certified;
+        s.n_fallback = s2.n_fallback;
+        s.n_retried = nf;
+        s.launches += s2.launches + 2;
+        s.passes += s2.passes;
+        s.bytes_streamed += s2.bytes_streamed;
+        retry_scan_ms = s2.scan_ms;
+        retry_total_ms = s2.total_ms;
+      } else {
+        if ((rc = launch_exact(h, k, h->flagged_host, nf, out_rows, out_scores, out_keys, st, &s.launches))) return rc;
+        s.n_fallback = nf;
+      }
     }
   }
   CUDA_TRY(h, cudaEventRecord(h->ev[2], st));
   CUDA_TRY(h, cudaStreamSynchronize(st));
   float ms = 0.f;
-  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]));
-  s.total_ms = ms;
-  double scan = 0.0;
+  double scan = first_scan_ms;
+  if (first_total_ms >= 0.0) {
+    s.total_ms = first_total_ms + retry_total_ms;
+  } else {
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]));
+    s.total_ms = ms;
+  }
   for (size_t i = 0; i + 1 < n_ev; i += 2) {
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
     scan += ms;
   }
-  s.scan_ms = scan;
-  s.finish_ms = s.total_ms - scan;
+  s.scan_ms = scan + retry_scan_ms;
+  s.finish_ms = s.total_ms - s.scan_ms;
   if (stats) *stats = s;
   return RASS_OK;
 }

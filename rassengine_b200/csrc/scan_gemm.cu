@@ -27,7 +27,6 @@
 #define G2_ACC 2                           // TMEM accumulator stages (256 columns each)
 #define G2_TMEM_COLS 512
 #define G2_THREADS 256
-#define G2_HIGH_WATER 128
 #define G2_HIT_STRIDE 36                   // floats per epilogue thread in the hit staging area (36: STS.128 conflict-free)
 
 namespace {
@@ -59,6 +58,7 @@ struct GemmPlan {
 
 }  // namespace
 
+template <int SEG>      // pool entries per (item, CTA, query) segment, see scan_umma.cu
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
     scan_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_q,
                      const float* __restrict__ sa, const float* __restrict__ sb, int64_t n_rows, GemmPlan plan,
@@ -213,8 +213,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
               m &= m - 1;
               const float s = mine[j];
               const int pos = atomicAdd(&ss->cnt[c + j], 1);
-              if (pos < RASS_UMMA_SEG) {
-                const size_t o = (slot0 + c + j) * pool_entries + (size_t)seg * RASS_UMMA_SEG + pos;
+              if (pos < SEG) {
+                const size_t o = (slot0 + c + j) * pool_entries + (size_t)seg * SEG + pos;
                 pool_key[o] = s;
                 pool_row[o] = (uint32_t)row;
               }
@@ -239,15 +239,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
             if (g > 0x007fffffu) ss->thr[q] = fmaxf(ss->thr[q], unord32(g));
           }
           __syncwarp();
-          unsigned need = __ballot_sync(0xffffffffu, ss->cnt[qb + 4 * lane + ew] > G2_HIGH_WATER);
+          unsigned need = __ballot_sync(0xffffffffu, ss->cnt[qb + 4 * lane + ew] > (SEG / 2));
           while (need) {
             const int q = qb + 4 * (__ffs(need) - 1) + ew;
             need &= need - 1;
-            const int n = min(ss->cnt[q], RASS_UMMA_SEG);
-            const size_t base = (slot0 + q) * pool_entries + (size_t)seg * RASS_UMMA_SEG;
-            uint32_t ok[RASS_UMMA_SEG / 32], rw[RASS_UMMA_SEG / 32];
+            const int n = min(ss->cnt[q], SEG);
+            const size_t base = (slot0 + q) * pool_entries + (size_t)seg * SEG;
+            uint32_t ok[SEG / 32], rw[SEG / 32];
 #pragma unroll
-            for (int i = 0; i < RASS_UMMA_SEG / 32; ++i) {
+            for (int i = 0; i < SEG / 32; ++i) {
               const int idx = i * 32 + lane;
               ok[i] = idx < n ? ord32(__ldcg(pool_key + base + idx)) : 0u;
               rw[i] = idx < n ? __ldcg(pool_row + base + idx) : 0xffffffffu;
@@ -255,7 +255,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
             __syncwarp();
             uint32_t pivot;
             const int kept =
-                warp_compact<RASS_UMMA_SEG / 32>(ok, rw, RASS_UMMA_KEEP, pool_key + base, pool_row + base, pivot);
+                warp_compact<SEG / 32>(ok, rw, (SEG / 8), pool_key + base, pool_row + base, pivot);
             __syncwarp();
             // everything dropped here, and every row rejected from now on, has key <= pivot
             if (lane == 0) {
@@ -269,7 +269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
       }
       // publish the segment sizes and bounds of this item
       for (int q = et; q < nq_here; q += 128) {
-        pool_cnt[(slot0 + q) * n_segs + seg] = min(ss->cnt[q], RASS_UMMA_SEG);
+        pool_cnt[(slot0 + q) * n_segs + seg] = min(ss->cnt[q], SEG);
         pool_thr[(slot0 + q) * n_segs + seg] = ss->thr[q];
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -316,7 +316,7 @@ __global__ void clear_gemm_segs_kernel(float* thr, int* cnt, size_t n) {
   cnt[i] = 0;
 }
 
-static int gemm_launch(rass_engine* h, int B, float* dbg_out, cudaStream_t st) {
+static int gemm_launch(rass_engine* h, int B, int seg, float* dbg_out, cudaStream_t st) {
   int rc;
   if (!h->tmap_x) h->tmap_x = calloc(1, sizeof(CUtensorMap));
   if (!h->tmap_q2) h->tmap_q2 = calloc(1, sizeof(CUtensorMap));
@@ -341,18 +341,22 @@ static int gemm_launch(rass_engine* h, int B, float* dbg_out, cudaStream_t st) {
   // timing experiments only (results are wrong): 1 = epilogue reads one column block, 2 = epilogue drops every hit
   static const int dbg_mode = getenv("RASS_GEMM_DEBUG_MODE") ? atoi(getenv("RASS_GEMM_DEBUG_MODE")) : 0;
   const size_t smem = gemm_smem_bytes();
-  CUDA_TRY(h, cudaFuncSetAttribute(scan_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  scan_gemm_kernel<<<grid, G2_THREADS, smem, st>>>(*(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q2, h->sa, h->sb_scan,
-                                                   h->n_rows, plan, h->dim_pad / G2_KBLK, B, h->pool_key, h->pool_row,
-                                                   h->pool_thr, h->pool_cnt, h->pool_entries, n_segs, h->q_gthr,
-                                                   dbg_out, dbg_mode);
+#define RASS_GEMM_LAUNCH(S)                                                                                          \
+  do {                                                                                                               \
+    CUDA_TRY(h, cudaFuncSetAttribute(scan_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    scan_gemm_kernel<S><<<grid, G2_THREADS, smem, st>>>(                                                             \
+        *(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q2, h->sa, h->sb_scan, h->n_rows, plan, h->dim_pad / G2_KBLK, \
+        B, h->pool_key, h->pool_row, h->pool_thr, h->pool_cnt, h->pool_entries, n_segs, h->q_gthr, dbg_out, dbg_mode); \
+  } while (0)
+  if (seg == 512) RASS_GEMM_LAUNCH(512); else RASS_GEMM_LAUNCH(256);
+#undef RASS_GEMM_LAUNCH
   CUDA_TRY(h, cudaGetLastError());
   return RASS_OK;
 }
 
 // all B prepared queries (q16 rows [0, B), padded with zero rows to a multiple of 256) against the whole shard;
 // query q's candidates land in pool slot q
-int launch_scan_gemm(rass_engine* h, int B, cudaStream_t st) { return gemm_launch(h, B, nullptr, st); }
+int launch_scan_gemm(rass_engine* h, int B, int seg, cudaStream_t st) { return gemm_launch(h, B, seg, nullptr, st); }
 
 // Debug/self-test entry: raw tensor-core dot products of the first 256 prepared queries against every row.
 // out_host: [n_rows, 256] fp32.
@@ -362,8 +366,8 @@ int gemm_selftest(rass_engine* h, int B, float* out_host, cudaStream_t st) {
   CUDA_TRY(h, cudaMalloc(&dbg, n * 4));
   CUDA_TRY(h, cudaMemsetAsync(dbg, 0, n * 4, st));
   const int n_segs = scan_gemm_segs(h, B);
-  int rc = ensure_pool(h, (size_t)n_segs * RASS_UMMA_SEG, (size_t)n_segs, B);
-  if (!rc) rc = gemm_launch(h, B, dbg, st);
+  int rc = ensure_pool(h, (size_t)n_segs * 256, (size_t)n_segs, B);
+  if (!rc) rc = gemm_launch(h, B, 256, dbg, st);
   if (!rc) {
     cudaError_t e = cudaMemcpyAsync(out_host, dbg, n * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

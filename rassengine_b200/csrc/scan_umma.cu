@@ -24,7 +24,6 @@
 #define UMMA_ACC 4                          // TMEM accumulator stages (64 columns each)
 #define UMMA_TMEM_COLS 256
 #define UMMA_THREADS 256
-#define UMMA_HIGH_WATER 128
 
 namespace {
 
@@ -45,6 +44,10 @@ struct UmmaSmem {
 
 }  // namespace
 
+// SEG = pool entries per (CTA, query) segment: a compaction keeps SEG/8 .. SEG/4 entries once SEG/2 is passed.
+// 256 (keep >= 32) serves k <= 32; 512 (keep >= 128) keeps at least k entries above every pivot for k <= 128, so
+// a cluster of near neighbours inside one segment cannot push the bound past the k-th best.
+template <int SEG>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
     scan_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_q,
                      const float* __restrict__ sa, const float* __restrict__ sb, int64_t n_rows, int n_tiles,
@@ -174,8 +177,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
 #pragma unroll
             for (int t = 1; t < 16; ++t) s = (j == t) ? sc[t] : s;
             const int pos = atomicAdd(&ss->cnt[c + j], 1);
-            if (pos < RASS_UMMA_SEG) {
-              const size_t o = (size_t)(c + j) * pool_entries + (size_t)cta * RASS_UMMA_SEG + pos;
+            if (pos < SEG) {
+              const size_t o = (size_t)(c + j) * pool_entries + (size_t)cta * SEG + pos;
               pool_key[o] = s;
               pool_row[o] = (uint32_t)row;
             }
@@ -194,20 +197,20 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
       if (g > 0x007fffffu) ss->thr[4 * lane + ew] = fmaxf(ss->thr[4 * lane + ew], unord32(g));
       __syncwarp();
       for (int q = ew; q < UMMA_NQ; q += 4) {
-        const int n = min(ss->cnt[q], RASS_UMMA_SEG);
-        if (n <= UMMA_HIGH_WATER) continue;
-        const size_t base = (size_t)q * pool_entries + (size_t)cta * RASS_UMMA_SEG;
+        const int n = min(ss->cnt[q], SEG);
+        if (n <= (SEG / 2)) continue;
+        const size_t base = (size_t)q * pool_entries + (size_t)cta * SEG;
         // keys as order-preserving integers; empty slots are 0
-        uint32_t ok[RASS_UMMA_SEG / 32], rw[RASS_UMMA_SEG / 32];
+        uint32_t ok[SEG / 32], rw[SEG / 32];
 #pragma unroll
-        for (int i = 0; i < RASS_UMMA_SEG / 32; ++i) {
+        for (int i = 0; i < SEG / 32; ++i) {
           const int idx = i * 32 + lane;
           ok[i] = idx < n ? ord32(__ldcg(pool_key + base + idx)) : 0u;
           rw[i] = idx < n ? __ldcg(pool_row + base + idx) : 0xffffffffu;
         }
         __syncwarp();
         uint32_t pivot;
-        const int kept = warp_compact<RASS_UMMA_SEG / 32>(ok, rw, RASS_UMMA_KEEP, pool_key + base, pool_row + base, pivot);
+        const int kept = warp_compact<SEG / 32>(ok, rw, (SEG / 8), pool_key + base, pool_row + base, pivot);
         __syncwarp();
         // everything dropped here, and every row rejected from now on, has key <= pivot
         if (lane == 0) {
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
     }
     // publish the segment sizes and bounds
     if (et < UMMA_NQ) {
-      pool_cnt[(size_t)et * n_segs + cta] = min(ss->cnt[et], RASS_UMMA_SEG);
+      pool_cnt[(size_t)et * n_segs + cta] = min(ss->cnt[et], SEG);
       pool_thr[(size_t)et * n_segs + cta] = ss->thr[et];
     }
   }
@@ -276,7 +279,7 @@ static size_t umma_smem_bytes(const rass_engine* h) {
 
 int scan_umma_segs(const rass_engine* h) { return h->num_sms; }
 
-static int umma_launch(rass_engine* h, int q0, int64_t n_rows, float* dbg_out, cudaStream_t st) {
+static int umma_launch(rass_engine* h, int q0, int64_t n_rows, int seg, float* dbg_out, cudaStream_t st) {
   int rc;
   if (!h->tmap_x) h->tmap_x = calloc(1, sizeof(CUtensorMap));
   if (!h->tmap_q) h->tmap_q = calloc(1, sizeof(CUtensorMap));
@@ -297,11 +300,16 @@ static int umma_launch(rass_engine* h, int q0, int64_t n_rows, float* dbg_out, c
   if (!keep_gthr)
     CUDA_TRY(h, cudaMemsetAsync(h->q_gthr + q0, 0, UMMA_NQ * sizeof(uint32_t), st));   // nothing published yet
   const size_t smem = umma_smem_bytes(h);
-  CUDA_TRY(h, cudaFuncSetAttribute(scan_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  scan_umma_kernel<<<grid, UMMA_THREADS, smem, st>>>(*(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q, h->sa, h->sb_scan,
-                                                     n_rows, n_tiles, h->dim_pad / UMMA_KBLK, q0, h->pool_key,
-                                                     h->pool_row, h->pool_thr, h->pool_cnt, h->pool_entries,
-                                                     scan_umma_segs(h), h->q_gthr + q0, dbg_out);
+#define RASS_UMMA_LAUNCH(S)                                                                                          \
+  do {                                                                                                               \
+    CUDA_TRY(h, cudaFuncSetAttribute(scan_umma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    scan_umma_kernel<S><<<grid, UMMA_THREADS, smem, st>>>(                                                           \
+        *(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q, h->sa, h->sb_scan, n_rows, n_tiles, h->dim_pad / UMMA_KBLK, \
+        q0, h->pool_key, h->pool_row, h->pool_thr, h->pool_cnt, h->pool_entries, scan_umma_segs(h), h->q_gthr + q0,  \
+        dbg_out);                                                                                                    \
+  } while (0)
+  if (seg == 512) RASS_UMMA_LAUNCH(512); else RASS_UMMA_LAUNCH(256);
+#undef RASS_UMMA_LAUNCH
   CUDA_TRY(h, cudaGetLastError());
   // segments of CTAs that did not launch (fewer tiles than SMs) were cleared by the caller and read as empty
   return RASS_OK;
@@ -314,12 +322,12 @@ __global__ void clear_segs_kernel(float* thr, int* cnt, size_t n) {
   cnt[i] = 0;
 }
 
-int launch_scan_umma(rass_engine* h, int q0, int nq, cudaStream_t st) {
+int launch_scan_umma(rass_engine* h, int q0, int nq, int seg, cudaStream_t st) {
   (void)nq;
   const size_t n = (size_t)scan_umma_segs(h) * RASS_GROUP_Q;
   clear_segs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pool_thr, h->pool_cnt, n);
   CUDA_TRY(h, cudaGetLastError());
-  return umma_launch(h, q0, h->n_rows, nullptr, st);
+  return umma_launch(h, q0, h->n_rows, seg, nullptr, st);
 }
 
 // Debug/self-test entry: raw tensor-core dot products of the first 64 prepared queries against every row.
@@ -330,11 +338,11 @@ int umma_selftest(rass_engine* h, int n_rows_unused, float* out_host, cudaStream
   const size_t n = (size_t)h->n_rows * UMMA_NQ;
   CUDA_TRY(h, cudaMalloc(&dbg, n * 4));
   CUDA_TRY(h, cudaMemsetAsync(dbg, 0, n * 4, st));
-  int rc = ensure_pool(h, (size_t)scan_umma_segs(h) * RASS_UMMA_SEG, (size_t)scan_umma_segs(h));
+  int rc = ensure_pool(h, (size_t)scan_umma_segs(h) * 256, (size_t)scan_umma_segs(h));
   if (!rc) {
     const size_t ns = (size_t)scan_umma_segs(h) * RASS_GROUP_Q;
     clear_segs_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(h->pool_thr, h->pool_cnt, ns);
-    rc = umma_launch(h, 0, h->n_rows, dbg, st);
+    rc = umma_launch(h, 0, h->n_rows, 256, dbg, st);
   }
   if (!rc) {
     cudaError_t e = cudaMemcpyAsync(out_host, dbg, n * 4, cudaMemcpyDeviceToHost, st);

@@ -262,3 +262,37 @@ def test_prefiltered_knn_matches_oracle_alive_mask(path):
         want_rows, _, want_scores = knn.knn_exact(X, Q, 10, alive=alive)
         rows, scores = e.search_knn(Q, 10)
         _check(rows, scores, want_rows, want_scores)
+
+
+@pytest.mark.parametrize("path", ["stream", "umma", "gemm"])
+def test_top100_inside_one_cluster_of_adjacent_rows_is_certified(path):
+    """Chunks of one document are adjacent rows and close to each other.  400 such rows hold the whole top-100 of a
+    query, so the fast pass (segments that keep 32..64 entries) cannot certify k = 100; the failed queries get a second
+    pass with 512-entry segments (>= 128 entries above every pivot) on the tensor cores, not the fp64 scan."""
+    rng = np.random.default_rng(61)
+    X = synth.embeddings(60000, 1024, 62)
+    centre = X[123].copy()
+    lo = 20000
+    X[lo:lo + 400] = centre[None, :] + 0.02 * rng.standard_normal((400, 1024)).astype(np.float32)
+    X[lo:lo + 400] /= np.linalg.norm(X[lo:lo + 400], axis=1, keepdims=True)
+    Q = (centre[None, :] + 0.01 * rng.standard_normal((70, 1024))).astype(np.float32)
+    Q[1::2] = synth.embeddings(35, 1024, 63)            # every other query is unrelated to the cluster
+    if path == "stream":
+        Q = Q[:2]
+    want_rows, _, want_scores = knn.knn_exact(X, Q, 100)
+    assert ((want_rows[0::2] >= lo) & (want_rows[0::2] < lo + 400)).mean() > 0.95
+    with _engine(dim=1024) as e:
+        e.set_path(_paths()[path])
+        e.append(X)
+        rows, scores = e.search_knn(Q, 100)
+        st = e.last_stats
+        rows10, scores10 = e.search_knn(Q, 10)          # k <= 32 never needs the second pass
+        st10 = e.last_stats
+    _check(rows, scores, want_rows, want_scores)
+    _check(rows10, scores10, want_rows[:, :10], want_scores[:, :10])
+    assert st["n_fallback"] == 0 and st["n_certified"] == Q.shape[0], st
+    if path == "stream":       # row groups are dealt round-robin to 2368 warps: no list ever sees more than a few of them
+        assert st["n_retried"] == 0, st
+    else:
+        assert 0 < st["n_retried"] <= (Q.shape[0] + 1) // 2, st
+    assert st10["n_retried"] == 0 and st10["n_fallback"] == 0, st10
