@@ -84,3 +84,50 @@ def text_total(fields: dict[str, Field], clauses, n_docs: int) -> np.ndarray:
     for query, specs, cb, fz in clauses:
         total += clause_score(fields, query, specs, cb, fz, n_docs).astype(np.float64)
     return total
+
+
+def phrase_score(f: Field, docs_tokens: list[list[str]], query: str, boost: float, prefix: bool = False) -> np.ndarray:
+    """multi_match type phrase / phrase_prefix on one field (Lucene PhraseQuery / MultiPhraseQuery, slop 0): a document
+    scores BM25 of its phrase frequency with weight boost * (float) sum of the idf of EVERY term of the query (all
+    prefix expansions included, at most 50 in term order); a one-position query degenerates to a disjunction of term
+    queries.  docs_tokens = the field's token list per document (positions)."""
+    n = len(docs_tokens)
+    out = np.zeros(n, dtype=np.float32)
+    tokens = [query] if f.kind == "keyword" else analyze(query)
+    if not tokens:
+        return out
+    tid = {t: i for i, t in enumerate(f.terms)}
+    positions = []
+    for i, tok in enumerate(tokens):
+        if prefix and i == len(tokens) - 1:
+            alts = [t for t in f.terms if t.startswith(tok)][:50]
+        else:
+            alts = [tok] if tok in tid else []
+        if not alts:
+            return out
+        positions.append(alts)
+    bo = np.float32(boost)
+    one = np.float32(1.0)
+    if len(positions) == 1:
+        ids = [tid[t] for t in positions[0]]
+        return fuzzy.score(f.index, ids, [np.float32(bo * f.index.idf(t)) for t in ids])
+    idf = np.float32(sum(float(f.index.idf(tid[t])) for alts in positions for t in alts))
+    w = np.float32(bo * idf)
+    for d, toks in enumerate(docs_tokens):
+        freq = 0
+        for s in range(len(toks) - len(positions) + 1):
+            if all(toks[s + j] in positions[j] for j in range(len(positions))):
+                freq += 1
+        if freq:
+            out[d] = w - w / (one + np.float32(freq) * f.index.inv[f.index.norm[d]])
+    return out
+
+
+def field_tokens(docs: list[dict], name: str, kind: str) -> list[list[str]]:
+    out = []
+    for d in docs:
+        v = d.get(name)
+        vals = v if isinstance(v, (list, tuple)) else [v]
+        out.append([str(x) for x in vals if x is not None] if kind == "keyword"
+                   else [t for x in vals if isinstance(x, str) for t in analyze(x)])
+    return out

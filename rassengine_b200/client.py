@@ -73,6 +73,7 @@ class _Index:
         types.setdefault(TEXT_FIELD, "text")
         self.text = TextIndex(types)
         self.n_docs = 0
+        self.host_views: dict = {}               # hostquery.FieldView cache (N4 host-side queries)
         self.kw: dict[str, dict[object, list[int]]] = {f: {} for f in FILTER_FIELDS}   # field -> value -> rows
 
     # -- engine ------------------------------------------------------------------------------------------
@@ -91,6 +92,38 @@ class _Index:
         if self.engine is not None:
             self.engine.close()
             self.engine = None
+
+    def field_type(self, name: str) -> str | None:
+        """Mapping type of a field; `X.keyword` resolves to the keyword sub-field of X when the mapping declares one."""
+        props = self.body.get("mappings", {}).get("properties", {})
+        if name in props and isinstance(props[name], dict):
+            return props[name].get("type")
+        if name.endswith(".keyword") and self.has_keyword_subfield(name[:-8]):
+            return "keyword"
+        return None
+
+    def has_keyword_subfield(self, base: str) -> bool:
+        spec = self.body.get("mappings", {}).get("properties", {}).get(base)
+        return isinstance(spec, dict) and isinstance(spec.get("fields"), dict) and \
+            spec["fields"].get("keyword", {}).get("type") == "keyword"
+
+    def host_search(self, body: dict):
+        """Query shapes outside the GPU hot path, evaluated on the host: -> (hits, aggs, total)."""
+        from .hostquery import HostSearcher
+        with self.lock:
+            self._sync_text()                 # per-field statistics and the device dictionary (fuzziness) are current
+            found, aggs, total = HostSearcher(self).search(body)
+        src_filter = body.get("_source")
+        hits = []
+        for row, score in found:
+            h = self._hit(row, 0.0)
+            h["_score"] = score
+            if isinstance(src_filter, (list, tuple)):
+                h["_source"] = {k: v for k, v in (h["_source"] or {}).items() if k in src_filter}
+            elif src_filter is False:
+                h.pop("_source")
+            hits.append(h)
+        return hits, aggs, total
 
     def _knn(self, q: np.ndarray, k: int):
         """kNN of one query; coalesced with concurrent callers when the client was given a batch window."""
@@ -118,6 +151,7 @@ class _Index:
             self._index_batch_locked(docs)
 
     def _index_batch_locked(self, docs: list[tuple[str, dict]]):
+        self.host_views = {}
         vf = self.vector_field or "embedding"
         fresh: list[tuple[str, dict]] = []
         seen: dict[str, int] = {}
@@ -413,12 +447,21 @@ class B200Client:
     def search(self, index: str | None = None, body: dict | None = None, routing=None, **_) -> dict:
         t0 = time.perf_counter()
         idx = self._get(index)
-        plan = parse_search_body(body or {})
-        hits = idx.search(plan)
-        return {"took": int((time.perf_counter() - t0) * 1e3), "timed_out": False,
+        aggs = None
+        try:
+            plan = parse_search_body(body or {})          # the hot path: knn / hybrid shapes, on the GPU
+            hits = idx.search(plan)
+            total = len(hits)
+        except NotImplementedError:
+            hits, aggs, total = idx.host_search(body or {})    # everything else: host-side (raises if unsupported)
+        scores = [h["_score"] for h in hits if h.get("_score") is not None]
+        resp = {"took": int((time.perf_counter() - t0) * 1e3), "timed_out": False,
                 "_shards": {"total": 1, "successful": 1, "skipped": 0, "failed": 0},
-                "hits": {"total": {"value": len(hits), "relation": "eq"},
-                         "max_score": max((h["_score"] for h in hits), default=None), "hits": hits}}
+                "hits": {"total": {"value": total, "relation": "eq"},
+                         "max_score": max(scores, default=None), "hits": hits}}
+        if aggs is not None:
+            resp["aggregations"] = aggs
+        return resp
 
     def close(self):
         for idx in self._indices.values():

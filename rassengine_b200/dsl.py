@@ -6,8 +6,9 @@
              "minimum_should_match": 1, "filter": [...]}}, "terminate_after": k}        app/main.py:1574-1605
              (multi_intent_search emits the same shape with other boosts            app/main.py:1982-2010)
 
-Anything else (phrase, phrase_prefix, range, sort, aggs, collapse ...) raises NotImplementedError; the reference wraps
-every search in `except Exception: return []` (app/main.py:1558-1560, 1613-1615), so callers see "no results".
+Anything else (phrase, phrase_prefix, range, sort, aggs, collapse ...) raises NotImplementedError here and is evaluated
+host-side by hostquery.py; shapes neither understands raise NotImplementedError to the caller, which
+the reference's `except Exception: return []` (app/main.py:1558-1560, 1613-1615) turns into "no results".
 `terminate_after` is ignored on purpose: the engine returns the true global top-k (reference defects).
 """
 from __future__ import annotations
@@ -67,9 +68,9 @@ def _parse_filters(nodes, plan: Plan):
 def parse_search_body(body: dict) -> Plan:
     if not isinstance(body, dict):
         raise ValueError("search body must be a dict")
-    for key in ("aggs", "aggregations", "sort", "collapse"):
+    for key in ("aggs", "aggregations", "sort", "collapse", "from", "_source"):
         if key in body:
-            raise NotImplementedError(f"'{key}' is outside the retrieval hot path")
+            raise NotImplementedError(f"'{key}' is outside the retrieval hot path (evaluated host-side)")
     plan = Plan(size=int(body.get("size", 10)))
     q = body.get("query")
     if q is None or q == {"match_all": {}}:
@@ -90,10 +91,14 @@ def parse_search_body(body: dict) -> Plan:
         must = [must]
     should = b.get("should") or []
     if must:
-        if should or len(must) != 1 or "knn" not in must[0]:
-            raise NotImplementedError("bool.must is supported for a single knn clause only")
-        _parse_knn(must[0]["knn"], plan)
-        return plan
+        if should or len(must) != 1:
+            raise NotImplementedError("bool.must with several clauses is evaluated host-side")
+        if "knn" in must[0]:
+            _parse_knn(must[0]["knn"], plan)
+            return plan
+        # a single scoring multi_match under must (explanatory_search, app/main.py:1924-1967) scores and matches
+        # exactly like the same clause under should with minimum_should_match 1
+        should = must
     if not should:
         raise NotImplementedError("bool query without must/should")
     if int(b.get("minimum_should_match", 1)) != 1:

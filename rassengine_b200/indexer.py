@@ -36,6 +36,9 @@ TEXT_FIELDS = [
     "medRequestNote", "procedureCodeText", "procedureNote", "allergyCodeText", "allergyNote^2", "practitionerName^3",
     "practitionerAddress", "practitionerTelecom", "organizationName^3", "organizationAddress", "organizationTelecom",
 ]
+DATE_FIELDS = ["patientDOB", "conditionOnsetDateTime", "conditionRecordedDate", "observationEffectiveDateTime",
+               "observationIssued", "encounterStart", "encounterEnd", "medRequestAuthoredOn",
+               "procedurePerformedDateTime", "allergyOnsetDateTime"]                           # app/main.py:1457-1468
 KEYWORD_FIELDS = [
     "patientGender^3", "patientMaritalStatus^2", "patientLanguage^3", "conditionCategory^2", "conditionClinicalStatus",
     "conditionVerificationStatus", "conditionSeverity", "observationUnit", "observationInterpretation",
@@ -50,7 +53,11 @@ def index_body(dim: int = EMBED_DIM) -> dict:
     knn_vector field, and the type (text / keyword) of every field the two multi_match clauses search."""
     props = {"doc_id": {"type": "keyword"}, "doc_type": {"type": "keyword"}, "patientId": {"type": "keyword"},
              "resourceType": {"type": "keyword"}, "file_path": {"type": "keyword"}, "file_type": {"type": "keyword"}}
-    props.update({f.split("^")[0]: {"type": "text"} for f in TEXT_FIELDS})
+    props.update({f.split("^")[0]: {"type": "text", "fields": {"keyword": {"type": "keyword", "ignore_above": 256}}}
+                  for f in TEXT_FIELDS})
+    props["unstructuredText"] = {"type": "text"}
+    props.update({f: {"type": "date", "format": "yyyy-MM-dd||strict_date_optional_time||epoch_millis"}
+                  for f in DATE_FIELDS})
     props.update({f.split("^")[0]: {"type": "keyword"} for f in KEYWORD_FIELDS})
     props["embedding"] = {"type": "knn_vector", "dimension": dim,
                           "method": {"name": "hnsw", "engine": "nmslib", "space_type": "cosinesimil",
@@ -217,12 +224,137 @@ class B200Indexer:
             logger.error(f"search error: {e}")
             return []
 
-    # keyword-only family (phrase / range / aggs / collapse DSL): outside the hot path -> no results, never raise
-    def _unsupported(self, *_, **__):
+    # -- the keyword-side family: same bodies as the reference, answered host-side by the client ------
+    DATE_FIELDS = DATE_FIELDS
+    STRUCTURED_FIELDS = ["patientName^3", "patientGender^3", "patientTelecom^3", "conditionCodeText^2",
+                         "conditionClinicalStatus", "conditionSeverity", "observationCodeText", "observationValue",
+                         "observationUnit", "encounterStatus", "encounterClass", "medRequestMedicationDisplay",
+                         "medRequestStatus", "procedureCodeText", "procedureStatus", "allergyCodeText",
+                         "allergyClinicalStatus", "practitionerName^3", "organizationName^3"]   # app/main.py:1722-1742
+
+    def _bool_body(self, bool_query: dict, k: int, filter_clause, patient_id, extra_filters=(), **top) -> dict:
+        flt = self._filters(filter_clause, patient_id) + list(extra_filters)
+        if flt:
+            bool_query["filter"] = flt
+        return {"size": k, "query": {"bool": bool_query}, "terminate_after": k, **top}
+
+    def exact_match_search(self, query: str, k: int = TOP_K, filter_clause=None, patient_id=None):
+        """app/main.py:1480-1525: phrase match over the text fields (boost 2) and the keyword fields."""
+        if not query.strip():
+            return []
+        should = [{"multi_match": {"query": query, "fields": self.text_fields, "type": "phrase", "boost": 2.0}},
+                  {"multi_match": {"query": query, "fields": self.keyword_fields, "type": "phrase"}}]
+        body = self._bool_body({"should": should, "minimum_should_match": 1}, k, filter_clause, patient_id)
+        return self._run(body, patient_id, "Exact match search")
+
+    def structured_search(self, query: str, k: int = TOP_K, filter_clause=None, patient_id=None):
+        """app/main.py:1617-1705 as intended (the reference reads an undefined `structured_fields` and raises
+        NameError): phrase_prefix over the structured fields, restricted to structured documents."""
+        if not query.strip():
+            return []
+        must = [{"multi_match": {"query": query, "fields": self.STRUCTURED_FIELDS, "type": "phrase_prefix",
+                                 "operator": "and"}}]
+        body = {"size": k, "query": {"bool": {"must": must, "filter": [{"term": {"doc_type": "structured"}}]}},
+                "terminate_after": k}
+        return self._run(body, patient_id, "Structured search")
+
+    def hybrid_structured_search(self, query: str, query_emb: np.ndarray, k: int = TOP_K, filter_clause=None,
+                                 patient_id=None):
+        """app/main.py:1707-1775: phrase_prefix (boost 1.5) + knn (boost 2.0) over structured documents.  (The
+        reference appends to a filter list that only exists when a filter or patient was given.)"""
+        if not query.strip() or query_emb.size == 0:
+            return []
+        should = [{"multi_match": {"query": query, "fields": self.STRUCTURED_FIELDS, "type": "phrase_prefix",
+                                   "operator": "and", "boost": 1.5}},
+                  {"knn": {"embedding": {"vector": self._unit_vector(query_emb), "k": k, "boost": 2.0}}}]
+        body = self._bool_body({"should": should, "minimum_should_match": 1}, k, filter_clause, patient_id,
+                               extra_filters=[{"term": {"doc_type": "structured"}}])
+        return self._run(body, patient_id, "Hybrid structured search")
+
+    def aggregate_search(self, query: str, filter_clause=None, patient_id=None) -> Dict:
+        """app/main.py:1777-1810: three terms aggregations, optionally under a filter; returns resp["aggregations"]."""
+        body = {"size": 0, "aggs": {
+            "by_condition": {"terms": {"field": "conditionCodeText.keyword", "size": 5}},
+            "by_resource": {"terms": {"field": "resourceType.keyword", "size": 5}},
+            "by_patient": {"terms": {"field": "patientId", "size": 5}}}}
+        flt = self._filters(filter_clause, patient_id)
+        if flt:
+            body["query"] = {"bool": {"filter": flt}}
+        try:
+            return self.client.search(index=self.index_name, body=body, routing=patient_id)["aggregations"]
+        except Exception as e:
+            logger.error(f"Aggregate search error: {e}")
+            return {}
+
+    def comparison_search(self, query: str, k: int = TOP_K, filter_clause=None, patient_id=None):
+        """app/main.py:1812-1866: best_fields AUTO over the comparable fields (+ an aggregation nobody reads)."""
+        if not query.strip():
+            return []
+        fields = ["conditionCodeText^2", "observationValue", "observationUnit", "medRequestMedicationDisplay",
+                  "procedureCodeText", "allergyCodeText"]
+        should = [{"multi_match": {"query": query, "fields": fields, "type": "best_fields", "operator": "or",
+                                   "fuzziness": "AUTO"}}]
+        body = self._bool_body({"should": should, "minimum_should_match": 1}, k, filter_clause, patient_id,
+                               aggs={"by_field": {"terms": {"field": "conditionCodeText.keyword", "size": 3}}})
+        return self._run(body, patient_id, "Comparison search")
+
+    def temporal_search(self, query: str, k: int = TOP_K, filter_clause=None, patient_id=None):
+        """app/main.py:1868-1922: text match AND any date field within the last year, newest condition first.  A
+        sorted search carries `_score: null`, so the reference's `float(hit["_score"])` raises and the method returns
+        [] whenever something matched; that behaviour is kept (use client.search with the same body for the hits)."""
+        if not query.strip():
+            return []
+        dates = {"bool": {"should": [{"range": {f: {"gte": "now-1y", "lte": "now"}}} for f in self.DATE_FIELDS],
+                          "minimum_should_match": 1}}
+        must = [{"multi_match": {"query": query, "fields": self.text_fields + self.keyword_fields,
+                                 "type": "best_fields", "operator": "or"}}, dates]
+        body = self._bool_body({"must": must}, k, filter_clause, patient_id,
+                               sort=[{"conditionOnsetDateTime": {"order": "desc"}}])
+        return self._run(body, patient_id, "Temporal search")
+
+    def explanatory_search(self, query: str, k: int = TOP_K, filter_clause=None, patient_id=None):
+        """app/main.py:1924-1967: best_fields AUTO over the note fields (GPU text path: one scoring clause under must)."""
+        if not query.strip():
+            return []
+        fields = ["conditionNote^3", "observationNote^3", "encounterNote^3", "medRequestNote^3", "procedureNote^3",
+                  "allergyNote^3", "unstructuredText^2"]
+        must = [{"multi_match": {"query": query, "fields": fields, "type": "best_fields", "operator": "or",
+                                 "fuzziness": "AUTO"}}]
+        body = self._bool_body({"must": must}, k, filter_clause, patient_id)
+        return self._run(body, patient_id, "Explanatory search")
+
+    def entity_specific_search(self, query: str, k: int = TOP_K, filter_clause=None, patient_id=None):
+        """app/main.py:2029-2075: phrase match over the entity fields."""
+        if not query.strip():
+            return []
+        fields = ["patientName^4", "patientId^4", "patientGender^3", "patientTelecom^3", "practitionerName^3",
+                  "organizationName^3"]
+        must = [{"multi_match": {"query": query, "fields": fields, "type": "phrase", "operator": "and"}}]
+        body = self._bool_body({"must": must}, k, filter_clause, patient_id)
+        return self._run(body, patient_id, "Entity-specific search")
+
+    def document_fetch_search(self, query: str, k: int = TOP_K, filter_clause=None, patient_id=None):
+        """app/main.py:2079-2110: the patient's documents collapsed on patientId (one hit per patient)."""
+        if not patient_id:
+            return []
+        flt = [{"term": {"patientId": patient_id}}] + ([filter_clause] if filter_clause else [])
+        body = {"size": k, "query": {"bool": {"filter": flt}}, "collapse": {"field": "patientId"},
+                "terminate_after": k}
+        return self._run(body, patient_id, "Document fetch search")
+
+
+def resolve_patient_ids(client, index_name: str, name: str, top_k: int = 5) -> List[str]:
+    """The lookup of resolve_patient_ids_from_name (app/main.py:2709-2744): exact keyword, phrase or fuzzy all-terms
+    match on patientName, one hit per patientId."""
+    body = {"size": top_k, "_source": ["patientId"], "collapse": {"field": "patientId"},
+            "query": {"bool": {"should": [
+                {"term": {"patientName.keyword": name}},
+                {"match_phrase": {"patientName": name}},
+                {"match": {"patientName": {"query": name, "operator": "and", "fuzziness": "AUTO"}}}],
+                "minimum_should_match": 1}}}
+    try:
+        resp = client.search(index=index_name, body=body)
+        return [h["_source"]["patientId"] for h in resp.get("hits", {}).get("hits", []) if h["_source"].get("patientId")]
+    except Exception as e:
+        logger.error(f"Patient ID resolution failed: {e}")
         return []
-
-    exact_match_search = structured_search = hybrid_structured_search = comparison_search = _unsupported
-    temporal_search = explanatory_search = entity_specific_search = document_fetch_search = _unsupported
-
-    def aggregate_search(self, *_, **__):
-        return {}

@@ -244,9 +244,12 @@ def test_indexer_surface_end_to_end():
     assert idxr.hybrid_search("   ", q_emb) == []
     assert ix.B200Indexer(client, "no-such-index").semantic_search(q_emb) == []
     assert idxr.semantic_search(q_emb, k=k, filter_clause=[{"text": "x", "label": "Y"}]) == []   # ask()'s NER list
-    assert idxr.exact_match_search("x") == [] and idxr.aggregate_search("x") == {}
+    assert idxr.exact_match_search("zzz not in any document") == []
+    assert sum(b["doc_count"] for b in idxr.aggregate_search("x")["by_patient"]["buckets"]) <= len(docs)
+    assert client.search(index=name, body={"size": 3, "query": {"match_phrase": {"unstructuredText": "zzz"}}}
+                         )["hits"]["hits"] == []                    # keyword-side shapes are answered host-side (N4)
     with pytest.raises(NotImplementedError):
-        client.search(index=name, body={"size": 3, "query": {"match_phrase": {"unstructuredText": "x"}}})
+        client.search(index=name, body={"size": 3, "query": {"span_near": {"clauses": []}}})
     client.close()
 
 

@@ -157,3 +157,24 @@ def test_sharded_search_two_ranks_gloo(tmp_path):
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+def test_hostquery_building_blocks_agree_with_the_oracle():
+    """The host-side (N4) evaluator restates SmallFloat norms, the edit distance and date math on its own; they must
+    agree with the oracle's independent restatements."""
+    import datetime as dt
+    from oracle import fuzzy, smallfloat
+    from rassengine_b200 import hostquery as hq
+    assert np.array_equal(hq.LENGTH_TABLE.astype(np.float32), smallfloat.LENGTH_TABLE)
+    lens = np.array([0, 1, 23, 24, 25, 39, 40, 41, 47, 48, 511, 512, 100000], dtype=np.int64)
+    assert np.array_equal(hq.norm_bytes(lens), smallfloat.encode_lengths(lens))
+    for a, b in (("paitent", "patient"), ("chest", "chets"), ("ca", "abc"), ("smith", "smyth"), ("a", "abcd")):
+        assert hq._osa(a, b, 10) == fuzzy.osa_distance(a, b)
+    now = dt.datetime(2026, 3, 31, 12, 0, tzinfo=dt.timezone.utc)
+    assert hq._parse_date("now", now) == now
+    assert hq._parse_date("now-1y", now) == now.replace(year=2025)
+    assert hq._parse_date("now-2M", now) == now.replace(month=1, day=28)
+    assert hq._parse_date("now-3d", now) == now - dt.timedelta(days=3)
+    assert hq._parse_date("2024-02-29", now) == dt.datetime(2024, 2, 29, tzinfo=dt.timezone.utc)
+    assert hq._parse_date("2024-02-29T10:00:00Z", now).hour == 10
+    assert hq._parse_date("not a date", now) is None
