@@ -105,7 +105,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
         for (int t = t0; t < t1; ++t) {
           const int x_row = t * 2 * G2_ROWS + (int)rank * G2_ROWS;
           for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(&ss->empty[stage], phase ^ 1);
+            mbar_wait_relaxed(&ss->empty[stage], phase ^ 1);
             const uint32_t bar = mapa_u32(smem_u32(&ss->full[stage]), 0);
             const bool warm = dbg_mode >= 3 && n_issued >= G2_STAGES;      // timing experiments only
             const bool skip_b = warm, skip_a = warm && dbg_mode == 4;
@@ -189,7 +189,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) dbg_out[(size_t)row * G2_NQ + c + j] = __uint_as_float(v[j]);
           }
-          uint32_t m = 0;
+          // hot loop: one FMA and one predicate-accumulating compare per score; survivors are rare (a few per
+          // warp and tile), so their bit mask is only built when this thread has one
+          bool any = false;
 #pragma unroll
           for (int j4 = 0; j4 < 32; j4 += 4) {
             const float4 t4 = *reinterpret_cast<const float4*>(&ss->thr[c + j4]);
@@ -198,8 +200,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
             for (int j = 0; j < 4; ++j) {
               const float s = fmaf(__uint_as_float(v[j4 + j]), a, b);
               v[j4 + j] = __float_as_uint(s);
-              m |= (s > tt[j]) ? (1u << (j4 + j)) : 0u;
+              any |= s > tt[j];
             }
+          }
+          uint32_t m = 0;
+          if (any) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m |= (__uint_as_float(v[j]) > ss->thr[c + j]) ? (1u << j) : 0u;
           }
           if (dbg_mode == 2) m = 0;
           // each lane walks its own hits

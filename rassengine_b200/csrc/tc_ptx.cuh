@@ -42,6 +42,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same for a waiter that is normally AHEAD of its partner (a TMA producer on a full ring): sleep between polls so the
+// spin does not burn issue slots and power next to the tensor pipe.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(100);
+    if (clock64() - t0 > 4000000000LL) {
+      printf("rass tcgen05 scan: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
                                             uint64_t policy) {
   asm volatile(
