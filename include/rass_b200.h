@@ -171,6 +171,16 @@ int rass_search_hybrid_weighted(rass_engine* h, const float* q_host, int B, cons
                                 const int32_t* qterms, const float* qweights, const uint8_t* qflags, float w_knn,
                                 int k, int64_t* out_rows, float* out_scores, rass_stats* stats);
 
+/* Row-sharded hybrid (postings sharded by the same row ranges, statistics global): the text clauses of
+ * rass_search_hybrid(_weighted) fused with an EXTERNAL knn list -- the global k nearest the caller all-gathered and
+ * merged (global rows; rows of other shards are ignored) -- leaving this shard's top-k on the device: out_rows_dev
+ * (global rows), out_scores_dev (fused float scores) and, for rass_merge_topk_dev, out_keys_dev (the scores as
+ * double).  qweights / qflags / knn_rows_dev may be NULL.  Synchronises the engine stream. */
+int rass_fuse_hybrid_dev(rass_engine* h, int B, const int32_t* qterm_indptr, const int32_t* qterms,
+                         const float* qweights, const uint8_t* qflags, float w_text, const int64_t* knn_rows_dev,
+                         const float* knn_scores_dev, float w_knn, int k, int64_t* out_rows_dev,
+                         float* out_scores_dev, double* out_keys_dev);
+
 /* The term dictionary of the text field, terms back to back in blob, term t = blob[offsets[t] .. offsets[t+1])
  * (ASCII: the analyzer emits [a-z0-9]+).  Needed only for rass_fuzzy_expand. */
 int rass_text_set_vocab(rass_engine* h, const char* blob, const int64_t* offsets, int64_t V);

@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
 }
 
 int launch_select_batch(rass_engine* h, size_t entries, int B, int k, int64_t* out_rows, float* out_scores,
-                        cudaStream_t st);
+                        double* out_keys, cudaStream_t st);
 
 static int ensure_hybrid_workspace(rass_engine* h, size_t n_terms_cap, int B) {
   Bm25State& b = h->bm25;
@@ -450,16 +450,27 @@ static int ensure_hybrid_workspace(rass_engine* h, size_t n_terms_cap, int B) {
 
 // qweights == null: weight of a term = float(w_text) * idf(term); otherwise the caller's per-term weights
 // (fuzzy expansions carry their own boost and blended idf)
+// Row-sharded corpora fuse against the GLOBAL k nearest (all-gathered and merged by the caller) and leave their local
+// top-k on the device for the next all-gather.
+struct HybridExt {
+  const int64_t* knn_rows_dev;   // [B, k] global rows (-1 = none); rows outside this shard are ignored
+  const float* knn_scores_dev;   // [B, k]
+  int64_t* out_rows_dev;         // [B, k] global rows
+  float* out_scores_dev;         // [B, k] fused float scores
+  double* out_keys_dev;          // [B, k] the same as double (what rass_merge_topk_dev ranks by), nullable
+};
+
 // qflags (nullable): per term, bit 0 = last term of its field group, bit 1 = last term of its clause; the clause score is
 // the maximum over its field groups (multi_match best_fields), the query's text score the sum over clauses.
 static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr, const int32_t* qterms,
                        const float* qweights, const uint8_t* qflags, float w_text, float w_knn, int k,
-                       int64_t* out_rows, float* out_scores, rass_stats* stats) {
+                       int64_t* out_rows, float* out_scores, rass_stats* stats, const HybridExt* ext = nullptr) {
   if (!h) return RASS_E_INVALID;
   cudaSetDevice(h->device);
-  if (B < 1 || !out_rows || !out_scores) return rass_fail(h, RASS_E_INVALID, "bad arguments");
+  if (B < 1 || (!ext && (!out_rows || !out_scores))) return rass_fail(h, RASS_E_INVALID, "bad arguments");
   if (k < 1 || k > RASS_MAX_K) return rass_fail(h, RASS_E_INVALID, "k must be in [1, %d], got %d", RASS_MAX_K, k);
-  if (!q_host && !qterm_indptr) return rass_fail(h, RASS_E_INVALID, "neither a vector nor a text clause");
+  if (!q_host && !qterm_indptr && !(ext && ext->knn_rows_dev))
+    return rass_fail(h, RASS_E_INVALID, "neither a vector nor a text clause");
   Bm25State& b = h->bm25;
   if (qterm_indptr && (!b.built || !qterms)) return rass_fail(h, RASS_E_INVALID, "text clause without rass_bm25_build");
   cudaStream_t st = eng_stream(h);
@@ -470,13 +481,17 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
   memset(&s, 0, sizeof(s));
   s.n_queries = B;
   // 1. the knn clause: exact top-k per query (results stay on the device in the second half of the staging)
-  int64_t* knn_rows = h->out_rows + n_out;
-  float* knn_scores = h->out_scores + n_out;
-  const bool have_vec = q_host != nullptr && h->n_rows > 0;
-  if (have_vec) {
+  const int64_t* knn_rows = h->out_rows + n_out;
+  const float* knn_scores = h->out_scores + n_out;
+  bool have_vec = q_host != nullptr && h->n_rows > 0;
+  if (ext && ext->knn_rows_dev) {
+    knn_rows = ext->knn_rows_dev;
+    knn_scores = ext->knn_scores_dev;
+    have_vec = true;
+  } else if (have_vec) {
     float* q_dev = nullptr;
     if ((rc = stage_queries(h, q_host, B, &q_dev))) return rc;
-    if ((rc = search_core(h, q_dev, B, k, knn_rows, knn_scores, nullptr, &s))) return rc;
+    if ((rc = search_core(h, q_dev, B, k, h->out_rows + n_out, h->out_scores + n_out, nullptr, &s))) return rc;
   }
   // 2. the query terms: posting ranges and float(boost) * idf weights, in query order
   const bool have_text = qterm_indptr != nullptr;
@@ -572,14 +587,20 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
     CUDA_TRY(h, cudaGetLastError());
     s.launches++;
   }
-  if ((rc = launch_select_batch(h, (size_t)a.n_tiles * k, B, k, h->out_rows, h->out_scores, st))) return rc;
+  if ((rc = launch_select_batch(h, (size_t)a.n_tiles * k, B, k, ext ? ext->out_rows_dev : h->out_rows,
+                                ext ? ext->out_scores_dev : h->out_scores, ext ? ext->out_keys_dev : nullptr, st)))
+    return rc;
   s.launches++;
   CUDA_TRY(h, cudaEventRecord(e1, st));
-  CUDA_TRY(h, cudaMemcpyAsync(h->out_rows_host, h->out_rows, n_out * 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(h, cudaMemcpyAsync(h->out_scores_host, h->out_scores, n_out * 4, cudaMemcpyDeviceToHost, st));
+  if (!ext) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->out_rows_host, h->out_rows, n_out * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(h->out_scores_host, h->out_scores, n_out * 4, cudaMemcpyDeviceToHost, st));
+  }
   CUDA_TRY(h, cudaStreamSynchronize(st));
-  memcpy(out_rows, h->out_rows_host, n_out * 8);
-  memcpy(out_scores, h->out_scores_host, n_out * 4);
+  if (!ext) {
+    memcpy(out_rows, h->out_rows_host, n_out * 8);
+    memcpy(out_scores, h->out_scores_host, n_out * 4);
+  }
   float ms = 0.f;
   CUDA_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
   s.finish_ms += ms;
@@ -602,6 +623,18 @@ extern "C" int rass_search_hybrid_weighted(rass_engine* h, const float* q_host, 
   if (h && qterm_indptr && !qweights) return rass_fail(h, RASS_E_INVALID, "null weights");
   return hybrid_core(h, q_host, B, qterm_indptr, qterms, qweights, qflags, 0.f, w_knn, k, out_rows, out_scores,
                      stats);
+}
+
+extern "C" int rass_fuse_hybrid_dev(rass_engine* h, int B, const int32_t* qterm_indptr, const int32_t* qterms,
+                                    const float* qweights, const uint8_t* qflags, float w_text,
+                                    const int64_t* knn_rows_dev, const float* knn_scores_dev, float w_knn, int k,
+                                    int64_t* out_rows_dev, float* out_scores_dev, double* out_keys_dev) {
+  if (!h) return RASS_E_INVALID;
+  if (!out_rows_dev || !out_scores_dev || (knn_rows_dev && !knn_scores_dev))
+    return rass_fail(h, RASS_E_INVALID, "null buffer");
+  HybridExt ext = {knn_rows_dev, knn_scores_dev, out_rows_dev, out_scores_dev, out_keys_dev};
+  return hybrid_core(h, nullptr, B, qterm_indptr, qterms, qweights, qflags, w_text, w_knn, k, nullptr, nullptr, nullptr,
+                     &ext);
 }
 
 // ---- fuzziness: AUTO -- edit-distance scan of the term dictionary -------------------------------------------

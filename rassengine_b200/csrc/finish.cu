@@ -435,9 +435,10 @@ int launch_exact(rass_engine* h, int k, const int* qids_host, int n_q, int64_t* 
 
 // top-k of B queries' fused (score, row) lists of `entries` entries each; the score is emitted as is (bm25.cu)
 int launch_select_batch(rass_engine* h, size_t entries, int B, int k, int64_t* out_rows, float* out_scores,
-                        cudaStream_t st) {
+                        double* out_keys, cudaStream_t st) {
+  // raw scores: "larger is better" whatever the vector metric of the engine is
   exact_select_kernel<<<B, 1024, 0, st>>>(h->xlist_key, h->xlist_row, entries, (int)entries, k, nullptr, 0, 1,
-                                          h->metric, h->row_base, out_rows, out_scores, nullptr);
+                                          RASS_METRIC_COSINE, h->row_base, out_rows, out_scores, out_keys);
   CUDA_TRY(h, cudaGetLastError());
   return RASS_OK;
 }

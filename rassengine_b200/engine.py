@@ -237,6 +237,26 @@ class Engine:
         self.last_stats = st.as_dict()
         return rows, scores
 
+    def fuse_hybrid_dev(self, B: int, qterms, w_text: float, knn_rows_ptr: int, knn_scores_ptr: int, w_knn: float, k: int,
+                        out_rows_ptr: int, out_scores_ptr: int, out_keys_ptr: int = 0, qweights=None, qflags=None):
+        """Text clauses fused with an external (global) knn list; this shard's top-k stays on the device."""
+        indptr = terms = w = fl = None
+        if qterms is not None:
+            if len(qterms) != B:
+                raise ValueError("qterms must hold one list per query")
+            indptr = np.zeros(B + 1, dtype=np.int32)
+            indptr[1:] = np.cumsum([len(t) for t in qterms])
+            cat = lambda xs, dt: np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=dt) for x in xs])
+                                                      if indptr[-1] else np.zeros(1, dtype=dt), dtype=dt)
+            terms = cat(qterms, np.int32)
+            w = cat(qweights, np.float32) if qweights is not None else None
+            fl = cat(qflags, np.uint8) if qflags is not None else None
+        vp = lambda p: C.c_void_p(p) if p else None
+        self._check(self._lib.rass_fuse_hybrid_dev(
+            self._h, B, _ptr(indptr) if indptr is not None else None, _ptr(terms) if terms is not None else None,
+            _ptr(w) if w is not None else None, _ptr(fl) if fl is not None else None, w_text, vp(knn_rows_ptr),
+            vp(knn_scores_ptr), w_knn, k, vp(out_rows_ptr), vp(out_scores_ptr), vp(out_keys_ptr)))
+
     def debug_umma_scores(self, q: np.ndarray) -> np.ndarray:
         """Raw tensor-core dot products bf16(q_hat) . bf16(x) of up to 64 queries against every row: [rows, 64]."""
         q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)

@@ -33,11 +33,23 @@ class _DeviceOps:
                                    packed[0].data_ptr())
         return self.engine.last_stats
 
-    def merge(self, gathered, world, B, k, out_rows, out_scores):
+    def merge(self, gathered, world, B, k, out_rows, out_scores, out_keys=None):
         """gathered: int64 [world * 2, B, k] = every rank's packed buffer, in rank order."""
         plane = B * k * 8
         self.engine.merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + plane, world, B, k,
-                                   out_rows.data_ptr(), out_scores.data_ptr(), 0, shard_stride=2 * B * k)
+                                   out_rows.data_ptr(), out_scores.data_ptr(),
+                                   out_keys.data_ptr() if out_keys is not None else 0, shard_stride=2 * B * k)
+
+    def bm25_build(self, indptr, doc, tf, doclen, doc_count, sum_ttf, df):
+        self.engine.bm25_build(indptr, doc, tf, doclen, global_doc_count=doc_count, global_sum_ttf=sum_ttf,
+                               global_df=df)
+
+    def fuse(self, B, qterms, w_text, knn_rows, knn_scores, w_knn, k, packed, scores, qweights=None, qflags=None):
+        """packed: int64 [2, B, k] -- plane 0 receives the fused scores as fp64 bits, plane 1 the global rows."""
+        self.engine.fuse_hybrid_dev(B, qterms, w_text, knn_rows.data_ptr() if knn_rows is not None else 0,
+                                    knn_scores.data_ptr() if knn_scores is not None else 0, w_knn, k,
+                                    packed[1].data_ptr(), scores.data_ptr(), packed[0].data_ptr(),
+                                    qweights=qweights, qflags=qflags)
 
 
 class ShardedIndex:
@@ -97,6 +109,57 @@ class ShardedIndex:
         self.ops.merge(gathered, self.world, B, k, out_rows, out_scores)
         self.merge_launches += 1
         return out_rows, out_scores
+
+    # -- hybrid over row-sharded postings ----------------------------------------------------------
+    def bm25_build(self, indptr, doc, tf, doclen):
+        """Local CSR postings of this rank's rows (doc = local row).  docCount, sumTotalTermFreq and df are summed
+        over the ranks first, so idf / avgdl -- and with them every score -- are the ones a single shard would
+        compute (deliberately not OpenSearch's per-shard statistics)."""
+        import numpy as np
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        doclen = np.ascontiguousarray(doclen, dtype=np.uint32)
+        stats = torch.from_numpy(np.concatenate([[np.count_nonzero(doclen), int(doclen.astype(np.int64).sum())],
+                                                 np.diff(indptr)]).astype(np.int64))
+        if self.world > 1:
+            dev = stats.device if dist.get_backend(self.group) != "nccl" else torch.device("cuda",
+                                                                                         torch.cuda.current_device())
+            stats = stats.to(dev)
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
+            stats = stats.cpu()
+        stats = stats.numpy()
+        self.ops.bm25_build(indptr, doc, tf, doclen, int(stats[0]), int(stats[1]), stats[2:].copy())
+
+    def search_hybrid_dev(self, q: torch.Tensor | None, qterms, w_text: float, w_knn: float, k: int, qweights=None,
+                          qflags=None):
+        """bool.should of text clauses + knn over the row-sharded index.  q: [B, dim] or None; qterms: B term-id lists
+        (global vocabulary) or None.  The knn clause matches the GLOBAL k nearest: they are found first (local top-k,
+        all-gather, merge), every rank fuses its own rows against that list, and the fused local top-k are merged by
+        a second all-gather.  Returns (global rows int64 [B, k], fused scores fp32 [B, k]) on the device."""
+        B = q.shape[0] if q is not None else len(qterms)
+        dev = q.device if q is not None else torch.device("cuda", torch.cuda.current_device()) \
+            if torch.cuda.is_available() else torch.device("cpu")
+        knn_rows = knn_scores = None
+        if q is not None:
+            r, s_ = self.search_dev(q, k)
+            knn_rows, knn_scores = r.clone(), s_.clone()       # search_dev hands out its work buffers
+        key = ("hyb", B, k, str(dev))
+        b = self._bufs.get(key)
+        if b is None:
+            b = {"packed": torch.empty((2, B, k), dtype=torch.int64, device=dev),
+                 "scores": torch.empty((B, k), dtype=torch.float32, device=dev),
+                 "gathered": torch.empty((self.world * 2, B, k), dtype=torch.int64, device=dev),
+                 "out_rows": torch.empty((B, k), dtype=torch.int64, device=dev),
+                 "out_scores": torch.empty((B, k), dtype=torch.float32, device=dev),
+                 "out_keys": torch.empty((B, k), dtype=torch.float64, device=dev)}
+            self._bufs[key] = b
+        self.ops.fuse(B, qterms, w_text, knn_rows, knn_scores, w_knn, k, b["packed"], b["scores"], qweights=qweights,
+                      qflags=qflags)
+        if self.world == 1:
+            return b["packed"][1], b["scores"]
+        dist.all_gather_into_tensor(b["gathered"], b["packed"], group=self.group)
+        self.ops.merge(b["gathered"], self.world, B, k, b["out_rows"], b["out_scores"], b["out_keys"])
+        self.merge_launches += 1
+        return b["out_rows"], b["out_keys"].to(torch.float32)
 
     def search(self, q_host, k: int):
         """Host-buffer flavour: q_host is a pinned or pageable [B, dim] fp32 tensor/array; results come back as

@@ -32,7 +32,40 @@ for k in (10, 100):
     r2, s2 = idx.search(Q, k)                       # host-buffer flavour
     assert np.array_equal(r2, want_rows)
     idx.close()
+
+# ---- hybrid over row-sharded postings: global statistics, global k nearest, two all-gathers ----
+from oracle import bm25, fusion  # noqa: E402
+Nh, V, Dh, Bh, k = 9000, 900, 256, 12, 10
+indptr, doc, tf, doclen = synth.text_corpus(Nh, vocab=V, seed=17, median_len=50, max_len=200)
+full = bm25.BM25Index(indptr, doc, tf, doclen)
+Xh = synth.embeddings(Nh, Dh, 43)
+Qh = synth.embeddings(Bh, Dh, 44)
+qterms = synth.text_queries(Bh, vocab=V, seed=18)
+lo, hi = shard_bounds(Nh, world, rank)
+term_of = np.repeat(np.arange(V), np.diff(indptr))
+mine = (doc >= lo) & (doc < hi)
+l_indptr = np.zeros(V + 1, dtype=np.int64)
+np.add.at(l_indptr, term_of[mine] + 1, 1)
+l_indptr = np.cumsum(l_indptr)
+idx = ShardedIndex(dim=Dh, capacity_rows=hi - lo)
+idx.set_row_base(lo)
+idx.append_dev(torch.from_numpy(Xh[lo:hi]).cuda())
+idx.bm25_build(l_indptr, (doc[mine] - lo).astype(np.int32), tf[mine], doclen[lo:hi])
+rows, scores = idx.search_hybrid_dev(torch.from_numpy(Qh).cuda(), qterms, 4.5, 2.0, k)
+torch.cuda.synchronize()
+rows, scores = rows.cpu().numpy(), scores.cpu().numpy()
+knn_rows, _, knn_scores = knn.knn_exact(Xh, Qh, k)
+for b in range(Bh):
+    wr, ws = fusion.hybrid(full, qterms[b], knn_rows[b], knn_scores[b], 4.5, 2.0, k)
+    assert rows[b, :len(wr)].tolist() == wr.tolist(), f"rank {rank}: sharded hybrid ids differ (query {b})"
+    np.testing.assert_allclose(scores[b, :len(wr)], ws, rtol=2e-6, atol=0)
+rows_t, scores_t = idx.search_hybrid_dev(None, qterms, 4.5, 0.0, k)          # text only
+torch.cuda.synchronize()
+for b in range(Bh):
+    tr, ts = bm25.topk(full.score(qterms[b], boost=4.5), k)
+    assert rows_t[b].cpu().tolist() == tr.tolist() and scores_t[b].cpu().tolist() == ts.tolist()
+idx.close()
 dist.barrier()
 if rank == 0:
-    print(f"sharded x{world}: merged top-k identical to the oracle")
+    print(f"sharded x{world}: merged top-k identical to the oracle (knn and hybrid)")
 dist.destroy_process_group()

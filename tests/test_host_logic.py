@@ -133,6 +133,55 @@ want_rows, _, want_scores = knn.knn_exact(X, Q.numpy(), k)
 assert np.array_equal(rows.numpy(), want_rows), (rank, rows, want_rows)
 np.testing.assert_allclose(scores.numpy(), want_scores, rtol=1e-6)
 assert idx.merge_launches == 1
+
+# hybrid: global knn list first, then every rank fuses its own rows, then a second all-gather + merge
+from oracle import bm25, fusion
+ip, dc, tf, dl = synth.text_corpus(4000, vocab=300, seed=3, median_len=30, max_len=90)
+full = bm25.BM25Index(ip, dc, tf, dl)
+qterms = synth.text_queries(5, vocab=300, seed=4)
+
+class HybridOps(OracleOps):
+    def bm25_build(self, indptr, doc, tf_, doclen, doc_count, sum_ttf, df):
+        self.stats = (doc_count, sum_ttf, np.asarray(df))
+    def fuse(self, B, qt, w_text, knn_rows, knn_scores, w_knn, k, packed, scores, qweights=None, qflags=None):
+        n_local = self.X.shape[0]
+        for b in range(B):
+            text = full.score(qt[b], boost=w_text)[self.base:self.base + n_local]
+            loc = [(int(r) - self.base, float(s)) for r, s in zip(knn_rows[b].tolist(), knn_scores[b].tolist())
+                   if self.base <= r < self.base + n_local]
+            fused = text.astype(np.float64); matched = text > 0
+            for r, s in loc:
+                fused[r] += np.float64(np.float32(w_knn) * np.float32(s)); matched[r] = True
+            final = fused.astype(np.float32); docs = np.flatnonzero(matched)
+            order = docs[np.lexsort((docs, -final[docs].astype(np.float64)))[:k]]
+            rr = np.full(k, -1, dtype=np.int64); kk = np.zeros(k); rr[:order.size] = order + self.base
+            kk[:order.size] = final[order].astype(np.float64)
+            packed[1][b] = torch.from_numpy(rr); packed[0][b] = torch.from_numpy(kk).view(torch.int64)
+            scores[b] = torch.from_numpy(kk.astype(np.float32))
+    def merge(self, gathered, world, B, k, out_rows, out_scores, out_keys=None):
+        g = gathered.view(world, 2, B, k)
+        keys = g[:, 0].contiguous().view(torch.float64).numpy(); rows = g[:, 1].numpy()
+        for b in range(B):
+            kk = keys[:, b].reshape(-1); rr = rows[:, b].reshape(-1)
+            ok = rr >= 0; kk, rr = kk[ok], rr[ok]
+            order = np.lexsort((rr, -kk))[:k]
+            out_rows[b, :order.size] = torch.from_numpy(rr[order]); out_rows[b, order.size:] = -1
+            if out_keys is not None:
+                out_keys[b, :order.size] = torch.from_numpy(kk[order]); out_keys[b, order.size:] = 0
+            out_scores[b, :order.size] = torch.from_numpy((1 / (2 - np.clip(kk[order], -1, 1))).astype(np.float32))
+
+hidx = ShardedIndex(dim=64, ops=HybridOps(X[lo:hi], lo))
+term_of = np.repeat(np.arange(300), np.diff(ip)); mine = (dc >= lo) & (dc < hi)
+lip = np.zeros(301, dtype=np.int64); np.add.at(lip, term_of[mine] + 1, 1); lip = np.cumsum(lip)
+hidx.bm25_build(lip, (dc[mine] - lo).astype(np.int32), tf[mine], dl[lo:hi])
+assert hidx.ops.stats[0] == full.doc_count and hidx.ops.stats[1] == full.sum_ttf       # summed over the ranks
+assert np.array_equal(hidx.ops.stats[2], full.df)
+hr, hs = hidx.search_hybrid_dev(Q, qterms, 4.5, 2.0, k)
+for b in range(5):
+    wr, ws = fusion.hybrid(full, qterms[b], want_rows[b], want_scores[b], 4.5, 2.0, k)
+    assert hr[b, :len(wr)].tolist() == wr.tolist(), (rank, b)
+    np.testing.assert_allclose(hs[b, :len(wr)].numpy(), ws, rtol=1e-6)
+assert hidx.merge_launches == 2          # one merge for the global knn list, one for the fused lists
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
