@@ -74,7 +74,7 @@ def workload_name(a):
 
 
 def scan_kernel_name(B):
-    if B <= 2:
+    if B <= 1:
         return "scan_stream_kernel (128-bit streaming GEMV + warp select)"
     if B <= 64:
         return "scan_umma_kernel (TMA + tcgen05, 64 queries/pass)"
@@ -402,7 +402,7 @@ def run_ours(a):
                       "kernel_ms": scan_ms_avg, "frac_of_nominal_2250TF": achieved / 2250.0} if tensor_bound else
                      {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                       "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                      "kernel": "scan_umma_kernel" if B > 2 else "scan_stream_kernel",
+                      "kernel": "scan_umma_kernel" if B > 1 else "scan_stream_kernel",
                       "algorithmic_bytes_per_launch": bytes_per_step, "kernel_ms": scan_ms_avg,
                       "frac_of_nominal_8TBs": achieved / 8000.0}),
         "parity": {"fast_path_ids_equal_fp64_scan": parity_ok, "certificate_fallbacks_in_timed_region": int(fallback)},

@@ -64,7 +64,7 @@ enum {
 
 /* rass_search_* path selection (rass_set_option RASS_OPT_PATH) */
 enum {
-  RASS_PATH_AUTO = 0,    /* B <= 2: streaming GEMV+select; B <= 64: tcgen05 tiles, 64 queries per pass;
+  RASS_PATH_AUTO = 0,    /* B = 1: streaming GEMV+select; B <= 64: tcgen05 tiles, 64 queries per pass;
                             larger: CTA-pair tcgen05 contraction, 256 queries per pass                */
   RASS_PATH_STREAM = 1,  /* force the CUDA-core streaming scan (passes of <= 2 queries)                */
   RASS_PATH_UMMA = 2,    /* force the TMA + tcgen05 scan (passes of <= 64 queries)                     */

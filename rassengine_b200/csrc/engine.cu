@@ -539,9 +539,9 @@ static int select_scan_offsets(rass_engine* h, cudaStream_t st) {
 
 static int resolve_path(const rass_engine* h, int B) {
   if (h->path != RASS_PATH_AUTO) return h->path;
-  // one 64-query tcgen05 pass costs ~3.1 ms at 10M rows, one 256-query CTA-pair pass ~5.1 ms: past 64 queries the
-  // pair kernel wins (two 64-query passes = 6.1 ms)
-  return B <= 2 ? RASS_PATH_STREAM : (B <= RASS_GROUP_Q ? RASS_PATH_UMMA : RASS_PATH_GEMM);
+  // measured at 10M rows: streaming scan 2.79 ms for one query, 3.10 ms for two; one tcgen05 pass 2.98-3.05 ms for
+  // 1..64 queries; one 256-query CTA-pair pass ~5.1 ms (two 64-query passes = 6.1 ms)
+  return B <= 1 ? RASS_PATH_STREAM : (B <= RASS_GROUP_Q ? RASS_PATH_UMMA : RASS_PATH_GEMM);
 }
 
 static cudaEvent_t get_event(rass_engine* h, size_t i) {
