@@ -51,7 +51,8 @@ enum {
   RASS_E_CUDA = -3,
   RASS_E_NCCL = -4,
   RASS_E_NOTFOUND = -5,
-  RASS_E_UNSUPPORTED = -6
+  RASS_E_UNSUPPORTED = -6,
+  RASS_E_AGAIN = -7      /* rass_search_knn_dev_wait: some query failed its certificate; repeat with the blocking call */
 };
 
 enum { RASS_METRIC_COSINE = 0, RASS_METRIC_L2 = 1 };
@@ -129,6 +130,15 @@ int rass_search_knn(rass_engine* h, const float* q_host, int B, int k,
 /* device-pointer flavour: q_dev and outputs in device memory; enqueued on the engine stream and synchronised */
 int rass_search_knn_dev(rass_engine* h, const float* q_dev, int B, int k,
                         int64_t* out_rows_dev, float* out_scores_dev, double* out_keys_dev, rass_stats* stats);
+
+/* Pipelined flavour for callers that keep two batches in flight (row-sharded serving: the all-gather and merge of
+ * batch i overlap the scan of batch i+1).  _async enqueues the whole search on the engine stream and returns without
+ * touching the host; slot is 0 or 1; flag_out_dev (nullable) receives the number of queries whose certificate failed,
+ * on the device, so it can travel with the gathered candidates.  _wait blocks until that slot's search is complete:
+ * RASS_OK = outputs final; RASS_E_AGAIN = repeat this batch with rass_search_knn_dev (which re-scans those queries). */
+int rass_search_knn_dev_async(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows_dev,
+                              float* out_scores_dev, double* out_keys_dev, int slot, int64_t* flag_out_dev);
+int rass_search_knn_dev_wait(rass_engine* h, int slot, rass_stats* stats);
 
 /* Merge G per-shard top-k lists (what each rank all-gathers) into the global top-k, (key desc, row asc).
  * keys_dev / rows_dev point at shard 0's [B, k] fp64 keys / int64 rows (-1 = empty); shard g's lists start

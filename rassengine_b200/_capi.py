@@ -13,9 +13,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librass_b200.so")
 
 RASS_OK = 0
-RASS_E_INVALID, RASS_E_OOM, RASS_E_CUDA, RASS_E_NCCL, RASS_E_NOTFOUND, RASS_E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
+RASS_E_INVALID, RASS_E_OOM, RASS_E_CUDA, RASS_E_NCCL, RASS_E_NOTFOUND, RASS_E_UNSUPPORTED, RASS_E_AGAIN = \
+    -1, -2, -3, -4, -5, -6, -7
 ERR_NAMES = {-1: "RASS_E_INVALID", -2: "RASS_E_OOM", -3: "RASS_E_CUDA", -4: "RASS_E_NCCL", -5: "RASS_E_NOTFOUND",
-             -6: "RASS_E_UNSUPPORTED"}
+             -6: "RASS_E_UNSUPPORTED", -7: "RASS_E_AGAIN"}
 METRIC_COSINE, METRIC_L2 = 0, 1
 KEEP_FP32, BF16_ONLY = 1, 2
 PATH_AUTO, PATH_STREAM, PATH_UMMA, PATH_EXACT, PATH_GEMM = 0, 1, 2, 3, 4
@@ -56,6 +57,8 @@ PROTOTYPES = {
     "rass_read_rows": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     "rass_search_knn": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.POINTER(RassStats)]),
     "rass_search_knn_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.POINTER(RassStats)]),
+    "rass_search_knn_dev_async": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P]),
+    "rass_search_knn_dev_wait": (C.c_int, [_P, C.c_int, C.POINTER(RassStats)]),
     "rass_merge_topk_dev": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "rass_bm25_build": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
     "rass_search_hybrid": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_float, C.c_float, C.c_int, _P, _P,

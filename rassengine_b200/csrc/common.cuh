@@ -130,6 +130,14 @@ struct rass_engine {
   double* retry_keys = nullptr;
   size_t retry_cap = 0;
   int retry_k = 0;
+  // two searches may be in flight through rass_search_knn_dev_async (one slot each)
+  struct AsyncSlot {
+    bool pending = false, trivial = false;
+    DevScalars* scal_host = nullptr;   // pinned
+    cudaEvent_t done = nullptr;
+    size_t n_ev = 0;
+    rass_stats stats;
+  } aslot[2];
   uint8_t* row_filter = nullptr;    // device [row_filter_rows] 1 = row passes the bool.filter of the running query
   bool knn_prefilter = false;       // RASS_OPT_KNN_PREFILTER: rass_search_knn scans only rows passing row_filter
   float* sb_filtered = nullptr;     // [cap] sb with -inf for rows failing the filter (built lazily)

@@ -143,6 +143,7 @@ extern "C" int rass_destroy(rass_engine* h) {
   cudaFree(h->sb_filtered);
   cudaFree(h->retry_ids); cudaFree(h->retry_q); cudaFree(h->retry_rows); cudaFree(h->retry_scores); cudaFree(h->retry_keys);
   for (cudaEvent_t e : h->ev_pool) if (e) cudaEventDestroy(e);
+  for (auto& a : h->aslot) { cudaFreeHost(a.scal_host); if (a.done) cudaEventDestroy(a.done); }
   for (int i = 0; i < 2; ++i) { cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   Bm25State& b = h->bm25;
@@ -573,20 +574,25 @@ __global__ void scatter_results_kernel(const int* __restrict__ ids, int k, const
 }
 
 static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
-                            double* out_keys, rass_stats* stats, bool robust);
+                            double* out_keys, rass_stats* stats, bool robust, int async_slot = -1,
+                            int64_t* async_flag_dev = nullptr);
 
 // q_dev: [B, dim] fp32 on this device; outputs on this device.  Synchronises the stream before returning.
 int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
                 double* out_keys, rass_stats* stats) {
-  return search_core_impl(h, q_dev, B, k, out_rows, out_scores, out_keys, stats, false);
+  return search_core_impl(h, q_dev, B, k, out_rows, out_scores, out_keys, stats, false, -1, nullptr);
 }
 
 // robust = false: 256-entry segments (a compaction keeps 32..64 entries): fastest, and every pivot has >= 32 >= k
 // entries above it when k <= 32.  For k > 32 a cluster of near neighbours inside one segment can lift a pivot above
 // the k-th best; those queries fail their certificate and get a second pass with robust = true (512-entry segments,
 // >= 128 entries above every pivot) at tensor-core speed instead of the fp64 scan.
+__global__ void publish_flag_kernel(const DevScalars* scal, int64_t* flag) { *flag = scal->flagged_n; }
+
+// async_slot >= 0: enqueue only -- no host synchronisation, no fallback; the certificate outcome lands in the slot's
+// pinned scalars (and, for row-sharded callers, in *async_flag_dev, which travels with the all-gathered candidates).
 static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
-                            double* out_keys, rass_stats* stats, bool robust) {
+                            double* out_keys, rass_stats* stats, bool robust, int async_slot, int64_t* async_flag_dev) {
   if (B < 1) return rass_fail(h, RASS_E_INVALID, "B must be >= 1");
   if (k < 1 || k > RASS_MAX_K) return rass_fail(h, RASS_E_INVALID, "k must be in [1, %d], got %d", RASS_MAX_K, k);
   cudaStream_t st = eng_stream(h);
@@ -598,9 +604,27 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
   s.rows_scanned = h->n_rows;
   double retry_scan_ms = 0.0, retry_total_ms = 0.0, first_scan_ms = 0.0, first_total_ms = -1.0;
   const size_t n_out = (size_t)B * k;
+  const size_t ev_base = async_slot >= 0 ? (size_t)1024 * (async_slot + 1) : 0;   // per-slot timing events
+  rass_engine::AsyncSlot* as = async_slot >= 0 ? &h->aslot[async_slot] : nullptr;
+  if (as) {
+    if (as->pending) return rass_fail(h, RASS_E_INVALID, "async slot %d still has a search in flight", async_slot);
+    if (!as->scal_host) CUDA_TRY(h, cudaMallocHost(&as->scal_host, sizeof(DevScalars)));
+    if (!as->done) CUDA_TRY(h, cudaEventCreateWithFlags(&as->done, cudaEventDisableTiming));
+  }
   if (h->n_rows == 0) {
     fill_empty_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(out_rows, out_scores, out_keys, n_out);
     CUDA_TRY(h, cudaGetLastError());
+    if (as) {
+      if (async_flag_dev) CUDA_TRY(h, cudaMemsetAsync(async_flag_dev, 0, sizeof(int64_t), st));
+      CUDA_TRY(h, cudaEventRecord(as->done, st));
+      s.n_certified = B;
+      s.launches = 1;
+      as->stats = s;
+      as->n_ev = 0;
+      as->trivial = true;
+      as->pending = true;
+      return RASS_OK;
+    }
     CUDA_TRY(h, cudaStreamSynchronize(st));
     s.n_certified = B;
     s.launches = 1;
@@ -628,9 +652,9 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
     const int n_segs = scan_gemm_segs(h, B);
     const int seg = robust ? rass_tc_seg(k) : 256;
     if ((rc = ensure_pool(h, (size_t)n_segs * seg, (size_t)n_segs, (size_t)B))) return rc;
-    CUDA_TRY(h, cudaEventRecord(get_event(h, n_ev++), st));
+    CUDA_TRY(h, cudaEventRecord(get_event(h, ev_base + n_ev++), st));
     if ((rc = launch_scan_gemm(h, B, seg, st))) return rc;
-    CUDA_TRY(h, cudaEventRecord(get_event(h, n_ev++), st));
+    CUDA_TRY(h, cudaEventRecord(get_event(h, ev_base + n_ev++), st));
     if ((rc = launch_finish(h, 0, B, k, n_segs, seg, true, true, out_rows, out_scores, out_keys, st)))
       return rc;
     s.launches += 3;
@@ -643,7 +667,7 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
     if ((rc = ensure_pool(h, (size_t)n_segs * seg, (size_t)n_segs))) return rc;
     for (int g0 = 0; g0 < B; g0 += RASS_GROUP_Q) {
       const int ng = std::min(RASS_GROUP_Q, B - g0);
-      CUDA_TRY(h, cudaEventRecord(get_event(h, n_ev++), st));
+      CUDA_TRY(h, cudaEventRecord(get_event(h, ev_base + n_ev++), st));
       if (umma) {
         if ((rc = launch_scan_umma(h, g0, ng, seg, st))) return rc;
         s.launches += 2;
@@ -655,11 +679,25 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
           s.passes += 1;
         }
       }
-      CUDA_TRY(h, cudaEventRecord(get_event(h, n_ev++), st));
+      CUDA_TRY(h, cudaEventRecord(get_event(h, ev_base + n_ev++), st));
       if ((rc = launch_finish(h, g0, ng, k, n_segs, seg, true, umma, out_rows, out_scores, out_keys, st))) return rc;
       s.launches += 1;
     }
     s.bytes_streamed = (int64_t)s.passes * h->n_rows * h->dim_pad * 2;
+  }
+  if (as) {
+    if (path == RASS_PATH_EXACT) return rass_fail(h, RASS_E_INVALID, "the fp64 scan has no async form");
+    if (async_flag_dev) {
+      publish_flag_kernel<<<1, 1, 0, st>>>(h->scal, async_flag_dev);
+      CUDA_TRY(h, cudaGetLastError());
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(as->scal_host, h->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaEventRecord(as->done, st));
+    as->stats = s;
+    as->n_ev = n_ev;
+    as->trivial = false;
+    as->pending = true;
+    return RASS_OK;
   }
   if (path != RASS_PATH_EXACT) {
     CUDA_TRY(h, cudaEventRecord(h->ev[1], st));
@@ -679,7 +717,7 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
         CUDA_TRY(h, cudaEventElapsedTime(&pre, h->ev[0], h->ev[1]));
         for (size_t i = 0; i + 1 < n_ev; i += 2) {
           float ms1 = 0.f;
-          CUDA_TRY(h, cudaEventElapsedTime(&ms1, h->ev_pool[i], h->ev_pool[i + 1]));
+          CUDA_TRY(h, cudaEventElapsedTime(&ms1, h->ev_pool[ev_base + i], h->ev_pool[ev_base + i + 1]));
           first_scan_ms += ms1;
         }
         n_ev = 0;
@@ -705,7 +743,8 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
         gather_queries_kernel<<<nf, 256, 0, st>>>(q_dev, h->retry_ids, h->dim, h->retry_q);
         CUDA_TRY(h, cudaGetLastError());
         rass_stats s2;
-        if ((rc = search_core_impl(h, h->retry_q, nf, k, h->retry_rows, h->retry_scores, h->retry_keys, &s2, true)))
+        if ((rc = search_core_impl(h, h->retry_q, nf, k, h->retry_rows, h->retry_scores, h->retry_keys, &s2, true, -1,
+                                   nullptr)))
           return rc;
         scatter_results_kernel<<<nf, 128, 0, st>>>(h->retry_ids, k, h->retry_rows, h->retry_scores, h->retry_keys,
                                                    out_rows, out_scores, out_keys);
@@ -735,13 +774,50 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
     s.total_ms = ms;
   }
   for (size_t i = 0; i + 1 < n_ev; i += 2) {
-    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev_pool[ev_base + i], h->ev_pool[ev_base + i + 1]));
     scan += ms;
   }
   s.scan_ms = scan + retry_scan_ms;
   s.finish_ms = s.total_ms - s.scan_ms;
   if (stats) *stats = s;
   return RASS_OK;
+}
+
+extern "C" int rass_search_knn_dev_async(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows_dev,
+                                         float* out_scores_dev, double* out_keys_dev, int slot,
+                                         int64_t* flag_out_dev) {
+  CHECK_HANDLE(h);
+  if (!q_dev || !out_rows_dev || !out_scores_dev) return rass_fail(h, RASS_E_INVALID, "null buffer");
+  if (slot < 0 || slot > 1) return rass_fail(h, RASS_E_INVALID, "slot must be 0 or 1");
+  return search_core_impl(h, q_dev, B, k, out_rows_dev, out_scores_dev, out_keys_dev, nullptr, false, slot,
+                          flag_out_dev);
+}
+
+extern "C" int rass_search_knn_dev_wait(rass_engine* h, int slot, rass_stats* stats) {
+  CHECK_HANDLE(h);
+  if (slot < 0 || slot > 1) return rass_fail(h, RASS_E_INVALID, "slot must be 0 or 1");
+  rass_engine::AsyncSlot& a = h->aslot[slot];
+  if (!a.pending) return rass_fail(h, RASS_E_INVALID, "no search in flight in slot %d", slot);
+  CUDA_TRY(h, cudaEventSynchronize(a.done));
+  a.pending = false;
+  rass_stats s = a.stats;
+  int nf = 0;
+  if (!a.trivial) {
+    nf = a.scal_host->flagged_n;
+    s.n_certified = a.scal_host->n_certified;
+    s.max_candidates = a.scal_host->max_cand;
+    const size_t base = (size_t)1024 * (slot + 1);
+    double scan = 0.0;
+    for (size_t i = 0; i + 1 < a.n_ev; i += 2) {
+      float ms = 0.f;
+      CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev_pool[base + i], h->ev_pool[base + i + 1]));
+      scan += ms;
+    }
+    s.scan_ms = scan;
+  }
+  s.n_fallback = nf;          // queries whose outputs are NOT final: the caller repeats the search with the blocking call
+  if (stats) *stats = s;
+  return nf > 0 ? RASS_E_AGAIN : RASS_OK;
 }
 
 extern "C" int rass_search_knn_dev(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows_dev,

@@ -132,6 +132,24 @@ class Engine:
         self.last_stats = st.as_dict()
         return self.last_stats
 
+    def search_knn_dev_async(self, q_ptr: int, B: int, k: int, rows_ptr: int, scores_ptr: int, keys_ptr: int = 0,
+                             slot: int = 0, flag_ptr: int = 0):
+        """Enqueue only (no host synchronisation); pair with search_knn_dev_wait(slot)."""
+        self._check(self._lib.rass_search_knn_dev_async(self._h, C.c_void_p(q_ptr), B, k, C.c_void_p(rows_ptr),
+                                                        C.c_void_p(scores_ptr),
+                                                        C.c_void_p(keys_ptr) if keys_ptr else None, slot,
+                                                        C.c_void_p(flag_ptr) if flag_ptr else None))
+
+    def search_knn_dev_wait(self, slot: int = 0) -> tuple[bool, dict]:
+        """(final, stats): final is False when some query failed its certificate and the batch must be repeated with
+        the blocking call."""
+        st = RassStats()
+        rc = self._lib.rass_search_knn_dev_wait(self._h, slot, C.byref(st))
+        if rc not in (0, capi.RASS_E_AGAIN):
+            self._check(rc)
+        self.last_stats = st.as_dict()
+        return rc == 0, self.last_stats
+
     def merge_topk_dev(self, keys_ptr: int, rows_ptr: int, G: int, B: int, k: int, out_rows_ptr: int,
                        out_scores_ptr: int, out_keys_ptr: int = 0, shard_stride: int = 0):
         """Enqueued on the engine stream; call sync() (or synchronise that stream) before reading the outputs."""

@@ -24,8 +24,9 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> tuple[int, int]:
 class _DeviceOps:
     """Tensor-level view of the raw-pointer engine calls (the seam the gloo tests replace with a CPU double)."""
 
-    def __init__(self, engine):
+    def __init__(self, engine, main_stream: int = 0):
         self.engine = engine
+        self.main_stream = main_stream     # the stream the engine normally runs on (torch's current stream)
 
     def search(self, q, k, packed, scores):
         """packed: int64 [2, B, k] -- plane 0 receives the fp64 key bits, plane 1 the global rows."""
@@ -33,12 +34,26 @@ class _DeviceOps:
                                    packed[0].data_ptr())
         return self.engine.last_stats
 
-    def merge(self, gathered, world, B, k, out_rows, out_scores, out_keys=None):
-        """gathered: int64 [world * 2, B, k] = every rank's packed buffer, in rank order."""
+    def merge(self, gathered, world, B, k, out_rows, out_scores, out_keys=None, stride=None, stream=None):
+        """gathered: every rank's packed buffer in rank order ([2, B, k] int64 each, `stride` elements apart)."""
         plane = B * k * 8
-        self.engine.merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + plane, world, B, k,
-                                   out_rows.data_ptr(), out_scores.data_ptr(),
-                                   out_keys.data_ptr() if out_keys is not None else 0, shard_stride=2 * B * k)
+        if stream is not None:
+            self.engine.set_stream(stream)
+        try:
+            self.engine.merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + plane, world, B, k,
+                                       out_rows.data_ptr(), out_scores.data_ptr(),
+                                       out_keys.data_ptr() if out_keys is not None else 0,
+                                       shard_stride=stride or 2 * B * k)
+        finally:
+            if stream is not None:
+                self.engine.set_stream(self.main_stream)
+
+    def search_async(self, q, k, packed, scores, slot, flag):
+        self.engine.search_knn_dev_async(q.data_ptr(), q.shape[0], k, packed[1].data_ptr(), scores.data_ptr(),
+                                         packed[0].data_ptr(), slot=slot, flag_ptr=flag.data_ptr())
+
+    def search_wait(self, slot):
+        return self.engine.search_knn_dev_wait(slot)
 
     def bm25_build(self, indptr, doc, tf, doclen, doc_count, sum_ttf, df):
         self.engine.bm25_build(indptr, doc, tf, doclen, global_doc_count=doc_count, global_sum_ttf=sum_ttf,
@@ -67,9 +82,13 @@ class ShardedIndex:
             # run on torch's current stream so NCCL and the engine's kernels are ordered by the stream
             engine.set_stream(torch.cuda.current_stream().cuda_stream)
         self.engine = engine
-        self.ops = ops if ops is not None else _DeviceOps(engine)
+        self.ops = ops if ops is not None else _DeviceOps(
+            engine, torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else 0)
         self.merge_launches = 0
         self._bufs: dict = {}          # (B, k, device) -> work tensors, reused across calls (no allocator traffic)
+        self._pending = [None, None]   # search_dev_async tickets
+        self._next_slot = 0
+        self._side = None              # side stream of the pipelined exchange
 
     def _buffers(self, B: int, k: int, dev):
         key = (B, k, str(dev))
@@ -88,6 +107,73 @@ class ShardedIndex:
 
     def set_row_base(self, base: int):
         self.engine.set_row_base(base)
+
+    # -- pipelined search: two batches in flight, the exchange of batch i overlaps the scan of batch i+1 ------------
+    def search_dev_async(self, q: torch.Tensor, k: int) -> int:
+        """Enqueues the whole sharded search of one batch and returns a ticket; `wait(ticket)` hands out the result.
+        At most two tickets may be outstanding.  The local search runs on the current stream; the all-gather and the
+        merge run on a side stream behind an event, so the next batch's scan does not wait for them.  Every rank
+        appends the number of its uncertified queries to its candidates, so after the gather all ranks know -- without
+        another collective -- whether the batch has to be repeated through the blocking path."""
+        slot = self._next_slot
+        if self._pending[slot] is not None:
+            raise RuntimeError("two batches are already in flight: wait() for the older ticket first")
+        self._next_slot ^= 1
+        B, dev = q.shape[0], q.device
+        key = ("async", slot, B, k, str(dev))
+        b = self._bufs.get(key)
+        if b is None:
+            n = 2 * B * k + 1                                     # candidates + the uncertified-queries count
+            b = {"flat": torch.zeros(n, dtype=torch.int64, device=dev),
+                 "scores": torch.empty((B, k), dtype=torch.float32, device=dev),
+                 "gathered": torch.zeros(self.world * n, dtype=torch.int64, device=dev),
+                 "out_rows": torch.empty((B, k), dtype=torch.int64, device=dev),
+                 "out_scores": torch.empty((B, k), dtype=torch.float32, device=dev),
+                 "flags_host": (torch.zeros(self.world, dtype=torch.int64).pin_memory() if dev.type == "cuda"
+                                else torch.zeros(self.world, dtype=torch.int64)),
+                 "ev_main": torch.cuda.Event() if dev.type == "cuda" else None,
+                 "ev_side": torch.cuda.Event() if dev.type == "cuda" else None}
+            b["packed"] = b["flat"][: 2 * B * k].view(2, B, k)
+            self._bufs[key] = b
+        self.ops.search_async(q, k, b["packed"], b["scores"], slot, b["flat"][-1:])
+        if self.world > 1:
+            cuda = dev.type == "cuda"
+            if cuda:
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=dev)
+                b["ev_main"].record(torch.cuda.current_stream())
+                ctx = torch.cuda.stream(self._side)
+                self._side.wait_event(b["ev_main"])
+            else:
+                import contextlib
+                ctx = contextlib.nullcontext()
+            with ctx:
+                dist.all_gather_into_tensor(b["gathered"], b["flat"], group=self.group)
+                self.ops.merge(b["gathered"], self.world, B, k, b["out_rows"], b["out_scores"], stride=2 * B * k + 1,
+                               stream=self._side.cuda_stream if cuda else None)
+                # every rank's uncertified-queries count to pinned host memory, still on the side stream: reading it
+                # in wait() must not touch the main stream, where the next batch's scan is already queued
+                n = b["flat"].numel()
+                b["flags_host"].copy_(b["gathered"][n - 1::n], non_blocking=True)
+                if cuda:
+                    b["ev_side"].record(self._side)
+            self.merge_launches += 1
+        self._pending[slot] = (q, k, b)
+        return slot
+
+    def wait(self, ticket: int):
+        """-> (rows int64 [B, k], scores fp32 [B, k]) of that batch, final on every rank."""
+        q, k, b = self._pending[ticket]
+        self._pending[ticket] = None
+        final, _ = self.ops.search_wait(ticket)
+        if self.world > 1:
+            if b["ev_side"] is not None:
+                b["ev_side"].synchronize()
+            final = int(b["flags_host"].sum()) == 0            # every rank reads the same gathered counts
+        if final:
+            return (b["out_rows"], b["out_scores"]) if self.world > 1 else (b["packed"][1], b["scores"])
+        rows, scores = self.search_dev(q, k)           # rare: repeat the batch through the blocking path (all ranks)
+        return rows.clone(), scores.clone()
 
     def append_dev(self, rows: torch.Tensor) -> int:
         assert rows.dtype == torch.float32 and rows.is_contiguous() and rows.shape[1] == self.dim

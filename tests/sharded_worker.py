@@ -31,6 +31,22 @@ for k in (10, 100):
     np.testing.assert_allclose(scores.cpu().numpy(), want_scores, rtol=1e-5)
     r2, s2 = idx.search(Q, k)                       # host-buffer flavour
     assert np.array_equal(r2, want_rows)
+    # pipelined flavour: two batches in flight, exchange on a side stream, same ids
+    Qd = torch.from_numpy(Q).cuda()
+    Qd2 = torch.from_numpy(Q[::-1].copy()).cuda()
+    tickets = [idx.search_dev_async(Qd, k), idx.search_dev_async(Qd2, k)]
+    got = []
+    for it in range(6):
+        r, sc = idx.wait(tickets.pop(0))
+        got.append((r.clone(), sc.clone()))
+        tickets.append(idx.search_dev_async(Qd if it % 2 == 0 else Qd2, k))
+    for t in tickets:
+        r, sc = idx.wait(t)
+        got.append((r.clone(), sc.clone()))
+    torch.cuda.synchronize()
+    for i, (r, sc) in enumerate(got):
+        w = want_rows if i % 2 == 0 else want_rows[::-1]
+        assert np.array_equal(r.cpu().numpy(), w), f"rank {rank}: pipelined ids differ (k={k}, batch {i})"
     idx.close()
 
 # ---- hybrid over row-sharded postings: global statistics, global k nearest, two all-gathers ----

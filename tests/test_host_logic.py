@@ -113,14 +113,19 @@ class OracleOps:                          # CPU test double for the device ops: 
         r, key, s = knn.knn_exact(self.X, q.numpy(), k)
         packed[1].copy_(torch.from_numpy(r + self.base)); scores.copy_(torch.from_numpy(s))
         packed[0].copy_(torch.from_numpy(key).view(torch.int64))
-    def merge(self, gathered, world, B, k, out_rows, out_scores):
-        g = gathered.view(world, 2, B, k)
+    def merge(self, gathered, world, B, k, out_rows, out_scores, out_keys=None, stride=None, stream=None):
+        g = gathered.view(world, -1)[:, :2 * B * k].reshape(world, 2, B, k)
         keys = g[:, 0].contiguous().view(torch.float64).numpy(); rows = g[:, 1].numpy()
         for b in range(B):
             kk = keys[:, b].reshape(-1); rr = rows[:, b].reshape(-1)
             order = np.lexsort((rr, -kk))[:k]
             out_rows[b] = torch.from_numpy(rr[order])
             out_scores[b] = torch.from_numpy((1 / (2 - kk[order])).astype(np.float32))
+    uncertified = 0                       # what the engine would report for the batch in flight
+    def search_async(self, q, k, packed, scores, slot, flag):
+        self.search(q, k, packed, scores); flag[0] = self.uncertified
+    def search_wait(self, slot):
+        return self.uncertified == 0, {}
 
 dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{os.environ['PORT']}", rank=int(os.environ["RANK"]), world_size=2)
 rank = dist.get_rank()
@@ -133,6 +138,22 @@ want_rows, _, want_scores = knn.knn_exact(X, Q.numpy(), k)
 assert np.array_equal(rows.numpy(), want_rows), (rank, rows, want_rows)
 np.testing.assert_allclose(scores.numpy(), want_scores, rtol=1e-6)
 assert idx.merge_launches == 1
+# pipelined flavour: two batches in flight, results identical; a batch with an uncertified query on ONE rank is
+# repeated through the blocking path on EVERY rank (they all read the gathered counts, no extra collective)
+Q2 = torch.from_numpy(synth.embeddings(5, 64, 3))
+want2 = knn.knn_exact(X, Q2.numpy(), k)[0]
+t0 = idx.search_dev_async(Q, k); t1 = idx.search_dev_async(Q2, k)
+try:
+    idx.search_dev_async(Q, k); raise SystemExit("a third ticket must be refused")
+except RuntimeError:
+    pass
+r0, _ = idx.wait(t0); r1, _ = idx.wait(t1)
+assert np.array_equal(r0.numpy(), want_rows) and np.array_equal(r1.numpy(), want2)
+before = idx.merge_launches
+idx.ops.uncertified = 1 if rank == 1 else 0
+r0, _ = idx.wait(idx.search_dev_async(Q, k))
+idx.ops.uncertified = 0
+assert np.array_equal(r0.numpy(), want_rows) and idx.merge_launches == before + 2      # async attempt + blocking repeat
 
 # hybrid: global knn list first, then every rank fuses its own rows, then a second all-gather + merge
 from oracle import bm25, fusion
@@ -158,7 +179,7 @@ class HybridOps(OracleOps):
             kk[:order.size] = final[order].astype(np.float64)
             packed[1][b] = torch.from_numpy(rr); packed[0][b] = torch.from_numpy(kk).view(torch.int64)
             scores[b] = torch.from_numpy(kk.astype(np.float32))
-    def merge(self, gathered, world, B, k, out_rows, out_scores, out_keys=None):
+    def merge(self, gathered, world, B, k, out_rows, out_scores, out_keys=None, stride=None, stream=None):
         g = gathered.view(world, 2, B, k)
         keys = g[:, 0].contiguous().view(torch.float64).numpy(); rows = g[:, 1].numpy()
         for b in range(B):
