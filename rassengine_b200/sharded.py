@@ -109,7 +109,7 @@ class ShardedIndex:
         self.engine.set_row_base(base)
 
     # -- pipelined search: two batches in flight, the exchange of batch i overlaps the scan of batch i+1 ------------
-    def search_dev_async(self, q: torch.Tensor, k: int) -> int:
+    def search_dev_async(self, q: torch.Tensor, k: int, to_host: bool = False) -> int:
         """Enqueues the whole sharded search of one batch and returns a ticket; `wait(ticket)` hands out the result.
         At most two tickets may be outstanding.  The local search runs on the current stream; the all-gather and the
         merge run on a side stream behind an event, so the next batch's scan does not wait for them.  Every rank
@@ -135,7 +135,17 @@ class ShardedIndex:
                  "ev_side": torch.cuda.Event() if dev.type == "cuda" else None}
             b["packed"] = b["flat"][: 2 * B * k].view(2, B, k)
             self._bufs[key] = b
+        if to_host and "rows_host" not in b:
+            pin = dev.type == "cuda"
+            b["rows_host"] = torch.empty((B, k), dtype=torch.int64, pin_memory=pin)
+            b["scores_host"] = torch.empty((B, k), dtype=torch.float32, pin_memory=pin)
+            b["ev_out"] = torch.cuda.Event() if pin else None
         self.ops.search_async(q, k, b["packed"], b["scores"], slot, b["flat"][-1:])
+        if self.world == 1 and to_host:
+            b["rows_host"].copy_(b["packed"][1], non_blocking=True)        # behind the search, ahead of the next batch
+            b["scores_host"].copy_(b["scores"], non_blocking=True)
+            if b["ev_out"] is not None:
+                b["ev_out"].record(torch.cuda.current_stream())
         if self.world > 1:
             cuda = dev.type == "cuda"
             if cuda:
@@ -155,14 +165,36 @@ class ShardedIndex:
                 # in wait() must not touch the main stream, where the next batch's scan is already queued
                 n = b["flat"].numel()
                 b["flags_host"].copy_(b["gathered"][n - 1::n], non_blocking=True)
+                if to_host:
+                    b["rows_host"].copy_(b["out_rows"], non_blocking=True)
+                    b["scores_host"].copy_(b["out_scores"], non_blocking=True)
                 if cuda:
                     b["ev_side"].record(self._side)
             self.merge_launches += 1
         self._pending[slot] = (q, k, b)
         return slot
 
+    def search_async(self, q_host, k: int) -> int:
+        """Host-buffer flavour of search_dev_async: pinned (or pageable) [B, dim] fp32 queries in, results staged to
+        pinned host memory behind the search; collect with wait_host(ticket)."""
+        q = torch.as_tensor(q_host, dtype=torch.float32)
+        qd = q.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
+        return self.search_dev_async(qd, k, to_host=True)
+
+    def wait_host(self, ticket: int):
+        """-> (rows, scores) of that batch as host numpy arrays."""
+        rows, scores, final, b = self._wait(ticket)
+        if final and "rows_host" in b:
+            if self.world == 1 and b.get("ev_out") is not None:
+                b["ev_out"].synchronize()
+            return b["rows_host"].numpy().copy(), b["scores_host"].numpy().copy()
+        return rows.cpu().numpy(), scores.cpu().numpy()          # repeated through the blocking path (or not staged)
+
     def wait(self, ticket: int):
         """-> (rows int64 [B, k], scores fp32 [B, k]) of that batch, final on every rank."""
+        return self._wait(ticket)[:2]
+
+    def _wait(self, ticket: int):
         q, k, b = self._pending[ticket]
         self._pending[ticket] = None
         final, _ = self.ops.search_wait(ticket)
@@ -171,9 +203,9 @@ class ShardedIndex:
                 b["ev_side"].synchronize()
             final = int(b["flags_host"].sum()) == 0            # every rank reads the same gathered counts
         if final:
-            return (b["out_rows"], b["out_scores"]) if self.world > 1 else (b["packed"][1], b["scores"])
+            return ((b["out_rows"], b["out_scores"]) if self.world > 1 else (b["packed"][1], b["scores"])) + (True, b)
         rows, scores = self.search_dev(q, k)           # rare: repeat the batch through the blocking path (all ranks)
-        return rows.clone(), scores.clone()
+        return rows.clone(), scores.clone(), False, b
 
     def append_dev(self, rows: torch.Tensor) -> int:
         assert rows.dtype == torch.float32 and rows.is_contiguous() and rows.shape[1] == self.dim

@@ -47,6 +47,12 @@ for k in (10, 100):
     for i, (r, sc) in enumerate(got):
         w = want_rows if i % 2 == 0 else want_rows[::-1]
         assert np.array_equal(r.cpu().numpy(), w), f"rank {rank}: pipelined ids differ (k={k}, batch {i})"
+    # ... and with host buffers on both ends
+    ta, tb = idx.search_async(Q, k), idx.search_async(Q[::-1].copy(), k)
+    ra, sa_ = idx.wait_host(ta)
+    rb, _ = idx.wait_host(tb)
+    assert np.array_equal(ra, want_rows) and np.array_equal(rb, want_rows[::-1])
+    np.testing.assert_allclose(sa_, want_scores, rtol=1e-5)
     idx.close()
 
 # ---- hybrid over row-sharded postings: global statistics, global k nearest, two all-gathers ----
