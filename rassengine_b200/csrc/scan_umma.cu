@@ -196,28 +196,48 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
       // certificate takes the maximum bound over segments, and this segment publishes the largest threshold it used.
       if (g > 0x007fffffu) ss->thr[4 * lane + ew] = fmaxf(ss->thr[4 * lane + ew], unord32(g));
       __syncwarp();
-      for (int q = ew; q < UMMA_NQ; q += 4) {
+      // segments past their high-water mark; the loads of the next one are in flight while this one is compacted
+      // (a compaction is mostly the L2 round trip of its 2 x SEG/32 loads per lane)
+      unsigned need = __ballot_sync(0xffffffffu, lane < UMMA_NQ / 4 && ss->cnt[4 * lane + ew] > (SEG / 2));
+      uint32_t ok[SEG / 32], rw[SEG / 32], ok_n[SEG / 32], rw_n[SEG / 32];
+      auto load_seg = [&](int q, uint32_t (&k_)[SEG / 32], uint32_t (&r_)[SEG / 32]) {
         const int n = min(ss->cnt[q], SEG);
-        if (n <= (SEG / 2)) continue;
         const size_t base = (size_t)q * pool_entries + (size_t)cta * SEG;
-        // keys as order-preserving integers; empty slots are 0
-        uint32_t ok[SEG / 32], rw[SEG / 32];
 #pragma unroll
         for (int i = 0; i < SEG / 32; ++i) {
           const int idx = i * 32 + lane;
-          ok[i] = idx < n ? ord32(__ldcg(pool_key + base + idx)) : 0u;
-          rw[i] = idx < n ? __ldcg(pool_row + base + idx) : 0xffffffffu;
+          // keys as order-preserving integers; empty slots are 0
+          k_[i] = idx < n ? ord32(__ldcg(pool_key + base + idx)) : 0u;
+          r_[i] = idx < n ? __ldcg(pool_row + base + idx) : 0xffffffffu;
         }
+      };
+      int q_cur = -1;
+      if (need) {
+        q_cur = 4 * (__ffs(need) - 1) + ew;
+        need &= need - 1;
+        load_seg(q_cur, ok, rw);
+      }
+      while (q_cur >= 0) {
+        int q_next = -1;
+        if (need) {
+          q_next = 4 * (__ffs(need) - 1) + ew;
+          need &= need - 1;
+          load_seg(q_next, ok_n, rw_n);
+        }
+        const size_t base = (size_t)q_cur * pool_entries + (size_t)cta * SEG;
         __syncwarp();
         uint32_t pivot;
         const int kept = warp_compact<SEG / 32>(ok, rw, (SEG / 8), pool_key + base, pool_row + base, pivot);
         __syncwarp();
         // everything dropped here, and every row rejected from now on, has key <= pivot
         if (lane == 0) {
-          ss->cnt[q] = kept;
-          ss->thr[q] = fmaxf(ss->thr[q], unord32(pivot));
-          atomicMax(gthr + q, pivot);
+          ss->cnt[q_cur] = kept;
+          ss->thr[q_cur] = fmaxf(ss->thr[q_cur], unord32(pivot));
+          atomicMax(gthr + q_cur, pivot);
         }
+#pragma unroll
+        for (int i = 0; i < SEG / 32; ++i) { ok[i] = ok_n[i]; rw[i] = rw_n[i]; }
+        q_cur = q_next;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
