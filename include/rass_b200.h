@@ -121,6 +121,8 @@ int rass_count(const rass_engine* h, int64_t* out_live_rows);
 int rass_rows(const rass_engine* h, int64_t* out_total_rows);
 /* stored values (fp32, or the bf16 values widened when RASS_BF16_ONLY) back to the host: [n, dim] */
 int rass_read_rows(rass_engine* h, int64_t first_row, int64_t n, float* out_host);
+/* same for a list of rows (the `_source.embedding` of the hits of one search): one gather, one copy */
+int rass_read_rows_list(rass_engine* h, const int64_t* rows_host, int64_t n, float* out_host);
 
 /* Exact top-k.  q: [B, dim] fp32 (need not be normalised).  out_rows: [B, k] (base + local row, -1 = no hit),
  * out_scores: [B, k] fp32 = 1/(2 - cos) (cosine) or 1/(1 + d^2) (L2).  out_keys (nullable): [B, k] fp64 cos / d^2.
@@ -204,6 +206,9 @@ int rass_fuzzy_expand(rass_engine* h, const char* token, int token_len, int max_
 /* bool.filter of the following rass_search_hybrid calls (app/main.py:1599-1604) as a per-row pass mask:
  * mask_host[n] bytes, 1 = the row satisfies the filter; rows >= n fail.  NULL clears the filter. */
 int rass_set_row_filter(rass_engine* h, const uint8_t* mask_host, int64_t n);
+/* The same filter given as the list of rows that pass (a term filter on patientId selects a few hundred rows of
+ * millions): the mask over [0, total_rows) is built on the device, the host moves n * 8 bytes. */
+int rass_set_row_filter_rows(rass_engine* h, const int64_t* rows_host, int64_t n, int64_t total_rows);
 
 int rass_sync(rass_engine* h);
 

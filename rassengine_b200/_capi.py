@@ -55,6 +55,8 @@ PROTOTYPES = {
     "rass_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "rass_rows": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "rass_read_rows": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
+    "rass_read_rows_list": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "rass_set_row_filter_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
     "rass_search_knn": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.POINTER(RassStats)]),
     "rass_search_knn_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.POINTER(RassStats)]),
     "rass_search_knn_dev_async": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P]),

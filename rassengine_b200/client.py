@@ -114,10 +114,10 @@ class _Index:
             self._sync_text()                 # per-field statistics and the device dictionary (fuzziness) are current
             found, aggs, total = HostSearcher(self).search(body)
         src_filter = body.get("_source")
+        vf = self.vector_field or "embedding"
+        need_vec = src_filter is not False and not (isinstance(src_filter, (list, tuple)) and vf not in src_filter)
         hits = []
-        for row, score in found:
-            h = self._hit(row, 0.0)
-            h["_score"] = score
+        for h in self._hits(found, with_vectors=need_vec):
             if isinstance(src_filter, (list, tuple)):
                 h["_source"] = {k: v for k, v in (h["_source"] or {}).items() if k in src_filter}
             elif src_filter is False:
@@ -216,18 +216,21 @@ class _Index:
             if rows and row in rows:
                 rows.remove(row)
 
-    def _filter_mask(self, filters) -> np.ndarray:
-        mask = np.ones(len(self.sources), dtype=np.uint8)
+    def _filter_rows(self, filters) -> np.ndarray:
+        """Rows passing every term filter, ascending.  The keyword fields the hot path filters on (patientId,
+        doc_type ...) keep value -> rows lists, so a patient filter costs O(rows of the patient), not O(index)."""
+        out = None
         for f, v in filters:
-            m = np.zeros(len(self.sources), dtype=np.uint8)
             if f in self.kw:
-                m[np.asarray(self.kw[f].get(v, []), dtype=np.int64)] = 1
+                rows = np.asarray(self.kw[f].get(v, []), dtype=np.int64)
             else:
-                for r, src in enumerate(self.sources):
-                    if src is not None and src.get(f) == v:
-                        m[r] = 1
-            mask &= m
-        return mask
+                rows = np.asarray([r for r, src in enumerate(self.sources) if src is not None and src.get(f) == v],
+                                  dtype=np.int64)
+            out = np.unique(rows) if out is None else np.intersect1d(out, rows)
+        return out if out is not None else np.arange(len(self.sources), dtype=np.int64)
+
+    def _apply_filter(self, filters):
+        self.engine.set_row_filter_rows(self._filter_rows(filters), len(self.sources))
 
     def _sync_text(self):
         if self.text.dirty and self.engine is not None:
@@ -237,15 +240,30 @@ class _Index:
             self.text.dirty = False
 
     # -- search ------------------------------------------------------------------------------------------
-    def _hit(self, row: int, score: float) -> dict:
-        """_source comes back whole, like OpenSearch returns it: the vector is read back from the device store
-        (float32 -> python floats, the same doubles the reference's JSON round trip yields)."""
-        src = self.sources[row]
-        if src is not None and self.has_vec[row]:
-            src = dict(src)
+    def _hits(self, pairs, with_vectors: bool = True) -> list[dict]:
+        """[(row, score)] -> hit dicts.  `_source` comes back whole, like OpenSearch returns it: the vectors of all
+        hits are read back from the device store in one gather (float32 -> python floats, the same doubles the
+        reference's JSON round trip yields)."""
+        pairs = list(pairs)
+        vf = self.vector_field or "embedding"
+        with_vec = [r for r, _ in pairs if self.sources[r] is not None and self.has_vec[r]] if with_vectors else []
+        vecs = {}
+        if with_vec:
             with self.lock:
-                src[self.vector_field or "embedding"] = self.engine.read_rows(row, 1)[0].tolist()
-        return {"_index": self.name, "_id": self.ids[row], "_score": float(score), "_source": src}
+                got = self.engine.read_rows_list(with_vec)
+            vecs = {r: got[i].tolist() for i, r in enumerate(with_vec)}
+        out = []
+        for r, s in pairs:
+            src = self.sources[r]
+            if r in vecs:
+                src = dict(src)
+                src[vf] = vecs[r]
+            out.append({"_index": self.name, "_id": self.ids[r], "_score": None if s is None else float(s),
+                        "_source": src})
+        return out
+
+    def _hit(self, row: int, score: float) -> dict:
+        return self._hits([(row, score)])[0]
 
     def _passes(self, row: int, filters) -> bool:
         src = self.sources[row] or {}
@@ -263,7 +281,7 @@ class _Index:
         eng = self.engine
         if plan.kind == "match_all":
             rows = [r for r in range(len(self.sources)) if self.sources[r] is not None][: plan.size]
-            return [self._hit(r, 1.0) for r in rows]
+            return self._hits((r, 1.0) for r in rows)
         if plan.vector is not None and plan.knn_field != (self.vector_field or "embedding"):
             raise RequestError(f"field {plan.knn_field!r} is not a knn_vector")
         q = None
@@ -276,7 +294,7 @@ class _Index:
             if plan.filters and self.knn_filter == "pre":
                 # exact filtered kNN: the scan itself skips rows failing the term filters, so the
                 # k best rows OF THE PATIENT come back instead of whichever of the global k nearest happen to pass
-                eng.set_row_filter(self._filter_mask(plan.filters))
+                self._apply_filter(plan.filters)
                 eng.set_knn_prefilter(True)
                 try:
                     rows, scores = eng.search_knn(q, k)
@@ -284,12 +302,12 @@ class _Index:
                     eng.set_knn_prefilter(False)
                     eng.set_row_filter(None)
                 hits = [(int(r), float(s) * plan.knn_boost) for r, s in zip(rows[0], scores[0]) if r >= 0]
-                return [self._hit(r, s) for r, s in hits[: plan.size]]
+                return self._hits(hits[: plan.size])
             rows, scores = self._knn(q, k)
             # OpenSearch applies bool.filter to the k nearest neighbours of the nmslib engine (post-filter)
             hits = [(int(r), float(s) * plan.knn_boost) for r, s in zip(rows[0], scores[0]) if r >= 0]
             hits = [(r, s) for r, s in hits if self._passes(r, plan.filters)]
-            return [self._hit(r, s) for r, s in hits[: plan.size]]
+            return self._hits(hits[: plan.size])
         # hybrid: bool.should boosted sum
         k = min(max(plan.size, 1), 128)
         # text clauses: multi_match best_fields = max over the fields of the field's term sum (every declared field the
@@ -333,13 +351,16 @@ class _Index:
         if q is None and qterms is None:
             return []
         # bool.filter: only rows that satisfy every term filter may score (device-side pass mask)
-        eng.set_row_filter(self._filter_mask(plan.filters) if plan.filters else None)
+        if plan.filters:
+            self._apply_filter(plan.filters)
+        else:
+            eng.set_row_filter(None)
         try:
             rows, scores = eng.search_hybrid(q, qterms, w_text, plan.knn_boost, k, qweights=qweights, qflags=qflags)
         finally:
             if plan.filters:
                 eng.set_row_filter(None)
-        return [self._hit(int(r), float(s)) for r, s in zip(rows[0], scores[0]) if r >= 0][: plan.size]
+        return self._hits([(int(r), float(s)) for r, s in zip(rows[0], scores[0]) if r >= 0][: plan.size])
 
 
 class IndicesClient:

@@ -139,6 +139,8 @@ struct rass_engine {
     rass_stats stats;
   } aslot[2];
   uint8_t* row_filter = nullptr;    // device [row_filter_rows] 1 = row passes the bool.filter of the running query
+  int64_t* filter_rows_dev = nullptr;   // staging of row lists (rass_set_row_filter_rows, rass_read_rows_list)
+  size_t filter_rows_cap = 0;
   bool knn_prefilter = false;       // RASS_OPT_KNN_PREFILTER: rass_search_knn scans only rows passing row_filter
   float* sb_filtered = nullptr;     // [cap] sb with -inf for rows failing the filter (built lazily)
   int64_t sb_filtered_cap = 0;

@@ -140,6 +140,7 @@ extern "C" int rass_destroy(rass_engine* h) {
   cudaFreeHost(h->q_stage_host);
   cudaFree(h->q_stage_dev);
   cudaFree(h->row_filter);
+  cudaFree(h->filter_rows_dev);
   cudaFree(h->sb_filtered);
   cudaFree(h->retry_ids); cudaFree(h->retry_q); cudaFree(h->retry_rows); cudaFree(h->retry_scores); cudaFree(h->retry_keys);
   for (cudaEvent_t e : h->ev_pool) if (e) cudaEventDestroy(e);
@@ -906,6 +907,82 @@ extern "C" int rass_set_row_filter(rass_engine* h, const uint8_t* mask_host, int
   CUDA_TRY(h, cudaStreamSynchronize(st));
   h->row_filter_rows = n;
   h->sb_filtered_dirty = true;
+  return RASS_OK;
+}
+
+// bool.filter as a list of the rows that pass (term filters select few rows: a patient's documents): the mask is
+// zeroed and the listed rows are set on the device, so the host never touches O(rows) bytes per query
+__global__ void set_mask_rows_kernel(const int64_t* __restrict__ rows, int64_t n, int64_t total, uint8_t* __restrict__ mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && rows[i] >= 0 && rows[i] < total) mask[rows[i]] = 1;
+}
+
+extern "C" int rass_set_row_filter_rows(rass_engine* h, const int64_t* rows_host, int64_t n, int64_t total_rows) {
+  CHECK_HANDLE(h);
+  if (n < 0 || total_rows < 0 || (n && !rows_host)) return rass_fail(h, RASS_E_INVALID, "bad filter rows");
+  cudaStream_t st = eng_stream(h);
+  if ((size_t)total_rows > h->row_filter_cap || !h->row_filter) {
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    cudaFree(h->row_filter);
+    h->row_filter = nullptr;
+    const size_t cap = std::max<size_t>((size_t)total_rows, 1024) * 2;
+    CUDA_TRY(h, cudaMalloc(&h->row_filter, cap));
+    h->row_filter_cap = cap;
+  }
+  if ((size_t)n > h->filter_rows_cap) {
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    cudaFree(h->filter_rows_dev);
+    h->filter_rows_dev = nullptr;
+    h->filter_rows_cap = 0;
+    const size_t cap = std::max<size_t>((size_t)n * 2, 4096);
+    CUDA_TRY(h, cudaMalloc(&h->filter_rows_dev, cap * sizeof(int64_t)));
+    h->filter_rows_cap = cap;
+  }
+  CUDA_TRY(h, cudaMemsetAsync(h->row_filter, 0, (size_t)std::max<int64_t>(total_rows, 1), st));
+  if (n) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->filter_rows_dev, rows_host, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    set_mask_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->filter_rows_dev, n, total_rows, h->row_filter);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(st));     // rows_host may be pageable and freed on return
+  h->row_filter_rows = total_rows;
+  h->sb_filtered_dirty = true;
+  return RASS_OK;
+}
+
+// stored values of a LIST of rows (the hits of one search) in one gather + one copy: [n, dim] fp32
+__global__ void gather_rows_kernel(const float* __restrict__ x32, const __nv_bfloat16* __restrict__ x16, int dim,
+                                   int dim_pad, const int64_t* __restrict__ rows, float* __restrict__ out) {
+  const int64_t r = rows[blockIdx.x];
+  for (int j = threadIdx.x; j < dim; j += blockDim.x)
+    out[(size_t)blockIdx.x * dim + j] = x32 ? x32[(size_t)r * dim_pad + j] : __bfloat162float(x16[(size_t)r * dim_pad + j]);
+}
+
+extern "C" int rass_read_rows_list(rass_engine* h, const int64_t* rows_host, int64_t n, float* out_host) {
+  CHECK_HANDLE(h);
+  if (n < 0 || (n && (!rows_host || !out_host))) return rass_fail(h, RASS_E_INVALID, "bad arguments");
+  if (n == 0) return RASS_OK;
+  for (int64_t i = 0; i < n; ++i)
+    if (rows_host[i] < 0 || rows_host[i] >= h->n_rows)
+      return rass_fail(h, RASS_E_NOTFOUND, "row %lld out of range", (long long)rows_host[i]);
+  cudaStream_t st = eng_stream(h);
+  int rc;
+  if ((size_t)n > h->filter_rows_cap) {
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    cudaFree(h->filter_rows_dev);
+    h->filter_rows_dev = nullptr;
+    h->filter_rows_cap = 0;
+    const size_t cap = std::max<size_t>((size_t)n * 2, 4096);
+    CUDA_TRY(h, cudaMalloc(&h->filter_rows_dev, cap * sizeof(int64_t)));
+    h->filter_rows_cap = cap;
+  }
+  if ((rc = ensure_dev_stage(h, (size_t)n * h->dim * 4))) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h->filter_rows_dev, rows_host, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  gather_rows_kernel<<<(unsigned)n, 256, 0, st>>>((h->flags & RASS_BF16_ONLY) ? nullptr : h->x32, h->x16, h->dim,
+                                                  h->dim_pad, h->filter_rows_dev, h->dev_stage);
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaMemcpyAsync(out_host, h->dev_stage, (size_t)n * h->dim * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
   return RASS_OK;
 }
 

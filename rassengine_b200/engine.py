@@ -109,6 +109,17 @@ class Engine:
         self._check(self._lib.rass_read_rows(self._h, first, n, _ptr(out)))
         return out
 
+    def read_rows_list(self, rows) -> np.ndarray:
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.empty((rows.size, self.dim), dtype=np.float32)
+        self._check(self._lib.rass_read_rows_list(self._h, _ptr(rows), rows.size, _ptr(out)))
+        return out
+
+    def set_row_filter_rows(self, rows, total_rows: int):
+        """The bool.filter as the list of rows that pass; rows >= total_rows fail."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        self._check(self._lib.rass_set_row_filter_rows(self._h, _ptr(rows), rows.size, total_rows))
+
     # -- search -----------------------------------------------------------------------------------------
     def search_knn(self, q: np.ndarray, k: int, want_keys: bool = False):
         """q: [B, dim] fp32 (host).  Returns rows int64 [B, k] (-1 = no hit), scores fp32 [B, k]
