@@ -26,6 +26,8 @@ class TextField:
         self.vocab: dict[str, int] = {}
         self.row_terms: dict[int, np.ndarray] = {}   # row -> int32 term ids (with repeats)
         self.dirty = True
+        self._fuzzy: dict = {}                       # token -> ranked expansion, as of the last postings()
+        self._terms: list[str] = []                  # id -> term, rebuilt when the vocabulary grew
         self.df = np.zeros(0, dtype=np.int64)        # document frequency per term, as of the last postings()
         self.doc_count = 0                           # documents with at least one token, as of the last postings()
 
@@ -55,6 +57,7 @@ class TextField:
         """CSR over the current rows: indptr int64 [V+1], doc int32 [nnz] ascending per term, tf uint16 [nnz],
         doclen uint32 [n_rows]."""
         V = len(self.vocab)
+        self._fuzzy = {}
         doclen = np.zeros(n_rows, dtype=np.uint32)
         if not self.row_terms:
             self.df, self.doc_count = np.zeros(V, dtype=np.int64), 0
@@ -70,10 +73,12 @@ class TextField:
         return indptr, d_of, tf, doclen
 
     def terms_in_id_order(self) -> list[str]:
-        out = [""] * len(self.vocab)
-        for t, i in self.vocab.items():
-            out[i] = t
-        return out
+        if len(self._terms) != len(self.vocab):
+            out = [""] * len(self.vocab)
+            for t, i in self.vocab.items():
+                out[i] = t
+            self._terms = out
+        return self._terms
 
     @staticmethod
     def auto_max_edits(n_chars: int) -> int:
@@ -102,31 +107,35 @@ class TextField:
         expand(token, max_edits) -> (term ids, edits) is the device dictionary scan.  Returns (term ids, float32
         weights = float(boost * term boost) * idf)."""
         import math
-        terms_by_id = None
         ids: list[int] = []
         ws: list[np.float32] = []
         bo = np.float32(boost)
         for tok in (analyze(text) if isinstance(text, str) else text):
-            me = self.auto_max_edits(len(tok))
-            if me == 0 or len(tok) > 64:
-                t = self.vocab.get(tok, -1)
-                cand = [(t, 0)] if t >= 0 else []
-            else:
-                tid, ed = expand(tok, me)
-                cand = list(zip(tid.tolist(), ed.tolist()))
-            cand = [(t, e) for t, e in cand if t < self.df.size and self.df[t] > 0]
-            if not cand:
-                continue
-            if terms_by_id is None:
-                terms_by_id = self.terms_in_id_order()
-            scored = []
-            for t, e in cand:
-                b = np.float32(1.0) if e == 0 else np.float32(1.0) - np.float32(e) / np.float32(min(len(terms_by_id[t]), len(tok)))
-                scored.append((t, np.float32(b)))
-            scored.sort(key=lambda x: (-float(x[1]), terms_by_id[x[0]]))
-            scored = scored[:max_expansions]
-            max_df = max(int(self.df[t]) for t, _ in scored)
-            idf = np.float32(math.log(1.0 + (self.doc_count - max_df + 0.5) / (max_df + 0.5)))
+            hit = self._fuzzy.get(tok)
+            if hit is None:
+                me = self.auto_max_edits(len(tok))
+                if me == 0 or len(tok) > 64:
+                    t = self.vocab.get(tok, -1)
+                    cand = [(t, 0)] if t >= 0 else []
+                else:
+                    tid, ed = expand(tok, me)
+                    cand = list(zip(tid.tolist(), ed.tolist()))
+                cand = [(t, e) for t, e in cand if t < self.df.size and self.df[t] > 0]
+                scored, idf = [], np.float32(0)
+                if cand:
+                    terms_by_id = self.terms_in_id_order()
+                    for t, e in cand:
+                        b = np.float32(1.0) if e == 0 else \
+                            np.float32(1.0) - np.float32(e) / np.float32(min(len(terms_by_id[t]), len(tok)))
+                        scored.append((t, np.float32(b)))
+                    scored.sort(key=lambda x: (-float(x[1]), terms_by_id[x[0]]))
+                    scored = scored[:max_expansions]
+                    max_df = max(int(self.df[t]) for t, _ in scored)
+                    idf = np.float32(math.log(1.0 + (self.doc_count - max_df + 0.5) / (max_df + 0.5)))
+                if len(self._fuzzy) > 50000:
+                    self._fuzzy.clear()
+                hit = self._fuzzy[tok] = (scored, idf)       # the dictionary scan and its ranking, per distinct token
+            scored, idf = hit
             for t, b in scored:
                 ids.append(int(t))
                 ws.append(np.float32(np.float32(bo * b) * idf))
