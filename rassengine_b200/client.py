@@ -131,10 +131,12 @@ class _Index:
             with self.lock:
                 return self.engine.search_knn(q, k)
         if self.batcher is None:
-            def locked(Q, kk):
-                with self.lock:
-                    return self.engine.search_knn(Q, kk)
-            self.batcher = MicroBatcher(locked, max_batch=64, max_wait_s=self.batch_window_s)
+            with self.lock:                   # threads race here on the first request
+                if self.batcher is None:
+                    def locked(Q, kk):
+                        with self.lock:
+                            return self.engine.search_knn(Q, kk)
+                    self.batcher = MicroBatcher(locked, max_batch=64, max_wait_s=self.batch_window_s)
         rows, scores = self.batcher.search(q, k)
         return rows[None, :], scores[None, :]
 
@@ -185,7 +187,7 @@ class _Index:
             self.has_vec.append(bool(has[i]))
             self.ids.append(_id)
             self.row_of[_id] = row
-            self.text.set_doc(row, src)
+            self.text.set_doc(row, src, fresh=True)
             self._kw_add(row, src)
         self.n_docs += len(fresh)
 
@@ -529,7 +531,7 @@ class B200Client:
                 idx._ensure_engine(idx.dim).load(vec)
             for row, src in enumerate(idx.sources):
                 if src is not None:
-                    idx.text.set_doc(row, src)
+                    idx.text.set_doc(row, src, fresh=True)
                     idx._kw_add(row, src)
             self._indices[name] = idx
             names.append(name)

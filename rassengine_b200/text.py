@@ -179,10 +179,12 @@ class TextIndex:
                 out.extend(analyze(v))
         return out
 
-    def set_doc(self, row: int, src: dict | None):
-        """(Re)index one row: every declared field the document carries; fields it no longer carries are cleared."""
+    def set_doc(self, row: int, src: dict | None, fresh: bool = False):
+        """(Re)index one row: every declared field the document carries; on an overwrite (fresh = False) the fields
+        it no longer carries are cleared."""
         src = src or {}
-        for name in self.types:
+        names = [n for n in src if n in self.types] if fresh else list(self.types)
+        for name in names:
             toks = self.tokens(name, src[name]) if name in src else []
             fld = self.fields.get(name)
             if fld is None:
