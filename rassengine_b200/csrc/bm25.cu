@@ -185,6 +185,8 @@ struct HybridArgs {
   float w_knn;
   double* xkey;                  // [B][n_tiles * k]
   uint32_t* xrow;
+  uint32_t* gthr;                // [B] per query: the largest k-th best fused key any tile has found so far (ordered
+                                 // integer image, 0 = none): k rows score at least this much, lower keys are out
 };
 
 // One CTA per (tile of 4096 docs, query): the whole bool.should of the reference for those docs.
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
   __shared__ __align__(16) int s_cnt[2][HYB_THREADS / 32];
   __shared__ uint32_t s_list[HYB_LIST];
   __shared__ int s_nout, s_nmatch, s_ns;
+  __shared__ uint32_t s_g;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, q = blockIdx.y;
   const int64_t d0 = (int64_t)tile * HYB_TILE;
@@ -332,7 +335,32 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
   const int n_match = s_nmatch;
   double* xk = a.xkey + ((size_t)q * a.n_tiles + tile) * a.k;
   uint32_t* xr = a.xrow + ((size_t)q * a.n_tiles + tile) * a.k;
-  if (n_match <= a.k) {
+  int buf = 0;
+  auto block_count = [&](int c) {
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) s_cnt[buf][warp] = c;
+    __syncthreads();
+    const int4 c0 = *reinterpret_cast<const int4*>(&s_cnt[buf][0]), c1 = *reinterpret_cast<const int4*>(&s_cnt[buf][4]);
+    buf ^= 1;       // the next count writes the other buffer, so one barrier per count is enough
+    return c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+  };
+  // Cross-tile pruning: some other tile of this query already holds k rows with key >= g, so keys below g cannot
+  // reach the query's top-k.  Most tiles of a batched launch then keep a handful of keys and skip the selection.
+  // (read once per CTA: other tiles raise the bound concurrently, and the branches below must be uniform)
+  if (tid == 0) s_g = n_match > a.k ? __ldcg(a.gthr + q) : 0u;
+  __syncthreads();
+  const uint32_t g = s_g;
+  int n_live = n_match;
+  if (g) {
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      if (key[i] < g) key[i] = 0;
+      c += key[i] != 0;
+    }
+    n_live = block_count(c);
+  }
+  if (n_live <= a.k) {
 #pragma unroll
     for (int i = 0; i < PER; ++i)
       if (key[i]) {
@@ -363,15 +391,6 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
     __syncthreads();
     const int ns = s_ns;
     // k-th largest key by most-significant-bit-first descent: prefix grows while >= k entries are >= it
-    int buf = 0;
-    auto block_count = [&](int c) {
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (lane == 0) s_cnt[buf][warp] = c;
-      __syncthreads();
-      const int4 c0 = *reinterpret_cast<const int4*>(&s_cnt[buf][0]), c1 = *reinterpret_cast<const int4*>(&s_cnt[buf][4]);
-      buf ^= 1;       // the next count writes the other buffer, so one barrier per count is enough
-      return c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
-    };
     uint32_t prefix = 0;
     if (ns <= HYB_LIST) {
       const uint32_t e0 = tid < ns ? s_list[tid] : 0u, e1 = tid + HYB_THREADS < ns ? s_list[tid + HYB_THREADS] : 0u;
@@ -395,6 +414,7 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
     for (int i = 0; i < PER; ++i) { n_gt += key[i] > prefix; n_eq += key[i] == prefix; }
     const int need_eq = a.k - block_count(n_gt);      // entries equal to the k-th key to take, lowest rows first
     const int tot_eq = block_count(n_eq);
+    if (tid == 0) atomicMax(a.gthr + q, prefix);      // k rows of this tile score >= prefix: publish for the others
     const bool all_eq = tot_eq == need_eq;    // the usual case: the k-th key is unique in the tile
 #pragma unroll
     for (int i = 0; i < PER; ++i)
@@ -437,6 +457,8 @@ static int ensure_hybrid_workspace(rass_engine* h, size_t n_terms_cap, int B) {
     // one pinned + one device block:
     // [t_lo i64 x tc][t_len u32 x tc][t_w f32 x tc][t_row i32 x tc][indptr i32 x qc][t_field u8 x tc][t_flag u8 x tc]
     const size_t bytes = tc * (8 + 4 + 4 + 4 + 1 + 1) + qc * 4;
+    cudaFree(b.hyb_gthr); b.hyb_gthr = nullptr;
+    CUDA_TRY(h, cudaMalloc(&b.hyb_gthr, qc * sizeof(uint32_t)));
     cudaFreeHost(b.qt_host); b.qt_host = nullptr;
     cudaFree(b.qt_dev); b.qt_dev = nullptr;
     CUDA_TRY(h, cudaMallocHost(&b.qt_host, bytes));
@@ -573,6 +595,9 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
   a.w_knn = w_knn;
   a.xkey = h->xlist_key;
   a.xrow = h->xlist_row;
+  if ((rc = ensure_hybrid_workspace(h, 0, B))) return rc;          // vector-only calls have not sized it yet
+  a.gthr = b.hyb_gthr;
+  CUDA_TRY(h, cudaMemsetAsync(b.hyb_gthr, 0, (size_t)B * sizeof(uint32_t), st));
   const size_t smem_single = (size_t)HYB_TILE * 8, smem_multi = (size_t)HYB_TILE * (8 + 8 + 4);
   CUDA_TRY(h, cudaFuncSetAttribute(hybrid_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi));
   for (int q0 = 0; q0 < B; q0 += 32768) {
@@ -582,6 +607,7 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
     if (aq.knn_rows) { aq.knn_rows += (size_t)q0 * k; aq.knn_scores += (size_t)q0 * k; }
     aq.xkey += (size_t)q0 * a.n_tiles * k;
     aq.xrow += (size_t)q0 * a.n_tiles * k;
+    aq.gthr += q0;
     if (multi) hybrid_tile_kernel<true><<<dim3((unsigned)a.n_tiles, (unsigned)nq), HYB_THREADS, smem_multi, st>>>(aq);
     else hybrid_tile_kernel<false><<<dim3((unsigned)a.n_tiles, (unsigned)nq), HYB_THREADS, smem_single, st>>>(aq);
     CUDA_TRY(h, cudaGetLastError());

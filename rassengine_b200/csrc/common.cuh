@@ -37,6 +37,7 @@ struct Bm25State {
   unsigned char* qt_host = nullptr;      // pinned staging of the per-call query-term arrays
   unsigned char* qt_dev = nullptr;
   size_t qt_cap = 0, qt_q_cap = 0, qt_bytes = 0;
+  uint32_t* hyb_gthr = nullptr;          // device [qt_q_cap] cross-tile pruning bound of the running hybrid batch
   unsigned char* vocab_blob = nullptr;   // device: the term dictionary, terms back to back (fuzziness: AUTO)
   int64_t* vocab_off = nullptr;          // device [vocab_V + 1]
   int64_t vocab_V = 0;
