@@ -296,3 +296,51 @@ def test_top100_inside_one_cluster_of_adjacent_rows_is_certified(path):
     else:
         assert 0 < st["n_retried"] <= (Q.shape[0] + 1) // 2, st
     assert st10["n_retried"] == 0 and st10["n_fallback"] == 0, st10
+
+
+def test_properties_at_2m_rows_all_paths_agree():
+    """Larger than the oracle can check in seconds: size-independent properties instead.  On 2M device-generated
+    rows every scan path returns the same ids for the same queries, the fp64 scan (the definition) agrees on a
+    sample, scores are sorted, ids are distinct, and tombstoning a query's best row shifts its list up by one."""
+    import torch
+    import rassengine_b200 as rb
+    n, d = 2_000_000, 1024
+    with _engine(dim=d, capacity_rows=n) as e:
+        g = torch.Generator(device="cuda").manual_seed(99)
+        for c0 in range(0, n, 500_000):
+            x = torch.randn((500_000, d), generator=g, device="cuda")
+            x /= x.norm(dim=1, keepdim=True) + 1e-9
+            torch.cuda.synchronize()
+            e.append_dev(x.data_ptr(), x.shape[0])
+            del x
+        q = torch.randn((300, d), generator=g, device="cuda")
+
+        def run(path, B, k):
+            e.set_path(path)
+            rows = torch.empty((B, k), dtype=torch.int64, device="cuda")
+            sc = torch.empty((B, k), dtype=torch.float32, device="cuda")
+            st = e.search_knn_dev(q.data_ptr(), B, k, rows.data_ptr(), sc.data_ptr())
+            assert st["n_fallback"] == 0 and st["n_certified"] == B, st
+            return rows.cpu().numpy(), sc.cpu().numpy()
+
+        for k in (10, 100):
+            r_gemm, s_gemm = run(rb.PATH_GEMM, 300, k)
+            r_umma, s_umma = run(rb.PATH_UMMA, 130, k)
+            r_str, s_str = run(rb.PATH_STREAM, 3, k)
+            e.set_path(rb.PATH_EXACT)
+            rows = torch.empty((4, k), dtype=torch.int64, device="cuda")
+            sc = torch.empty((4, k), dtype=torch.float32, device="cuda")
+            e.search_knn_dev(q.data_ptr(), 4, k, rows.data_ptr(), sc.data_ptr())
+            assert np.array_equal(r_gemm[:130], r_umma) and np.array_equal(r_gemm[:3], r_str)
+            assert np.array_equal(r_gemm[:4], rows.cpu().numpy())
+            np.testing.assert_array_equal(s_gemm[:130], s_umma)            # same fp64 rerank -> same float scores
+            assert (np.diff(s_gemm, axis=1) <= 0).all()
+            assert all(len(set(r.tolist())) == k for r in r_gemm) and r_gemm.min() >= 0 and r_gemm.max() < n
+        best = int(r_gemm[0, 0])
+        e.tombstone(best)
+        r2, _ = run(rb.PATH_UMMA, 64, 10)
+        r_before, _ = r_gemm[:64, :], None
+        assert best not in r2[0].tolist() and r2[0, :9].tolist() == r_before[0, 1:10].tolist()
+        for b in range(1, 64):
+            if best not in r_before[b, :10].tolist():
+                assert r2[b].tolist() == r_before[b, :10].tolist()
