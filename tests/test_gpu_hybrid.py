@@ -344,3 +344,29 @@ def test_mixed_index_multi_field_dismax_matches_oracle():
     hits = idxr.hybrid_search("john smith", rng.standard_normal((1, dim)).astype(np.float32), k=k)
     assert {h[0]["doc_type"] for h in hits} == {"structured", "unstructured"} or len(hits) == k
     client.close()
+
+
+def test_hybrid_many_tiles_batched_matches_oracle():
+    """74 tiles of 4096 docs and a batched launch: tiles prune each other through the per-query bound, the frequent
+    terms go through the per-tile posting offsets; ids identical, fused float32 scores bit-identical."""
+    n_docs, vocab, dim, nq, k = 300_000, 4000, 256, 24, 10
+    indptr, doc, tf, doclen = synth.text_corpus(n_docs, vocab=vocab, seed=71, median_len=40, max_len=160)
+    idx = bm25.BM25Index(indptr, doc, tf, doclen)
+    assert int(np.diff(indptr).max()) > 512 * 20          # some terms take the offset table, most of the rest do not
+    X = synth.embeddings(n_docs, dim, 72)
+    Q = synth.embeddings(nq, dim, 73)
+    qterms = synth.text_queries(nq, vocab=vocab, seed=74)
+    knn_rows, _, knn_scores = knn.knn_exact(X, Q, k)
+    with _engine(dim=dim, capacity_rows=n_docs) as e:
+        e.append(X)
+        e.bm25_build(indptr, doc, tf, doclen)
+        rows_b, scores_b = e.search_hybrid(Q, qterms, 4.5, 2.0, k)
+        rows_t, scores_t = e.search_hybrid(None, qterms, 4.5, 0.0, k)
+        for b in range(nq):
+            wr, ws = fusion.hybrid(idx, qterms[b], knn_rows[b], knn_scores[b], 4.5, 2.0, k)
+            assert rows_b[b].tolist() == wr.tolist(), b
+            np.testing.assert_allclose(scores_b[b], ws, rtol=2e-6, atol=0)
+            tr, ts = bm25.topk(idx.score(qterms[b], boost=4.5), k)
+            assert rows_t[b].tolist() == tr.tolist() and scores_t[b].tolist() == ts.tolist(), b
+        one_r, one_s = e.search_hybrid(Q[5:6], [qterms[5]], 4.5, 2.0, k)          # the same query on its own
+        assert one_r[0].tolist() == rows_b[5].tolist() and one_s[0].tolist() == scores_b[5].tolist()
