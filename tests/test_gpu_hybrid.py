@@ -370,3 +370,50 @@ def test_hybrid_many_tiles_batched_matches_oracle():
             assert rows_t[b].tolist() == tr.tolist() and scores_t[b].tolist() == ts.tolist(), b
         one_r, one_s = e.search_hybrid(Q[5:6], [qterms[5]], 4.5, 2.0, k)          # the same query on its own
         assert one_r[0].tolist() == rows_b[5].tolist() and one_s[0].tolist() == scores_b[5].tolist()
+
+
+def test_multi_field_many_tiles_matches_oracle():
+    """rass_bm25_build_fields + group / clause marks over 13 tiles: clause = max over its field groups of the float
+    field sums, text score = double sum of the clauses, then the knn clause; batched, with cross-tile pruning."""
+    n_docs, dim, nq, k = 50_000, 128, 10, 10
+    V0, V1 = 800, 600
+    ip0, d0, tf0, dl0 = synth.text_corpus(n_docs, vocab=V0, seed=81, median_len=30, max_len=100)
+    ip1, d1, tf1, dl1 = synth.text_corpus(n_docs, vocab=V1, seed=82, median_len=8, max_len=30)
+    has1 = (np.arange(n_docs) % 3) != 0                      # a third of the documents lack the second field
+    keep = has1[d1]
+    t_of = np.repeat(np.arange(V1), np.diff(ip1))[keep]
+    ip1 = np.zeros(V1 + 1, dtype=np.int64)
+    np.add.at(ip1, t_of + 1, 1)
+    ip1 = np.cumsum(ip1)
+    d1, tf1 = d1[keep], tf1[keep]
+    dl1 = np.where(has1, dl1, 0).astype(np.uint32)
+    f0, f1 = bm25.BM25Index(ip0, d0, tf0, dl0), bm25.BM25Index(ip1, d1, tf1, dl1)
+    indptr = np.concatenate([ip0[:-1], ip1 + ip0[-1]])
+    term_field = np.concatenate([np.zeros(V0, np.int32), np.ones(V1, np.int32)])
+    X = synth.embeddings(n_docs, dim, 83)
+    Q = synth.embeddings(nq, dim, 84)
+    knn_rows, _, knn_scores = knn.knn_exact(X, Q, k)
+    rng = np.random.default_rng(85)
+    qterms, qweights, qflags, want = [], [], [], []
+    for b in range(nq):
+        a0 = [int(t) for t in rng.integers(0, 60, size=3)]          # frequent terms of field 0
+        a1 = [int(t) for t in rng.integers(0, V1, size=3)]
+        c1 = [int(t) for t in rng.integers(0, 40, size=2)]          # second clause: field 1 only
+        w0, w1, w2 = f0.term_weights(a0, 4.5), f1.term_weights(a1, 3.0), f1.term_weights(c1, 1.5)
+        qterms.append(a0 + [V0 + t for t in a1] + [V0 + t for t in c1])
+        qweights.append(np.concatenate([w0, w1, w2]))
+        qflags.append([0, 0, 1, 0, 0, 1 | 2, 0, 1 | 2])
+        clause1 = np.maximum(f0.score(a0, boost=4.5), f1.score(a1, boost=3.0))
+        total = clause1.astype(np.float64) + f1.score(c1, boost=1.5).astype(np.float64)
+        want.append(fusion.hybrid(None, None, knn_rows[b], knn_scores[b], 0.0, 2.0, k, text64=total))
+    with _engine(dim=dim, capacity_rows=n_docs) as e:
+        e.append(X)
+        e.bm25_build_fields(indptr, np.concatenate([d0, d1]), np.concatenate([tf0, tf1]), term_field,
+                            np.stack([dl0, dl1]))
+        rows, scores = e.search_hybrid(Q, qterms, 0.0, 2.0, k, qweights=qweights, qflags=qflags)
+        for b in range(nq):
+            wr, ws = want[b]
+            assert rows[b].tolist() == wr.tolist(), b
+            np.testing.assert_allclose(scores[b], ws, rtol=2e-6, atol=0)
+        r1, s1 = e.search_hybrid(Q[3:4], [qterms[3]], 0.0, 2.0, k, qweights=[qweights[3]], qflags=[qflags[3]])
+        assert r1[0].tolist() == rows[3].tolist() and s1[0].tolist() == scores[3].tolist()
