@@ -193,6 +193,13 @@ int rass_fuse_hybrid_dev(rass_engine* h, int B, const int32_t* qterm_indptr, con
                          const float* knn_scores_dev, float w_knn, int k, int64_t* out_rows_dev,
                          float* out_scores_dev, double* out_keys_dev);
 
+/* Host-pointer flavour: the k nearest come from an earlier rass_search_knn -- e.g. one corpus pass shared by several
+ * concurrent requests -- while text clauses and bool.filter are this request's own.  knn_rows_host (rows as
+ * rass_search_knn returned them, -1 = none) may be NULL for a text-only query. */
+int rass_fuse_hybrid(rass_engine* h, int B, const int32_t* qterm_indptr, const int32_t* qterms,
+                     const float* qweights, const uint8_t* qflags, float w_text, const int64_t* knn_rows_host,
+                     const float* knn_scores_host, float w_knn, int k, int64_t* out_rows, float* out_scores);
+
 /* The term dictionary of the text field, terms back to back in blob, term t = blob[offsets[t] .. offsets[t+1])
  * (ASCII: the analyzer emits [a-z0-9]+).  Needed only for rass_fuzzy_expand. */
 int rass_text_set_vocab(rass_engine* h, const char* blob, const int64_t* offsets, int64_t V);

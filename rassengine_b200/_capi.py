@@ -68,6 +68,7 @@ PROTOTYPES = {
     "rass_search_hybrid_weighted": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P, _P,
                                               C.POINTER(RassStats)]),
     "rass_bm25_build_fields": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int]),
+    "rass_fuse_hybrid": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_float, _P, _P, C.c_float, C.c_int, _P, _P]),
     "rass_fuse_hybrid_dev": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_float, _P, _P, C.c_float, C.c_int, _P, _P, _P]),
     "rass_text_set_vocab": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
     "rass_fuzzy_expand": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _P, _P,

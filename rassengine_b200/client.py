@@ -358,7 +358,23 @@ class _Index:
         else:
             eng.set_row_filter(None)
         try:
-            rows, scores = eng.search_hybrid(q, qterms, w_text, plan.knn_boost, k, qweights=qweights, qflags=qflags)
+            if q is not None and self.batch_window_s is not None:
+                # the corpus pass of the knn clause is shared with concurrent requests (MicroBatcher); the text
+                # clauses and the filter of THIS request are fused against its k nearest afterwards
+                self.lock.release()
+                try:
+                    knn_rows, knn_scores = self._knn(q, k)
+                finally:
+                    self.lock.acquire()
+                if plan.filters:
+                    self._apply_filter(plan.filters)        # another request may have changed it meanwhile
+                else:
+                    eng.set_row_filter(None)
+                rows, scores = eng.fuse_hybrid(qterms, w_text, knn_rows, knn_scores, plan.knn_boost, k,
+                                               qweights=qweights, qflags=qflags)
+            else:
+                rows, scores = eng.search_hybrid(q, qterms, w_text, plan.knn_boost, k, qweights=qweights,
+                                                 qflags=qflags)
         finally:
             if plan.filters:
                 eng.set_row_filter(None)

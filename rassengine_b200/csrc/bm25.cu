@@ -663,6 +663,41 @@ extern "C" int rass_fuse_hybrid_dev(rass_engine* h, int B, const int32_t* qterm_
                      &ext);
 }
 
+// host-pointer flavour: the k nearest come from an earlier rass_search_knn (possibly shared with other requests by a
+// request coalescer), the text clauses and the bool.filter are this request's own
+extern "C" int rass_fuse_hybrid(rass_engine* h, int B, const int32_t* qterm_indptr, const int32_t* qterms,
+                                const float* qweights, const uint8_t* qflags, float w_text,
+                                const int64_t* knn_rows_host, const float* knn_scores_host, float w_knn, int k,
+                                int64_t* out_rows, float* out_scores) {
+  if (!h) return RASS_E_INVALID;
+  cudaSetDevice(h->device);
+  if (B < 1 || k < 1 || k > RASS_MAX_K || !out_rows || !out_scores || (knn_rows_host && !knn_scores_host))
+    return rass_fail(h, RASS_E_INVALID, "bad arguments");
+  cudaStream_t st = eng_stream(h);
+  int rc;
+  const size_t n_out = (size_t)B * k;
+  if ((rc = ensure_out_workspace(h, 2 * n_out))) return rc;
+  // second half of the result staging = the external knn list, first half = this call's results
+  int64_t* knn_rows_dev = h->out_rows + n_out;
+  float* knn_scores_dev = h->out_scores + n_out;
+  if (knn_rows_host) {
+    memcpy(h->out_rows_host + n_out, knn_rows_host, n_out * 8);
+    memcpy(h->out_scores_host + n_out, knn_scores_host, n_out * 4);
+    CUDA_TRY(h, cudaMemcpyAsync(knn_rows_dev, h->out_rows_host + n_out, n_out * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(knn_scores_dev, h->out_scores_host + n_out, n_out * 4, cudaMemcpyHostToDevice, st));
+  }
+  HybridExt ext = {knn_rows_host ? knn_rows_dev : nullptr, knn_scores_dev, h->out_rows, h->out_scores, nullptr};
+  if ((rc = hybrid_core(h, nullptr, B, qterm_indptr, qterms, qweights, qflags, w_text, w_knn, k, nullptr, nullptr, nullptr,
+                        &ext)))
+    return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h->out_rows_host, h->out_rows, n_out * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaMemcpyAsync(h->out_scores_host, h->out_scores, n_out * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  memcpy(out_rows, h->out_rows_host, n_out * 8);
+  memcpy(out_scores, h->out_scores_host, n_out * 4);
+  return RASS_OK;
+}
+
 // ---- fuzziness: AUTO -- edit-distance scan of the term dictionary -------------------------------------------
 #define FUZZY_MAX_TOKEN 64
 

@@ -266,6 +266,33 @@ class Engine:
         self.last_stats = st.as_dict()
         return rows, scores
 
+    def fuse_hybrid(self, qterms, w_text: float, knn_rows, knn_scores, w_knn: float, k: int, qweights=None,
+                    qflags=None):
+        """Text clauses + bool.filter of this request fused with a knn list obtained earlier (host arrays [B, k], or
+        None for text only).  Returns (rows, scores) like search_hybrid."""
+        B = len(qterms) if qterms is not None else np.asarray(knn_rows).shape[0]
+        indptr = terms = w = fl = None
+        if qterms is not None:
+            indptr = np.zeros(B + 1, dtype=np.int32)
+            indptr[1:] = np.cumsum([len(t) for t in qterms])
+            cat = lambda xs, dt: np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=dt) for x in xs])
+                                                      if indptr[-1] else np.zeros(1, dtype=dt), dtype=dt)
+            terms = cat(qterms, np.int32)
+            w = cat(qweights, np.float32) if qweights is not None else None
+            fl = cat(qflags, np.uint8) if qflags is not None else None
+        kr = ks = None
+        if knn_rows is not None:
+            kr = np.ascontiguousarray(knn_rows, dtype=np.int64).reshape(B, k)
+            ks = np.ascontiguousarray(knn_scores, dtype=np.float32).reshape(B, k)
+        rows = np.empty((B, k), dtype=np.int64)
+        scores = np.empty((B, k), dtype=np.float32)
+        self._check(self._lib.rass_fuse_hybrid(
+            self._h, B, _ptr(indptr) if indptr is not None else None, _ptr(terms) if terms is not None else None,
+            _ptr(w) if w is not None else None, _ptr(fl) if fl is not None else None, w_text,
+            _ptr(kr) if kr is not None else None, _ptr(ks) if ks is not None else None, w_knn, k, _ptr(rows),
+            _ptr(scores)))
+        return rows, scores
+
     def fuse_hybrid_dev(self, B: int, qterms, w_text: float, knn_rows_ptr: int, knn_scores_ptr: int, w_knn: float, k: int,
                         out_rows_ptr: int, out_scores_ptr: int, out_keys_ptr: int = 0, qweights=None, qflags=None):
         """Text clauses fused with an external (global) knn list; this shard's top-k stays on the device."""

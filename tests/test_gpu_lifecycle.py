@@ -143,3 +143,40 @@ def test_client_batch_window_coalesces_threads():
     assert mb is not None and mb.requests == len(qs) and mb.batches < len(qs)
     plain.close()
     windowed.close()
+
+
+def test_hybrid_requests_share_the_knn_pass_under_a_batch_window():
+    """Concurrent hybrid requests with DIFFERENT patient filters: their knn clauses share corpus passes through the
+    MicroBatcher, text clauses and filters are fused per request (rass_fuse_hybrid); answers equal the plain client's."""
+    from rassengine_b200.client import B200Client
+    from rassengine_b200 import indexer as ix
+    docs, raw = _chunk_docs(n_docs=900)
+    dim = raw.shape[1]
+    name = ix.get_index_name("hw")
+    plain, windowed = B200Client(), B200Client(batch_window_ms=40.0)
+    for c in (plain, windowed):
+        ix.ensure_index_exists(c, name, ix.index_body(dim))
+        ix.store_chunks(c, name, docs, raw, as_lists=False, flush=900)
+    rng = np.random.default_rng(14)
+    qs = rng.standard_normal((10, 1, dim)).astype(np.float32)
+    texts = [" ".join(docs[int(i)]["unstructuredText"].split()[:3]) for i in rng.integers(0, len(docs), size=10)]
+    pats = [None if i % 4 == 0 else f"pat-{i % 5}" for i in range(10)]
+    ip = ix.B200Indexer(plain, name)
+    want = [ip.hybrid_search(texts[i], qs[i], k=5, patient_id=pats[i]) for i in range(10)]
+    assert all(want)
+    iw = ix.B200Indexer(windowed, name)
+    got = [None] * 10
+
+    def ask(i):
+        got[i] = iw.hybrid_search(texts[i], qs[i], k=5, patient_id=pats[i])
+
+    ts = [threading.Thread(target=ask, args=(i,)) for i in range(10)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert got == want
+    mb = windowed._indices[name].batcher
+    assert mb is not None and mb.requests == 10 and mb.batches < 10
+    plain.close()
+    windowed.close()
