@@ -344,3 +344,42 @@ def test_properties_at_2m_rows_all_paths_agree():
         for b in range(1, 64):
             if best not in r_before[b, :10].tolist():
                 assert r2[b].tolist() == r_before[b, :10].tolist()
+
+
+def test_edge_shapes_and_degenerate_indices():
+    """Ragged batch sizes across the path thresholds, k = 1 and k = 128, tiny / emptied indices, filters that pass
+    nothing -- through the AUTO path selection, the way a caller reaches them."""
+    import rassengine_b200 as rb
+    X = synth.embeddings(3000, 256, 91)
+    Qall = synth.embeddings(300, 256, 92)
+    with _engine(dim=256) as e:
+        e.append(X)
+        for B, k in ((1, 1), (2, 128), (63, 7), (64, 10), (65, 10), (129, 33), (257, 1), (300, 128)):
+            want_rows, _, want_scores = knn.knn_exact(X, Qall[:B], k)
+            rows, scores = e.search_knn(Qall[:B], k)
+            _check(rows, scores, want_rows, want_scores)
+        with pytest.raises(rb.RassError):
+            e.search_knn(Qall[:1], 129)                      # k beyond RASS_MAX_K
+        # a filter nothing passes, as an exact pre-filter
+        e.set_knn_prefilter(True)
+        e.set_row_filter(np.zeros(3000, dtype=np.uint8))
+        for B in (1, 40, 100):
+            rows, scores = e.search_knn(Qall[:B], 5)
+            assert (rows == -1).all() and (scores == 0).all()
+        e.set_row_filter_rows(np.array([7, 2999, 11], dtype=np.int64), 3000)      # the same filter as a row list
+        rows, _ = e.search_knn(Qall[:3], 5)
+        assert all(sorted(r[:3].tolist()) == [7, 11, 2999] and (r[3:] == -1).all() for r in rows)
+        e.set_row_filter(None)
+        e.set_knn_prefilter(False)
+        for r in range(3000):
+            if r % 1000 != 5:
+                e.tombstone(r)                               # three live rows left
+        for B in (1, 30, 200):
+            rows, _ = e.search_knn(Qall[:B], 10)
+            assert all(sorted(r[:3].tolist()) == [5, 1005, 2005] and (r[3:] == -1).all() for r in rows)
+    with _engine(dim=256) as e:                              # fewer rows than one tile, more queries than rows
+        e.append(X[:5])
+        want_rows, _, want_scores = knn.knn_exact(X[:5], Qall[:70], 5)
+        rows, scores = e.search_knn(Qall[:70], 8)
+        _check(rows[:, :5], scores[:, :5], want_rows, want_scores)
+        assert (rows[:, 5:] == -1).all()
