@@ -82,7 +82,8 @@ class BM25Index:
     def term_weights(self, qterms, boost: float) -> np.ndarray:
         """float32 weight per query term occurrence = boost * idf (float multiply)."""
         bo = np.float32(boost)
-        return np.array([bo * self.idf(int(t)) for t in qterms], dtype=np.float32)
+        return np.array([bo * self.idf(int(t)) if 0 <= int(t) < self.vocab else np.float32(0) for t in qterms],
+                        dtype=np.float32)           # tokens outside the dictionary match nothing (skipped in score)
 
     def score(self, qterms, boost: float = 1.0) -> np.ndarray:
         """Dense float32 score per doc for `or` over qterms (duplicates count twice);

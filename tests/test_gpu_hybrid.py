@@ -417,3 +417,36 @@ def test_multi_field_many_tiles_matches_oracle():
             np.testing.assert_allclose(scores[b], ws, rtol=2e-6, atol=0)
         r1, s1 = e.search_hybrid(Q[3:4], [qterms[3]], 0.0, 2.0, k, qweights=[qweights[3]], qflags=[qflags[3]])
         assert r1[0].tolist() == rows[3].tolist() and s1[0].tolist() == scores[3].tolist()
+
+
+def test_hybrid_degenerate_queries():
+    """Queries with no known term, no text at all, more hits requested than documents match, and a batch that mixes
+    them; a filter that passes nothing."""
+    idx, X, Q, _ = _text_case(n_docs=3000, vocab=500, dim=256, nq=6)
+    k = 10
+    knn_rows, _, knn_scores = knn.knn_exact(X, Q, k)
+    rare = int(np.argmin(np.where(idx.df > 0, idx.df, 1 << 30)))           # a term very few documents carry
+    qterms = [[idx.vocab + 3, -1], [], [rare], [rare, rare], [0, 1, 2], [rare, idx.vocab + 9]]
+    with _engine(dim=256) as e:
+        e.append(X)
+        e.bm25_build(idx.indptr, idx.doc, idx.tf, idx.doclen)
+        rows, scores = e.search_hybrid(Q, qterms, 4.5, 2.0, k)
+        rows_t, scores_t = e.search_hybrid(None, qterms, 4.5, 0.0, k)
+        for b in range(6):
+            wr, ws = fusion.hybrid(idx, qterms[b], knn_rows[b], knn_scores[b], 4.5, 2.0, k)
+            assert rows[b, :len(wr)].tolist() == wr.tolist() and (rows[b, len(wr):] == -1).all(), b
+            np.testing.assert_allclose(scores[b, :len(wr)], ws, rtol=2e-6, atol=0)
+            tr, ts = bm25.topk(idx.score(qterms[b], boost=4.5), k)
+            assert rows_t[b, :len(tr)].tolist() == tr.tolist() and (rows_t[b, len(tr):] == -1).all(), b
+            assert scores_t[b, :len(tr)].tolist() == ts.tolist()
+        assert (rows_t[0] == -1).all() and (rows_t[1] == -1).all()         # nothing matches -> no hits, not an error
+        df_rare = int(idx.df[rare])
+        rows_big, _ = e.search_hybrid(None, [[rare]], 4.5, 0.0, 128)       # more hits requested than documents match
+        assert df_rare < 128 and (rows_big[0] >= 0).sum() == df_rare and (rows_big[0, df_rare:] == -1).all()
+        e.set_row_filter(np.zeros(3000, dtype=np.uint8))
+        rows_f, _ = e.search_hybrid(Q, qterms, 4.5, 2.0, k)
+        assert (rows_f == -1).all()
+        e.set_row_filter(None)
+        rows_v, scores_v = e.search_hybrid(Q, None, 0.0, 2.0, k)           # vector-only bool.should
+        assert np.array_equal(rows_v, knn_rows)
+        np.testing.assert_allclose(scores_v, np.float32(2.0) * knn_scores, rtol=1e-6)
