@@ -66,7 +66,7 @@ enum {
 /* rass_search_* path selection (rass_set_option RASS_OPT_PATH) */
 enum {
   RASS_PATH_AUTO = 0,    /* B = 1: streaming GEMV+select; B <= 64: tcgen05 tiles, 64 queries per pass;
-                            larger: CTA-pair tcgen05 contraction, 256 queries per pass                */
+                            larger: CTA-pair tcgen05 contraction, 128 (B <= 128) or 256 queries per pass  */
   RASS_PATH_STREAM = 1,  /* force the CUDA-core streaming scan (passes of <= 2 queries)                */
   RASS_PATH_UMMA = 2,    /* force the TMA + tcgen05 scan (passes of <= 64 queries)                     */
   RASS_PATH_EXACT = 3,   /* force the fp64 full scan (the certificate-failure fallback), for tests     */
