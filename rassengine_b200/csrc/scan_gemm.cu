@@ -185,7 +185,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
         // the pivots other CTAs have published for this lane's two queries (used after the tile, latency hidden)
         const uint32_t g0 = __ldcg(gthr + slot0 + 4 * lane + ew);
         const uint32_t g1 = NQ > 128 ? __ldcg(gthr + slot0 + 128 + 4 * lane + ew) : 0u;
-        mbar_wait(&ss->acc_full[acc], acc_phase);
+        // one lane polls (sleeping between polls: the epilogue is normally far ahead of the tensor pipe), the warp
+        // follows through the warp barrier; 127 spinning threads next to the MMAs only cost power
+        if (lane == 0) mbar_wait_relaxed(&ss->acc_full[acc], acc_phase);
+        __syncwarp();
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * NQ;
 #pragma unroll 1

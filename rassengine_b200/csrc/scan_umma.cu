@@ -144,7 +144,10 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
       if (row < n_rows) { a = __ldg(sa + row); b = __ldg(sb + row); }
       // the largest pivot any CTA has published for the query this lane looks after (used after the tile)
       const uint32_t g = lane < UMMA_NQ / 4 ? __ldcg(gthr + 4 * lane + ew) : 0u;
-      mbar_wait(&ss->acc_full[acc], acc_phase);
+      // one lane polls (sleeping between polls: the epilogue is normally far ahead of the tensor pipe), the warp
+      // follows through the warp barrier; 127 spinning threads next to the MMAs only cost power
+      if (lane == 0) mbar_wait_relaxed(&ss->acc_full[acc], acc_phase);
+      __syncwarp();
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * UMMA_NQ;
 #pragma unroll
