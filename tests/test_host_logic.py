@@ -248,3 +248,68 @@ def test_hostquery_building_blocks_agree_with_the_oracle():
     assert hq._parse_date("2024-02-29", now) == dt.datetime(2024, 2, 29, tzinfo=dt.timezone.utc)
     assert hq._parse_date("2024-02-29T10:00:00Z", now).hour == 10
     assert hq._parse_date("not a date", now) is None
+
+
+def test_text_index_multi_field_postings_equal_oracle_fields():
+    """TextIndex (host side of rass_bm25_build_fields): one CSR over all analysed / keyword fields whose per-field slices
+    carry the same postings, lengths and statistics as the oracle's per-field indices; fuzzy term lists agree too."""
+    from oracle import fuzzy, multifield
+    from rassengine_b200.text import TextIndex
+    docs = [{"unstructuredText": "chest pain today chest"}, {"patientName": "John Smith", "patientGender": "male"},
+            {"unstructuredText": "pain in the chest wall", "patientGender": "female"}, {},
+            {"patientName": ["Jon", "Smyth Smith"], "conditionNote": "pain"}]
+    types = {"unstructuredText": "text", "patientName": "text", "patientGender": "keyword", "conditionNote": "text",
+             "neverUsed": "text"}
+    ti = TextIndex(types)
+    for r, d in enumerate(docs):
+        ti.set_doc(r, d, fresh=True)
+    indptr, doc, tf, term_field, doclen = ti.postings(len(docs))
+    fields = multifield.build(docs, types)
+    assert set(ti.order) == set(fields) and "neverUsed" not in ti.fields
+    terms = ti.terms_in_id_order()
+    for fid, name in enumerate(ti.order):
+        f = fields[name]
+        base, n = ti.base[name], len(ti.fields[name].vocab)
+        assert (term_field[base:base + n] == fid).all()
+        assert np.array_equal(doclen[fid], f.index.doclen)
+        for t in range(n):
+            ot = f.terms.index(terms[base + t])
+            lo, hi = indptr[base + t], indptr[base + t + 1]
+            olo, ohi = f.index.indptr[ot], f.index.indptr[ot + 1]
+            assert np.array_equal(doc[lo:hi], f.index.doc[olo:ohi]) and np.array_equal(tf[lo:hi], f.index.tf[olo:ohi])
+        assert ti.fields[name].doc_count == f.index.doc_count
+    # overwrite: a field the document no longer carries is cleared
+    ti.set_doc(1, {"patientGender": "other"})
+    indptr2, doc2, *_ = ti.postings(len(docs))
+    assert 1 not in doc2[indptr2[ti.base["patientName"]]:indptr2[ti.base["patientName"] + len(ti.fields["patientName"].vocab)]]
+    # fuzzy rewrite on the host side (dictionary scan replaced by the oracle's distance) equals the oracle's term list
+    name_f = ti.fields["unstructuredText"]
+    ti.postings(len(docs))
+    f = multifield.build(docs[:1] + [{}] + docs[2:], types)["unstructuredText"]        # document 1 lost nothing here
+
+    def expand(tok, me):
+        ids = [(i, fuzzy.osa_distance(tok, t)) for i, t in enumerate(name_f.terms_in_id_order())
+               if abs(len(t) - len(tok)) <= me]
+        ids = [(i, d) for i, d in ids if d <= me]
+        return np.array([i for i, _ in ids], dtype=np.int64), np.array([d for _, d in ids], dtype=np.int64)
+
+    ids, ws = name_f.fuzzy_weighted_terms("chets pian wall", 4.5, expand)
+    oids, ows = fuzzy.weighted_terms(f.index, f.terms, ["chets", "pian", "wall"], 4.5)
+    assert [name_f.terms_in_id_order()[i] for i in ids] == [f.terms[i] for i in oids]
+    np.testing.assert_array_equal(np.asarray(ws, dtype=np.float32), ows)
+
+
+def test_dsl_text_only_and_fuzziness_shapes():
+    must = {"size": 3, "query": {"bool": {"must": [{"multi_match": {"query": "x y", "fields": ["conditionNote^3", "unstructuredText^2"],
+                                                                 "type": "best_fields", "operator": "or", "fuzziness": "AUTO"}}],
+                                          "filter": [{"term": {"patientId": "p1"}}]}}, "terminate_after": 3}
+    p = dsl.parse_search_body(must)
+    assert p.kind == "hybrid" and p.vector is None and p.text[0].fuzziness == "AUTO" and p.filters == [("patientId", "p1")]
+    assert dict(p.text[0].fields) == {"conditionNote": 3.0, "unstructuredText": 2.0}
+    p = dsl.parse_search_body({"query": {"bool": {"should": [{"multi_match": {"query": "x", "fields": ["a"]}}]}}})
+    assert p.kind == "hybrid" and p.text[0].fuzziness is None and p.size == 10
+    for bad in ({"query": {"bool": {"should": [{"multi_match": {"query": "x", "fields": ["a"], "fuzziness": 2}}]}}},
+                {"query": {"bool": {"must": [{"multi_match": {"query": "x", "fields": ["a"]}}, {"range": {"d": {"gte": 1}}}]}}},
+                {"_source": ["patientId"], "query": {"match_all": {}}}):
+        with pytest.raises(NotImplementedError):
+            dsl.parse_search_body(bad)
