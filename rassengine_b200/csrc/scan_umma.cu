@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
                      const float* __restrict__ sa, const float* __restrict__ sb, int64_t n_rows, int n_tiles,
                      int k_blocks, int q_row0, float* __restrict__ pool_key, uint32_t* __restrict__ pool_row,
                      float* __restrict__ pool_thr, int* __restrict__ pool_cnt, size_t pool_entries, int n_segs,
-                     uint32_t* __restrict__ gthr, float* __restrict__ dbg_out) {
+                     uint32_t* __restrict__ gthr, float* __restrict__ dbg_out, int relaxed_wait) {
   extern __shared__ unsigned char smem_dyn[];
   // 128B-swizzled tiles need 1024-byte alignment: [ Q: k_blocks * 8 KB ][ stages: UMMA_STAGES * 16 KB ][ UmmaSmem ]
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -146,7 +146,10 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
       const uint32_t g = lane < UMMA_NQ / 4 ? __ldcg(gthr + 4 * lane + ew) : 0u;
       // one lane polls (sleeping between polls: the epilogue is normally far ahead of the tensor pipe), the warp
       // follows through the warp barrier; 127 spinning threads next to the MMAs only cost power
-      if (lane == 0) mbar_wait_relaxed(&ss->acc_full[acc], acc_phase);
+      // every thread polls: measured ~1 % faster here than one sleeping lane per warp (A/B on the same box, cfg2),
+      // unlike in the tensor-bound pair kernel; RASS_DEBUG_RELAXED_WAIT switches for the comparison
+      if (!relaxed_wait) mbar_wait(&ss->acc_full[acc], acc_phase);
+      else if (lane == 0) mbar_wait_relaxed(&ss->acc_full[acc], acc_phase);
       __syncwarp();
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * UMMA_NQ;
@@ -320,6 +323,7 @@ static int umma_launch(rass_engine* h, int q0, int64_t n_rows, int seg, float* d
   const int grid = n_tiles < h->num_sms ? n_tiles : h->num_sms;
   // timing experiment only: keeping the previous search's pivots shows what a perfect threshold seed would save
   static const bool keep_gthr = getenv("RASS_DEBUG_KEEP_GTHR") != nullptr;
+  static const int relaxed_wait = getenv("RASS_DEBUG_RELAXED_WAIT") != nullptr;
   if (!keep_gthr)
     CUDA_TRY(h, cudaMemsetAsync(h->q_gthr + q0, 0, UMMA_NQ * sizeof(uint32_t), st));   // nothing published yet
   const size_t smem = umma_smem_bytes(h);
@@ -329,7 +333,7 @@ static int umma_launch(rass_engine* h, int q0, int64_t n_rows, int seg, float* d
     scan_umma_kernel<S><<<grid, UMMA_THREADS, smem, st>>>(                                                           \
         *(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q, h->sa, h->sb_scan, n_rows, n_tiles, h->dim_pad / UMMA_KBLK, \
         q0, h->pool_key, h->pool_row, h->pool_thr, h->pool_cnt, h->pool_entries, scan_umma_segs(h), h->q_gthr + q0,  \
-        dbg_out);                                                                                                    \
+        dbg_out, relaxed_wait);                                                                                        \
   } while (0)
   if (seg == 512) RASS_UMMA_LAUNCH(512); else RASS_UMMA_LAUNCH(256);
 #undef RASS_UMMA_LAUNCH
