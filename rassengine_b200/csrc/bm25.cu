@@ -1,11 +1,15 @@
 // BM25 term scoring over CSR postings and the bool.should boosted-sum fusion with the kNN clause.
 //
-// Replaces the Lucene side of OpenSearchIndexer.hybrid_search (reference app/main.py:1574-1598):
-//   multi_match(best_fields, operator or) over `unstructuredText`  -> BM25Similarity postings walk
-//   knn clause                                                       -> only the k nearest docs score
-//   bool.should                                                      -> sum of the matching clauses
-// Arithmetic follows oracle/bm25.py and oracle/fusion.py operation for operation (float ops rounded
-// individually, clause sums in double, final cast to float) so ranked ids and scores are identical.
+// Replaces the Lucene side of OpenSearchIndexer.hybrid_search / multi_intent_search (reference app/main.py:1574-1598,
+// 1982-2010):
+//   multi_match(best_fields, operator or, fuzziness AUTO) over the 26 text fields   -> per-field BM25Similarity postings
+//   multi_match(best_fields) over the 24 keyword fields                                walk, max over a clause's fields
+//   knn clause                                                                      -> only the k nearest docs score
+//   bool.should (+ bool.filter)                                                     -> sum of the matching clauses
+// Arithmetic follows oracle/bm25.py, oracle/fuzzy.py, oracle/multifield.py and oracle/fusion.py operation for operation
+// (float ops rounded individually, field sums in double cast to float, clause sums in double, final cast to float) so
+// ranked ids and scores are identical.  One fused kernel per batch (hybrid_tile_kernel) + one select; the term
+// dictionary scan of fuzziness AUTO (fuzzy_scan_kernel) lives here too.
 #include <math.h>
 #include <string.h>
 
