@@ -186,3 +186,44 @@ def test_fuzzy_auto_restatement_known_answers():
                                                dtype=np.float32))
     dense = fuzzy.score(idx, ids, ws)
     assert dense.shape == (5,) and dense[4] == 0 and (dense[:4] > 0).all()
+
+
+def test_multifield_and_phrase_restatement_known_answers():
+    """oracle/multifield.py on a corpus small enough to check by hand: per-field statistics, max over fields, sum over
+    clauses, keyword fields as whole-value terms of length 1, phrase frequency and prefix expansion."""
+    from oracle import bm25, multifield
+    docs = [{"a": "red apple pie", "b": "apple"},            # 0
+            {"a": "apple pie apple pie", "g": "red"},        # 1
+            {"a": "pie of apple", "b": "green apple tree"},  # 2
+            {"g": "apple pie"}]                              # 3: keyword value with a space
+    types = {"a": "text", "b": "text", "g": "keyword"}
+    F = multifield.build(docs, types)
+    assert F["a"].index.doc_count == 3 and F["b"].index.doc_count == 2 and F["g"].index.doc_count == 2
+    assert F["g"].terms == ["apple pie", "red"] and F["g"].index.doclen.tolist() == [0, 1, 0, 1]
+    n = len(docs)
+    # best_fields: per document the better of the two fields (scores are per-field BM25 with per-field idf)
+    sa = multifield.clause_score(F, "apple", [("a", 1.0)], 1.0, False, n)
+    sb = multifield.clause_score(F, "apple", [("b", 2.0)], 1.0, False, n)
+    both = multifield.clause_score(F, "apple", [("a", 1.0), ("b", 2.0)], 1.0, False, n)
+    np.testing.assert_array_equal(both, np.maximum(sa, sb))
+    assert sa[3] == 0 and sb[1] == 0 and (sa[:3] > 0).all() and sb[0] > sb[2] > 0        # shorter field scores higher
+    # a keyword field matches the whole, unanalysed query string only
+    kw = multifield.clause_score(F, "apple pie", [("g", 3.0)], 1.0, False, n)
+    assert kw.nonzero()[0].tolist() == [3]
+    assert multifield.clause_score(F, "apple", [("g", 3.0)], 1.0, False, n).sum() == 0
+    # bool.should: double sum of the float clause scores
+    total = multifield.text_total(F, [("apple", [("a", 1.0), ("b", 2.0)], 1.5, False), ("apple pie", [("g", 3.0)], 1.0, False)], n)
+    want = multifield.clause_score(F, "apple", [("a", 1.0), ("b", 2.0)], 1.5, False, n).astype(np.float64) + kw.astype(np.float64)
+    np.testing.assert_array_equal(total, want)
+    # phrase: "apple pie" occurs once in doc 0, twice in doc 1, not in doc 2 ("pie of apple")
+    toks = multifield.field_tokens(docs, "a", "text")
+    ph = multifield.phrase_score(F["a"], toks, "apple pie", 2.0)
+    assert ph[2] == 0 and ph[3] == 0 and ph[0] > 0 and ph[1] > 0
+    idx = F["a"].index
+    w = np.float32(np.float32(2.0) * np.float32(float(idx.idf(F["a"].terms.index("apple"))) + float(idx.idf(F["a"].terms.index("pie")))))
+    for d, freq in ((0, 1), (1, 2)):
+        assert ph[d] == w - w / (np.float32(1.0) + np.float32(freq) * idx.inv[idx.norm[d]])
+    # phrase_prefix: "apple p" -> apple followed by any term starting with p
+    pp = multifield.phrase_score(F["a"], toks, "apple p", 1.0, prefix=True)
+    assert (pp > 0).tolist() == [True, True, False, False]
+    assert multifield.phrase_score(F["a"], toks, "pie apple", 1.0)[1] > 0 and multifield.phrase_score(F["a"], toks, "pie apple", 1.0)[0] == 0
