@@ -7,8 +7,10 @@
 // Work split: warp w of W owns row groups g = w, w + W, ... (a group = R consecutive rows, R * NQ = 4), which
 // interleaves neighbouring rows over the lists.  Each lane holds its 8-element slices of the query in
 // registers, issues all R * VEC 16-byte loads of a group before using them, and the 4 partial dot products
-// of a group are reduced with one transposing butterfly (6 shuffles).  Every row a warp drops has a score
-// <= the final threshold of that warp's list, which is what the certificate in finish.cu relies on.
+// of a group are reduced with one transposing butterfly (6 shuffles).  At the end of the pass the 8 warp lists of
+// a CTA are merged to one segment of 32..64 entries per query (296 segments instead of 2368 for finish.cu to
+// read).  Every row a warp dropped has a score <= the final threshold of that warp's list and every entry the
+// merge dropped is <= its pivot; the maximum of the two is the bound the certificate in finish.cu relies on.
 #include "common.cuh"
 
 template <int NQ, int VEC>
