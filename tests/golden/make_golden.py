@@ -23,7 +23,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-from oracle import bm25, fusion, knn, smallfloat, synth  # noqa: E402
+from oracle import bm25, fusion, knn, multifield, smallfloat, synth  # noqa: E402
 
 
 def f32(x: float) -> float:
@@ -109,6 +109,116 @@ def make_fusion_micro(bm):
     return {"cases": cases}
 
 
+# ----------------------------------------------------------------------------------
+# independent scalar multi-field scorer: per-field statistics, fuzziness AUTO, dis-max over fields, sum over clauses
+# ----------------------------------------------------------------------------------
+def scalar_osa(a: str, b: str) -> int:
+    """Optimal string alignment distance by memoised recursion (oracle/fuzzy.py uses the row DP)."""
+    memo = {}
+
+    def go(i, j):
+        if i == 0 or j == 0:
+            return i + j
+        if (i, j) not in memo:
+            v = min(go(i - 1, j) + 1, go(i, j - 1) + 1, go(i - 1, j - 1) + (a[i - 1] != b[j - 1]))
+            if i > 1 and j > 1 and a[i - 1] == b[j - 2] and a[i - 2] == b[j - 1]:
+                v = min(v, go(i - 2, j - 2) + 1)
+            memo[(i, j)] = v
+        return memo[(i, j)]
+    return go(len(a), len(b))
+
+
+def scalar_field_score(docs_tokens: list[list[str]], keyword: bool, tokens: list[str], boost: float, fuzzy_auto: bool):
+    """float score per document of one field of one clause; docs_tokens[d] = the field's tokens ([] = field absent)."""
+    n_with = sum(1 for t in docs_tokens if t)
+    lens = [min(len(t), 1) if keyword else len(t) for t in docs_tokens]
+    avgdl = f32(sum(lens) / float(n_with))
+    k1, b = f32(1.2), f32(0.75)
+    df = {}
+    for toks in docs_tokens:
+        for t in set(toks):
+            df[t] = df.get(t, 0) + 1
+    idf_of = lambda d_f: f32(math.log(1.0 + (n_with - d_f + 0.5) / (d_f + 0.5)))
+    weighted = []                                     # (term, float weight), one entry per term query
+    for tok in tokens:
+        edits = 0 if (not fuzzy_auto or len(tok) <= 2) else (1 if len(tok) <= 5 else 2)
+        cands = []
+        for term in df:
+            if term == tok:
+                cands.append((1.0, term))
+            elif edits and abs(len(term) - len(tok)) <= edits:
+                ed = scalar_osa(tok, term)
+                if ed <= edits:
+                    cands.append((f32(1.0 - f32(f32(ed) / f32(min(len(term), len(tok))))), term))
+        if not cands:
+            continue
+        cands.sort(key=lambda c: (-c[0], c[1]))
+        cands = cands[:50]
+        idf = idf_of(max(df[t] for _, t in cands))    # blended: the largest df among the survivors
+        for tb, term in cands:
+            weighted.append((term, f32(f32(f32(boost) * tb) * idf) if fuzzy_auto else f32(f32(boost) * idf)))
+    out = []
+    for toks, ln in zip(docs_tokens, lens):
+        L = float(smallfloat.byte4_to_int(smallfloat.int_to_byte4(ln)))
+        inv = f32(1.0 / f32(k1 * f32(f32(1.0 - b) + f32(f32(b * L) / avgdl))))
+        tot = 0.0
+        for term, w in weighted:
+            tf = float(toks.count(term))
+            if tf:
+                tot += f32(w - f32(w / f32(1.0 + f32(tf * inv))))
+        out.append(f32(tot))
+    return out
+
+
+def make_multifield_micro():
+    long_body = " ".join(["patient", "reports"] * 22 + ["severe", "chronic", "pian"])  # 47 tokens -> quantised to 46
+    docs = [
+        {"title": "type two diabetes", "body": "patient with diabetes mellitus on metformin", "tag": "active"},
+        {"title": "diabetis follow up", "body": "diabetse controlled of late", "tag": "resolved"},
+        {"title": "chest pain", "body": "chronic chest pain radiating to the arm", "tag": "active"},
+        {"body": long_body, "tag": "type two"},
+        {"title": "pain clinic", "tag": "chest pain"},
+        {"title": "of", "body": "of on to"},
+        {"body": "no complaints today"},
+        {"title": "diabetes diabetes diabetes", "body": "pain", "tag": "inactive"},
+        {"tag": "active"},
+        {"title": "chronic chest pian", "body": "diabetic neuropathy with pain"},
+    ]
+    types = {"title": "text", "body": "text", "tag": "keyword"}
+    text_specs, kw_specs = [["title", 3.0], ["body", 1.0]], [["tag", 2.0]]
+    fields = multifield.build(docs, types)
+    n = len(docs)
+    toks = {f: [(([d[f]] if f in d else []) if k == "keyword" else d.get(f, "").split()) for d in docs]
+            for f, k in types.items()}
+    cases = []
+    for query in ("diabetes pain", "active", "chronic chest pian", "type two", "of", "zzzz", "diabetes diabetes"):
+        for w_text, w_kw in ((1.5, 1.0), (1.0, 0.5)):
+            want = [0.0] * n
+            for specs, cb, fz in ((text_specs, w_text, True), (kw_specs, w_kw, False)):
+                best = [0.0] * n
+                for fname, fb in specs:
+                    kw = types[fname] == "keyword"
+                    sc = scalar_field_score(toks[fname], kw, [query] if kw else query.split(),
+                                            f32(f32(cb) * f32(fb)), fz and not kw)
+                    best = [max(x, y) for x, y in zip(best, sc)]
+                want = [x + y for x, y in zip(want, best)]
+            got = multifield.text_total(fields, [(query, [tuple(x) for x in text_specs], w_text, True),
+                                                 (query, [tuple(x) for x in kw_specs], w_kw, False)], n)
+            assert got.tolist() == want, (query, got.tolist(), want)
+            cases.append({"query": query, "w_text": w_text, "w_keyword": w_kw, "totals": want})
+    # the cases exercise what they are meant to: a transposition counts as one edit, 2-character tokens do not expand,
+    # a keyword value only matches as a whole string, the 47-token body is quantised
+    by = {(c["query"], c["w_text"]): c["totals"] for c in cases}
+    assert by[("chronic chest pian", 1.5)][2] > 0 and by[("chronic chest pian", 1.5)][9] > by[("chronic chest pian", 1.5)][2]
+    assert [i for i, v in enumerate(by[("of", 1.5)]) if v > 0] == [1, 5]
+    assert by[("type two", 1.5)][3] > 0 and by[("type two", 1.5)][0] > 0          # keyword value / analysed title
+    act = by[("active", 1.5)]                                                      # "inactive" is 2 edits away but the
+    assert act[7] == 0 and act[0] == act[2] == act[8] > 0                          # keyword clause is not fuzzy
+    assert all(v == 0 for v in by[("zzzz", 1.5)])
+    assert len(long_body.split()) == 47 and smallfloat.byte4_to_int(smallfloat.int_to_byte4(47)) == 46
+    return {"docs": docs, "types": types, "text_fields": text_specs, "keyword_fields": kw_specs, "cases": cases}
+
+
 def data_digest(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -139,6 +249,8 @@ def main():
         json.dump(bm, f, indent=1)
     with open(os.path.join(HERE, "fusion_micro.json"), "w") as f:
         json.dump(fu, f, indent=1)
+    with open(os.path.join(HERE, "multifield_micro.json"), "w") as f:
+        json.dump(make_multifield_micro(), f, indent=1)
     # seeded kNN cases: small + cfg-1, plus a clustered/duplicate stress case
     make_knn_seeded("knn_small", n=20000, nq=64, k=10)
     make_knn_seeded("knn_clustered_dups", n=20000, nq=64, k=10, clustered=True, dup_pairs=16)

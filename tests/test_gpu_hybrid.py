@@ -346,6 +346,34 @@ def test_mixed_index_multi_field_dismax_matches_oracle():
     client.close()
 
 
+def test_multifield_micro_golden_through_the_client(golden_dir):
+    """tests/golden/multifield_micro.json (hand-sized corpus: per-field statistics, a transposition typo, a 2-character
+    token, keyword values with a space, a 47-token field quantised to 46) through the OpenSearch-shaped client:
+    ranked ids equal the golden totals' order (score desc, row asc), scores their float32 image."""
+    from rassengine_b200.client import B200Client
+    g = json.load(open(os.path.join(golden_dir, "multifield_micro.json")))
+    props = {f: {"type": t} for f, t in g["types"].items()}
+    props["embedding"] = {"type": "knn_vector", "dimension": 8, "method": {"space_type": "cosinesimil"}}
+    client = B200Client()
+    client.indices.create(index="micro", body={"mappings": {"properties": props}})
+    ok, errs = client.bulk_actions([{"_op_type": "index", "_index": "micro", "_id": f"d{i}", "_source": d}
+                                    for i, d in enumerate(g["docs"])])
+    assert (ok, errs) == (len(g["docs"]), [])
+    spec = lambda lst: [f"{f}^{b:g}" for f, b in lst]
+    for c in g["cases"]:
+        body = {"size": len(g["docs"]), "query": {"bool": {"should": [
+            {"multi_match": {"query": c["query"], "fields": spec(g["text_fields"]), "type": "best_fields",
+                             "operator": "or", "fuzziness": "AUTO", "boost": c["w_text"]}},
+            {"multi_match": {"query": c["query"], "fields": spec(g["keyword_fields"]), "type": "best_fields",
+                             "operator": "or", "boost": c["w_keyword"]}}], "minimum_should_match": 1}}}
+        hits = client.search(index="micro", body=body)["hits"]["hits"]
+        tot32 = np.asarray(c["totals"], dtype=np.float64).astype(np.float32)
+        want = sorted((i for i in range(len(tot32)) if c["totals"][i] > 0), key=lambda i: (-float(tot32[i]), i))
+        assert [h["_id"] for h in hits] == [f"d{i}" for i in want], c["query"]
+        assert [np.float32(h["_score"]) for h in hits] == [tot32[i] for i in want], c["query"]
+    client.close()
+
+
 def test_hybrid_many_tiles_batched_matches_oracle():
     """74 tiles of 4096 docs and a batched launch: tiles prune each other through the per-query bound, the frequent
     terms go through the per-tile posting offsets; ids identical, fused float32 scores bit-identical."""

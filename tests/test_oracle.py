@@ -227,3 +227,16 @@ def test_multifield_and_phrase_restatement_known_answers():
     pp = multifield.phrase_score(F["a"], toks, "apple p", 1.0, prefix=True)
     assert (pp > 0).tolist() == [True, True, False, False]
     assert multifield.phrase_score(F["a"], toks, "pie apple", 1.0)[1] > 0 and multifield.phrase_score(F["a"], toks, "pie apple", 1.0)[0] == 0
+
+
+def test_multifield_micro_golden(golden_dir):
+    """oracle/multifield.py + oracle/fuzzy.py against tests/golden/multifield_micro.json, whose totals come from the
+    independent scalar scorer in tests/golden/make_golden.py (struct-rounded float32 maths, recursive edit distance)."""
+    from oracle import multifield
+    g = json.load(open(os.path.join(golden_dir, "multifield_micro.json")))
+    fields = multifield.build(g["docs"], g["types"])
+    n = len(g["docs"])
+    for c in g["cases"]:
+        got = multifield.text_total(fields, [(c["query"], [tuple(x) for x in g["text_fields"]], c["w_text"], True),
+                                             (c["query"], [tuple(x) for x in g["keyword_fields"]], c["w_keyword"], False)], n)
+        assert got.tolist() == c["totals"], c["query"]
