@@ -18,6 +18,8 @@
 // pool entries per (CTA, query) segment of the tcgen05 scans: 256 (a compaction keeps 32..64) for k <= 32,
 // 512 (keeps 128..256) for larger k
 static inline int rass_tc_seg(int k) { return k > 32 ? 512 : 256; }
+// entries a compaction of such a segment keeps at least (at most twice as many)
+__host__ __device__ constexpr int rass_tc_keep(int seg) { return seg == 512 ? 128 : seg / 8; }
 #define RASS_EXACT_NQ 4        // queries per pass of the fp64 scan
 #define RASS_FINISH_THREADS 1024
 
@@ -88,7 +90,7 @@ struct rass_engine {
   __nv_bfloat16* q16 = nullptr;     // [q_cap rounded to 64, dim_pad]
   double* q_norm = nullptr;         // [q_cap]
   float* q_rho = nullptr;           // [q_cap] ||q_hat - bf16(q_hat)|| / ||q_hat||
-  uint32_t* q_gthr = nullptr;       // [q_cap] scan_gemm: largest pivot any CTA has published for the query
+  uint32_t* q_gthr = nullptr;       // [q_cap] tcgen05 scans: threshold seed, then the largest pivot any CTA published
   // candidate pool of one query group (RASS_GROUP_Q queries)
   size_t pool_entries = 0;          // per query: stride of the running search
   size_t pool_alloc_entries = 0;    // allocated, in entries
@@ -396,6 +398,7 @@ __device__ __forceinline__ float score_from_key(double key, int metric) {
 int launch_store_convert(rass_engine* h, const float* src_dev, int64_t src_stride, int64_t first_row, int64_t n,
                          cudaStream_t st);
 int launch_query_prep(rass_engine* h, const float* q_dev, int B, cudaStream_t st);
+int launch_seed_thresholds(rass_engine* h, int B, int seg, cudaStream_t st);
 // streaming scan of queries [q0, q0+nq) (nq = 1 or 2); their pool slots are q - g0
 int launch_scan_stream(rass_engine* h, int q0, int nq, int g0, cudaStream_t st);
 int scan_stream_segs(const rass_engine* h);

@@ -653,12 +653,13 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
     const int n_segs = scan_gemm_segs(h, B);
     const int seg = robust ? rass_tc_seg(k) : 256;
     if ((rc = ensure_pool(h, (size_t)n_segs * seg, (size_t)n_segs, (size_t)B))) return rc;
+    if ((rc = launch_seed_thresholds(h, B, seg, st))) return rc;
     CUDA_TRY(h, cudaEventRecord(get_event(h, ev_base + n_ev++), st));
     if ((rc = launch_scan_gemm(h, B, seg, st))) return rc;
     CUDA_TRY(h, cudaEventRecord(get_event(h, ev_base + n_ev++), st));
     if ((rc = launch_finish(h, 0, B, k, n_segs, seg, true, true, out_rows, out_scores, out_keys, st)))
       return rc;
-    s.launches += 3;
+    s.launches += 4;
     s.passes = (B + 255) / 256;
     s.bytes_streamed = (int64_t)s.passes * h->n_rows * h->dim_pad * 2;
   } else {
@@ -666,6 +667,10 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
     const int n_segs = umma ? scan_umma_segs(h) : scan_stream_segs(h);
     const int seg = umma ? (robust ? rass_tc_seg(k) : 256) : RASS_STREAM_SEG;
     if ((rc = ensure_pool(h, (size_t)n_segs * seg, (size_t)n_segs))) return rc;
+    if (umma) {
+      if ((rc = launch_seed_thresholds(h, B, seg, st))) return rc;
+      s.launches += 1;
+    }
     for (int g0 = 0; g0 < B; g0 += RASS_GROUP_Q) {
       const int ng = std::min(RASS_GROUP_Q, B - g0);
       CUDA_TRY(h, cudaEventRecord(get_event(h, ev_base + n_ev++), st));

@@ -273,7 +273,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
             __syncwarp();
             uint32_t pivot;
             const int kept =
-                warp_compact<SEG / 32>(ok, rw, (SEG / 8), pool_key + base, pool_row + base, pivot);
+                warp_compact<SEG / 32>(ok, rw, rass_tc_keep(SEG), pool_key + base, pool_row + base, pivot);
             __syncwarp();
             // everything dropped here, and every row rejected from now on, has key <= pivot
             if (lane == 0) {
@@ -362,8 +362,9 @@ static int gemm_launch(rass_engine* h, int B, int seg, float* dbg_out, cudaStrea
   const size_t n = (size_t)n_segs * B;
   clear_gemm_segs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pool_thr, h->pool_cnt, n);
   CUDA_TRY(h, cudaGetLastError());
-  // per-query bound shared between the CTAs (ordered-integer image of a float; 0 = nothing published yet)
-  CUDA_TRY(h, cudaMemsetAsync(h->q_gthr, 0, (size_t)h->q_cap * sizeof(uint32_t), st));
+  // per-query bound shared between the CTAs (ordered-integer image of a float; 0 = nothing published yet): seeded by
+  // launch_seed_thresholds before a search; the self-test has no seed
+  if (dbg_out) CUDA_TRY(h, cudaMemsetAsync(h->q_gthr, 0, (size_t)h->q_cap * sizeof(uint32_t), st));
   const int grid = 2 * (plan.n_items < n_pairs ? plan.n_items : n_pairs);
   // timing experiments only (results are wrong): 1 = epilogue reads one column block, 2 = epilogue drops every hit
   static const int dbg_mode = getenv("RASS_GEMM_DEBUG_MODE") ? atoi(getenv("RASS_GEMM_DEBUG_MODE")) : 0;

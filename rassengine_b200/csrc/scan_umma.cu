@@ -44,16 +44,17 @@ struct UmmaSmem {
 
 }  // namespace
 
-// SEG = pool entries per (CTA, query) segment: a compaction keeps SEG/8 .. SEG/4 entries once SEG/2 is passed.
-// 256 (keep >= 32) serves k <= 32; 512 (keep >= 128) keeps at least k entries above every pivot for k <= 128, so
-// a cluster of near neighbours inside one segment cannot push the bound past the k-th best.
+// SEG = pool entries per (CTA, query) segment: once SEG/2 is passed a compaction keeps rass_tc_keep(SEG) .. twice
+// that many entries.  256 (keeps 32..64) serves k <= 32; 512 (keeps 128..256) keeps at least k entries above every
+// pivot for k <= 128, so a cluster of near neighbours inside one segment cannot push the bound past the k-th best.
 template <int SEG>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
     scan_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_q,
                      const float* __restrict__ sa, const float* __restrict__ sb, int64_t n_rows, int n_tiles,
                      int k_blocks, int q_row0, float* __restrict__ pool_key, uint32_t* __restrict__ pool_row,
                      float* __restrict__ pool_thr, int* __restrict__ pool_cnt, size_t pool_entries, int n_segs,
-                     uint32_t* __restrict__ gthr, float* __restrict__ dbg_out, int relaxed_wait) {
+                     uint32_t* __restrict__ gthr, float* __restrict__ dbg_out, int relaxed_wait,
+                     unsigned long long* __restrict__ dbg_t) {
   extern __shared__ unsigned char smem_dyn[];
   // 128B-swizzled tiles need 1024-byte alignment: [ Q: k_blocks * 8 KB ][ stages: UMMA_STAGES * 16 KB ][ UmmaSmem ]
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x;
+  if (dbg_t && threadIdx.x == 0) dbg_t[cta * 4 + 0] = globaltimer_ns();
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < UMMA_STAGES; ++i) { mbar_init(&ss->full[i], 1); mbar_init(&ss->empty[i], 1); }
@@ -72,7 +74,9 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (threadIdx.x < UMMA_NQ) {
-    ss->thr[threadIdx.x] = neg_inf<float>();
+    // the seed launch_seed_thresholds left for the query (0 = none): see store.cu
+    const uint32_t g = __ldcg(gthr + threadIdx.x);
+    ss->thr[threadIdx.x] = g > 0x007fffffu ? unord32(g) : neg_inf<float>();
     ss->cnt[threadIdx.x] = 0;
   }
   if (warp == 2) {
@@ -152,6 +156,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
       else if (lane == 0) mbar_wait_relaxed(&ss->acc_full[acc], acc_phase);
       __syncwarp();
       tc_fence_after();
+      if (dbg_t && et == 0 && tile == cta) dbg_t[cta * 4 + 1] = globaltimer_ns();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * UMMA_NQ;
 #pragma unroll
       for (int c = 0; c < UMMA_NQ; c += 16) {
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
         const size_t base = (size_t)q_cur * pool_entries + (size_t)cta * SEG;
         __syncwarp();
         uint32_t pivot;
-        const int kept = warp_compact<SEG / 32>(ok, rw, (SEG / 8), pool_key + base, pool_row + base, pivot);
+        const int kept = warp_compact<SEG / 32>(ok, rw, rass_tc_keep(SEG), pool_key + base, pool_row + base, pivot);
         __syncwarp();
         // everything dropped here, and every row rejected from now on, has key <= pivot
         if (lane == 0) {
@@ -246,7 +251,9 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
         q_cur = q_next;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (dbg_t && et == 0 && cta == 0 && tile / (int)gridDim.x < 64) dbg_t[1024 + tile / (int)gridDim.x] = globaltimer_ns();
     }
+    if (dbg_t && et == 0) dbg_t[cta * 4 + 2] = globaltimer_ns();
     // publish the segment sizes and bounds
     if (et < UMMA_NQ) {
       pool_cnt[(size_t)et * n_segs + cta] = min(ss->cnt[et], SEG);
@@ -256,6 +263,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
 
   tc_fence_before();
   __syncthreads();
+  if (dbg_t && threadIdx.x == 0) dbg_t[cta * 4 + 3] = globaltimer_ns();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)UMMA_TMEM_COLS)
                  : "memory");
@@ -305,6 +313,38 @@ static size_t umma_smem_bytes(const rass_engine* h) {
 
 int scan_umma_segs(const rass_engine* h) { return h->num_sms; }
 
+// RASS_DEBUG_TIMES: where a pass spends its fixed cost (start skew, first accumulator, spread of the CTAs' last tile)
+static void umma_report_times(rass_engine* h, unsigned long long* dbg_t, int grid, cudaStream_t st) {
+  static int n_reports = 0;
+  std::vector<unsigned long long> t(1024 + 64);
+  if (cudaStreamSynchronize(st) != cudaSuccess) return;
+  if (cudaMemcpy(t.data(), dbg_t, t.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  if (++n_reports > 400 || (n_reports % 20) != 0) return;
+  fprintf(stderr, "[umma times] CTA 0, epilogue done with tile i (us since start):");
+  for (int i = 0; i < 64 && i < (int)((h->n_rows + 127) / 128 + grid - 1) / grid; ++i)
+    fprintf(stderr, " %.1f", (double)(t[1024 + i] - t[0]) * 1e-3);
+  fprintf(stderr, "\n");
+  unsigned long long t0 = ~0ull, s_max = 0, e_min = ~0ull, e_max = 0, x_max = 0;
+  double first = 0, first_max = 0, e_mean = 0;
+  for (int c = 0; c < grid; ++c) {
+    t0 = std::min(t0, t[c * 4]);
+    s_max = std::max(s_max, t[c * 4]);
+  }
+  for (int c = 0; c < grid; ++c) {
+    const double f = (double)(t[c * 4 + 1] - t[c * 4]) * 1e-3;
+    first += f / grid;
+    first_max = std::max(first_max, f);
+    e_min = std::min(e_min, t[c * 4 + 2]);
+    e_max = std::max(e_max, t[c * 4 + 2]);
+    e_mean += (double)(t[c * 4 + 2] - t0) * 1e-3 / grid;
+    x_max = std::max(x_max, t[c * 4 + 3]);
+  }
+  fprintf(stderr, "[umma times] rows %lld grid %d: start skew %.1f us, first accumulator after %.1f us (max %.1f), "
+          "last tile done min %.1f mean %.1f max %.1f us, kernel end %.1f us\n", (long long)h->n_rows, grid,
+          (double)(s_max - t0) * 1e-3, first, first_max, (double)(e_min - t0) * 1e-3, e_mean, (double)(e_max - t0) * 1e-3,
+          (double)(x_max - t0) * 1e-3);
+}
+
 static int umma_launch(rass_engine* h, int q0, int64_t n_rows, int seg, float* dbg_out, cudaStream_t st) {
   int rc;
   if (!h->tmap_x) h->tmap_x = calloc(1, sizeof(CUtensorMap));
@@ -321,23 +361,25 @@ static int umma_launch(rass_engine* h, int q0, int64_t n_rows, int seg, float* d
   }
   const int n_tiles = (int)((n_rows + UMMA_ROWS - 1) / UMMA_ROWS);
   const int grid = n_tiles < h->num_sms ? n_tiles : h->num_sms;
-  // timing experiment only: keeping the previous search's pivots shows what a perfect threshold seed would save
-  static const bool keep_gthr = getenv("RASS_DEBUG_KEEP_GTHR") != nullptr;
+  // q_gthr[q0 .. q0 + 64) was initialised by launch_seed_thresholds (or cleared by the self-test)
   static const int relaxed_wait = getenv("RASS_DEBUG_RELAXED_WAIT") != nullptr;
-  if (!keep_gthr)
-    CUDA_TRY(h, cudaMemsetAsync(h->q_gthr + q0, 0, UMMA_NQ * sizeof(uint32_t), st));   // nothing published yet
   const size_t smem = umma_smem_bytes(h);
+  // timing experiment only (RASS_DEBUG_TIMES): per-CTA timestamps, printed after a blocking wait
+  static const bool want_times = getenv("RASS_DEBUG_TIMES") != nullptr;
+  static unsigned long long* dbg_t = nullptr;
+  if (want_times && !dbg_t) CUDA_TRY(h, cudaMalloc(&dbg_t, 4 * 1024 * sizeof(unsigned long long)));
 #define RASS_UMMA_LAUNCH(S)                                                                                          \
   do {                                                                                                               \
     CUDA_TRY(h, cudaFuncSetAttribute(scan_umma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
     scan_umma_kernel<S><<<grid, UMMA_THREADS, smem, st>>>(                                                           \
         *(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q, h->sa, h->sb_scan, n_rows, n_tiles, h->dim_pad / UMMA_KBLK, \
         q0, h->pool_key, h->pool_row, h->pool_thr, h->pool_cnt, h->pool_entries, scan_umma_segs(h), h->q_gthr + q0,  \
-        dbg_out, relaxed_wait);                                                                                        \
+        dbg_out, relaxed_wait, dbg_t);                                                                                 \
   } while (0)
   if (seg == 512) RASS_UMMA_LAUNCH(512); else RASS_UMMA_LAUNCH(256);
 #undef RASS_UMMA_LAUNCH
   CUDA_TRY(h, cudaGetLastError());
+  if (dbg_t) umma_report_times(h, dbg_t, grid, st);
   // segments of CTAs that did not launch (fewer tiles than SMs) were cleared by the caller and read as empty
   return RASS_OK;
 }
@@ -369,6 +411,7 @@ int umma_selftest(rass_engine* h, int n_rows_unused, float* out_host, cudaStream
   if (!rc) {
     const size_t ns = (size_t)scan_umma_segs(h) * RASS_GROUP_Q;
     clear_segs_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(h->pool_thr, h->pool_cnt, ns);
+    cudaMemsetAsync(h->q_gthr, 0, UMMA_NQ * sizeof(uint32_t), st);
     rc = umma_launch(h, 0, h->n_rows, 256, dbg, st);
   }
   if (!rc) {

@@ -4,6 +4,8 @@
 // (reference app/main.py:1256-1269): it lays one appended row down as the resident fp32 row, its bf16
 // shadow (the array the scan streams), its fp64-accumulated norm and the per-row scan scale/offset.
 // query_prep is the device half of the query normalisation at app/main.py:1536-1537.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 // one warp per row
@@ -121,6 +123,158 @@ int launch_query_prep(rass_engine* h, const float* q_dev, int B, cudaStream_t st
   query_prep_kernel<<<(B_pad + warps - 1) / warps, warps * 32, 0, st>>>(q_dev, h->dim, h->dim_pad, h->metric, B, B_pad,
                                                                         h->q_raw, h->q_hat, h->q16, h->q_norm,
                                                                         h->q_rho);
+  CUDA_TRY(h, cudaGetLastError());
+  return RASS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Threshold seed for the tcgen05 scans.
+//
+// A scan CTA starts with threshold -inf, so every score of its first two tiles is a "hit": measured on the 64-query
+// kernel, tile 0 takes 13.6 us and tile 1 (64 first compactions) 45.7 us against 5.5 us in steady state -- a fixed
+// 36-48 us per pass (profiles/r1_scan_kernels_ncu.md).  One CTA pair per query scores RASS_SEED_ROWS corpus rows (16 evenly
+// spaced runs of 32) with the arithmetic the scan uses (bf16 operands, fp32 accumulate, key = dot * sa + sb_scan) and publishes in
+// q_gthr the largest T with at least `rank` sampled keys strictly above it.  T is a legal pivot: those rows are part of
+// the corpus, so the scan meets at least `rank` >= (entries a compaction keeps) keys above it -- the same guarantee a
+// pivot found by warp_compact carries -- and every scan CTA starts from it.  The accumulation order differs from the
+// tensor pipe's, so a sampled key within an ulp of T can land on the other side; `rank` leaves 8 (16) spare rows over
+// what the certificate needs, and the certificate in finish.cu is what guarantees exactness in any case.
+// ---------------------------------------------------------------------------------------------
+#define RASS_SEED_ROWS 512
+#define RASS_SEED_BLOCKS (RASS_SEED_ROWS / 32)
+#define RASS_SEED_THREADS 512
+
+// A CTA pair (cluster of 2) per query: reading the 1 MB sample through one SM's L2 port takes ~9 us, so each CTA scores
+// half of it and the second one hands its keys over through distributed shared memory.  NVEC = dim_pad / 256 when it is
+// known at compile time (all 16-byte loads of four rows are then issued before the first use), 0 = run-time loop.
+template <int NVEC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RASS_SEED_THREADS, 1) seed_thresholds_kernel(
+    const uint4* __restrict__ x16, const float* __restrict__ sa, const float* __restrict__ sb,
+    const __nv_bfloat16* __restrict__ q16, int dim_pad, int64_t n_rows, int B, int rank, uint32_t* __restrict__ gthr) {
+  namespace cg = cooperative_groups;
+  const int b = blockIdx.x >> 1;                 // uniform over the pair: both CTAs leave here, or neither
+  if (b >= B) {
+    if (threadIdx.x == 0 && (blockIdx.x & 1) == 0) gthr[b] = 0u;
+    return;
+  }
+  cg::cluster_group pair = cg::this_cluster();
+  const int half = (int)pair.block_rank();
+  extern __shared__ float seed_smem[];
+  float* qs = seed_smem;                                             // [dim_pad] the bf16 query, widened
+  uint32_t* keys = reinterpret_cast<uint32_t*>(seed_smem + dim_pad);  // [RASS_SEED_ROWS] ordered images (CTA 0's copy is used)
+  uint32_t* keys0 = pair.map_shared_rank(keys, 0);
+  for (int j = threadIdx.x; j < dim_pad; j += RASS_SEED_THREADS) qs[j] = __bfloat162float(q16[(size_t)b * dim_pad + j]);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = NVEC ? NVEC : (dim_pad >> 8);                     // 16-byte loads per lane per row
+  // the sample: RASS_SEED_BLOCKS evenly spaced runs of 32 consecutive rows (few distinct pages: 512 scattered rows cost
+  // a TLB miss each)
+  const int64_t block_stride = n_rows / RASS_SEED_BLOCKS;
+  constexpr int ROWS_PER_WARP = RASS_SEED_ROWS / 2 / (RASS_SEED_THREADS / 32);
+  static_assert(ROWS_PER_WARP % 4 == 0 && 32 % ROWS_PER_WARP == 0, "a warp scores its rows four at a time, inside one run");
+  for (int i0 = 0; i0 < ROWS_PER_WARP; i0 += 4) {
+    const int i = half * (RASS_SEED_ROWS / 2) + warp * ROWS_PER_WARP + i0;   // sample index of the first of four rows
+    const int64_t row0 = (int64_t)(i >> 5) * block_stride + (i & 31);
+    float a = 0.f, off = 0.f;
+    if (lane < 4) { a = __ldg(sa + row0 + lane); off = __ldg(sb + row0 + lane); }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    auto fma_block = [&](const uint4 (&x)[4], int v) {
+      const float4 qa = *reinterpret_cast<const float4*>(qs + (v * 32 + lane) * 8);
+      const float4 qb = *reinterpret_cast<const float4*>(qs + (v * 32 + lane) * 8 + 4);
+      const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const uint32_t w[4] = {x[r].x, x[r].y, x[r].z, x[r].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[r] = fmaf(__uint_as_float(w[e] << 16), qv[2 * e], acc[r]);
+          acc[r] = fmaf(__uint_as_float(w[e] & 0xffff0000u), qv[2 * e + 1], acc[r]);
+        }
+      }
+    };
+    const uint4* p = x16 + (size_t)row0 * (dim_pad >> 3) + lane;
+    if (NVEC) {
+      // all 4 * NVEC loads are issued before the first use: the volatile loads keep their order, and the empty
+      // volatile statements after them pin every loaded register, so no FMA can be scheduled in between (left to
+      // itself the compiler interleaves them, two loads in flight per warp, and the kernel is a chain of round trips)
+      uint4 x[NVEC ? NVEC : 1][4];
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint4* src = p + (size_t)r * (dim_pad >> 3) + v * 32;
+          asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(x[v][r].x), "=r"(x[v][r].y), "=r"(x[v][r].z), "=r"(x[v][r].w)
+                       : "l"(src));
+        }
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          asm volatile("" : "+r"(x[v][r].x), "+r"(x[v][r].y), "+r"(x[v][r].z), "+r"(x[v][r].w));
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) fma_block(x[v], v);
+    } else {
+      for (int v = 0; v < nvec; ++v) {
+        uint4 x[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) x[r] = __ldg(p + (size_t)r * (dim_pad >> 3) + v * 32);
+        fma_block(x, v);
+      }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float dot = acc[r];
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, m);
+      if (lane == r) mine = dot;
+    }
+    if (lane < 4) keys0[i + lane] = ord32(fmaf(mine, a, off));
+  }
+  pair.sync();                                   // both halves of the keys are in CTA 0's shared memory
+  if (half == 0 && warp == 0) {
+    uint32_t kk[RASS_SEED_ROWS / 32];
+#pragma unroll
+    for (int i = 0; i < RASS_SEED_ROWS / 32; ++i) kk[i] = keys[i * 32 + lane];
+    // v = the rank-th largest key: the largest value with at least `rank` keys >= it
+    uint32_t v = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = v | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < RASS_SEED_ROWS / 32; ++i) c += kk[i] >= cand;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= rank) v = cand;
+    }
+    // strictly above v - 1 = at or above v; nothing is published unless `rank` sampled keys are finite (> -inf)
+    const uint32_t t = v ? v - 1 : 0u;
+    if (lane == 0) gthr[b] = t > 0x007fffffu ? t : 0u;
+  }
+}
+
+// Initialises q_gthr[0, B_pad) for the scans that follow: a seed per query, or 0 ("nothing published") when the corpus
+// is too small to sample or RASS_DEBUG_NO_SEED is set (the A/B switch of the measurement).  seg = the segment size the
+// scan will use: its compactions keep >= 32 (seg 256) or >= 128 (seg 512) entries above a pivot, and so must the seed.
+int launch_seed_thresholds(rass_engine* h, int B, int seg, cudaStream_t st) {
+  static const bool no_seed = getenv("RASS_DEBUG_NO_SEED") != nullptr;
+  const int B_pad = (B + RASS_QPAD - 1) / RASS_QPAD * RASS_QPAD;
+  const int rank = seg == 512 ? 144 : 40;
+  if (no_seed || h->n_rows < 16 * RASS_SEED_ROWS) {
+    CUDA_TRY(h, cudaMemsetAsync(h->q_gthr, 0, (size_t)B_pad * sizeof(uint32_t), st));
+    return RASS_OK;
+  }
+  const size_t smem = (size_t)h->dim_pad * sizeof(float) + RASS_SEED_ROWS * sizeof(uint32_t);
+  const uint4* x = reinterpret_cast<const uint4*>(h->x16);
+  if (h->dim_pad == 1024) {
+    seed_thresholds_kernel<4><<<2 * B_pad, RASS_SEED_THREADS, smem, st>>>(x, h->sa, h->sb_scan, h->q16, h->dim_pad,
+                                                                         h->n_rows, B, rank, h->q_gthr);
+  } else {
+    if (smem > 48 * 1024)
+      CUDA_TRY(h, cudaFuncSetAttribute(seed_thresholds_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    seed_thresholds_kernel<0><<<2 * B_pad, RASS_SEED_THREADS, smem, st>>>(x, h->sa, h->sb_scan, h->q16, h->dim_pad,
+                                                                         h->n_rows, B, rank, h->q_gthr);
+  }
   CUDA_TRY(h, cudaGetLastError());
   return RASS_OK;
 }
