@@ -59,7 +59,8 @@ struct DevScalars {
   int flagged_n;      // queries that failed the certificate in the running search
   int max_cand;       // largest rerank candidate set in the running search
   int n_certified;
-  int pad[3];
+  int finish_done;    // CTAs of the running finish launch that are through (the last one publishes flagged_n, resets this)
+  int pad[2];
 };
 
 struct rass_engine {
@@ -398,23 +399,24 @@ __device__ __forceinline__ float score_from_key(double key, int metric) {
 int launch_store_convert(rass_engine* h, const float* src_dev, int64_t src_stride, int64_t first_row, int64_t n,
                          cudaStream_t st);
 int launch_query_prep(rass_engine* h, const float* q_dev, int B, cudaStream_t st);
-int launch_seed_thresholds(rass_engine* h, int B, int seg, cudaStream_t st);
+int launch_seed_thresholds(rass_engine* h, int B, int seg, size_t n_clear, bool* cleared, cudaStream_t st);
 // streaming scan of queries [q0, q0+nq) (nq = 1 or 2); their pool slots are q - g0
 int launch_scan_stream(rass_engine* h, int q0, int nq, int g0, cudaStream_t st);
 int scan_stream_segs(const rass_engine* h);
 // tcgen05 scan of queries [q0, q0+nq) (nq <= 64) into pool slots 0..nq
-int launch_scan_umma(rass_engine* h, int q0, int nq, int seg, cudaStream_t st);
+int launch_scan_umma(rass_engine* h, int q0, int nq, int seg, cudaStream_t st, bool pool_cleared = false);
 int scan_umma_segs(const rass_engine* h);
 int umma_selftest(rass_engine* h, int n_rows_tile, float* out_host, cudaStream_t st);
 // CTA-pair tcgen05 scan of all B prepared queries (groups of 256) into pool slots 0..B
-int launch_scan_gemm(rass_engine* h, int B, int seg, cudaStream_t st);
+int launch_scan_gemm(rass_engine* h, int B, int seg, cudaStream_t st, bool pool_cleared = false);
 int scan_gemm_segs(const rass_engine* h, int B);
 int gemm_selftest(rass_engine* h, int B, float* out_host, cudaStream_t st);
 // CUtensorMap over a [rows, dim_pad] bf16 matrix: boxes of box_rows x 64 elements, 128B swizzle
 int encode_rows_map(rass_engine* h, void* map, const void* base, int64_t rows, int box_rows);
 // merge the pool of queries [g0, g0+ng), rerank in fp64, emit top-k, flag uncertified queries
 int launch_finish(rass_engine* h, int g0, int ng, int k, int n_segs, int seg_size, bool has_cnt, bool q_is_bf16,
-                  int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st);
+                  int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st,
+                  int64_t* flag_out = nullptr);
 // fp64 scan of the listed queries (qids host array, n_q of them)
 int launch_exact(rass_engine* h, int k, const int* qids_host, int n_q, int64_t* out_rows, float* out_scores,
                  double* out_keys, cudaStream_t st, int* launches);

@@ -588,7 +588,6 @@ int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_r
 // entries above it when k <= 32.  For k > 32 a cluster of near neighbours inside one segment can lift a pivot above
 // the k-th best; those queries fail their certificate and get a second pass with robust = true (512-entry segments,
 // >= 128 entries above every pivot) at tensor-core speed instead of the fp64 scan.
-__global__ void publish_flag_kernel(const DevScalars* scal, int64_t* flag) { *flag = scal->flagged_n; }
 
 // async_slot >= 0: enqueue only -- no host synchronisation, no fallback; the certificate outcome lands in the slot's
 // pinned scalars (and, for row-sharded callers, in *async_flag_dev, which travels with the all-gathered candidates).
@@ -633,6 +632,7 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
     return RASS_OK;
   }
   int path = resolve_path(h, B);
+  int64_t* flag_out = as ? async_flag_dev : nullptr;   // published by the last CTA of the last finish launch
   if (robust && path == RASS_PATH_STREAM) path = RASS_PATH_UMMA;    // the streaming scan keeps 32 per warp only
   s.path = path;
   if ((rc = select_scan_offsets(h, st))) return rc;
@@ -653,13 +653,14 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
     const int n_segs = scan_gemm_segs(h, B);
     const int seg = robust ? rass_tc_seg(k) : 256;
     if ((rc = ensure_pool(h, (size_t)n_segs * seg, (size_t)n_segs, (size_t)B))) return rc;
-    if ((rc = launch_seed_thresholds(h, B, seg, st))) return rc;
+    bool cleared = false;
+    if ((rc = launch_seed_thresholds(h, B, seg, (size_t)n_segs * B, &cleared, st))) return rc;
     CUDA_TRY(h, cudaEventRecord(get_event(h, ev_base + n_ev++), st));
-    if ((rc = launch_scan_gemm(h, B, seg, st))) return rc;
+    if ((rc = launch_scan_gemm(h, B, seg, st, cleared))) return rc;
     CUDA_TRY(h, cudaEventRecord(get_event(h, ev_base + n_ev++), st));
-    if ((rc = launch_finish(h, 0, B, k, n_segs, seg, true, true, out_rows, out_scores, out_keys, st)))
+    if ((rc = launch_finish(h, 0, B, k, n_segs, seg, true, true, out_rows, out_scores, out_keys, st, flag_out)))
       return rc;
-    s.launches += 4;
+    s.launches += cleared ? 3 : 4;
     s.passes = (B + 255) / 256;
     s.bytes_streamed = (int64_t)s.passes * h->n_rows * h->dim_pad * 2;
   } else {
@@ -667,16 +668,18 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
     const int n_segs = umma ? scan_umma_segs(h) : scan_stream_segs(h);
     const int seg = umma ? (robust ? rass_tc_seg(k) : 256) : RASS_STREAM_SEG;
     if ((rc = ensure_pool(h, (size_t)n_segs * seg, (size_t)n_segs))) return rc;
+    bool cleared = false;
     if (umma) {
-      if ((rc = launch_seed_thresholds(h, B, seg, st))) return rc;
+      if ((rc = launch_seed_thresholds(h, B, seg, (size_t)n_segs * RASS_GROUP_Q, &cleared, st))) return rc;
       s.launches += 1;
     }
     for (int g0 = 0; g0 < B; g0 += RASS_GROUP_Q) {
       const int ng = std::min(RASS_GROUP_Q, B - g0);
       CUDA_TRY(h, cudaEventRecord(get_event(h, ev_base + n_ev++), st));
       if (umma) {
-        if ((rc = launch_scan_umma(h, g0, ng, seg, st))) return rc;
-        s.launches += 2;
+        const bool skip_clear = cleared && g0 == 0;      // the seed kernel emptied the pool for the first group
+        if ((rc = launch_scan_umma(h, g0, ng, seg, st, skip_clear))) return rc;
+        s.launches += skip_clear ? 1 : 2;
         s.passes += 1;
       } else {
         for (int q0 = g0; q0 < g0 + ng; q0 += 2) {
@@ -686,17 +689,14 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
         }
       }
       CUDA_TRY(h, cudaEventRecord(get_event(h, ev_base + n_ev++), st));
-      if ((rc = launch_finish(h, g0, ng, k, n_segs, seg, true, umma, out_rows, out_scores, out_keys, st))) return rc;
+      if ((rc = launch_finish(h, g0, ng, k, n_segs, seg, true, umma, out_rows, out_scores, out_keys, st, flag_out)))
+        return rc;
       s.launches += 1;
     }
     s.bytes_streamed = (int64_t)s.passes * h->n_rows * h->dim_pad * 2;
   }
   if (as) {
     if (path == RASS_PATH_EXACT) return rass_fail(h, RASS_E_INVALID, "the fp64 scan has no async form");
-    if (async_flag_dev) {
-      publish_flag_kernel<<<1, 1, 0, st>>>(h->scal, async_flag_dev);
-      CUDA_TRY(h, cudaGetLastError());
-    }
     CUDA_TRY(h, cudaMemcpyAsync(as->scal_host, h->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaEventRecord(as->done, st));
     as->stats = s;

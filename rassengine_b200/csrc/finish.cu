@@ -38,6 +38,7 @@ struct FinishArgs {
   int64_t* out_rows;
   float* out_scores;
   double* out_keys;
+  int64_t* flag_out;        // null, or where the launch leaves scal->flagged_n once all its CTAs are through
 };
 
 template <bool BF16_ROWS>
@@ -192,6 +193,15 @@ __global__ void __launch_bounds__(RASS_FINISH_THREADS, 1) finish_kernel(FinishAr
       a.flagged[pos] = q;
     }
     atomicMax(&a.scal->max_cand, ncand_raw);
+    if (a.flag_out) {
+      // the last CTA of the launch publishes the running count of uncertified queries (what a row-sharded caller
+      // gathers with the candidates); a later launch of the same search overwrites it with the later count
+      __threadfence();
+      if (atomicAdd(&a.scal->finish_done, 1) == (int)gridDim.x - 1) {
+        a.scal->finish_done = 0;
+        *a.flag_out = (int64_t)atomicAdd(&a.scal->flagged_n, 0);
+      }
+    }
   }
 }
 
@@ -200,8 +210,9 @@ static size_t finish_smem(int dim_pad) {
 }
 
 int launch_finish(rass_engine* h, int g0, int ng, int k, int n_segs, int seg_size, bool has_cnt, bool q_is_bf16,
-                  int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st) {
+                  int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st, int64_t* flag_out) {
   FinishArgs a;
+  a.flag_out = flag_out;
   a.pool_key = h->pool_key;
   a.pool_row = h->pool_row;
   a.pool_thr = h->pool_thr;

@@ -338,7 +338,7 @@ __global__ void clear_gemm_segs_kernel(float* thr, int* cnt, size_t n) {
   cnt[i] = 0;
 }
 
-static int gemm_launch(rass_engine* h, int B, int seg, float* dbg_out, cudaStream_t st) {
+static int gemm_launch(rass_engine* h, int B, int seg, float* dbg_out, cudaStream_t st, bool pool_cleared = false) {
   int rc;
   if (!h->tmap_x) h->tmap_x = calloc(1, sizeof(CUtensorMap));
   if (!h->tmap_q2) h->tmap_q2 = calloc(1, sizeof(CUtensorMap));
@@ -360,8 +360,10 @@ static int gemm_launch(rass_engine* h, int B, int seg, float* dbg_out, cudaStrea
   const GemmPlan plan = make_plan(h, B, n_pairs);
   const int n_segs = scan_gemm_segs(h, B);
   const size_t n = (size_t)n_segs * B;
-  clear_gemm_segs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pool_thr, h->pool_cnt, n);
-  CUDA_TRY(h, cudaGetLastError());
+  if (!pool_cleared) {
+    clear_gemm_segs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pool_thr, h->pool_cnt, n);
+    CUDA_TRY(h, cudaGetLastError());
+  }
   // per-query bound shared between the CTAs (ordered-integer image of a float; 0 = nothing published yet): seeded by
   // launch_seed_thresholds before a search; the self-test has no seed
   if (dbg_out) CUDA_TRY(h, cudaMemsetAsync(h->q_gthr, 0, (size_t)h->q_cap * sizeof(uint32_t), st));
@@ -388,7 +390,9 @@ static int gemm_launch(rass_engine* h, int B, int seg, float* dbg_out, cudaStrea
 
 // all B prepared queries (q16 rows [0, B), padded with zero rows to a multiple of 256) against the whole shard;
 // query q's candidates land in pool slot q
-int launch_scan_gemm(rass_engine* h, int B, int seg, cudaStream_t st) { return gemm_launch(h, B, seg, nullptr, st); }
+int launch_scan_gemm(rass_engine* h, int B, int seg, cudaStream_t st, bool pool_cleared) {
+  return gemm_launch(h, B, seg, nullptr, st, pool_cleared);
+}
 
 // Debug/self-test entry: raw tensor-core dot products of the first 256 prepared queries against every row.
 // out_host: [n_rows, 256] fp32.

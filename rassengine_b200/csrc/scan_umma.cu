@@ -391,11 +391,13 @@ __global__ void clear_segs_kernel(float* thr, int* cnt, size_t n) {
   cnt[i] = 0;
 }
 
-int launch_scan_umma(rass_engine* h, int q0, int nq, int seg, cudaStream_t st) {
+int launch_scan_umma(rass_engine* h, int q0, int nq, int seg, cudaStream_t st, bool pool_cleared) {
   (void)nq;
-  const size_t n = (size_t)scan_umma_segs(h) * RASS_GROUP_Q;
-  clear_segs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pool_thr, h->pool_cnt, n);
-  CUDA_TRY(h, cudaGetLastError());
+  if (!pool_cleared) {       // the seed kernel clears for the first group of a search
+    const size_t n = (size_t)scan_umma_segs(h) * RASS_GROUP_Q;
+    clear_segs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pool_thr, h->pool_cnt, n);
+    CUDA_TRY(h, cudaGetLastError());
+  }
   return umma_launch(h, q0, h->n_rows, seg, nullptr, st);
 }
 

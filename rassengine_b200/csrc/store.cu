@@ -150,8 +150,15 @@ int launch_query_prep(rass_engine* h, const float* q_dev, int B, cudaStream_t st
 template <int NVEC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RASS_SEED_THREADS, 1) seed_thresholds_kernel(
     const uint4* __restrict__ x16, const float* __restrict__ sa, const float* __restrict__ sb,
-    const __nv_bfloat16* __restrict__ q16, int dim_pad, int64_t n_rows, int B, int rank, uint32_t* __restrict__ gthr) {
+    const __nv_bfloat16* __restrict__ q16, int dim_pad, int64_t n_rows, int B, int rank, uint32_t* __restrict__ gthr,
+    float* __restrict__ pool_thr, int* __restrict__ pool_cnt, size_t n_clear) {
   namespace cg = cooperative_groups;
+  // the segment bounds and sizes of the pass that follows start empty (saves the scans' own clearing launch)
+  for (size_t i = (size_t)blockIdx.x * RASS_SEED_THREADS + threadIdx.x; i < n_clear;
+       i += (size_t)gridDim.x * RASS_SEED_THREADS) {
+    pool_thr[i] = neg_inf<float>();
+    pool_cnt[i] = 0;
+  }
   const int b = blockIdx.x >> 1;                 // uniform over the pair: both CTAs leave here, or neither
   if (b >= B) {
     if (threadIdx.x == 0 && (blockIdx.x & 1) == 0) gthr[b] = 0u;
@@ -254,9 +261,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RASS_SEED_THREADS, 1
 }
 
 // Initialises q_gthr[0, B_pad) for the scans that follow: a seed per query, or 0 ("nothing published") when the corpus
-// is too small to sample or RASS_DEBUG_NO_SEED is set (the A/B switch of the measurement).  seg = the segment size the
+// is too small to sample or RASS_DEBUG_NO_SEED is set (the A/B switch of the measurement).  When the kernel runs it
+// also empties the first n_clear segment bounds / sizes of the candidate pool (*cleared = true).  seg = the segment size the
 // scan will use: its compactions keep >= 32 (seg 256) or >= 128 (seg 512) entries above a pivot, and so must the seed.
-int launch_seed_thresholds(rass_engine* h, int B, int seg, cudaStream_t st) {
+int launch_seed_thresholds(rass_engine* h, int B, int seg, size_t n_clear, bool* cleared, cudaStream_t st) {
+  *cleared = false;
   static const bool no_seed = getenv("RASS_DEBUG_NO_SEED") != nullptr;
   const int B_pad = (B + RASS_QPAD - 1) / RASS_QPAD * RASS_QPAD;
   const int rank = seg == 512 ? 144 : 40;
@@ -268,13 +277,16 @@ int launch_seed_thresholds(rass_engine* h, int B, int seg, cudaStream_t st) {
   const uint4* x = reinterpret_cast<const uint4*>(h->x16);
   if (h->dim_pad == 1024) {
     seed_thresholds_kernel<4><<<2 * B_pad, RASS_SEED_THREADS, smem, st>>>(x, h->sa, h->sb_scan, h->q16, h->dim_pad,
-                                                                         h->n_rows, B, rank, h->q_gthr);
+                                                                         h->n_rows, B, rank, h->q_gthr, h->pool_thr,
+                                                                         h->pool_cnt, n_clear);
   } else {
     if (smem > 48 * 1024)
       CUDA_TRY(h, cudaFuncSetAttribute(seed_thresholds_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     seed_thresholds_kernel<0><<<2 * B_pad, RASS_SEED_THREADS, smem, st>>>(x, h->sa, h->sb_scan, h->q16, h->dim_pad,
-                                                                         h->n_rows, B, rank, h->q_gthr);
+                                                                         h->n_rows, B, rank, h->q_gthr, h->pool_thr,
+                                                                         h->pool_cnt, n_clear);
   }
   CUDA_TRY(h, cudaGetLastError());
+  *cleared = true;
   return RASS_OK;
 }

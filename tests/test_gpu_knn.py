@@ -298,6 +298,44 @@ def test_top100_inside_one_cluster_of_adjacent_rows_is_certified(path):
     assert st10["n_retried"] == 0 and st10["n_fallback"] == 0, st10
 
 
+def test_async_search_publishes_the_certificate_outcome():
+    """rass_search_knn_dev_async leaves the number of uncertified queries in *flag_out_dev -- the word a row-sharded
+    caller all-gathers with its candidates (sharded.py) -- written by the last CTA of the last finish launch: 0 on
+    ordinary queries, the number of failed queries when a top-100 sits inside one cluster of adjacent rows (the async
+    form does not retry; the caller repeats with the blocking call).  The word is overwritten, not accumulated."""
+    import torch
+    rng = np.random.default_rng(61)
+    X = synth.embeddings(60000, 1024, 62)
+    centre = X[123].copy()
+    lo = 20000
+    X[lo:lo + 400] = centre[None, :] + 0.02 * rng.standard_normal((400, 1024)).astype(np.float32)
+    X[lo:lo + 400] /= np.linalg.norm(X[lo:lo + 400], axis=1, keepdims=True)
+    Q = (centre[None, :] + 0.01 * rng.standard_normal((70, 1024))).astype(np.float32)
+    Q[1::2] = synth.embeddings(35, 1024, 63)
+    want_rows, _, _ = knn.knn_exact(X, Q, 10)
+    B = Q.shape[0]
+    with _engine(dim=1024) as e:
+        e.append(X)
+        Qd = torch.from_numpy(Q).cuda()
+        rows = torch.empty((B, 100), dtype=torch.int64, device="cuda")
+        scores = torch.empty((B, 100), dtype=torch.float32, device="cuda")
+        flag = torch.empty(1, dtype=torch.int64, device="cuda")
+        for path in ("umma", "gemm"):           # 70 queries: two finish launches on the 64-per-pass path, one on the other
+            e.set_path(_paths()[path])
+            flag.fill_(-5)
+            torch.cuda.synchronize()
+            e.search_knn_dev_async(Qd.data_ptr(), B, 10, rows.data_ptr(), scores.data_ptr(), 0, 0, flag.data_ptr())
+            final, st = e.search_knn_dev_wait(0)
+            assert final and int(flag.item()) == 0 and st["n_certified"] == B, (path, st, int(flag.item()))
+            assert np.array_equal(rows.cpu().numpy().reshape(-1)[:B * 10].reshape(B, 10), want_rows), path
+            flag.fill_(-5)
+            torch.cuda.synchronize()
+            e.search_knn_dev_async(Qd.data_ptr(), B, 100, rows.data_ptr(), scores.data_ptr(), 0, 1, flag.data_ptr())
+            final, st = e.search_knn_dev_wait(1)
+            assert not final and 0 < st["n_fallback"] <= 35 and int(flag.item()) == st["n_fallback"], (path, st)
+            assert st["n_certified"] == B - st["n_fallback"], (path, st)
+
+
 def test_properties_at_2m_rows_all_paths_agree():
     """Larger than the oracle can check in seconds: size-independent properties instead.  On 2M device-generated
     rows every scan path returns the same ids for the same queries, the fp64 scan (the definition) agrees on a
