@@ -588,7 +588,7 @@ int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_r
 // entries above it when k <= 32.  For k > 32 a cluster of near neighbours inside one segment can lift a pivot above
 // the k-th best; those queries fail their certificate and get a second pass with robust = true (512-entry segments,
 // >= 128 entries above every pivot) at tensor-core speed instead of the fp64 scan.
-
+//
 // async_slot >= 0: enqueue only -- no host synchronisation, no fallback; the certificate outcome lands in the slot's
 // pinned scalars (and, for row-sharded callers, in *async_flag_dev, which travels with the all-gathered candidates).
 static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
