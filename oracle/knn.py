@@ -41,7 +41,12 @@ def cos64(X: np.ndarray, q: np.ndarray, xnorm64: np.ndarray | None = None) -> np
     """fp64-accumulated cosine of every row of X (fp32) with q (fp32)."""
     X64 = np.asarray(X, dtype=np.float64)
     q64 = np.asarray(q, dtype=np.float64).reshape(-1)
-    dot = X64 @ q64
+    # not `X64 @ q64`: a BLAS gemv reduces a row differently depending on where it sits in the matrix, so two
+    # identical rows could get keys one ulp apart and the (key desc, row asc) rule would not see the tie.  The
+    # row-wise pairwise sum below depends on the row's values only.
+    dot = np.empty(X64.shape[0], dtype=np.float64)
+    for c0 in range(0, X64.shape[0], 16384):
+        dot[c0:c0 + 16384] = (X64[c0:c0 + 16384] * q64[None, :]).sum(axis=1)
     if xnorm64 is None:
         xnorm64 = np.sqrt(np.einsum("ij,ij->i", X64, X64))
     qn = np.sqrt(np.dot(q64, q64))

@@ -97,7 +97,7 @@ def _parse_date(v, now: _dt.datetime):
         n = int(m.group(2)) * (1 if m.group(1) == "+" else -1)
         unit = m.group(3)
         if unit == "y":
-            return now.replace(year=now.year + n)
+            return now.replace(year=now.year + n, day=min(now.day, 28) if now.month == 2 else now.day)
         if unit == "M":
             mm = now.month - 1 + n
             return now.replace(year=now.year + mm // 12, month=mm % 12 + 1, day=min(now.day, 28))

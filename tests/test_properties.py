@@ -1,0 +1,167 @@
+"""Property tests (hypothesis, CPU only) of the oracle's building blocks and of the host-side mirrors the product keeps
+of them: size-independent facts that hold for every input, next to the known answers in test_oracle.py."""
+import datetime as dt
+
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from oracle import analyzer, bm25, fusion, fuzzy, knn, smallfloat
+from rassengine_b200 import hostquery, text
+from rassengine_b200.sharded import shard_bounds
+
+FAST = settings(max_examples=200, deadline=None)
+SLOW = settings(max_examples=40, deadline=None)
+words = st.text(alphabet="abcdeio", min_size=0, max_size=9)
+
+
+@FAST
+@given(st.integers(0, 2**31 - 1))
+def test_smallfloat_rounds_down_to_four_significant_bits(i):
+    """SmallFloat.intToByte4 (Lucene norms): exact below 40, otherwise the largest representable value <= i, never
+    more than 1/8 below it; the host mirror used by hostquery.py encodes to the same byte."""
+    b = smallfloat.int_to_byte4(i)
+    back = smallfloat.byte4_to_int(b)
+    assert 0 <= b <= 255 and back <= i
+    if i < 40:
+        assert back == i
+    else:
+        assert i - back < max(1, (i - 24) / 8 + 1)
+    if b < 255:
+        assert smallfloat.byte4_to_int(b + 1) > i                     # the next byte would overshoot
+    assert int(hostquery.norm_bytes(np.array([i]))[0]) == b
+    assert int(smallfloat.encode_lengths(np.array([i]))[0]) == b
+
+
+@FAST
+@given(st.integers(0, 2**31 - 2))
+def test_smallfloat_is_monotone(i):
+    assert smallfloat.int_to_byte4(i) <= smallfloat.int_to_byte4(i + 1)
+
+
+@FAST
+@given(words, words)
+def test_osa_distance_properties(a, b):
+    """Optimal string alignment (what `fuzziness: AUTO` with transpositions accepts): a metric-like distance bounded by
+    the lengths; the host mirror (capped) agrees with the oracle wherever the cap allows."""
+    d = fuzzy.osa_distance(a, b)
+    assert d == fuzzy.osa_distance(b, a)
+    assert (d == 0) == (a == b)
+    assert abs(len(a) - len(b)) <= d <= max(len(a), len(b))
+    for cap in (1, 2):
+        h = hostquery._osa(a, b, cap)
+        assert (h == d) if d <= cap else (h > cap)
+
+
+@FAST
+@given(words.filter(lambda w: len(w) >= 2), st.integers(0, 7))
+def test_adjacent_swap_is_one_edit(w, i):
+    i %= len(w) - 1
+    s = w[:i] + w[i + 1] + w[i] + w[i + 2:]
+    assert fuzzy.osa_distance(w, s) == (0 if s == w else 1)
+
+
+@FAST
+@given(st.lists(words, min_size=0, max_size=40, unique=True), words)
+def test_fuzzy_expansion_is_sorted_and_within_auto_edits(vocab, token):
+    vocab = sorted(vocab)
+    out = fuzzy.expand(vocab, token)
+    me = fuzzy.auto_max_edits(len(token))
+    assert len(out) <= fuzzy.MAX_EXPANSIONS
+    keys = [(-float(b), vocab[t]) for t, _, b in out]
+    assert keys == sorted(keys)
+    for t, ed, boost in out:
+        assert ed <= me and ed == fuzzy.osa_distance(token, vocab[t])
+        assert 0.0 <= float(boost) <= 1.0 and (float(boost) == 1.0) == (ed == 0)
+    got = {t for t, _, _ in out}
+    if len(out) < fuzzy.MAX_EXPANSIONS:                              # nothing within reach was left out
+        for t, term in enumerate(vocab):
+            if t not in got:
+                assert term != token and (me == 0 or fuzzy.osa_distance(token, term) > me)
+
+
+@FAST
+@given(st.text(max_size=60))
+def test_product_analyzer_equals_oracle_analyzer(s):
+    """rassengine_b200.text.analyze and oracle.analyzer.analyze are written independently; they must tokenise alike."""
+    assert text.analyze(s) == analyzer.analyze(s)
+    for tok in text.analyze(s):
+        assert tok and tok == tok.lower()
+
+
+@SLOW
+@given(st.integers(1, 60), st.integers(1, 8), st.integers(1, 12), st.integers(0, 2**31 - 1))
+def test_knn_chunked_oracle_equals_the_definition(n, nq, k, seed):
+    """knn_exact (chunked, what the GPU tests compare against) == knn_exact_full (the plain definition), duplicates and
+    an all-zero row included; ids sorted by (key desc, row asc), fewer than k rows -> -1 padding."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, 16)).astype(np.float32)
+    if n > 3:
+        X[n - 1] = X[0]
+        X[n // 2] = 0
+    Q = rng.standard_normal((nq, 16)).astype(np.float32)
+    for metric in (knn.COSINE, knn.L2):
+        r1, k1, s1 = knn.knn_exact(X, Q, k, metric=metric)
+        r2, k2, s2 = knn.knn_exact_full(X, Q, k, metric=metric)
+        assert np.array_equal(r1, r2) and np.array_equal(s1, s2)
+        for b in range(nq):
+            valid = r1[b] >= 0
+            assert valid.sum() == min(k, n) and len(set(r1[b][valid].tolist())) == valid.sum()
+            keys = k1[b][valid] if metric == knn.COSINE else -k1[b][valid]      # L2 reports the squared distance
+            assert np.all(keys[:-1] >= keys[1:])
+            ties = np.flatnonzero(keys[:-1] == keys[1:])
+            assert np.all(r1[b][valid][ties] < r1[b][valid][ties + 1])
+
+
+@SLOW
+@given(st.integers(2, 40), st.integers(0, 2**31 - 1), st.floats(0.5, 5.0), st.floats(0.5, 3.0))
+def test_fusion_is_a_boosted_sum_over_the_matching_docs(n, seed, w_text, w_knn):
+    """bool.should: a doc matches when a clause matches; S = float(double(text) + double(float(w_knn * knn))); ranking
+    (S desc, row asc); with no kNN rows the fusion is the BM25 ranking itself."""
+    rng = np.random.default_rng(seed)
+    docs = [rng.integers(0, 12, size=int(rng.integers(0, 30))).tolist() for _ in range(n)]
+    idx = bm25.BM25Index.from_token_ids(docs, 12)
+    q = rng.integers(0, 12, size=3).tolist()
+    kk = min(5, n)
+    knn_rows = rng.choice(n, size=kk, replace=False).astype(np.int64)
+    knn_scores = np.sort(rng.uniform(0.4, 1.0, size=kk).astype(np.float32))[::-1]
+    rows, sc = fusion.hybrid(idx, q, knn_rows, knn_scores, w_text, w_knn, k=n)
+    text32 = idx.score(q, boost=w_text)
+    want = {d: float(text32[d]) for d in range(n) if text32[d] > 0}
+    for r, s in zip(knn_rows.tolist(), knn_scores.tolist()):
+        want[r] = want.get(r, 0.0) + float(np.float32(np.float32(w_knn) * np.float32(s)))
+    assert set(rows.tolist()) == set(want)
+    assert [np.float32(want[r]) for r in rows.tolist()] == sc.tolist()
+    order = sorted(want, key=lambda d: (-float(np.float32(want[d])), d))
+    assert rows.tolist() == order
+    rows0, sc0 = fusion.hybrid(idx, q, np.empty(0, dtype=np.int64), np.empty(0, dtype=np.float32), w_text, w_knn, k=n)
+    tr, ts = bm25.topk(text32, n)
+    assert rows0.tolist() == tr.tolist() and sc0.tolist() == ts.tolist()
+
+
+@FAST
+@given(st.integers(0, 10**9), st.integers(1, 16))
+def test_shard_bounds_partition_the_rows(n, world):
+    cuts = [shard_bounds(n, world, r) for r in range(world)]
+    assert cuts[0][0] == 0 and cuts[-1][1] == n
+    for (lo, hi), (lo2, _) in zip(cuts, cuts[1:]):
+        assert lo <= hi == lo2
+    sizes = [hi - lo for lo, hi in cuts]
+    assert max(sizes) <= -(-n // world)
+
+
+@FAST
+@given(st.datetimes(min_value=dt.datetime(1971, 1, 1), max_value=dt.datetime(2090, 12, 31)),
+       st.sampled_from("yMwdhms"), st.integers(0, 30), st.sampled_from("+-"))
+def test_date_math_never_raises_and_moves_the_right_way(now, unit, n, sign):
+    """`now-1y` style bounds of the reference's range clauses (app/main.py:1890-1900): any calendar day, leap days included."""
+    now = now.replace(tzinfo=dt.timezone.utc)
+    got = hostquery._parse_date(f"now{sign}{n}{unit}", now)
+    assert got is not None
+    if n == 0:
+        assert abs((got - now).total_seconds()) <= 3 * 86400          # month/year arithmetic may clamp the day
+    elif sign == "+":
+        assert got > now - dt.timedelta(days=4)
+    else:
+        assert got < now + dt.timedelta(days=4)
+    assert hostquery._parse_date("now", now) == now
+    assert hostquery._parse_date("not a date", now) is None
