@@ -165,3 +165,73 @@ def test_date_math_never_raises_and_moves_the_right_way(now, unit, n, sign):
         assert got < now + dt.timedelta(days=4)
     assert hostquery._parse_date("now", now) == now
     assert hostquery._parse_date("not a date", now) is None
+
+
+def _scalar():
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py")
+    spec = importlib.util.spec_from_file_location("make_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@SLOW
+@given(st.integers(1, 25), st.integers(0, 2**31 - 1), st.sampled_from([1.0, 1.5, 4.5]))
+def test_bm25_oracle_equals_the_independent_scalar_scorer(n, seed, boost):
+    """oracle/bm25.py (numpy, vectorised) against the pure-Python scalar restatement that made the golden fixtures
+    (struct-rounded float32 arithmetic), on random corpora with empty documents, repeated query terms, absent terms and
+    lengths on both sides of the SmallFloat quantisation."""
+    mg = _scalar()
+    rng = np.random.default_rng(seed)
+    docs = [rng.integers(0, 9, size=int(rng.choice([0, 3, 17, 41, 90]))).tolist() for _ in range(n)]
+    if not any(docs):
+        docs[0] = [1, 2]
+    q = rng.integers(0, 11, size=int(rng.integers(1, 5))).tolist()          # ids 9, 10 never occur
+    idx = bm25.BM25Index.from_token_ids(docs, 11)
+    assert [mg.f32(v) for v in idx.score(q, boost=boost).tolist()] == mg.scalar_bm25(docs, q, boost)
+
+
+@SLOW
+@given(st.integers(2, 14), st.integers(0, 2**31 - 1))
+def test_multifield_oracle_equals_the_independent_scalar_scorer(n, seed):
+    """oracle/multifield.py + oracle/fuzzy.py against the scalar scorer: random documents over two analysed fields and
+    one keyword field, words drawn from a pool full of one- and two-edit neighbours."""
+    from oracle import multifield
+    mg = _scalar()
+    rng = np.random.default_rng(seed)
+    pool = ["pain", "pian", "paint", "gain", "of", "on", "diabetes", "diabetis", "diabetse", "dibetes", "chest", "chst",
+            "active", "inactive", "ab", "abc", "abcd"]
+    pick = lambda lo, hi: " ".join(pool[int(i)] for i in rng.integers(0, len(pool), size=int(rng.integers(lo, hi))))
+    docs = []
+    for _ in range(n):
+        d = {}
+        if rng.random() < 0.8:
+            d["t"] = pick(1, 5)
+        if rng.random() < 0.8:
+            d["b"] = pick(1, 50)
+        if rng.random() < 0.6:
+            d["g"] = pick(1, 3)
+        docs.append(d)
+    if not any("t" in d for d in docs):
+        docs[0]["t"] = "pain"
+    types = {"t": "text", "b": "text", "g": "keyword"}
+    fields = multifield.build(docs, types)
+    toks = {f: [(([d[f]] if f in d else []) if k == "keyword" else d.get(f, "").split()) for d in docs]
+            for f, k in types.items()}
+    query = pick(1, 4)
+    text_specs, kw_specs = [("t", 3.0), ("b", 1.0)], [("g", 2.0)]
+    want = [0.0] * n
+    for specs, cb, fz in ((text_specs, 1.5, True), (kw_specs, 1.0, False)):
+        best = [0.0] * n
+        for fname, fb in specs:
+            if fname not in fields:
+                continue
+            kw = types[fname] == "keyword"
+            sc = mg.scalar_field_score(toks[fname], kw, [query] if kw else query.split(),
+                                       mg.f32(mg.f32(cb) * mg.f32(fb)), fz and not kw)
+            best = [max(x, y) for x, y in zip(best, sc)]
+        want = [x + y for x, y in zip(want, best)]
+    got = multifield.text_total(fields, [(query, text_specs, 1.5, True), (query, kw_specs, 1.0, False)], n)
+    assert got.tolist() == want, query
