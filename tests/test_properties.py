@@ -235,3 +235,40 @@ def test_multifield_oracle_equals_the_independent_scalar_scorer(n, seed):
         want = [x + y for x, y in zip(want, best)]
     got = multifield.text_total(fields, [(query, text_specs, 1.5, True), (query, kw_specs, 1.0, False)], n)
     assert got.tolist() == want, query
+
+
+@SLOW
+@given(st.integers(1, 30), st.integers(0, 2**31 - 1), st.sampled_from([1.0, 4.5]))
+def test_host_fuzzy_rewrite_equals_the_oracle(n, seed, boost):
+    """TextField.fuzzy_weighted_terms (product: ranks the device dictionary scan's hits, blends the statistics, builds
+    the (term, weight) list the kernel consumes) against oracle/fuzzy.py.  The dictionary scan itself -- the device
+    kernel in production, compared with the oracle in test_gpu_hybrid.py -- is played by a brute-force scan here.
+    Term ids differ (insertion order vs sorted), so terms are compared by string."""
+    rng = np.random.default_rng(seed)
+    pool = ["pain", "pian", "paint", "gain", "of", "on", "diabetes", "diabetis", "diabetse", "dibetes", "chest", "chst",
+            "active", "inactive", "ab", "abc", "abcd", "pains", "spain"]
+    fld = text.TextField()
+    docs_tokens = []
+    for row in range(n):
+        toks = [pool[int(i)] for i in rng.integers(0, len(pool), size=int(rng.integers(0, 12)))]
+        docs_tokens.append(toks)
+        fld.set_row_tokens(row, toks)
+    fld.postings(n)
+    by_id = fld.terms_in_id_order()
+
+    def expand(tok, me):
+        hits = [(t, fuzzy.osa_distance(tok, term)) for t, term in enumerate(by_id)]
+        hits = [(t, e) for t, e in hits if e <= me]
+        return np.array([t for t, _ in hits], dtype=np.int64), np.array([e for _, e in hits], dtype=np.int64)
+
+    terms = sorted({t for toks in docs_tokens for t in toks})
+    tid = {t: i for i, t in enumerate(terms)}
+    idx = bm25.BM25Index.from_token_ids([[tid[t] for t in toks] for toks in docs_tokens], len(terms))
+    query = " ".join(pool[int(i)] for i in rng.integers(0, len(pool), size=3)) + " zzzz q"
+    ids, ws = fld.fuzzy_weighted_terms(query, boost, expand)
+    o_ids, o_ws = fuzzy.weighted_terms(idx, terms, analyzer.analyze(query), boost)
+    assert [by_id[t] for t in ids] == [terms[t] for t in o_ids]
+    assert [np.float32(w) for w in ws] == list(o_ws)
+    e_ids, e_ws = fld.exact_weighted_terms(analyzer.analyze(query), boost)
+    want = [(t, np.float32(np.float32(boost) * idx.idf(tid[t]))) for t in analyzer.analyze(query) if t in tid]
+    assert [(by_id[t], w) for t, w in zip(e_ids, e_ws)] == want
