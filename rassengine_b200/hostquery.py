@@ -439,6 +439,10 @@ class HostSearcher:
                     conv = [(_parse_date(x, self.now).timestamp() if is_date and x is not None and
                              _parse_date(x, self.now) is not None else
                              (float(x) if isinstance(x, (int, float)) else None)) for x in raw]
+                    if not is_date and any(isinstance(x, str) for x in raw):
+                        # keyword field: lexicographic order of the values (their rank among the distinct values)
+                        rank = {v: float(i) for i, v in enumerate(sorted({x for x in raw if isinstance(x, str)}))}
+                        conv = [rank.get(x) if isinstance(x, str) else None for x in raw]
                     missing = np.array([c is None for c in conv], dtype=bool)
                     vals = np.array([0.0 if c is None else c for c in conv], dtype=np.float64)
                 keys.append(np.where(missing, np.inf, -vals if desc else vals))      # missing values sort last
