@@ -49,7 +49,8 @@ def byte4_to_int(b: int) -> int:
     return _NUM_FREE + _int4_to_long(b - _NUM_FREE)
 
 
-LENGTH_TABLE = np.array([byte4_to_int(b) for b in range(256)], dtype=np.float32)
+_DECODED = np.array([byte4_to_int(b) for b in range(256)], dtype=np.int64)
+LENGTH_TABLE = _DECODED.astype(np.float32)       # what BM25Similarity multiplies with (float)
 
 
 def encode_lengths(lengths: np.ndarray) -> np.ndarray:
@@ -57,6 +58,6 @@ def encode_lengths(lengths: np.ndarray) -> np.ndarray:
     lengths = np.asarray(lengths, dtype=np.int64)
     if lengths.size and lengths.min() < 0:
         raise ValueError("negative length")
-    # LENGTH_TABLE is strictly increasing: largest byte whose decoded value <= length
-    table = LENGTH_TABLE.astype(np.int64)
-    return (np.searchsorted(table, lengths, side="right") - 1).astype(np.uint8)
+    # the decoded values are strictly increasing: largest byte whose decoded value <= length (the integer table, not
+    # its float image, which rounds above 2^24)
+    return (np.searchsorted(_DECODED, lengths, side="right") - 1).astype(np.uint8)
