@@ -145,3 +145,60 @@ def test_aggregations_collapse_sort_and_ranges(setup):
     assert [h["_id"] for h in client.search(index=name, body=body)["hits"]["hits"]] == ["c1", "c2", "c4"]
     with pytest.raises(NotImplementedError):
         client.search(index=name, body={"query": {"more_like_this": {"fields": ["x"], "like": "y"}}})
+
+
+# ---- random bool trees of keyword filters against plain python set logic -------------------------------------------
+from hypothesis import given, settings, strategies as st   # noqa: E402
+
+_FILTER_FIELDS = {"patientId": ["pat-1", "pat-2", "pat-3", "pat-4", "pat-9"],
+                  "doc_type": ["structured", "unstructured", "other"],
+                  "resourceType": ["Patient", "Condition", "Practitioner"],
+                  "conditionClinicalStatus": ["active", "resolved"]}
+
+
+def _leaf():
+    def term(f):
+        return st.sampled_from(_FILTER_FIELDS[f]).map(lambda v: {"term": {f: v}})
+
+    def terms(f):
+        return st.lists(st.sampled_from(_FILTER_FIELDS[f]), min_size=1, max_size=3).map(lambda vs: {"terms": {f: vs}})
+    fields = st.sampled_from(sorted(_FILTER_FIELDS))
+    return st.one_of(fields.flatmap(term), fields.flatmap(terms), fields.map(lambda f: {"exists": {"field": f}}))
+
+
+def _tree():
+    def bool_of(children):
+        return st.fixed_dictionaries({}, optional={
+            "must": st.lists(children, min_size=1, max_size=2), "filter": st.lists(children, min_size=1, max_size=2),
+            "must_not": st.lists(children, min_size=1, max_size=2), "should": st.lists(children, min_size=1, max_size=3),
+        }).filter(lambda d: d).map(lambda d: {"bool": d})
+    return st.recursive(_leaf(), bool_of, max_leaves=8)
+
+
+def _naive(node, doc):
+    (kind, body), = node.items()
+    if kind == "term":
+        (f, v), = body.items()
+        return doc.get(f) == v
+    if kind == "terms":
+        (f, vs), = body.items()
+        return doc.get(f) in vs
+    if kind == "exists":
+        return doc.get(body["field"]) is not None
+    ok = all(_naive(c, doc) for c in body.get("must", []) + body.get("filter", []))
+    ok = ok and not any(_naive(c, doc) for c in body.get("must_not", []))
+    if "should" in body:
+        need = 0 if ("must" in body or "filter" in body) else 1          # Lucene's default minimum_should_match
+        ok = ok and sum(_naive(c, doc) for c in body["should"]) >= need
+    return ok
+
+
+@pytest.mark.filterwarnings("ignore::hypothesis.errors.HypothesisWarning")
+@settings(max_examples=150, deadline=None, derandomize=True)
+@given(_tree())
+def test_random_bool_trees_of_keyword_filters_match_set_logic(setup, query):
+    client, name, *_ = setup
+    body = {"size": 50, "sort": [{"doc_id": "asc"}], "query": query}
+    got = [h["_id"] for h in client.search(index=name, body=body)["hits"]["hits"]]
+    want = sorted(d["doc_id"] for d in DOCS if _naive(query, d))
+    assert got == want, query
