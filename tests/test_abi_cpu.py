@@ -52,3 +52,36 @@ def test_invalid_arguments_are_rejected_before_cuda(lib):
     assert lib.rass_create(1024, 7, 0, 0, 0, ctypes.byref(h)) == -1
     assert lib.rass_create(1024, 0, 0, 0, 3, ctypes.byref(h)) == -1
     assert lib.rass_count(None, None) == -1
+
+
+def _declarations():
+    """name -> list of parameter declarations, parsed from the header (comments stripped)."""
+    text = open(os.path.join(ROOT, "include", "rass_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for ret, name, params in re.findall(r"\b(int|const char\s*\*)\s*(rass_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = " ".join(params.split())
+        out[name] = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+    return out
+
+
+def test_ctypes_prototypes_follow_the_header():
+    """The Python binding (what INTEGRATION.md shows a maintainer) must not drift from include/rass_b200.h: same
+    arity, pointers bound as pointers, 64-bit integers as 64-bit, the status / string return types."""
+    import ctypes as C
+    from rassengine_b200 import _capi
+    decl = _declarations()
+    assert set(decl) == set(_capi.PROTOTYPES), set(decl) ^ set(_capi.PROTOTYPES)
+    for name, params in decl.items():
+        res, args = _capi.PROTOTYPES[name]
+        assert len(params) == len(args), (name, params, args)
+        for p, a in zip(params, args):
+            is_ptr = "*" in p
+            bound_ptr = a in (C.c_void_p, C.c_char_p) or (isinstance(a, type) and issubclass(a, C._Pointer))
+            assert is_ptr == bound_ptr, (name, p, a)
+            if not is_ptr:
+                base = p.rsplit(" ", 1)[0].replace("const ", "").strip()
+                want = {"int": C.c_int, "int64_t": C.c_int64, "uint32_t": C.c_uint32, "float": C.c_float,
+                        "double": C.c_double, "size_t": C.c_size_t}[base]
+                assert a is want, (name, p, a)
+        assert res is (C.c_char_p if name in ("rass_version", "rass_last_error") else C.c_int), name
