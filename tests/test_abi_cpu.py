@@ -85,3 +85,23 @@ def test_ctypes_prototypes_follow_the_header():
                         "double": C.c_double, "size_t": C.c_size_t}[base]
                 assert a is want, (name, p, a)
         assert res is (C.c_char_p if name in ("rass_version", "rass_last_error") else C.c_int), name
+
+
+def test_stats_struct_and_constants_follow_the_header():
+    import ctypes as C
+    from rassengine_b200 import _capi
+    text = open(os.path.join(ROOT, "include", "rass_b200.h")).read()
+    body = re.search(r"typedef struct rass_stats \{(.*?)\} rass_stats;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = [tuple(f.split()) for f in body.split(";") if f.strip()]
+    ctype = {"double": C.c_double, "int64_t": C.c_int64, "int32_t": C.c_int32}
+    assert [(n, ctype[t]) for t, n in fields] == list(_capi.RassStats._fields_)
+    # enumerators / defines the binding mirrors as module constants
+    consts = dict(re.findall(r"\b(RASS_[A-Z0-9_]+)\s*=\s*(-?\d+)", text))
+    consts.update(dict(re.findall(r"#define\s+(RASS_[A-Z0-9_]+)\s+(-?\d+)\b", text)))
+    mirrored = {"RASS_PATH_AUTO": "PATH_AUTO", "RASS_PATH_STREAM": "PATH_STREAM", "RASS_PATH_UMMA": "PATH_UMMA",
+                "RASS_PATH_EXACT": "PATH_EXACT", "RASS_PATH_GEMM": "PATH_GEMM", "RASS_METRIC_COSINE": "METRIC_COSINE",
+                "RASS_METRIC_L2": "METRIC_L2", "RASS_OPT_KNN_PREFILTER": "OPT_KNN_PREFILTER", "RASS_E_AGAIN": "RASS_E_AGAIN"}
+    for c_name, py_name in mirrored.items():
+        assert c_name in consts, c_name
+        assert int(consts[c_name]) == getattr(_capi, py_name), c_name
