@@ -272,3 +272,63 @@ def test_host_fuzzy_rewrite_equals_the_oracle(n, seed, boost):
     e_ids, e_ws = fld.exact_weighted_terms(analyzer.analyze(query), boost)
     want = [(t, np.float32(np.float32(boost) * idx.idf(tid[t]))) for t in analyzer.analyze(query) if t in tid]
     assert [(by_id[t], w) for t, w in zip(e_ids, e_ws)] == want
+
+
+def _bf16(a):
+    """float32 -> nearest-even bfloat16, returned as float32 (what store_convert_kernel / query_prep_kernel keep)."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).reshape(np.shape(a))
+
+
+@SLOW
+@given(st.integers(1, 200), st.sampled_from([8, 64, 256, 1024]), st.integers(0, 2**31 - 1), st.sampled_from([1e-3, 1.0, 50.0]))
+def test_certificate_error_allowance_bounds_the_bf16_scan_error(n, d, seed, scale):
+    """The premise of the certificate in finish.cu: for every row, |scan key - exact key| <= eps with
+    eps = rho_x (1 + rho_q) + rho_q + d 2^-23, rho = relative bf16 rounding residual of the rows / of the query
+    (Cauchy-Schwarz), the last term covering the fp32 accumulation and the scale multiply.  Checked in numpy: bf16
+    operands, float32 accumulation, key = dot * float(1 / ||x||), against the fp64 cosine of the stored fp32 values."""
+    rng = np.random.default_rng(seed)
+    X = (rng.standard_normal((n, d)) * scale * rng.uniform(0.2, 3.0, size=(n, 1))).astype(np.float32)
+    q = rng.standard_normal(d).astype(np.float32)
+    X64, q64 = X.astype(np.float64), q.astype(np.float64)
+    xn = np.sqrt((X64 * X64).sum(axis=1))
+    q_hat = (q64 / np.sqrt((q64 * q64).sum())).astype(np.float32)
+    X16, q16 = _bf16(X), _bf16(q_hat)
+    rho_x = float((np.sqrt(((X64 - X16.astype(np.float64)) ** 2).sum(axis=1)) / xn).max())
+    qh64 = q_hat.astype(np.float64)
+    rho_q = float(np.sqrt(((qh64 - q16.astype(np.float64)) ** 2).sum()) / np.sqrt((qh64 * qh64).sum()))
+    eps = (rho_x * (1.0 + rho_q) + rho_q + d * 2.0 ** -23) * 1.0001
+    acc = np.zeros(n, dtype=np.float32)
+    for j in range(d):                                   # float32 accumulation, the plainest order
+        acc = (acc + X16[:, j] * q16[j]).astype(np.float32)
+    key = acc * (1.0 / xn).astype(np.float32)
+    exact = knn.cos64(X, q)
+    assert np.abs(key.astype(np.float64) - exact).max() <= eps
+    assert rho_x <= 2.0 ** -8 and rho_q <= 2.0 ** -8      # bf16 keeps 8 significant bits
+
+
+@SLOW
+@given(st.integers(1, 200), st.sampled_from([8, 64, 256, 1024]), st.integers(0, 2**31 - 1), st.sampled_from([1e-2, 1.0, 20.0]))
+def test_certificate_error_allowance_l2(n, d, seed, scale):
+    """Same premise for the L2 metric: scan key = dot(bf16 x, bf16 q) - fl32(||x||^2 / 2), exact surrogate
+    (||q||^2 - d^2) / 2 = x.q - ||x||^2 / 2; the allowance scales with max ||x|| * ||q|| and adds the rounding of the
+    per-row offset (finish.cu)."""
+    rng = np.random.default_rng(seed)
+    X = (rng.standard_normal((n, d)) * scale * rng.uniform(0.2, 3.0, size=(n, 1))).astype(np.float32)
+    q = (rng.standard_normal(d) * rng.uniform(0.1, 4.0)).astype(np.float32)
+    X64, q64 = X.astype(np.float64), q.astype(np.float64)
+    n2 = (X64 * X64).sum(axis=1)
+    xn, qn = np.sqrt(n2), float(np.sqrt((q64 * q64).sum()))
+    X16, q16 = _bf16(X), _bf16(q)
+    rho_x = float((np.sqrt(((X64 - X16.astype(np.float64)) ** 2).sum(axis=1)) / xn).max())
+    rho_q = float(np.sqrt(((q64 - q16.astype(np.float64)) ** 2).sum()) / qn)
+    xm = float(xn.max())
+    e = rho_x * (1.0 + rho_q) + rho_q + d * 2.0 ** -23
+    eps = (e * xm * qn * 1.0001 + 6.0e-8 * xm * xm) * 1.0001
+    acc = np.zeros(n, dtype=np.float32)
+    for j in range(d):
+        acc = (acc + X16[:, j] * q16[j]).astype(np.float32)
+    key = (acc + (-0.5 * n2).astype(np.float32)).astype(np.float32)
+    exact = (X64 * q64[None, :]).sum(axis=1) - 0.5 * n2
+    assert np.abs(key.astype(np.float64) - exact).max() <= eps
