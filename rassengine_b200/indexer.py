@@ -127,6 +127,44 @@ def store_chunks(client, index_name: str, docs: List[Dict], embeddings: np.ndarr
     return ok, errors
 
 
+async def store_fhir_docs_in_opensearch(structured_docs: List[Dict], unstructured_docs: List[Dict], client,
+                                        index_name: str, embed=None) -> None:
+    """The reference's ingest entry point under its own name, signature and error behaviour
+    (app/main.py:1211-1282; app/embedding_gen.py:1061-1132): structured documents first, then the chunks with their
+    embeddings, nothing raised to the caller.  `embed` stands for the reference's `embed_texts_in_batches`
+    (app/main.py:1247-1248, the Ollama client -- outside the retrieval path): an async or plain callable
+    `(texts, batch_size=...) -> float32 [n, dim]`; a host app passes its own or assigns `indexer.embed_texts_in_batches`.
+    The float32 rows go to the engine as numpy views (no `.tolist()` / JSON detour): the stored
+    values are the ones the reference would store."""
+    if not client:
+        print("[store_fhir_docs_in_opensearch] No OS client.")
+        return
+    ensure_index_exists(client, index_name)
+    if structured_docs:
+        try:
+            ok, errors = store_structured(client, index_name, structured_docs)
+            logger.info("Indexed %d structured docs, errors: %s", ok, errors)
+        except Exception as exc:
+            logger.error("Structured docs indexing error: %s", exc)
+    if not unstructured_docs:
+        return
+    try:
+        fn = embed or embed_texts_in_batches
+        if fn is None:
+            raise RuntimeError("no embedding function: pass embed= or assign indexer.embed_texts_in_batches")
+        out = fn([d["unstructuredText"] for d in unstructured_docs], batch_size=BATCH_SIZE)
+        if hasattr(out, "__await__"):
+            out = await out
+        ok, errors = store_chunks(client, index_name, unstructured_docs, np.asarray(out, dtype=np.float32),
+                                  as_lists=False)
+        logger.info("Indexed %d unstructured docs, errors: %s", ok, errors)
+    except Exception as exc:
+        logger.error("Unstructured docs indexing error: %s", exc)
+
+
+embed_texts_in_batches = None     # the host application's embedding client (app/main.py:240-262), assigned by it
+
+
 class B200Indexer:
     text_fields = TEXT_FIELDS
     keyword_fields = KEYWORD_FIELDS

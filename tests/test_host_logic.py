@@ -313,3 +313,67 @@ def test_dsl_text_only_and_fuzziness_shapes():
                 {"_source": ["patientId"], "query": {"match_all": {}}}):
         with pytest.raises(NotImplementedError):
             dsl.parse_search_body(bad)
+
+
+def test_store_fhir_docs_entry_point_keeps_the_reference_shape():
+    """store_fhir_docs_in_opensearch(structured_docs, unstructured_docs, client, index_name): structured documents in
+    one bulk call, chunks normalised like app/main.py:1250-1251 and flushed in BATCH_SIZE bulks with `_id = doc_id` and
+    `_routing = patientId`; async, returns None, swallows errors.  A recording client stands in for the engine."""
+    import asyncio
+    import inspect
+    from rassengine_b200 import indexer as ix
+
+    class Indices:
+        def __init__(self):
+            self.created = []
+
+        def exists(self, name):
+            return name in self.created
+
+        def create(self, index, body=None):
+            self.created.append(index)
+
+    class Recorder:
+        def __init__(self, fail=False):
+            self.indices, self.calls, self.fail = Indices(), [], fail
+
+        def bulk_actions(self, actions):
+            if self.fail:
+                raise RuntimeError("boom")
+            self.calls.append(list(actions))
+            return len(actions), []
+
+    assert inspect.iscoroutinefunction(ix.store_fhir_docs_in_opensearch)
+    assert list(inspect.signature(ix.store_fhir_docs_in_opensearch).parameters)[:4] == \
+        ["structured_docs", "unstructured_docs", "client", "index_name"]
+    structured = [{"doc_id": f"s{i}", "doc_type": "structured", "patientId": "pat-1"} for i in range(3)]
+    n = ix.BATCH_SIZE + 5
+    chunks = [{"doc_id": f"c{i}", "doc_type": "unstructured", "patientId": "pat-2", "unstructuredText": f"text {i}"}
+              for i in range(n)]
+    raw = np.random.default_rng(3).standard_normal((n, 8)).astype(np.float32) * 7
+    seen = {}
+
+    async def embed(texts, batch_size):
+        seen["texts"], seen["batch_size"] = list(texts), batch_size
+        return raw
+
+    c = Recorder()
+    assert asyncio.run(ix.store_fhir_docs_in_opensearch(structured, chunks, c, "idx", embed=embed)) is None
+    assert c.indices.created == ["idx"]
+    assert seen == {"texts": [d["unstructuredText"] for d in chunks], "batch_size": ix.BATCH_SIZE}
+    assert [len(b) for b in c.calls] == [3, ix.BATCH_SIZE, 5]
+    first = c.calls[0][0]
+    assert first == {"_op_type": "index", "_index": "idx", "_id": "s0", "_source": structured[0], "_routing": "pat-1"}
+    want = raw / (np.linalg.norm(raw, axis=1, keepdims=True) + 1e-9)
+    got = np.stack([a["_source"]["embedding"] for b in c.calls[1:] for a in b])
+    assert got.dtype == np.float32 and np.array_equal(got, want.astype(np.float32))
+    assert [a["_id"] for b in c.calls[1:] for a in b] == [d["doc_id"] for d in chunks]
+    assert "embedding" not in chunks[0]                  # the caller's dicts are left alone
+    # plain (non-async) embedders work too; failures are logged, never raised (app/main.py:1239-1240, 1275-1276)
+    c2 = Recorder()
+    asyncio.run(ix.store_fhir_docs_in_opensearch([], chunks[:2], c2, "idx", embed=lambda t, batch_size: raw[:2]))
+    assert [len(b) for b in c2.calls] == [2]
+    asyncio.run(ix.store_fhir_docs_in_opensearch(structured, chunks, Recorder(fail=True), "idx", embed=embed))
+    asyncio.run(ix.store_fhir_docs_in_opensearch(structured, chunks, c2, "idx"))       # no embedder: logged, structured stored
+    assert len(c2.calls) == 2 and len(c2.calls[1]) == 3
+    asyncio.run(ix.store_fhir_docs_in_opensearch(structured, chunks, None, "idx"))
