@@ -149,6 +149,12 @@ int rass_search_knn_dev_wait(rass_engine* h, int slot, rass_stats* stats);
 int rass_merge_topk_dev(rass_engine* h, const double* keys_dev, const int64_t* rows_dev, int64_t shard_stride,
                         int G, int B, int k, int64_t* out_rows_dev, float* out_scores_dev, double* out_keys_dev);
 
+/* The same merge for the per-shard FUSED lists of a row-sharded hybrid query (rass_fuse_hybrid_dev's out_keys_dev /
+ * out_rows_dev): the keys are bool.should scores, larger is better whatever the engine's vector metric is, and the
+ * merged score is the key itself (app/main.py:1574-1598 executed per shard, merged by the coordinator). */
+int rass_merge_scores_dev(rass_engine* h, const double* scores_dev, const int64_t* rows_dev, int64_t shard_stride,
+                          int G, int B, int k, int64_t* out_rows_dev, float* out_scores_dev, double* out_keys_dev);
+
 /* CSR postings of the text field: indptr[V+1], doc[nnz] (local rows, ascending per term), tf[nnz], doclen[N]
  * (token count per row).  Statistics (docCount, sumTotalTermFreq, df) are taken from these arrays unless the
  * global_* overrides are given (row-sharded corpora share global statistics so scores are shard-invariant). */

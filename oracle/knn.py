@@ -103,6 +103,45 @@ def knn_exact_full(X: np.ndarray, Q: np.ndarray, k: int, metric: int = COSINE,
     return out_rows, out_key, score
 
 
+def _row_norms64(X: np.ndarray, block: int = 1024) -> np.ndarray:
+    """||x||_2 of every row, accumulated in fp64, in cache-sized row blocks (no n x d fp64 temporary)."""
+    out = np.empty(X.shape[0], dtype=np.float64)
+    for c0 in range(0, X.shape[0], block):
+        x64 = X[c0:c0 + block].astype(np.float64)
+        out[c0:c0 + block] = np.sqrt(np.einsum("ij,ij->i", x64, x64))
+    return out
+
+
+def merge_topk(parts, k: int, metric: int = COSINE):
+    """Top-k of the union of per-row-range top-k lists: parts = [(rows int64 [B, k_i], key64 [B, k_i]), ...] with
+    GLOBAL row ids (-1 = empty slot).  Ranking (cos desc | d^2 asc, row asc) -- what a coordinator does with the
+    per-shard lists (app/main.py:357).  Returns rows [B, k'], key64 [B, k'], score32 [B, k'], k' = min(k, #entries)."""
+    rows = np.concatenate([np.asarray(r, dtype=np.int64) for r, _ in parts], axis=1)
+    keys = np.concatenate([np.asarray(v, dtype=np.float64) for _, v in parts], axis=1)
+    B = rows.shape[0]
+    kk = min(k, int((rows >= 0).sum(axis=1).min())) if rows.size else 0
+    out_rows = np.full((B, kk), -1, dtype=np.int64)
+    out_key = np.zeros((B, kk), dtype=np.float64)
+    for b in range(B):
+        ok = rows[b] >= 0
+        r, v = rows[b][ok], keys[b][ok]
+        sel = _rank(v if metric == COSINE else -v, r, kk)
+        out_rows[b], out_key[b] = r[sel], v[sel]
+    score = score_from_cos(out_key) if metric == COSINE else score_from_l2sq(out_key)
+    return out_rows, out_key, score
+
+
+def knn_exact_stream(chunks, Q: np.ndarray, k: int, metric: int = COSINE):
+    """knn_exact over a corpus that arrives as (first_global_row, X_chunk) pieces (a 10M x 1024 corpus does not fit
+    one numpy array comfortably): exact top-k per piece, merged by the same total order.  Identical to knn_exact on
+    the concatenation -- the top-k of a union is the top-k of the per-part top-k lists."""
+    parts = []
+    for base, X in chunks:
+        r, key, _ = knn_exact(X, Q, k, metric)
+        parts.append((np.where(r >= 0, r + int(base), -1), key))
+    return merge_topk(parts, k, metric)
+
+
 def knn_exact(X: np.ndarray, Q: np.ndarray, k: int, metric: int = COSINE,
               alive: np.ndarray | None = None, chunk: int = 262144, guard: int = 8):
     """Same result as knn_exact_full, computed as an fp32 BLAS prefilter plus an
@@ -128,7 +167,7 @@ def knn_exact(X: np.ndarray, Q: np.ndarray, k: int, metric: int = COSINE,
         return out_rows, out_key, np.zeros((B, 0), dtype=np.float32)
 
     # fp32 surrogate: cosine -> dot(x, qhat) / ||x||;  L2 -> dot(x,q) - 0.5||x||^2 (monotone in -d^2)
-    xn32 = np.linalg.norm(X.astype(np.float64), axis=1)
+    xn32 = _row_norms64(X)
     if metric == COSINE:
         qn = np.linalg.norm(Q.astype(np.float64), axis=1)
         Qs = (Q / np.where(qn > 0, qn, 1.0)[:, None]).astype(np.float32)

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "rass_search_knn_dev_async": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P]),
     "rass_search_knn_dev_wait": (C.c_int, [_P, C.c_int, C.POINTER(RassStats)]),
     "rass_merge_topk_dev": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "rass_merge_scores_dev": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "rass_bm25_build": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
     "rass_search_hybrid": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_float, C.c_float, C.c_int, _P, _P,
                                      C.POINTER(RassStats)]),

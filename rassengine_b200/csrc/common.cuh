@@ -420,8 +420,10 @@ int launch_finish(rass_engine* h, int g0, int ng, int k, int n_segs, int seg_siz
 // fp64 scan of the listed queries (qids host array, n_q of them)
 int launch_exact(rass_engine* h, int k, const int* qids_host, int n_q, int64_t* out_rows, float* out_scores,
                  double* out_keys, cudaStream_t st, int* launches);
+// raw_score: the keys are fused scores (larger is better whatever the engine's metric), emitted as they are
 int launch_merge_topk(rass_engine* h, const double* keys, const int64_t* rows, int64_t shard_stride, int G, int B,
-                      int k, int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st);
+                      int k, int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st,
+                      bool raw_score = false);
 int ensure_query_workspace(rass_engine* h, int B);
 int ensure_pool(rass_engine* h, size_t entries_per_query, size_t segs_per_query, size_t n_queries = RASS_GROUP_Q);
 int ensure_xlist_workspace(rass_engine* h, size_t entries);

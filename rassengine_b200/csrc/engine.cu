@@ -886,6 +886,17 @@ extern "C" int rass_merge_topk_dev(rass_engine* h, const double* keys_dev, const
   return RASS_OK;   // enqueued on the engine stream; the caller synchronises (rass_sync) when it needs the result
 }
 
+// the same merge for per-shard FUSED hybrid lists: the keys are raw scores, larger is better whatever the vector metric
+extern "C" int rass_merge_scores_dev(rass_engine* h, const double* scores_dev, const int64_t* rows_dev,
+                                     int64_t shard_stride, int G, int B, int k, int64_t* out_rows_dev,
+                                     float* out_scores_dev, double* out_keys_dev) {
+  CHECK_HANDLE(h);
+  if (!scores_dev || !rows_dev || !out_rows_dev || !out_scores_dev || G < 1 || B < 1 || k < 1)
+    return rass_fail(h, RASS_E_INVALID, "bad merge arguments");
+  return launch_merge_topk(h, scores_dev, rows_dev, shard_stride, G, B, k, out_rows_dev, out_scores_dev, out_keys_dev,
+                           eng_stream(h), true);
+}
+
 // bool.filter of the next hybrid queries as a per-row pass mask (NULL clears it)
 extern "C" int rass_set_row_filter(rass_engine* h, const uint8_t* mask_host, int64_t n) {
   CHECK_HANDLE(h);

@@ -460,7 +460,7 @@ int launch_select_batch(rass_engine* h, size_t entries, int B, int k, int64_t* o
 __global__ void __launch_bounds__(256) merge_topk_kernel(const double* __restrict__ keys,
                                                          const int64_t* __restrict__ rows, int64_t shard_stride,
                                                          int G, int B, int k,
-                                                         int metric, int64_t* __restrict__ out_rows,
+                                                         int metric, int raw_score, int64_t* __restrict__ out_rows,
                                                          float* __restrict__ out_scores,
                                                          double* __restrict__ out_keys) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const double* __restric
     const int g = i / k, j = i % k;
     const size_t src = (size_t)g * shard_stride + (size_t)q * k + j;
     const double v = keys[src];
-    sk[i] = metric == RASS_METRIC_COSINE ? v : -v;
+    sk[i] = (raw_score || metric == RASS_METRIC_COSINE) ? v : -v;     // raw fused scores: larger is better
     sr[i] = rows[src];
   }
   __syncthreads();
@@ -489,8 +489,8 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const double* __restric
     if (rank < k) {
       const size_t o = (size_t)q * k + rank;
       out_rows[o] = r;
-      out_scores[o] = score_from_key(key, metric);
-      if (out_keys) out_keys[o] = metric == RASS_METRIC_COSINE ? key : -key;
+      out_scores[o] = raw_score ? (float)key : score_from_key(key, metric);
+      if (out_keys) out_keys[o] = (raw_score || metric == RASS_METRIC_COSINE) ? key : -key;
     }
   }
   // pad: count the valid entries (every thread, cheap) and blank the tail
@@ -504,13 +504,13 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const double* __restric
 }
 
 int launch_merge_topk(rass_engine* h, const double* keys, const int64_t* rows, int64_t shard_stride, int G, int B,
-                      int k, int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st) {
+                      int k, int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st, bool raw_score) {
   if (shard_stride <= 0) shard_stride = (int64_t)B * k;
   const size_t smem = (size_t)G * k * 16;
   if (smem > 200 * 1024) return rass_fail(h, RASS_E_INVALID, "merge of %d lists of %d exceeds shared memory", G, k);
   CUDA_TRY(h, cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_topk_kernel<<<B, 256, smem, st>>>(keys, rows, shard_stride, G, B, k, h->metric, out_rows, out_scores,
-                                          out_keys);
+  merge_topk_kernel<<<B, 256, smem, st>>>(keys, rows, shard_stride, G, B, k, h->metric, raw_score ? 1 : 0, out_rows,
+                                          out_scores, out_keys);
   CUDA_TRY(h, cudaGetLastError());
   return RASS_OK;
 }

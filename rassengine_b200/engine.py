@@ -109,6 +109,10 @@ class Engine:
         self._check(self._lib.rass_read_rows(self._h, first, n, _ptr(out)))
         return out
 
+    def read_rows_into(self, first: int, n: int, out_ptr: int):
+        """Same into caller memory ([n, dim] fp32, e.g. a pinned buffer: the copy then runs at PCIe rate)."""
+        self._check(self._lib.rass_read_rows(self._h, first, n, C.c_void_p(out_ptr)))
+
     def read_rows_list(self, rows) -> np.ndarray:
         rows = np.ascontiguousarray(rows, dtype=np.int64)
         out = np.empty((rows.size, self.dim), dtype=np.float32)
@@ -168,6 +172,14 @@ class Engine:
                                                   G, B, k,
                                                   C.c_void_p(out_rows_ptr), C.c_void_p(out_scores_ptr),
                                                   C.c_void_p(out_keys_ptr) if out_keys_ptr else None))
+
+    def merge_scores_dev(self, scores_ptr: int, rows_ptr: int, G: int, B: int, k: int, out_rows_ptr: int,
+                         out_scores_ptr: int, out_keys_ptr: int = 0, shard_stride: int = 0):
+        """merge_topk_dev for fused hybrid lists: raw scores, larger is better whatever the vector metric."""
+        self._check(self._lib.rass_merge_scores_dev(self._h, C.c_void_p(scores_ptr), C.c_void_p(rows_ptr),
+                                                    shard_stride, G, B, k, C.c_void_p(out_rows_ptr),
+                                                    C.c_void_p(out_scores_ptr),
+                                                    C.c_void_p(out_keys_ptr) if out_keys_ptr else None))
 
     # -- text -------------------------------------------------------------------------------------------
     def bm25_build(self, indptr, doc, tf, doclen, global_doc_count: int = 0, global_sum_ttf: int = 0,

@@ -34,13 +34,15 @@ class _DeviceOps:
                                    packed[0].data_ptr())
         return self.engine.last_stats
 
-    def merge(self, gathered, world, B, k, out_rows, out_scores, out_keys=None, stride=None, stream=None):
-        """gathered: every rank's packed buffer in rank order ([2, B, k] int64 each, `stride` elements apart)."""
+    def merge(self, gathered, world, B, k, out_rows, out_scores, out_keys=None, stride=None, stream=None, raw=False):
+        """gathered: every rank's packed buffer in rank order ([2, B, k] int64 each, `stride` elements apart).
+        raw: the keys are fused hybrid scores (larger is better whatever the vector metric), not cos / d^2."""
         plane = B * k * 8
         if stream is not None:
             self.engine.set_stream(stream)
         try:
-            self.engine.merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + plane, world, B, k,
+            fn = self.engine.merge_scores_dev if raw else self.engine.merge_topk_dev
+            fn(gathered.data_ptr(), gathered.data_ptr() + plane, world, B, k,
                                        out_rows.data_ptr(), out_scores.data_ptr(),
                                        out_keys.data_ptr() if out_keys is not None else 0,
                                        shard_stride=stride or 2 * B * k)
@@ -275,9 +277,9 @@ class ShardedIndex:
         if self.world == 1:
             return b["packed"][1], b["scores"]
         dist.all_gather_into_tensor(b["gathered"], b["packed"], group=self.group)
-        self.ops.merge(b["gathered"], self.world, B, k, b["out_rows"], b["out_scores"], b["out_keys"])
+        self.ops.merge(b["gathered"], self.world, B, k, b["out_rows"], b["out_scores"], b["out_keys"], raw=True)
         self.merge_launches += 1
-        return b["out_rows"], b["out_keys"].to(torch.float32)
+        return b["out_rows"], b["out_scores"]
 
     def search(self, q_host, k: int):
         """Host-buffer flavour: q_host is a pinned or pageable [B, dim] fp32 tensor/array; results come back as

@@ -87,6 +87,22 @@ for b in range(Bh):
     tr, ts = bm25.topk(full.score(qterms[b], boost=4.5), k)
     assert rows_t[b].cpu().tolist() == tr.tolist() and scores_t[b].cpu().tolist() == ts.tolist()
 idx.close()
+
+# ---- the same hybrid on an L2 engine: the fused lists are raw scores (larger is better), whatever the vector metric --
+import rassengine_b200 as rb  # noqa: E402
+idx = ShardedIndex(dim=Dh, metric=rb.METRIC_L2, capacity_rows=hi - lo)
+idx.set_row_base(lo)
+idx.append_dev(torch.from_numpy(Xh[lo:hi]).cuda())
+idx.bm25_build(l_indptr, (doc[mine] - lo).astype(np.int32), tf[mine], doclen[lo:hi])
+rows, scores = idx.search_hybrid_dev(torch.from_numpy(Qh).cuda(), qterms, 4.5, 2.0, k)
+torch.cuda.synchronize()
+rows, scores = rows.cpu().numpy(), scores.cpu().numpy()
+knn_rows, _, knn_scores = knn.knn_exact(Xh, Qh, k, metric=knn.L2)
+for b in range(Bh):
+    wr, ws = fusion.hybrid(full, qterms[b], knn_rows[b], knn_scores[b], 4.5, 2.0, k)
+    assert rows[b, :len(wr)].tolist() == wr.tolist(), f"rank {rank}: sharded L2 hybrid ids differ (query {b})"
+    np.testing.assert_allclose(scores[b, :len(wr)], ws, rtol=2e-6, atol=0)
+idx.close()
 dist.barrier()
 if rank == 0:
     print(f"sharded x{world}: merged top-k identical to the oracle (knn and hybrid)")

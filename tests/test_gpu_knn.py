@@ -205,6 +205,29 @@ def test_unnormalised_rows_and_l2_seeded():
             _check(rows, scores, want_rows, want_scores)
 
 
+@pytest.mark.parametrize("dim", [1024, 768])
+@pytest.mark.parametrize("metric_name", ["cosine", "l2"])
+def test_seeded_threshold_paths_l2_and_dim768(dim, metric_name):
+    """The threshold seed (store.cu) only runs from 8192 rows up, and takes a generic path when dim_pad != 1024; the L2
+    metric scales its bound by the row / query norms.  20k unnormalised rows, both tcgen05 scans, k = 10 and 100."""
+    import rassengine_b200 as rb
+    rng = np.random.default_rng(71 + dim)
+    n = 20000
+    X = (rng.standard_normal((n, dim)) * rng.uniform(0.5, 2.0, size=(n, 1))).astype(np.float32)
+    Q = rng.standard_normal((70, dim)).astype(np.float32)
+    metric, om = (rb.METRIC_COSINE, knn.COSINE) if metric_name == "cosine" else (rb.METRIC_L2, knn.L2)
+    for k in (10, 100):
+        want_rows, _, want_scores = knn.knn_exact(X, Q, k, metric=om)
+        for path in ("umma", "gemm"):
+            with _engine(dim=dim, metric=metric) as e:
+                e.set_path(_paths()[path])
+                e.append(X)
+                rows, scores = e.search_knn(Q, k)
+                st = e.last_stats
+            _check(rows, scores, want_rows, want_scores)
+            assert st["n_certified"] + st["n_fallback"] == Q.shape[0], st
+
+
 def test_merge_topk_matches_single_shard():
     """Row-sharded corpus: per-shard top-k merged on the device equals the single-engine answer."""
     import torch
@@ -374,6 +397,12 @@ def test_properties_at_2m_rows_all_paths_agree():
             np.testing.assert_array_equal(s_gemm[:130], s_umma)            # same fp64 rerank -> same float scores
             assert (np.diff(s_gemm, axis=1) <= 0).all()
             assert all(len(set(r.tolist())) == k for r in r_gemm) and r_gemm.min() >= 0 and r_gemm.max() < n
+        # the CPU oracle over all 2M rows (read back from the device store) for 8 of the queries, top-100: the merged
+        # chain "fast path == fp64 GPU scan == CPU oracle" closed at a size the 100k fixtures do not reach
+        qh = q[:8].cpu().numpy()
+        want_rows, _, want_scores = knn.knn_exact_stream(
+            ((c0, e.read_rows(c0, 250_000)) for c0 in range(0, n, 250_000)), qh, 100)
+        _check(r_gemm[:8], s_gemm[:8], want_rows, want_scores)
         best = int(r_gemm[0, 0])
         e.tombstone(best)
         r2, _ = run(rb.PATH_UMMA, 64, 10)

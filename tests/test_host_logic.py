@@ -113,7 +113,8 @@ class OracleOps:                          # CPU test double for the device ops: 
         r, key, s = knn.knn_exact(self.X, q.numpy(), k)
         packed[1].copy_(torch.from_numpy(r + self.base)); scores.copy_(torch.from_numpy(s))
         packed[0].copy_(torch.from_numpy(key).view(torch.int64))
-    def merge(self, gathered, world, B, k, out_rows, out_scores, out_keys=None, stride=None, stream=None):
+    def merge(self, gathered, world, B, k, out_rows, out_scores, out_keys=None, stride=None, stream=None, raw=False):
+        assert not raw
         g = gathered.view(world, -1)[:, :2 * B * k].reshape(world, 2, B, k)
         keys = g[:, 0].contiguous().view(torch.float64).numpy(); rows = g[:, 1].numpy()
         for b in range(B):
@@ -179,7 +180,9 @@ class HybridOps(OracleOps):
             kk[:order.size] = final[order].astype(np.float64)
             packed[1][b] = torch.from_numpy(rr); packed[0][b] = torch.from_numpy(kk).view(torch.int64)
             scores[b] = torch.from_numpy(kk.astype(np.float32))
-    def merge(self, gathered, world, B, k, out_rows, out_scores, out_keys=None, stride=None, stream=None):
+    def merge(self, gathered, world, B, k, out_rows, out_scores, out_keys=None, stride=None, stream=None, raw=False):
+        if not raw:                       # the knn list: the base class's cosine merge
+            return OracleOps.merge(self, gathered, world, B, k, out_rows, out_scores, out_keys, stride, stream)
         g = gathered.view(world, 2, B, k)
         keys = g[:, 0].contiguous().view(torch.float64).numpy(); rows = g[:, 1].numpy()
         for b in range(B):
@@ -189,7 +192,7 @@ class HybridOps(OracleOps):
             out_rows[b, :order.size] = torch.from_numpy(rr[order]); out_rows[b, order.size:] = -1
             if out_keys is not None:
                 out_keys[b, :order.size] = torch.from_numpy(kk[order]); out_keys[b, order.size:] = 0
-            out_scores[b, :order.size] = torch.from_numpy((1 / (2 - np.clip(kk[order], -1, 1))).astype(np.float32))
+            out_scores[b, :order.size] = torch.from_numpy(kk[order].astype(np.float32))     # raw fused scores
 
 hidx = ShardedIndex(dim=64, ops=HybridOps(X[lo:hi], lo))
 term_of = np.repeat(np.arange(300), np.diff(ip)); mine = (dc >= lo) & (dc < hi)
