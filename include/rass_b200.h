@@ -206,10 +206,12 @@ int rass_fuse_hybrid(rass_engine* h, int B, const int32_t* qterm_indptr, const i
                      const float* qweights, const uint8_t* qflags, float w_text, const int64_t* knn_rows_host,
                      const float* knn_scores_host, float w_knn, int k, int64_t* out_rows, float* out_scores);
 
-/* The term dictionary of the text field, terms back to back in blob, term t = blob[offsets[t] .. offsets[t+1])
- * (ASCII: the analyzer emits [a-z0-9]+).  Needed only for rass_fuzzy_expand. */
+/* The term dictionary of the text field, terms back to back in blob, term t = blob[offsets[t] .. offsets[t+1]),
+ * UTF-8 (offsets in bytes).  The engine keeps it as code points: Lucene's FuzzyQuery counts edits in code points.
+ * Needed only for rass_fuzzy_expand. */
 int rass_text_set_vocab(rass_engine* h, const char* blob, const int64_t* offsets, int64_t V);
-/* Lucene FuzzyQuery term enumeration on the device: every dictionary term within max_edits (0..2) of the token under
+/* Lucene FuzzyQuery term enumeration on the device: every dictionary term within max_edits (0..2) of the token (UTF-8,
+ * token_len bytes, at most 64 code points) under
  * the optimal-string-alignment distance (an adjacent swap is one edit), among the terms [term_lo, term_hi) (one
  * field's slice of the dictionary; term_hi < 0 = to the end).  *out_n = number of matches; the first
  * min(*out_n, max_out) (term id, edits) pairs are written, in no particular order. */

@@ -33,6 +33,7 @@ class MicroBatcher:
         self.max_wait_s = max_wait_s
         self._q: queue.Queue = queue.Queue()
         self._closed = False
+        self._gate = threading.Lock()        # submit() and close() are serialised: nothing is queued behind the stop marker
         self.batches = 0            # engine calls issued
         self.requests = 0           # queries answered
         self._worker = threading.Thread(target=self._run, name="rass-microbatcher", daemon=True)
@@ -41,12 +42,14 @@ class MicroBatcher:
     # -- callers -----------------------------------------------------------------------------------------
     def submit(self, q: np.ndarray, k: int) -> Future:
         """q: one query [dim] or [1, dim].  The future resolves to (rows [k], scores [k])."""
-        if self._closed:
-            raise RuntimeError("MicroBatcher is closed")
         if k < 1:
             raise ValueError("k must be >= 1")
         fut: Future = Future()
-        self._q.put((np.asarray(q, dtype=np.float32).reshape(-1), int(k), fut))
+        item = (np.asarray(q, dtype=np.float32).reshape(-1), int(k), fut)
+        with self._gate:
+            if self._closed:
+                raise RuntimeError("MicroBatcher is closed")
+            self._q.put(item)
         return fut
 
     def search(self, q: np.ndarray, k: int):
@@ -56,10 +59,20 @@ class MicroBatcher:
         return await asyncio.wrap_future(self.submit(q, k))
 
     def close(self):
-        if not self._closed:
+        with self._gate:
+            if self._closed:
+                return
             self._closed = True
-            self._q.put(None)
-            self._worker.join(timeout=10)
+            self._q.put(None)                # the last item the queue will ever hold
+        self._worker.join(timeout=10)
+        # whatever the worker did not get to (it died, or the join timed out) must not leave callers blocked
+        while True:
+            try:
+                item = self._q.get_nowait()
+            except queue.Empty:
+                break
+            if item is not None and not item[2].done():
+                item[2].set_exception(RuntimeError("MicroBatcher is closed"))
 
     def __enter__(self):
         return self

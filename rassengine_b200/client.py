@@ -31,6 +31,7 @@ from .text import TextIndex
 TEXT_FIELD = "unstructuredText"      # the only analysed field chunk documents carry (app/main.py:1120-1130)
 FILTER_FIELDS = ("patientId", "doc_type", "resourceType", "doc_id")   # keyword fields the hot path filters on
 _SPACE = {"cosinesimil": capi.METRIC_COSINE, "l2": capi.METRIC_L2}
+MAX_K = 128                          # RASS_MAX_K: the largest top-k one engine call returns
 
 
 class NotFoundError(KeyError):
@@ -218,10 +219,25 @@ class _Index:
             if rows and row in rows:
                 rows.remove(row)
 
-    def _filter_rows(self, filters) -> np.ndarray:
+    def _host_filter_rows(self, nodes) -> np.ndarray:
+        """Rows matching every non-term bool.filter clause (the NER filter_clause, app/main.py:2589-2609): only this
+        sub-tree is evaluated on the host (postings for match_phrase, cached columns for range); the knn / hybrid
+        search it restricts stays on the GPU.  The result is cached per index version and clause."""
+        from .hostquery import HostSearcher
+        key = ("filter", json.dumps(nodes, sort_keys=True, default=str))
+        hit = self.host_views.get(key)
+        if hit is None:
+            hs = HostSearcher(self)
+            match = np.ones(len(self.sources), dtype=bool)
+            for node in nodes:
+                match &= hs.eval(node)[1]
+            hit = self.host_views[key] = np.flatnonzero(match).astype(np.int64)
+        return hit
+
+    def _filter_rows(self, filters, host_filters=()) -> np.ndarray:
         """Rows passing every term filter, ascending.  The keyword fields the hot path filters on (patientId,
         doc_type ...) keep value -> rows lists, so a patient filter costs O(rows of the patient), not O(index)."""
-        out = None
+        out = self._host_filter_rows(list(host_filters)) if host_filters else None
         for f, v in filters:
             if f in self.kw:
                 rows = np.asarray(self.kw[f].get(v, []), dtype=np.int64)
@@ -231,8 +247,8 @@ class _Index:
             out = np.unique(rows) if out is None else np.intersect1d(out, rows)
         return out if out is not None else np.arange(len(self.sources), dtype=np.int64)
 
-    def _apply_filter(self, filters):
-        self.engine.set_row_filter_rows(self._filter_rows(filters), len(self.sources))
+    def _apply_filter(self, plan: Plan):
+        self.engine.set_row_filter_rows(self._filter_rows(plan.filters, plan.host_filters), len(self.sources))
 
     def _sync_text(self):
         if self.text.dirty and self.engine is not None:
@@ -267,14 +283,20 @@ class _Index:
     def _hit(self, row: int, score: float) -> dict:
         return self._hits([(row, score)])[0]
 
-    def _passes(self, row: int, filters) -> bool:
+    def _passes(self, row: int, plan: Plan) -> bool:
         src = self.sources[row] or {}
-        return all(src.get(f) == v for f, v in filters)
+        if not all(src.get(f) == v for f, v in plan.filters):
+            return False
+        if plan.host_filters:
+            rows = self._host_filter_rows(plan.host_filters)
+            i = int(np.searchsorted(rows, row))
+            return i < rows.size and rows[i] == row
+        return True
 
     def search(self, plan: Plan) -> list[dict]:
         if plan.size <= 0 or self.engine is None or not self.sources:
             return []
-        if plan.kind == "knn" and not (plan.filters and self.knn_filter == "pre"):
+        if plan.kind == "knn" and not plan.host_filters and not (plan.filters and self.knn_filter == "pre"):
             return self._search(plan)         # takes the lock per engine call, so concurrent callers can coalesce
         with self.lock:
             return self._search(plan)
@@ -291,12 +313,15 @@ class _Index:
             q = np.asarray(plan.vector, dtype=np.float32).reshape(1, -1)
             if q.shape[1] != self.dim:
                 raise RequestError(f"query vector length {q.shape[1]} != dimension {self.dim}")
+        has_filter = bool(plan.filters or plan.host_filters)
+        if max(plan.knn_k, plan.size) > MAX_K:
+            raise RequestError(f"size / k above {MAX_K} is not supported (asked for {max(plan.knn_k, plan.size)})")
         if plan.kind == "knn":
-            k = min(max(plan.knn_k, 1), 128)
-            if plan.filters and self.knn_filter == "pre":
+            k = max(plan.knn_k, 1)
+            if has_filter and self.knn_filter == "pre":
                 # exact filtered kNN: the scan itself skips rows failing the term filters, so the
                 # k best rows OF THE PATIENT come back instead of whichever of the global k nearest happen to pass
-                self._apply_filter(plan.filters)
+                self._apply_filter(plan)
                 eng.set_knn_prefilter(True)
                 try:
                     rows, scores = eng.search_knn(q, k)
@@ -308,10 +333,10 @@ class _Index:
             rows, scores = self._knn(q, k)
             # OpenSearch applies bool.filter to the k nearest neighbours of the nmslib engine (post-filter)
             hits = [(int(r), float(s) * plan.knn_boost) for r, s in zip(rows[0], scores[0]) if r >= 0]
-            hits = [(r, s) for r, s in hits if self._passes(r, plan.filters)]
+            hits = [(r, s) for r, s in hits if self._passes(r, plan)]
             return self._hits(hits[: plan.size])
         # hybrid: bool.should boosted sum
-        k = min(max(plan.size, 1), 128)
+        k = max(plan.size, 1)
         # text clauses: multi_match best_fields = max over the fields of the field's term sum (every declared field the
         # index holds postings for), bool.should = sum over the clauses; term weights and structure marks go to the
         # device as (term, weight, flag) lists (bit 0 = last term of a field group, bit 1 = last term of a clause)
@@ -348,13 +373,13 @@ class _Index:
         qweights = [ws] if have_text else None
         qflags = [flags] if have_text else None
         w_text = 0.0
-        if q is not None and min(max(plan.knn_k, 1), 128) != k:
+        if q is not None and max(plan.knn_k, 1) != k:
             raise NotImplementedError("knn k different from size in a hybrid query")
         if q is None and qterms is None:
             return []
         # bool.filter: only rows that satisfy every term filter may score (device-side pass mask)
-        if plan.filters:
-            self._apply_filter(plan.filters)
+        if has_filter:
+            self._apply_filter(plan)
         else:
             eng.set_row_filter(None)
         try:
@@ -366,8 +391,8 @@ class _Index:
                     knn_rows, knn_scores = self._knn(q, k)
                 finally:
                     self.lock.acquire()
-                if plan.filters:
-                    self._apply_filter(plan.filters)        # another request may have changed it meanwhile
+                if has_filter:
+                    self._apply_filter(plan)                # another request may have changed it meanwhile
                 else:
                     eng.set_row_filter(None)
                 rows, scores = eng.fuse_hybrid(qterms, w_text, knn_rows, knn_scores, plan.knn_boost, k,
@@ -376,7 +401,7 @@ class _Index:
                 rows, scores = eng.search_hybrid(q, qterms, w_text, plan.knn_boost, k, qweights=qweights,
                                                  qflags=qflags)
         finally:
-            if plan.filters:
+            if has_filter:
                 eng.set_row_filter(None)
         return self._hits([(int(r), float(s)) for r, s in zip(rows[0], scores[0]) if r >= 0][: plan.size])
 

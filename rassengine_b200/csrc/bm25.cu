@@ -703,16 +703,40 @@ extern "C" int rass_fuse_hybrid(rass_engine* h, int B, const int32_t* qterm_indp
 }
 
 // ---- fuzziness: AUTO -- edit-distance scan of the term dictionary -------------------------------------------
+// Lucene's FuzzyQuery measures edits in Unicode code points, so the dictionary is kept on the device as code points
+// (decoded once from the UTF-8 the host hands over) and so is the query token.
 #define FUZZY_MAX_TOKEN 64
 
 struct FuzzyToken {
   int len;
-  unsigned char c[FUZZY_MAX_TOKEN];
+  uint32_t c[FUZZY_MAX_TOKEN];
 };
+
+// UTF-8 -> code points; false on a malformed sequence
+static bool utf8_decode(const unsigned char* p, size_t n, std::vector<uint32_t>& out) {
+  size_t i = 0;
+  while (i < n) {
+    const unsigned char b = p[i];
+    uint32_t cp;
+    int extra;
+    if (b < 0x80) { cp = b; extra = 0; }
+    else if ((b & 0xe0) == 0xc0) { cp = b & 0x1f; extra = 1; }
+    else if ((b & 0xf0) == 0xe0) { cp = b & 0x0f; extra = 2; }
+    else if ((b & 0xf8) == 0xf0) { cp = b & 0x07; extra = 3; }
+    else return false;
+    for (int e = 1; e <= extra; ++e) {
+      if (i + e >= n || (p[i + e] & 0xc0) != 0x80) return false;
+      cp = (cp << 6) | (p[i + e] & 0x3f);
+    }
+    out.push_back(cp);
+    i += (size_t)extra + 1;
+  }
+  return true;
+}
 
 // One thread per dictionary term: optimal-string-alignment distance (insert / delete / substitute / adjacent swap)
 // to the query token, cut off at max_edits; matches are appended to (out_terms, out_edits) in no particular order.
-__global__ void __launch_bounds__(256) fuzzy_scan_kernel(const unsigned char* __restrict__ blob,
+__global__ void __launch_bounds__(256) fuzzy_scan_kernel(const uint32_t* __restrict__ blob,
                                                          const int64_t* __restrict__ off, int64_t t_lo, int64_t V,
                                                          const __grid_constant__ FuzzyToken tok, int max_edits,
                                                          int32_t* __restrict__ out_terms,
@@ -722,16 +746,16 @@ __global__ void __launch_bounds__(256) fuzzy_scan_kernel(const unsigned char* __
   const int64_t o = off[t];
   const int lt = (int)(off[t + 1] - o), m = tok.len;
   if (lt == 0 || abs(lt - m) > max_edits) return;
-  const unsigned char* term = blob + o;
+  const uint32_t* term = blob + o;
   // rows of the DP over the token (columns 0..m); row i = prefix of the term of length i
   unsigned char prev2[FUZZY_MAX_TOKEN + 1], prev[FUZZY_MAX_TOKEN + 1], cur[FUZZY_MAX_TOKEN + 1];
   for (int j = 0; j <= m; ++j) prev[j] = (unsigned char)j;
   for (int i = 1; i <= lt; ++i) {
-    const unsigned char ci = term[i - 1];
+    const uint32_t ci = term[i - 1];
     cur[0] = (unsigned char)min(i, 255);
     int row_min = cur[0];
     for (int j = 1; j <= m; ++j) {
-      const unsigned char cj = tok.c[j - 1];
+      const uint32_t cj = tok.c[j - 1];
       int v = min(min(prev[j] + 1, cur[j - 1] + 1), prev[j - 1] + (ci != cj));
       if (i > 1 && j > 1 && ci == tok.c[j - 2] && term[i - 2] == cj) v = min(v, prev2[j - 2] + 1);
       cur[j] = (unsigned char)min(v, 255);
@@ -753,9 +777,18 @@ extern "C" int rass_text_set_vocab(rass_engine* h, const char* blob, const int64
   if (V < 0 || !offsets || (offsets[V] > 0 && !blob)) return rass_fail(h, RASS_E_INVALID, "bad vocabulary");
   Bm25State& b = h->bm25;
   CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+  std::vector<uint32_t> cps;
+  std::vector<int64_t> cp_off((size_t)V + 1, 0);
+  cps.reserve((size_t)offsets[V]);
+  for (int64_t t = 0; t < V; ++t) {
+    if (offsets[t + 1] < offsets[t]) return rass_fail(h, RASS_E_INVALID, "vocabulary offsets must not decrease");
+    if (!utf8_decode(reinterpret_cast<const unsigned char*>(blob) + offsets[t], (size_t)(offsets[t + 1] - offsets[t]), cps))
+      return rass_fail(h, RASS_E_INVALID, "term %lld is not valid UTF-8", (long long)t);
+    cp_off[(size_t)t + 1] = (int64_t)cps.size();
+  }
   int rc;
-  if ((rc = upload(h, &b.vocab_blob, reinterpret_cast<const unsigned char*>(blob), (size_t)offsets[V]))) return rc;
-  if ((rc = upload(h, &b.vocab_off, offsets, (size_t)V + 1))) return rc;
+  if ((rc = upload(h, &b.vocab_blob, cps.data(), cps.size()))) return rc;
+  if ((rc = upload(h, &b.vocab_off, cp_off.data(), (size_t)V + 1))) return rc;
   cudaFree(b.fz_terms); b.fz_terms = nullptr;
   cudaFree(b.fz_edits); b.fz_edits = nullptr;
   CUDA_TRY(h, cudaMalloc(&b.fz_terms, std::max<size_t>((size_t)V, 1) * sizeof(int32_t)));
@@ -774,15 +807,18 @@ extern "C" int rass_fuzzy_expand(rass_engine* h, const char* token, int token_le
   if (!token || token_len < 1 || max_edits < 0 || max_edits > 2 || !out_n || (max_out > 0 && (!out_terms || !out_edits)))
     return rass_fail(h, RASS_E_INVALID, "bad arguments");
   if (!b.vocab_off) return rass_fail(h, RASS_E_INVALID, "rass_fuzzy_expand before rass_text_set_vocab");
-  if (token_len > FUZZY_MAX_TOKEN) return rass_fail(h, RASS_E_INVALID, "token longer than %d bytes", FUZZY_MAX_TOKEN);
+  std::vector<uint32_t> cps;
+  if (!utf8_decode(reinterpret_cast<const unsigned char*>(token), (size_t)token_len, cps))
+    return rass_fail(h, RASS_E_INVALID, "the token is not valid UTF-8");
+  if (cps.size() > FUZZY_MAX_TOKEN) return rass_fail(h, RASS_E_INVALID, "token longer than %d code points", FUZZY_MAX_TOKEN);
   *out_n = 0;
   if (term_hi < 0 || term_hi > b.vocab_V) term_hi = b.vocab_V;
   if (term_lo < 0) term_lo = 0;
   if (term_lo >= term_hi) return RASS_OK;
   FuzzyToken tok;
   memset(&tok, 0, sizeof(tok));
-  tok.len = token_len;
-  memcpy(tok.c, token, (size_t)token_len);
+  tok.len = (int)cps.size();
+  memcpy(tok.c, cps.data(), cps.size() * sizeof(uint32_t));
   cudaStream_t st = eng_stream(h);
   CUDA_TRY(h, cudaMemsetAsync(b.fz_n, 0, sizeof(int), st));
   fuzzy_scan_kernel<<<(unsigned)((term_hi - term_lo + 255) / 256), 256, 0, st>>>(

@@ -40,8 +40,8 @@ struct Bm25State {
   unsigned char* qt_dev = nullptr;
   size_t qt_cap = 0, qt_q_cap = 0, qt_bytes = 0;
   uint32_t* hyb_gthr = nullptr;          // device [qt_q_cap] cross-tile pruning bound of the running hybrid batch
-  unsigned char* vocab_blob = nullptr;   // device: the term dictionary, terms back to back (fuzziness: AUTO)
-  int64_t* vocab_off = nullptr;          // device [vocab_V + 1]
+  uint32_t* vocab_blob = nullptr;        // device: the term dictionary as code points, terms back to back (fuzziness: AUTO)
+  int64_t* vocab_off = nullptr;          // device [vocab_V + 1], in code points
   int64_t vocab_V = 0;
   int32_t* fz_terms = nullptr;           // device [vocab_V] matches of the running fuzzy scan
   int32_t* fz_edits = nullptr;

@@ -6,7 +6,9 @@
              "minimum_should_match": 1, "filter": [...]}}, "terminate_after": k}        app/main.py:1574-1605
              (multi_intent_search emits the same shape with other boosts            app/main.py:1982-2010)
 
-Anything else (phrase, phrase_prefix, range, sort, aggs, collapse ...) raises NotImplementedError here and is evaluated
+Filters other than `term` (the NER filter_clause: match_phrase / range under a bool, app/main.py:2589-2609) stay in the
+plan verbatim: the client turns that sub-tree alone into a row list on the host and the search itself stays on the
+GPU.  Anything else (phrase, phrase_prefix, sort, aggs, collapse ...) raises NotImplementedError here and is evaluated
 host-side by hostquery.py; shapes neither understands raise NotImplementedError to the caller, which
 the reference's `except Exception: return []` (app/main.py:1558-1560, 1613-1615) turns into "no results".
 `terminate_after` is ignored on purpose: the engine returns the true global top-k (reference defects).
@@ -33,6 +35,9 @@ class Plan:
     knn_field: str = "embedding"
     text: list[TextClause] = field(default_factory=list)
     filters: list[tuple[str, object]] = field(default_factory=list)   # (field, value) term filters
+    # any other bool.filter clause, verbatim: ner_preprocess hands {"bool": {"must": [match_phrase | range ...]}}
+    # (app/main.py:2589-2609) to every search method; only THIS sub-tree is evaluated host-side, into a row list
+    host_filters: list[dict] = field(default_factory=list)
     kind: str = "knn"                    # "knn" | "hybrid" | "match_all"
 
 
@@ -57,12 +62,15 @@ def _parse_filters(nodes, plan: Plan):
     if isinstance(nodes, dict):
         nodes = [nodes]
     for f in nodes or []:
-        if not isinstance(f, dict) or set(f) != {"term"} or len(f["term"]) != 1:
+        if not isinstance(f, dict) or len(f) != 1:
             raise NotImplementedError(f"unsupported filter clause: {f!r}")
-        (fld, val), = f["term"].items()
-        if isinstance(val, dict):
-            val = val.get("value")
-        plan.filters.append((fld, val))
+        if set(f) == {"term"} and len(f["term"]) == 1:
+            (fld, val), = f["term"].items()
+            if isinstance(val, dict):
+                val = val.get("value")
+            plan.filters.append((fld, val))
+        else:
+            plan.host_filters.append(f)      # match_phrase / range / nested bool ...: rows via hostquery, scan on GPU
 
 
 def parse_search_body(body: dict) -> Plan:

@@ -215,7 +215,7 @@ class Engine:
 
     def set_vocab(self, terms: list[str]):
         """The text field's term dictionary in term-id order (needed by fuzzy_expand)."""
-        enc = [t.encode("ascii", "replace") for t in terms]
+        enc = [t.encode("utf-8", "replace") for t in terms]
         off = np.zeros(len(enc) + 1, dtype=np.int64)
         if enc:
             off[1:] = np.cumsum([len(e) for e in enc])
@@ -229,7 +229,7 @@ class Engine:
         terms = np.empty(n_cap, dtype=np.int32)
         edits = np.empty(n_cap, dtype=np.int32)
         n = C.c_int64(0)
-        tok = token.encode("ascii", "replace")
+        tok = token.encode("utf-8", "replace")
         self._check(self._lib.rass_fuzzy_expand(self._h, tok, len(tok), max_edits, term_lo, term_hi, n_cap,
                                                 _ptr(terms), _ptr(edits), C.byref(n)))
         return terms[: n.value].copy(), edits[: n.value].copy()

@@ -242,6 +242,8 @@ class HostSearcher:
         sets = [np.asarray(ids, dtype=np.int64) for ids in positions]
         for row in cand.tolist():
             seq = v.fld.row_terms[row]
+            if seq.size < len(sets):         # shorter than the phrase (a repeated query token against a short field)
+                continue
             ok = np.isin(seq[: seq.size - len(sets) + 1], sets[0])
             for j in range(1, len(sets)):
                 ok &= np.isin(seq[j: seq.size - len(sets) + 1 + j], sets[j])
@@ -296,26 +298,51 @@ class HostSearcher:
         match = np.array([s is not None and s.get(fname) is not None for s in self.ix.sources], dtype=bool)
         return match.astype(np.float32), match
 
+    def _column(self, fname: str, is_date: bool):
+        """(values float64 [rows], present bool [rows]) of one source field -- dates as epoch seconds -- cached per index
+        version, so a range filter costs one vectorised comparison per query instead of a Python pass over the rows."""
+        key = ("column", fname, is_date)
+        col = self._views.get(key)
+        if col is None:
+            vals = np.zeros(self.n, dtype=np.float64)
+            ok = np.zeros(self.n, dtype=bool)
+            for row, src in enumerate(self.ix.sources):
+                raw = (src or {}).get(fname)
+                if raw is None:
+                    continue
+                try:
+                    if is_date:
+                        d = _parse_date(raw, self.now)
+                        x = None if d is None else d.timestamp()
+                    else:
+                        x = float(raw)
+                except (TypeError, ValueError):
+                    continue
+                if x is not None:
+                    vals[row], ok[row] = x, True
+            col = self._views[key] = (vals, ok)
+        return col
+
     def _q_range(self, body):
         (fname, cond), = body.items()
         is_date = self.ix.field_type(fname) == "date" or any(isinstance(x, str) for x in cond.values())
-        conv = (lambda x: _parse_date(x, self.now)) if is_date else (lambda x: float(x))
-        bounds = {op: conv(val) for op, val in cond.items() if op in ("gt", "gte", "lt", "lte")}
-        match = np.zeros(self.n, dtype=bool)
-        for row, src in enumerate(self.ix.sources):
-            raw = (src or {}).get(fname)
-            if raw is None:
-                continue
-            try:
-                x = conv(raw)
-            except (TypeError, ValueError):
-                continue
-            if x is None:
-                continue
-            ok = all(b is not None for b in bounds.values())
-            ok = ok and ("gt" not in bounds or x > bounds["gt"]) and ("gte" not in bounds or x >= bounds["gte"])
-            ok = ok and ("lt" not in bounds or x < bounds["lt"]) and ("lte" not in bounds or x <= bounds["lte"])
-            match[row] = ok
+        if is_date:
+            bounds = {op: _parse_date(val, self.now) for op, val in cond.items() if op in ("gt", "gte", "lt", "lte")}
+            if any(b is None for b in bounds.values()):           # an unparseable bound (free text from the NER) matches nothing
+                return self._empty()
+            bounds = {op: b.timestamp() for op, b in bounds.items()}
+        else:
+            bounds = {op: float(val) for op, val in cond.items() if op in ("gt", "gte", "lt", "lte")}
+        vals, match = self._column(fname, is_date)
+        match = match.copy()
+        if "gt" in bounds:
+            match &= vals > bounds["gt"]
+        if "gte" in bounds:
+            match &= vals >= bounds["gte"]
+        if "lt" in bounds:
+            match &= vals < bounds["lt"]
+        if "lte" in bounds:
+            match &= vals <= bounds["lte"]
         return match.astype(np.float32) * np.float32(cond.get("boost", 1.0)), match      # constant score 1
 
     def _q_match(self, body):
@@ -373,7 +400,9 @@ class HostSearcher:
         (fname, spec), = body.items()
         eng = self.ix.engine
         q = np.asarray(spec["vector"], dtype=np.float32).reshape(1, -1)
-        k = min(max(int(spec.get("k", 10)), 1), 128)
+        k = max(int(spec.get("k", 10)), 1)
+        if k > 128:
+            raise NotImplementedError("knn k above 128")
         with self.ix.lock:
             rows, scores = eng.search_knn(q, k)
         score, match = self._empty()

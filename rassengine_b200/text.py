@@ -1,22 +1,15 @@
 """Host side of the text clause: analysis and the inverted index handed to rass_bm25_build.
 
 The reference maps `unstructuredText` as {"type": "text"} with the default (standard) analyzer
-(app/main.py:555-556): word segmentation + lower-casing, no stop words.  For ASCII text that is "lower-case, split
-on runs of non-alphanumerics", which is what `analyze` does; the reference's own chunker splits on whitespace
-(app/main.py:2160-2170).  Postings are CSR (term -> ascending doc rows with term frequencies) plus a token count per
-row, the layout the device BM25 kernel walks.
+(app/main.py:555-556): UAX#29 word segmentation + lower-casing, no stop words -- `analysis.analyze`; the reference's
+own chunker splits on whitespace (app/main.py:2160-2170).  Postings are CSR (term -> ascending doc rows with term
+frequencies) plus a token count per row, the layout the device BM25 kernel walks.
 """
 from __future__ import annotations
 
-import re
-
 import numpy as np
 
-_WORD = re.compile(r"[a-z0-9]+")
-
-
-def analyze(text: str) -> list[str]:
-    return _WORD.findall(text.lower()) if text else []
+from .analysis import analyze  # noqa: F401  (re-exported: client.py, hostquery.py and the tests import it from here)
 
 
 class TextField:

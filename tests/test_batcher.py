@@ -76,3 +76,36 @@ def test_asyncio_front_end_and_error_propagation():
             mb.submit(np.ones(4, dtype=np.float32), 0)
     with pytest.raises(RuntimeError):
         mb.submit(np.ones(4, dtype=np.float32), 1)
+
+
+def test_close_races_with_submit_without_stranding_a_caller():
+    """submit() and close() are serialised: a request is either answered or refused, never queued behind the stop
+    marker with a future nobody resolves (indices.delete / client.close run while other threads search)."""
+    for _ in range(20):
+        eng = FakeEngine(delay=0.001)
+        mb = MicroBatcher(eng.search, max_batch=8, max_wait_s=0.001)
+        results, refused = [], []
+
+        def worker(tag):
+            for j in range(50):
+                try:
+                    fut = mb.submit(np.array([tag, 0.0], dtype=np.float32), 2)
+                except RuntimeError:
+                    refused.append(tag)
+                    return
+                try:
+                    results.append(fut.result(timeout=5))
+                except RuntimeError:                      # refused after the fact: closed before the worker got to it
+                    refused.append(tag)
+                    return
+
+        ts = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+        for t in ts:
+            t.start()
+        time.sleep(0.005)
+        mb.close()
+        for t in ts:
+            t.join(timeout=10)
+            assert not t.is_alive(), "a caller is blocked on a future that will never resolve"
+        with pytest.raises(RuntimeError):
+            mb.submit(np.zeros(2, dtype=np.float32), 1)

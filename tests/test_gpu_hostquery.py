@@ -181,3 +181,27 @@ def test_aggregations_collapse_sort_and_filters(setup):
     assert [h[0]["doc_id"] for h in hits] == ["c1", "c2"] and all(h[0]["doc_type"] == "structured" for h in hits)
     with pytest.raises(NotImplementedError):
         client.search(index=name, body={"query": {"more_like_this": {"fields": ["x"], "like": "y"}}})
+
+
+def test_ner_filter_clause_keeps_hybrid_and_knn_on_the_gpu(setup):
+    """filter_clause from ner_preprocess is {"bool": {"must": [match_phrase | range]}} (app/main.py:2589-2609).  The
+    hybrid / knn search it restricts must run on the device (row list from the host filter sub-tree) and return what the
+    complete host evaluation of the same body returns."""
+    client, name, idxr, fields, types, emb = setup
+    idx = client._get(name)
+    ner = {"bool": {"must": [{"match_phrase": {"unstructuredText": "chest pain"}}]}}
+    q = emb[0:1] + 0.01
+    before = idx.engine.last_stats.copy() if idx.engine.last_stats else {}
+    got = idxr.hybrid_search("chest pain breath", q, k=3, filter_clause=ner, patient_id="pat-1")
+    assert idx.engine.last_stats != before and idx.engine.last_stats["launches"] > 0       # the engine ran the search
+    assert [d["doc_id"] for d, _ in got] == ["n1"]
+    body = idxr._hybrid_body("chest pain breath", q, 3, 1.5, 1.0, 2.0, ner, "pat-1")
+    hits, _, _ = idx.host_search(body)
+    assert [h["_id"] for h in hits] == [d["doc_id"] for d, _ in got]
+    np.testing.assert_allclose([h["_score"] for h in hits], [s for _, s in got], rtol=1e-6)
+    # knn + NER filter (semantic_search): post-filter of the k nearest, like the nmslib engine
+    got = idxr.semantic_search(q, k=2, filter_clause={"bool": {"must": [{"match_phrase": {"unstructuredText": "diabetes"}}]}})
+    assert [d["doc_id"] for d, _ in got] == ["n2"]
+    # size above RASS_MAX_K is refused, not silently truncated
+    with pytest.raises(Exception):
+        client.search(index=name, body={"size": 200, "query": {"knn": {"embedding": {"vector": q[0].tolist(), "k": 200}}}})

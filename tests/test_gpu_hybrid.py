@@ -120,6 +120,27 @@ def test_fuzzy_expand_matches_oracle_on_the_term_dictionary():
             assert dict(zip(tid.tolist(), ed.tolist())) == want, tok
 
 
+def test_fuzzy_expand_counts_edits_in_code_points():
+    """Lucene's FuzzyQuery works on code points: "jose" is ONE edit from "jos\u00e9" (two UTF-8 bytes), a token of
+    accented letters is as long as it looks.  Names (`patientName`) and note text carry such letters."""
+    vocab = ["jos\u00e9", "jose", "josef", "m\u00fcller", "muller", "mueller", "\u00e9\u00e8\u00ea", "na\u00efve",
+             "naive", "\u60a3\u8005", "o'neil", "oneil", "3.5", "35"]
+    with _engine(dim=4) as e:
+        e.append(np.eye(4, dtype=np.float32))
+        e.set_vocab(vocab)
+        for tok in ["jose", "jos\u00e9", "m\u00fcller", "muller", "\u00e9\u00e8\u00eb", "naive", "\u60a3\u8005", "oneil",
+                    "3.5"]:
+            me = fuzzy.auto_max_edits(len(tok))
+            want = {}
+            for tid, term in enumerate(vocab):
+                if abs(len(term) - len(tok)) <= me:
+                    d = fuzzy.osa_distance(tok, term)
+                    if d <= me:
+                        want[tid] = d
+            tid, ed = e.fuzzy_expand(tok, me)
+            assert dict(zip(tid.tolist(), ed.tolist())) == want, tok
+
+
 def test_weighted_hybrid_matches_fuzzy_oracle():
     """rass_search_hybrid_weighted with the fuzzy rewrite's (term, weight) lists: fused float32 scores bit-identical to
     the oracle's, with and without the knn clause."""

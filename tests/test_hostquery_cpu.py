@@ -202,3 +202,39 @@ def test_random_bool_trees_of_keyword_filters_match_set_logic(setup, query):
     got = [h["_id"] for h in client.search(index=name, body=body)["hits"]["hits"]]
     want = sorted(d["doc_id"] for d in DOCS if _naive(query, d))
     assert got == want, query
+
+
+def test_ner_filter_clause_becomes_a_row_list_and_the_plan_stays_on_the_gpu_path(setup):
+    """ner_preprocess (app/main.py:2589-2609) hands every search {"bool": {"must": [match_phrase | range ...]}} as
+    filter_clause.  The DSL parser keeps such a clause in the plan (so knn / hybrid still run on the device) and the
+    client turns that sub-tree alone into a row list."""
+    from rassengine_b200.dsl import parse_search_body
+    client, name, idxr, _ = setup
+    ner = {"bool": {"must": [{"match_phrase": {"conditionCodeText": "chest pain"}},
+                             {"range": {"conditionOnsetDateTime": {"gte": cases._days_ago(400), "lte": cases._days_ago(1)}}}]}}
+    body = {"size": 3, "query": {"bool": {"should": [
+        {"multi_match": {"query": "pain", "fields": ["conditionNote^2"], "type": "best_fields", "operator": "or",
+                         "fuzziness": "AUTO", "boost": 1.5}},
+        {"knn": {"embedding": {"vector": [0.0] * 16, "k": 3, "boost": 2.0}}}],
+        "minimum_should_match": 1, "filter": [ner, {"term": {"patientId": "pat-1"}}]}}, "terminate_after": 3}
+    plan = parse_search_body(body)
+    assert plan.kind == "hybrid" and plan.filters == [("patientId", "pat-1")] and plan.host_filters == [ner]
+    idx = client._get(name)
+    rows = idx._filter_rows(plan.filters, plan.host_filters)
+    assert [DOCS[r]["doc_id"] for r in rows.tolist()] == ["c1", "c2"]        # c3: other patient and too old
+    assert idx._passes(4, plan) and not idx._passes(6, plan) and not idx._passes(0, plan)
+    assert idx._filter_rows([], [ner]).tolist() == [4, 5]                        # cached per index version
+    # an unparseable date (free text from the NER, app/main.py:2596-2601) matches nothing instead of raising
+    bad = {"bool": {"must": [{"range": {"conditionOnsetDateTime": {"gte": "last tuesday", "lte": "last tuesday"}}}]}}
+    assert idx._filter_rows([], [bad]).size == 0
+
+
+def test_phrase_longer_than_the_field_value_is_no_match_not_an_error(setup):
+    """A repeated-token phrase against a shorter field value: 'pain pain pain pain' vs 'Chest pain' must score 0
+    (hostquery._phrase used to raise a broadcast error that the indexer's `except` turned into [])."""
+    client, name, idxr, _ = setup
+    body = {"size": 5, "query": {"multi_match": {"query": "pain pain pain pain", "fields": ["conditionCodeText"],
+                                                 "type": "phrase"}}}
+    assert client.search(index=name, body=body)["hits"]["hits"] == []
+    body["query"]["multi_match"]["query"] = "chest pain"
+    assert {h["_id"] for h in client.search(index=name, body=body)["hits"]["hits"]} == {"c1", "c2", "c3"}

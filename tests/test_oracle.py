@@ -157,7 +157,15 @@ def test_text_corpus_csr_is_consistent():
         assert np.all(np.diff(d) > 0)
     texts = synth.docs_as_text(indptr, doc, tf, 2000)
     assert len(analyzer.analyze(texts[5])) == doclen[5]
-    assert analyzer.analyze("Hello, World-2 FOO_bar") == ["hello", "world", "2", "foo", "bar"]
+    assert analyzer.analyze("Hello, World-2 FOO_bar") == ["hello", "world", "2", "foo_bar"]
+
+
+def test_analyzer_known_answers(golden_dir):
+    """UAX#29 + lower-casing on FHIR-like strings: hand-derived tokenisations (tests/golden/analyzer_cases.json)."""
+    import json
+    import os
+    for case in json.load(open(os.path.join(golden_dir, "analyzer_cases.json")))["cases"]:
+        assert analyzer.analyze(case["text"]) == case["tokens"], case
 
 
 def test_fuzzy_auto_restatement_known_answers():

@@ -79,13 +79,24 @@ def test_fuzzy_expansion_is_sorted_and_within_auto_edits(vocab, token):
                 assert term != token and (me == 0 or fuzzy.osa_distance(token, term) > me)
 
 
+_TRICKY = "abzAZ019_'\".,;:/-@ \u00e9\u00fc\u0301\u0130\u03a3\u05d0\u05d1\u30ab\u30ad\u3072\u60a3\u0e2a\u0e31\u200d\u2019\u00b7\u2044\u00b0"
+
+
 @FAST
-@given(st.text(max_size=60))
+@given(st.one_of(st.text(max_size=60), st.text(alphabet=_TRICKY, max_size=40)))
 def test_product_analyzer_equals_oracle_analyzer(s):
-    """rassengine_b200.text.analyze and oracle.analyzer.analyze are written independently; they must tokenise alike."""
-    assert text.analyze(s) == analyzer.analyze(s)
-    for tok in text.analyze(s):
-        assert tok and tok == tok.lower()
+    """rassengine_b200.analysis.analyze (a character scanner) and oracle.analyzer.analyze (one regular expression over
+    word-break classes) are written independently; they must tokenise alike -- arbitrary text, and text drawn from
+    the characters the UAX#29 rules turn on (mid-letter / mid-number punctuation, combining marks, Hebrew, kana, Han,
+    Thai)."""
+    got = text.analyze(s)
+    assert got == analyzer.analyze(s)
+    for tok in got:
+        assert tok and len(tok) <= 255
+        assert all(len(c.lower()) != 1 or c.lower() == c for c in tok)
+    if s.isascii():      # the ASCII fast path states the same rules as the general scanner
+        from rassengine_b200 import analysis
+        assert analysis._analyze_unicode(s) == got
 
 
 @SLOW
