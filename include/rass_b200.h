@@ -20,6 +20,7 @@
  *   rass_text_set_vocab,                                                        app/main.py:1577-1585
  *   rass_fuzzy_expand
  *   rass_set_row_filter             bool.filter [term patientId / doc_type] of the hybrid query               app/main.py:1599-1604
+ *   rass_create_sharded             settings.index.number_of_shards of the same create call            app/main.py:357
  *   rass_merge_topk_dev             the OpenSearch coordinator's per-shard top-k merge (number_of_shards, app/main.py:357)
  *   rass_save / rass_load           the on-disk Lucene index of the OpenSearch container (docker-compose.yml:4-17)
  *
@@ -49,7 +50,7 @@ enum {
   RASS_E_INVALID = -1,
   RASS_E_OOM = -2,
   RASS_E_CUDA = -3,
-  RASS_E_NCCL = -4,
+  RASS_E_NCCL = -4,      /* the inter-GPU exchange of a sharded handle failed (peer mapping / peer copy) */
   RASS_E_NOTFOUND = -5,
   RASS_E_UNSUPPORTED = -6,
   RASS_E_AGAIN = -7      /* rass_search_knn_dev_wait: some query failed its certificate; repeat with the blocking call */
@@ -73,10 +74,17 @@ enum {
   RASS_PATH_GEMM = 4     /* force the CTA-pair (cta_group::2) tcgen05 scan (groups of 256 queries)     */
 };
 
+/* rass_stats.path of a hybrid call: the kNN path in the low byte, plus this bit when the text clauses ran through the
+ * order-free tile kernel (every query's clause sums provably exact in double, so the order of the additions is free) */
+enum { RASS_PATH_HYBRID_ORDER_FREE = 0x100 };
+
 enum {
   RASS_OPT_PATH = 1,
   RASS_OPT_STREAM = 2,   /* value = cudaStream_t to enqueue on (0 = the legacy default stream, which is what
                             torch's default stream is); -1 = back to the engine-owned stream           */
+  RASS_OPT_HYBRID_ORDERED = 4,  /* 1: the text clauses of hybrid calls always walk the query terms in order (one barrier
+                            per term); 0 (default): queries whose clause sums are exact in double in ANY order take the
+                            order-free kernel.  Both give bit-identical scores; the switch exists for tests and A/B runs */
   RASS_OPT_KNN_PREFILTER = 3  /* 1: rass_search_knn honours rass_set_row_filter as an exact PRE-filter (top-k of
                             the rows that pass); 0 (default): the filter only applies to rass_search_hybrid and
                             the host post-filters the k nearest, which is what OpenSearch's nmslib engine does
@@ -106,6 +114,16 @@ const char* rass_last_error(const rass_engine* h);  /* h may be NULL: last creat
 /* dim: embedding dimension (<= 1024; padded to a multiple of 256 on device).  device: CUDA ordinal.
  * capacity_rows: initial reservation (grows by doubling). */
 int rass_create(int dim, int metric, int device, int64_t capacity_rows, uint32_t flags, rass_engine** out);
+/* One handle over several GPUs of the box, in the caller's process -- the B200 form of `number_of_shards`
+ * (settings.index.number_of_shards, app/main.py:357) with the coordinator's merge.  Global row r lives
+ * on device_ids[(r >> 10) % n_devices]; EVERY entry point of this header takes the returned handle (debug entries and
+ * rass_fuse_hybrid_dev excepted), row ids stay global, dense and append-ordered, and results are bit-identical to a
+ * single-device handle holding the same rows.  device_ids[0] is the coordinator: the *_dev entry points take and leave
+ * their buffers there.  Each shard's finish kernel stores its [B, k] list straight into the coordinator's gather buffer
+ * through peer-mapped memory (NVLink), then one merge kernel runs -- no all-gather.  RASS_E_NCCL = the inter-GPU exchange
+ * failed (peer copy / peer mapping).  n_devices == 1 is rass_create. */
+int rass_create_sharded(int dim, int metric, int n_devices, const int* device_ids, int64_t capacity_rows,
+                        uint32_t flags, rass_engine** out);
 int rass_destroy(rass_engine* h);
 int rass_set_option(rass_engine* h, int opt, int64_t value);
 /* global row id of local row 0 (row-sharded corpora); search outputs carry base + local row */
@@ -226,6 +244,9 @@ int rass_set_row_filter(rass_engine* h, const uint8_t* mask_host, int64_t n);
 int rass_set_row_filter_rows(rass_engine* h, const int64_t* rows_host, int64_t n, int64_t total_rows);
 
 int rass_sync(rass_engine* h);
+/* statistics of the last blocking search / hybrid / fuse call on the handle (the entry points without a stats argument,
+ * rass_fuse_hybrid(_dev), leave theirs here: scan_ms = the kNN scan, finish_ms = text clauses + fusion + select) */
+int rass_last_stats(const rass_engine* h, rass_stats* out);
 
 /* Snapshot / restore of the vector store (the reference relies on the OpenSearch container's own Lucene index
  * directory, docker-compose.yml:4-17).  rass_save writes header + tombstones + the stored values; rass_load fills an

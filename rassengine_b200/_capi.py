@@ -20,7 +20,8 @@ ERR_NAMES = {-1: "RASS_E_INVALID", -2: "RASS_E_OOM", -3: "RASS_E_CUDA", -4: "RAS
 METRIC_COSINE, METRIC_L2 = 0, 1
 KEEP_FP32, BF16_ONLY = 1, 2
 PATH_AUTO, PATH_STREAM, PATH_UMMA, PATH_EXACT, PATH_GEMM = 0, 1, 2, 3, 4
-OPT_PATH, OPT_STREAM, OPT_KNN_PREFILTER = 1, 2, 3
+OPT_PATH, OPT_STREAM, OPT_KNN_PREFILTER, OPT_HYBRID_ORDERED = 1, 2, 3, 4
+PATH_HYBRID_ORDER_FREE = 0x100
 
 
 class RassStats(C.Structure):
@@ -45,6 +46,8 @@ PROTOTYPES = {
     "rass_version": (C.c_char_p, []),
     "rass_last_error": (C.c_char_p, [_P]),
     "rass_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_uint32, C.POINTER(_P)]),
+    "rass_create_sharded": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int64, C.c_uint32,
+                                      C.POINTER(_P)]),
     "rass_destroy": (C.c_int, [_P]),
     "rass_set_option": (C.c_int, [_P, C.c_int, C.c_int64]),
     "rass_set_row_base": (C.c_int, [_P, C.c_int64]),
@@ -76,6 +79,7 @@ PROTOTYPES = {
                                     C.POINTER(C.c_int64)]),
     "rass_set_row_filter": (C.c_int, [_P, _P, C.c_int64]),
     "rass_sync": (C.c_int, [_P]),
+    "rass_last_stats": (C.c_int, [_P, C.POINTER(RassStats)]),
     "rass_save": (C.c_int, [_P, C.c_char_p]),
     "rass_load": (C.c_int, [_P, C.c_char_p]),
     "rass_debug_umma_scores": (C.c_int, [_P, _P, C.c_int, _P]),

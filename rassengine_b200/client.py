@@ -42,11 +42,49 @@ class RequestError(ValueError):
     """resource_already_exists_exception / bad request"""
 
 
+def resolve_devices(devices, device: int, body: dict | None) -> list[int]:
+    """GPUs of one index, in this order of precedence: an explicit `devices` list, the RASS_B200_DEVICES environment
+    variable ("0,1,2,3" or "all"), `settings.index.number_of_shards` of the create body (app/main.py:357: the reference
+    passes SHARD_COUNT there) capped by the GPUs present, else the single `device`."""
+    if devices:
+        return [int(d) for d in devices]
+    env = os.environ.get("RASS_B200_DEVICES", "").strip()
+    if env:
+        if env.lower() == "all":
+            import ctypes
+            n = ctypes.c_int(0)
+            try:
+                ctypes.CDLL("libcudart.so").cudaGetDeviceCount(ctypes.byref(n))
+            except OSError:
+                n.value = 0
+            return list(range(max(1, n.value)))
+        return [int(x) for x in env.split(",") if x.strip() != ""]
+    shards = 1
+    try:
+        shards = int((body or {}).get("settings", {}).get("index", {}).get("number_of_shards", 1))
+    except (TypeError, ValueError):
+        shards = 1
+    if shards > 1:
+        n_gpu = _gpu_count()
+        if n_gpu > 1:
+            return list(range(device, device + min(shards, n_gpu - device)))
+    return [device]
+
+
+def _gpu_count() -> int:
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 1
+
+
 class _Index:
-    def __init__(self, name: str, body: dict | None, device: int, knn_filter: str = "post"):
+    def __init__(self, name: str, body: dict | None, device: int, knn_filter: str = "post", devices=None):
         self.name = name
         self.body = body or {}
         self.device = device
+        self.devices = resolve_devices(devices, device, body)
         self.knn_filter = knn_filter
         props = self.body.get("mappings", {}).get("properties", {})
         self.vector_field = None
@@ -83,7 +121,7 @@ class _Index:
             if self.dim is None:
                 self.dim = dim or 1024
                 self.vector_field = self.vector_field or "embedding"
-            self.engine = Engine(dim=self.dim, metric=self.metric, device=self.device)
+            self.engine = Engine(dim=self.dim, metric=self.metric, device=self.device, devices=self.devices)
         return self.engine
 
     def close(self):
@@ -416,7 +454,7 @@ class IndicesClient:
     def create(self, index: str, body: dict | None = None, **_) -> dict:
         if index in self._c._indices:
             raise RequestError(f"resource_already_exists_exception: index [{index}] already exists")
-        idx = _Index(index, body, self._c.device, self._c.knn_filter)
+        idx = _Index(index, body, self._c.device, self._c.knn_filter, self._c.devices)
         idx.batch_window_s = self._c.batch_window_s
         self._c._indices[index] = idx
         return {"acknowledged": True, "shards_acknowledged": True, "index": index}
@@ -436,12 +474,15 @@ class B200Client:
     """Drop-in for `OpenSearch(hosts=[...], ...)`; connection arguments are accepted and ignored."""
 
     def __init__(self, hosts=None, device: int = 0, knn_filter: str = "post", batch_window_ms: float | None = None,
-                 **_ignored):
+                 devices=None, **_ignored):
         """knn_filter: "post" (default) applies bool.filter to the k nearest neighbours, as OpenSearch's nmslib engine
         does; "pre" returns the exact top-k among the rows passing the filter (device-side pass mask in the scan)."""
         if knn_filter not in ("post", "pre"):
             raise ValueError("knn_filter must be 'post' or 'pre'")
         self.device = device
+        # devices: spread every index over these GPUs in THIS process (one sharded engine handle); otherwise
+        # RASS_B200_DEVICES or the create body's settings.index.number_of_shards decide (resolve_devices)
+        self.devices = list(devices) if devices else None
         self.knn_filter = knn_filter
         # batch_window_ms: concurrent knn searches (threads) wait up to this long to share one corpus pass
         self.batch_window_s = None if batch_window_ms is None else batch_window_ms / 1e3
@@ -561,7 +602,7 @@ class B200Client:
             name = meta["name"]
             if name in self._indices:
                 raise RequestError(f"resource_already_exists_exception: index [{name}] already exists")
-            idx = _Index(name, meta["body"], self.device, self.knn_filter)
+            idx = _Index(name, meta["body"], self.device, self.knn_filter, self.devices)
             idx.batch_window_s = self.batch_window_s
             idx.ids, idx.sources, idx.has_vec = meta["ids"], meta["sources"], meta["has_vec"]
             idx.n_docs = meta["n_docs"]

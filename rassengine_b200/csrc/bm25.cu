@@ -19,7 +19,6 @@
 
 int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
                 double* out_keys, rass_stats* stats);
-int stage_queries(rass_engine* h, const float* q_host, int B, float** q_dev_out);
 
 // ---- Lucene SmallFloat.intToByte4 / byte4ToInt (restated from the published algorithm) --------------------
 static int long_to_int4(int64_t v) {
@@ -63,6 +62,42 @@ __global__ void tile_offsets_kernel(const int64_t* __restrict__ indptr, const in
   tile_off[i] = (uint32_t)(a - lo);
 }
 
+// Per-term range of x = tf * inv[norm] over the term's postings (one CTA per term), computed with the scoring kernel's
+// own float ops.  s(x) = w - w / (1 + x) is non-decreasing in x under round-to-nearest, so s(xmin) / s(xmax) bound every
+// score the term can contribute -- what hybrid_core needs to decide whether a query's clause sums are exact in double
+// whatever the order of the additions (see hybrid_tile_fast_kernel).
+__global__ void __launch_bounds__(256) term_xrange_kernel(const int64_t* __restrict__ indptr,
+                                                          const int32_t* __restrict__ doc,
+                                                          const uint16_t* __restrict__ tf,
+                                                          const uint8_t* __restrict__ norm, const float* __restrict__ inv,
+                                                          const uint8_t* __restrict__ term_field, int64_t norm_rows,
+                                                          float* __restrict__ xmin, float* __restrict__ xmax) {
+  const int64_t t = blockIdx.x;
+  const int64_t lo = indptr[t], hi = indptr[t + 1];
+  const int f = term_field[t];
+  const uint8_t* nf = norm + (size_t)f * norm_rows;
+  const float* iv = inv + f * 256;
+  float mn = __int_as_float(0x7f800000), mx = 0.f;
+  for (int64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
+    const float x = __fmul_rn((float)tf[p], iv[nf[doc[p]]]);
+    mn = fminf(mn, x);
+    mx = fmaxf(mx, x);
+  }
+  __shared__ float smn[8], smx[8];
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, m));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+  }
+  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) { mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
+    xmin[t] = mn;
+    xmax[t] = mx;
+  }
+}
+
 template <typename T>
 static int upload(rass_engine* h, T** dst, const T* src, size_t n) {
   cudaFree(*dst);
@@ -74,9 +109,9 @@ static int upload(rass_engine* h, T** dst, const T* src, size_t n) {
 
 // F analysed fields share one CSR: term t belongs to field term_field[t]; doclen is [F][N] (tokens of the field per
 // row, 0 = the row does not have the field).  Statistics (docCount, avgdl, idf) are per field, as in Lucene.
-static int bm25_build_impl(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
-                           const int32_t* term_field, const uint32_t* doclen, int64_t V, int64_t N, int F,
-                           int64_t global_doc_count, int64_t global_sum_ttf, const int64_t* global_df) {
+int bm25_build_impl(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
+                    const int32_t* term_field, const uint32_t* doclen, int64_t V, int64_t N, int F,
+                    const int64_t* g_doc_count, const int64_t* g_sum_ttf, const int64_t* global_df) {
   if (!h) return RASS_E_INVALID;
   cudaSetDevice(h->device);
   if (V < 0 || N < 0 || F < 1 || F > 255 || !indptr || (N && !doclen)) return rass_fail(h, RASS_E_INVALID, "bad postings");
@@ -100,7 +135,7 @@ static int bm25_build_impl(rass_engine* h, const int64_t* indptr, const int32_t*
       sum_ttf += dl[i];
       norm[(size_t)f * N + i] = int_to_byte4(dl[i]);
     }
-    if (F == 1 && global_doc_count > 0) { dc = global_doc_count; sum_ttf = global_sum_ttf; }
+    if (g_doc_count && g_sum_ttf && g_doc_count[f] > 0) { dc = g_doc_count[f]; sum_ttf = g_sum_ttf[f]; }
     doc_count[(size_t)f] = dc;
     const float avgdl = dc ? (float)((double)sum_ttf / (double)dc) : 0.f;
     if (f == 0) { b.doc_count = dc; b.avgdl = avgdl; }
@@ -119,7 +154,7 @@ static int bm25_build_impl(rass_engine* h, const int64_t* indptr, const int32_t*
   for (int64_t t = 0; t < V; ++t) {
     const int f = term_field ? term_field[t] : 0;
     b.term_field_host[(size_t)t] = (uint8_t)f;
-    const int64_t df = (F == 1 && global_df) ? global_df[t] : indptr[t + 1] - indptr[t];
+    const int64_t df = global_df ? global_df[t] : indptr[t + 1] - indptr[t];
     const double dc = (double)doc_count[(size_t)f];
     b.idf_host[(size_t)t] = (float)log(1.0 + (dc - (double)df + 0.5) / ((double)df + 0.5));
   }
@@ -150,6 +185,23 @@ static int bm25_build_impl(rass_engine* h, const int64_t* indptr, const int32_t*
     cudaFree(tt_dev);
     if (e != cudaSuccess) return rass_fail(h, RASS_E_CUDA, "tile_offsets_kernel: %s", cudaGetErrorString(e));
   }
+  // per-term score ranges (order-free fast path of hybrid_core)
+  b.xmin_host.assign((size_t)V, 0.f);
+  b.xmax_host.assign((size_t)V, 0.f);
+  if (V > 0) {
+    uint8_t* tfield_dev = nullptr;
+    float *xmin_dev = nullptr, *xmax_dev = nullptr;
+    if ((rc = upload(h, &tfield_dev, b.term_field_host.data(), (size_t)V))) return rc;
+    cudaError_t e = cudaMalloc(&xmin_dev, (size_t)V * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&xmax_dev, (size_t)V * 4);
+    if (e == cudaSuccess) {
+      term_xrange_kernel<<<(unsigned)V, 256>>>(b.indptr, b.doc, b.tf, b.norm, b.inv_dev, tfield_dev, N, xmin_dev, xmax_dev);
+      e = cudaMemcpy(b.xmin_host.data(), xmin_dev, (size_t)V * 4, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(b.xmax_host.data(), xmax_dev, (size_t)V * 4, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(tfield_dev); cudaFree(xmin_dev); cudaFree(xmax_dev);
+    if (e != cudaSuccess) return rass_fail(h, RASS_E_CUDA, "term_xrange_kernel: %s", cudaGetErrorString(e));
+  }
   b.built = true;
   return RASS_OK;
 }
@@ -157,13 +209,17 @@ static int bm25_build_impl(rass_engine* h, const int64_t* indptr, const int32_t*
 extern "C" int rass_bm25_build(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
                                const uint32_t* doclen, int64_t V, int64_t N, int64_t global_doc_count,
                                int64_t global_sum_ttf, const int64_t* global_df) {
-  return bm25_build_impl(h, indptr, doc, tf, nullptr, doclen, V, N, 1, global_doc_count, global_sum_ttf, global_df);
+  SHARDED(h, sharded_bm25_build(h, indptr, doc, tf, nullptr, doclen, V, N, 1));
+  const bool global = global_doc_count > 0;
+  return bm25_build_impl(h, indptr, doc, tf, nullptr, doclen, V, N, 1, global ? &global_doc_count : nullptr,
+                         global ? &global_sum_ttf : nullptr, global_df);
 }
 
 extern "C" int rass_bm25_build_fields(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
                                       const int32_t* term_field, const uint32_t* doclen, int64_t V, int64_t N, int F) {
+  SHARDED(h, sharded_bm25_build(h, indptr, doc, tf, term_field, doclen, V, N, F));
   if (h && !term_field) return rass_fail(h, RASS_E_INVALID, "null term_field");
-  return bm25_build_impl(h, indptr, doc, tf, term_field, doclen, V, N, F, 0, 0, nullptr);
+  return bm25_build_impl(h, indptr, doc, tf, term_field, doclen, V, N, F, nullptr, nullptr, nullptr);
 }
 
 // ---- kernels ------------------------------------------------------------------------------------------------
@@ -180,11 +236,14 @@ struct HybridArgs {
   const int32_t* t_row;          // row of tile_off, -1 for rare terms
   const uint8_t* t_field;        // field of the term (selects norm plane and inv table)
   const uint8_t* t_flag;         // bit 0: last term of its field group (dis-max over fields), bit 1: last of its clause
+  const float* t_bound;          // order-free kernel: upper bound of the score of a doc matching only this term and the
+                                 // terms of the query with smaller bounds (MaxScore); null = no pruning
   const int64_t* knn_rows;       // [B, k] or null
   const float* knn_scores;
   const uint8_t* row_filter;
   int64_t filter_rows;
-  int64_t row_base, n_docs, norm_rows;   // norm is [F][norm_rows]
+  RowMap rmap;                   // local doc <-> global row (knn lists and outputs carry global rows)
+  int64_t n_docs, norm_rows;     // norm is [F][norm_rows]
   int n_tiles, table_tiles, k;   // tiles of this launch; tiles the offset table covers (docs known to the postings)
   float w_knn;
   double* xkey;                  // [B][n_tiles * k]
@@ -193,127 +252,24 @@ struct HybridArgs {
                                  // integer image, 0 = none): k rows score at least this much, lower keys are out
 };
 
-// One CTA per (tile of 4096 docs, query): the whole bool.should of the reference for those docs.
-//   text clause : for every query term in order, s = w - w / (1 + tf * inv[norm[d]]) in float (each op rounded),
-//                 summed in double per doc -- a term's postings name a doc once, so plain shared-memory adds
-//                 between barriers are race free and the summation order is the oracle's; cast to float
-//   knn clause  : the k nearest rows get float(w_knn * knn_score) added in double
-//   bool.filter : rows failing the pass mask never match
-//   top-k       : 32-bit radix select over the tile's fused float scores, ties by row ascending
-// The tile's best k (score, row) go to the query's list; exact_select_kernel ranks n_tiles * k entries.
-// MULTI = false: one analysed field, one text clause (chunk-only indices): the clause sum stays in acc.
-// MULTI = true : several field groups / clauses: acc = running sum of the current field group, best = dis-max over
-//                the groups of the current clause (float, like every Lucene scorer's score()), total = sum over the
-//                finished clauses in double; dynamic shared memory holds total and best behind acc.
+// The rest of a (tile, query) CTA once the text clauses are summed in `fused` (double per doc, 0 = no match): the knn
+// clause, then the tile's top-k by (fused float score desc, row asc) into the query's list.  MULTI: `fused` holds clause
+// sums in double (the knn score is one more clause); otherwise the single text clause is rounded to float first.
 template <bool MULTI>
-__global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_constant__ HybridArgs a) {
-  extern __shared__ __align__(16) unsigned char hyb_smem[];
-  double* acc = reinterpret_cast<double*>(hyb_smem);                       // [HYB_TILE]
-  double* total = acc + (MULTI ? HYB_TILE : 0);                            // [HYB_TILE] (MULTI)
-  float* best = reinterpret_cast<float*>(total + HYB_TILE);               // [HYB_TILE] (MULTI)
-  __shared__ float s_inv[256];
-  __shared__ int64_t s_lo[HYB_THREADS];
-  __shared__ uint32_t s_n[HYB_THREADS];
-  __shared__ float s_w[HYB_THREADS];
-  __shared__ uint8_t s_field[HYB_THREADS], s_flag[HYB_THREADS];
+__device__ __forceinline__ void hybrid_tile_tail(const HybridArgs& a, double* fused, int q, int tile, int64_t d0,
+                                                 int64_t d1, bool knn_done = false) {
   __shared__ __align__(16) int s_cnt[2][HYB_THREADS / 32];
   __shared__ uint32_t s_list[HYB_LIST];
   __shared__ int s_nout, s_nmatch, s_ns;
   __shared__ uint32_t s_g;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x, q = blockIdx.y;
-  const int64_t d0 = (int64_t)tile * HYB_TILE;
-  const int64_t d1 = min(d0 + HYB_TILE, a.n_docs);
-  for (int i = tid; i < HYB_TILE; i += HYB_THREADS) {
-    acc[i] = 0.0;
-    if (MULTI) { total[i] = 0.0; best[i] = 0.f; }
-  }
   if (tid == 0) { s_nout = 0; s_nmatch = 0; s_ns = 0; }
-  __syncthreads();
-
-  // ---- text clauses ----
-  if (a.qt_indptr) {
-    const int j_begin = a.qt_indptr[q], j_end = a.qt_indptr[q + 1];
-    int cur_field = -1;
-    const uint8_t* norm_f = a.norm;
-    bool group_touched = false, clause_touched = false;     // uniform across the CTA
-    for (int j0 = j_begin; j0 < j_end; j0 += HYB_THREADS) {
-      const int nt = min(HYB_THREADS, j_end - j0);
-      // posting range of every term inside this tile, fetched by one thread per term (one latency for all terms)
-      if (tid < nt) {
-        const int j = j0 + tid;
-        const int row = a.t_row[j];
-        uint32_t pa = 0, pb = a.t_len[j];
-        if (row >= 0) {
-          if (tile < a.table_tiles) {
-            const uint32_t* off = a.tile_off + (size_t)row * (a.table_tiles + 1) + tile;
-            pa = off[0];
-            pb = off[1];
-          } else {
-            pb = 0;      // rows appended after rass_bm25_build carry no postings
-          }
-        }
-        s_lo[tid] = a.t_lo[j] + pa;
-        s_n[tid] = pb - pa;
-        s_w[tid] = a.t_w[j];
-        s_field[tid] = a.t_field[j];
-        s_flag[tid] = a.t_flag[j];
-      }
-      __syncthreads();
-      for (int j = 0; j < nt; ++j) {
-        const uint32_t n = s_n[j];
-        if (n != 0) {                         // uniform: a term without postings in the tile needs no barrier
-          const int field = s_field[j];
-          if (field != cur_field) {           // per-field length table and norm plane
-            s_inv[tid] = a.inv[field * 256 + tid];
-            norm_f = a.norm + (size_t)field * a.norm_rows;
-            cur_field = field;
-            __syncthreads();
-          }
-          const int64_t lo = s_lo[j];
-          const float w = s_w[j];
-          for (uint32_t p = tid; p < n; p += HYB_THREADS) {
-            const int64_t d = (int64_t)__ldg(a.doc + lo + p);
-            if (d < d0 || d >= d1) continue;                                             // rare terms scan their whole list
-            if (a.row_filter && (d >= a.filter_rows || !a.row_filter[d])) continue;       // bool.filter
-            const float x = __fmul_rn((float)__ldg(a.tf + lo + p), s_inv[norm_f[d]]);
-            const float s = __fsub_rn(w, __fdiv_rn(w, __fadd_rn(1.0f, x)));
-            if (s > 0.f) acc[d - d0] += (double)s;
-          }
-          group_touched = true;
-          __syncthreads();
-        }
-        if (MULTI) {
-          const int flag = s_flag[j];
-          if ((flag & 1) && group_touched) {  // end of a field group: dis-max of the float field scores
-            for (int i = tid; i < HYB_TILE; i += HYB_THREADS) {
-              const double v = acc[i];
-              if (v != 0.0) { best[i] = fmaxf(best[i], (float)v); acc[i] = 0.0; }
-            }
-            group_touched = false;
-            clause_touched = true;
-            __syncthreads();
-          }
-          if ((flag & 2) && clause_touched) { // end of a clause: the bool sums clause scores in double
-            for (int i = tid; i < HYB_TILE; i += HYB_THREADS) {
-              const float v = best[i];
-              if (v != 0.f) { total[i] += (double)v; best[i] = 0.f; }
-            }
-            clause_touched = false;
-            __syncthreads();
-          }
-        }
-      }
-      __syncthreads();                        // the next chunk overwrites s_lo / s_n / s_w
-    }
-  }
-  double* fused = MULTI ? total : acc;
-
+  double* acc = fused;
   // ---- knn clause ----
-  if (a.knn_rows && tid < a.k) {
+  if (!knn_done && a.knn_rows && tid < a.k) {
     const int64_t r = a.knn_rows[(size_t)q * a.k + tid];
     if (r >= 0) {
-      const int64_t d = r - a.row_base;
+      const int64_t d = row_global_to_local(a.rmap, r);     // -1: a row of another shard
       if (d >= d0 && d < d1 && !(a.row_filter && (d >= a.filter_rows || !a.row_filter[d])))
         // a clause's score is a float; the bool sums the clause scores in double (and the final cast to float below
         // is the identity for rows without a knn contribution)
@@ -322,7 +278,6 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
     }
   }
   __syncthreads();
-  acc = fused;
 
   // ---- top-k of the tile: keys as order-preserving integers, 0 = no match ----
   constexpr int PER = HYB_TILE / HYB_THREADS;
@@ -450,8 +405,479 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
   }
 }
 
+// One CTA per (tile of 4096 docs, query): the whole bool.should of the reference for those docs.
+//   text clause : for every query term in order, s = w - w / (1 + tf * inv[norm[d]]) in float (each op rounded),
+//                 summed in double per doc -- a term's postings name a doc once, so plain shared-memory adds
+//                 between barriers are race free and the summation order is the oracle's; cast to float
+//   knn clause  : the k nearest rows get float(w_knn * knn_score) added in double
+//   bool.filter : rows failing the pass mask never match
+//   top-k       : 32-bit radix select over the tile's fused float scores, ties by row ascending
+// The tile's best k (score, row) go to the query's list; exact_select_kernel ranks n_tiles * k entries.
+// MULTI = false: one analysed field, one text clause (chunk-only indices): the clause sum stays in acc.
+// MULTI = true : several field groups / clauses: acc = running sum of the current field group, best = dis-max over
+//                the groups of the current clause (float, like every Lucene scorer's score()), total = sum over the
+//                finished clauses in double; dynamic shared memory holds total and best behind acc.
+template <bool MULTI>
+__global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_constant__ HybridArgs a) {
+  extern __shared__ __align__(16) unsigned char hyb_smem[];
+  double* acc = reinterpret_cast<double*>(hyb_smem);                       // [HYB_TILE]
+  double* total = acc + (MULTI ? HYB_TILE : 0);                            // [HYB_TILE] (MULTI)
+  float* best = reinterpret_cast<float*>(total + HYB_TILE);               // [HYB_TILE] (MULTI)
+  __shared__ float s_inv[256];
+  __shared__ int64_t s_lo[HYB_THREADS];
+  __shared__ uint32_t s_n[HYB_THREADS];
+  __shared__ float s_w[HYB_THREADS];
+  __shared__ uint8_t s_field[HYB_THREADS], s_flag[HYB_THREADS];
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.y, q = blockIdx.x;            // queries fastest: the CTAs in flight cover a few tiles of EVERY
+                                                          // query, so a query's pruning bound exists after its first tiles
+  const int64_t d0 = (int64_t)tile * HYB_TILE;
+  const int64_t d1 = min(d0 + HYB_TILE, a.n_docs);
+  for (int i = tid; i < HYB_TILE; i += HYB_THREADS) {
+    acc[i] = 0.0;
+    if (MULTI) { total[i] = 0.0; best[i] = 0.f; }
+  }
+  __syncthreads();
+
+  // ---- text clauses ----
+  if (a.qt_indptr) {
+    const int j_begin = a.qt_indptr[q], j_end = a.qt_indptr[q + 1];
+    int cur_field = -1;
+    const uint8_t* norm_f = a.norm;
+    bool group_touched = false, clause_touched = false;     // uniform across the CTA
+    for (int j0 = j_begin; j0 < j_end; j0 += HYB_THREADS) {
+      const int nt = min(HYB_THREADS, j_end - j0);
+      // posting range of every term inside this tile, fetched by one thread per term (one latency for all terms)
+      if (tid < nt) {
+        const int j = j0 + tid;
+        const int row = a.t_row[j];
+        uint32_t pa = 0, pb = a.t_len[j];
+        if (row >= 0) {
+          if (tile < a.table_tiles) {
+            const uint32_t* off = a.tile_off + (size_t)row * (a.table_tiles + 1) + tile;
+            pa = off[0];
+            pb = off[1];
+          } else {
+            pb = 0;      // rows appended after rass_bm25_build carry no postings
+          }
+        }
+        s_lo[tid] = a.t_lo[j] + pa;
+        s_n[tid] = pb - pa;
+        s_w[tid] = a.t_w[j];
+        s_field[tid] = a.t_field[j];
+        s_flag[tid] = a.t_flag[j];
+      }
+      __syncthreads();
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t n = s_n[j];
+        if (n != 0) {                         // uniform: a term without postings in the tile needs no barrier
+          const int field = s_field[j];
+          if (field != cur_field) {           // per-field length table and norm plane
+            s_inv[tid] = a.inv[field * 256 + tid];
+            norm_f = a.norm + (size_t)field * a.norm_rows;
+            cur_field = field;
+            __syncthreads();
+          }
+          const int64_t lo = s_lo[j];
+          const float w = s_w[j];
+          for (uint32_t p = tid; p < n; p += HYB_THREADS) {
+            const int64_t d = (int64_t)__ldg(a.doc + lo + p);
+            if (d < d0 || d >= d1) continue;                                             // rare terms scan their whole list
+            if (a.row_filter && (d >= a.filter_rows || !a.row_filter[d])) continue;       // bool.filter
+            const float x = __fmul_rn((float)__ldg(a.tf + lo + p), s_inv[norm_f[d]]);
+            const float s = __fsub_rn(w, __fdiv_rn(w, __fadd_rn(1.0f, x)));
+            if (s > 0.f) acc[d - d0] += (double)s;
+          }
+          group_touched = true;
+          __syncthreads();
+        }
+        if (MULTI) {
+          const int flag = s_flag[j];
+          if ((flag & 1) && group_touched) {  // end of a field group: dis-max of the float field scores
+            for (int i = tid; i < HYB_TILE; i += HYB_THREADS) {
+              const double v = acc[i];
+              if (v != 0.0) { best[i] = fmaxf(best[i], (float)v); acc[i] = 0.0; }
+            }
+            group_touched = false;
+            clause_touched = true;
+            __syncthreads();
+          }
+          if ((flag & 2) && clause_touched) { // end of a clause: the bool sums clause scores in double
+            for (int i = tid; i < HYB_TILE; i += HYB_THREADS) {
+              const float v = best[i];
+              if (v != 0.f) { total[i] += (double)v; best[i] = 0.f; }
+            }
+            clause_touched = false;
+            __syncthreads();
+          }
+        }
+      }
+      __syncthreads();                        // the next chunk overwrites s_lo / s_n / s_w
+    }
+  }
+  hybrid_tile_tail<MULTI>(a, MULTI ? total : acc, q, tile, d0, d1);
+}
+
+// Order-free form of the single-clause kernel above, for queries whose clause sums are EXACT in double whatever the
+// order of the additions (hybrid_core checks it per query from the per-term score ranges: every addend is a float that
+// is a multiple of 2^L, every partial sum stays below 2^(L + 53)).  Exact sums do not depend on the order, so the
+// result is bit-identical to the ordered walk -- and the CTA is free to
+//   * take the postings of all the query's terms in the tile at once: warps draw 128-posting chunks of any term, no
+//     barrier per term, four independent postings in flight per lane, shared-memory atomics (two terms may name the same
+//     doc at the same time);
+//   * skip work the way Lucene's MaxScore scorer does.  g = the query's pruning bound (k rows already score >= g,
+//     published by earlier tiles).  With the terms sorted by their largest possible score, the longest prefix whose
+//     summed bounds stay below g is NON-ESSENTIAL: a doc matching only such terms scores below g and cannot reach the
+//     top-k.  So essential terms are accumulated first and mark the docs they touch (the knn rows of the tile are marked
+//     too); the postings of non-essential terms -- the frequent terms, i.e. most postings -- are then only looked at
+//     (one doc id each) and scored for marked docs alone.  Every doc that can still reach the top-k gets its complete,
+//     exact score; the others are never emitted.  Tiles that start before a bound exists simply treat every term as
+//     essential.
+#define HYB_FAST_TERMS 64      // terms staged per round
+#define HYB_CHUNK 128          // postings a warp draws at a time (4 per lane)
+#define HYB_QUEUE 64           // per-warp queue of non-essential postings that hit a marked doc
+#define HYB_SPARSE_CAP 512     // marked docs at or above the bound a tile can rank without the dense select
+
+// one scored posting: s = w - w / (1 + tf * inv[norm]) with every float op rounded (Lucene's BM25Similarity), added to
+// the doc's clause sum
+__device__ __forceinline__ bool hyb_score_add(double* acc, const float* s_inv, int rel, uint32_t tfv, uint32_t nb, float w) {
+  const float x = __fmul_rn((float)tfv, s_inv[nb]);
+  const float sc = __fsub_rn(w, __fdiv_rn(w, __fadd_rn(1.0f, x)));
+  if (sc > 0.f) atomicAdd(&acc[rel], (double)sc);
+  return sc > 0.f;
+}
+
+template <bool FILTER>
+__global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_fast_kernel(const __grid_constant__ HybridArgs a) {
+  __shared__ double acc[HYB_TILE];
+  __shared__ uint32_t s_bits[HYB_TILE / 32];      // docs touched by an essential term or named by the knn clause
+  __shared__ float s_inv[256];
+  __shared__ int64_t s_lo[HYB_FAST_TERMS];
+  __shared__ uint32_t s_n[HYB_FAST_TERMS];
+  __shared__ uint32_t s_cpre[2][HYB_FAST_TERMS + 1];   // chunk prefix of the essential [0] / non-essential [1] terms
+  __shared__ float s_w[HYB_FAST_TERMS];
+  __shared__ int s_qrel[HYB_THREADS / 32][HYB_QUEUE];      // per-warp queue: doc slot, posting, weight
+  __shared__ uint32_t s_qtf[HYB_THREADS / 32][HYB_QUEUE];
+  __shared__ float s_qw[HYB_THREADS / 32][HYB_QUEUE];
+  __shared__ int s_cn;
+  __shared__ uint32_t s_go;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.y, q = blockIdx.x;
+  const int64_t d0 = (int64_t)tile * HYB_TILE;
+  const int64_t d1 = min(d0 + HYB_TILE, a.n_docs);
+  const uint32_t tile_len = (uint32_t)(d1 - d0);
+  uint32_t go = 0;                          // the query's pruning bound as this CTA starts (ordered image, 0 = none)
+  bool pruned = false;
+  if (a.qt_indptr) {
+    const int j_begin = a.qt_indptr[q], j_end = a.qt_indptr[q + 1];
+    const uint8_t* norm_t = a.norm + d0;    // the tile's slice of the norm plane
+    // MaxScore needs all essential terms done before the first non-essential one: one staging round only
+    const bool may_prune = a.t_bound != nullptr && j_end - j_begin <= HYB_FAST_TERMS;
+    // The bound is read ONCE per CTA (other tiles raise it while this one runs, and every branch on it must be
+    // uniform): warp 0 reads it and stages the first round right away, the other warps clear the tile meanwhile.
+    float g0 = neg_inf<float>();
+    if (warp == 0) {
+      uint32_t v = 0;
+      if (lane == 0 && may_prune) v = __ldcg(a.gthr + q);
+      v = __shfl_sync(0xffffffffu, v, 0);
+      if (lane == 0) s_go = v;
+      if (v) g0 = unord32(v);
+    }
+    if (j_begin < j_end) {                  // every term of the query is of one field (hybrid_core checked)
+      const int field = a.t_field[j_begin];
+      s_inv[tid] = a.inv[field * 256 + tid];
+      norm_t = a.norm + (size_t)field * a.norm_rows + d0;
+    }
+    if (warp != 0 || j_begin == j_end) {
+      for (int i = tid - (j_begin == j_end ? 0 : 32); i < HYB_TILE; i += HYB_THREADS - (j_begin == j_end ? 0 : 32))
+        acc[i] = 0.0;
+    }
+    if (warp == 1) {
+      for (int i = lane; i < HYB_TILE / 32; i += 32) s_bits[i] = 0u;
+      if (lane == 0) s_cn = 0;
+    }
+    for (int j0 = j_begin; j0 < j_end; j0 += HYB_FAST_TERMS) {
+      const int nt = min(HYB_FAST_TERMS, j_end - j0);
+      if (j0 != j_begin) __syncthreads();   // the previous round is through with the staging arrays
+      if (tid < 32) {
+        const bool pruned = g0 > neg_inf<float>();
+        const float g = g0;
+        // posting range of the round's terms inside this tile (two terms per lane), chunk counts per class
+        uint32_t ce[2] = {0, 0}, cn[2] = {0, 0};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int t = 2 * tid + h;
+          if (t < nt) {
+            const int j = j0 + t;
+            const int row = a.t_row[j];
+            uint32_t pa = 0, pb = a.t_len[j];
+            if (row >= 0) {
+              if (tile < a.table_tiles) {
+                const uint32_t* off = a.tile_off + (size_t)row * (a.table_tiles + 1) + tile;
+                pa = off[0];
+                pb = off[1];
+              } else {
+                pb = 0;      // rows appended after rass_bm25_build carry no postings
+              }
+            }
+            s_lo[t] = a.t_lo[j] + pa;
+            s_n[t] = pb - pa;
+            s_w[t] = a.t_w[j];
+            const uint32_t chunks = (pb - pa + HYB_CHUNK - 1) / HYB_CHUNK;
+            const bool ne = pruned && a.t_bound[j] < g;         // summed bounds up to this term stay below g
+            if (ne) cn[h] = chunks; else ce[h] = chunks;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t v0 = c ? cn[0] : ce[0], v1 = c ? cn[1] : ce[1];
+          uint32_t incl = v0 + v1;
+#pragma unroll
+          for (int m = 1; m < 32; m <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, m);
+            if (tid >= m) incl += o;
+          }
+          const uint32_t excl = incl - v0 - v1;
+          if (2 * tid <= nt) s_cpre[c][2 * tid] = excl;
+          if (2 * tid + 1 <= nt) s_cpre[c][2 * tid + 1] = excl + v0;
+          if (tid == 31 && nt == HYB_FAST_TERMS) s_cpre[c][HYB_FAST_TERMS] = incl;
+        }
+      }
+      __syncthreads();                      // (first round: the tile is cleared, s_go / s_inv are set as well)
+      if (j0 == j_begin) {
+        go = s_go;
+        pruned = go != 0;
+        if (pruned && a.knn_rows) {         // the knn rows of the tile can reach the top-k whatever their text score
+          if (tid < a.k) {
+            const int64_t r = a.knn_rows[(size_t)q * a.k + tid];
+            const int64_t d = r >= 0 ? row_global_to_local(a.rmap, r) : -1;
+            if (d >= d0 && d < d1) atomicOr(&s_bits[(d - d0) >> 5], 1u << ((d - d0) & 31));
+          }
+          // (ordered before the non-essential phase by the barrier that phase starts with)
+        }
+      }
+      // ---- essential terms: every posting is scored ----
+      {
+        const uint32_t n_chunks = s_cpre[0][nt];
+        int j = 0;
+        for (uint32_t c = warp; c < n_chunks; c += HYB_THREADS / 32) {
+          while (c >= s_cpre[0][j + 1]) ++j;                   // warp-uniform: once per chunk
+          const uint32_t first = (c - s_cpre[0][j]) * HYB_CHUNK, n_rem = s_n[j] - first;
+          const int32_t* pd = a.doc + s_lo[j] + first;
+          const uint16_t* pt = a.tf + s_lo[j] + first;
+          const float w = s_w[j];
+          int rel[HYB_CHUNK / 32];
+          uint32_t tfv[HYB_CHUNK / 32], nb[HYB_CHUNK / 32];
+#pragma unroll
+          for (int u = 0; u < HYB_CHUNK / 32; ++u) {
+            const uint32_t i = u * 32 + lane;
+            const int dd = i < n_rem ? __ldg(pd + i) : -1;
+            rel[u] = dd - (int)d0;                             // in the tile iff 0 <= rel < tile_len (rare terms scan
+            if ((uint32_t)rel[u] >= tile_len) rel[u] = -1;     // their whole list); -1 and out-of-range ids fall out
+            if (FILTER && rel[u] >= 0 && (dd >= a.filter_rows || !a.row_filter[dd])) rel[u] = -1;      // bool.filter
+            if (rel[u] >= 0) tfv[u] = __ldg(pt + i);
+          }
+#pragma unroll
+          for (int u = 0; u < HYB_CHUNK / 32; ++u) nb[u] = rel[u] >= 0 ? norm_t[rel[u]] : 0u;
+#pragma unroll
+          for (int u = 0; u < HYB_CHUNK / 32; ++u) {
+            if (rel[u] < 0) continue;
+            if (hyb_score_add(acc, s_inv, rel[u], tfv[u], nb[u], w) && pruned)
+              atomicOr(&s_bits[rel[u] >> 5], 1u << (rel[u] & 31));
+          }
+        }
+      }
+      // ---- non-essential terms: a doc id per posting, scored for marked docs only ----
+      if (s_cpre[1][nt] != 0) {                                // uniform over the CTA
+        __syncthreads();                                       // the marks are complete
+        const uint32_t n_chunks = s_cpre[1][nt];
+        int j = 0;
+        int qn = 0;                                            // entries queued by this warp (uniform)
+        int* qrel = s_qrel[warp];
+        uint32_t* qtf = s_qtf[warp];
+        float* qw = s_qw[warp];
+        auto drain = [&](int n_take) {                         // score the first n_take queued postings, one per lane
+          __syncwarp();
+          if (lane < n_take) {
+            const int r = qrel[lane];
+            hyb_score_add(acc, s_inv, r, qtf[lane], norm_t[r], qw[lane]);
+          }
+          __syncwarp();
+          // move what is left to the front
+          const int left = qn - n_take;
+          int r2 = 0; uint32_t t2 = 0; float w2 = 0.f;
+          if (lane < left) { r2 = qrel[n_take + lane]; t2 = qtf[n_take + lane]; w2 = qw[n_take + lane]; }
+          __syncwarp();
+          if (lane < left) { qrel[lane] = r2; qtf[lane] = t2; qw[lane] = w2; }
+          qn = left;
+          __syncwarp();
+        };
+        for (uint32_t c = warp; c < n_chunks; c += HYB_THREADS / 32) {
+          while (c >= s_cpre[1][j + 1]) ++j;
+          const uint32_t first = (c - s_cpre[1][j]) * HYB_CHUNK, n_rem = s_n[j] - first;
+          const int32_t* pd = a.doc + s_lo[j] + first;
+          const uint16_t* pt = a.tf + s_lo[j] + first;
+          const float w = s_w[j];
+          int dd[HYB_CHUNK / 32];
+#pragma unroll
+          for (int u = 0; u < HYB_CHUNK / 32; ++u) {
+            const uint32_t i = u * 32 + lane;
+            dd[u] = i < n_rem ? __ldg(pd + i) : -1;
+          }
+#pragma unroll
+          for (int u = 0; u < HYB_CHUNK / 32; ++u) {
+            int rel = dd[u] - (int)d0;
+            bool hit = (uint32_t)rel < tile_len && ((s_bits[rel >> 5] >> (rel & 31)) & 1u);
+            if (FILTER && hit && (dd[u] >= a.filter_rows || !a.row_filter[dd[u]])) hit = false;
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (bal) {                                          // warp-uniform
+              if (hit) {
+                const int pos = qn + __popc(bal & ((1u << lane) - 1));
+                qrel[pos] = rel;
+                qtf[pos] = __ldg(pt + u * 32 + lane);
+                qw[pos] = w;
+              }
+              qn += __popc(bal);
+              if (qn >= 32) drain(32);                          // qn <= 31 + 32 before, so one drain suffices
+            }
+          }
+        }
+        if (qn > 0) drain(qn);
+      }
+    }
+  } else {
+    for (int i = tid; i < HYB_TILE; i += HYB_THREADS) acc[i] = 0.0;      // vector-only: nothing but the knn clause
+  }
+  __syncthreads();
+  if (!pruned) {
+    hybrid_tile_tail<false>(a, acc, q, tile, d0, d1);
+    return;
+  }
+  // ---- sparse tail: only marked docs can have a score; rank those at or above the bound ----
+  static_assert(HYB_SPARSE_CAP == (HYB_THREADS / 32) * HYB_QUEUE, "the candidate list reuses the warps' queues");
+  uint32_t* c_key = reinterpret_cast<uint32_t*>(&s_qrel[0][0]);      // the queues are drained: reuse their memory
+  uint32_t* c_doc = &s_qtf[0][0];
+  if (a.knn_rows && tid < a.k) {            // the knn clause (see hybrid_tile_tail)
+    const int64_t r = a.knn_rows[(size_t)q * a.k + tid];
+    if (r >= 0) {
+      const int64_t d = row_global_to_local(a.rmap, r);
+      if (d >= d0 && d < d1 && !(FILTER && (d >= a.filter_rows || !a.row_filter[d])))
+        acc[d - d0] = (double)(float)acc[d - d0] + (double)__fmul_rn(a.w_knn, a.knn_scores[(size_t)q * a.k + tid]);
+    }
+  }
+  __syncthreads();
+  if (tid < HYB_TILE / 32) {
+    uint32_t wbits = s_bits[tid];
+    while (wbits) {
+      const int b = __ffs(wbits) - 1;
+      wbits &= wbits - 1;
+      const int slot = tid * 32 + b;
+      const double v = acc[slot];
+      if (v != 0.0) {
+        const uint32_t key = ord32((float)v);
+        if (key >= go) {
+          const int pos = atomicAdd(&s_cn, 1);
+          if (pos < HYB_SPARSE_CAP) { c_key[pos] = key; c_doc[pos] = (uint32_t)slot; }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int n_c = s_cn;
+  if (n_c > HYB_SPARSE_CAP) {               // a wall of docs above the bound: the dense select handles any count
+    hybrid_tile_tail<false>(a, acc, q, tile, d0, d1, true);
+    return;
+  }
+  double* xk = a.xkey + ((size_t)q * a.n_tiles + tile) * a.k;
+  uint32_t* xr = a.xrow + ((size_t)q * a.n_tiles + tile) * a.k;
+  for (int c = tid; c < n_c; c += HYB_THREADS) {
+    const uint32_t mk = c_key[c], md = c_doc[c];
+    int rank = c;
+    if (n_c >= a.k) {
+      rank = 0;
+      for (int j = 0; j < n_c; ++j) rank += (c_key[j] > mk) || (c_key[j] == mk && c_doc[j] < md);
+    }
+    if (rank < a.k) {
+      xk[rank] = (double)unord32(mk);
+      xr[rank] = (uint32_t)(d0 + md);
+      if (n_c >= a.k && rank == a.k - 1) atomicMax(a.gthr + q, mk);      // k rows of this tile score >= mk
+    }
+  }
+  for (int i = min(n_c, a.k) + tid; i < a.k; i += HYB_THREADS) {
+    xk[i] = neg_inf<double>();
+    xr[i] = 0xffffffffu;
+  }
+}
+
+// Per-query top-k of the tile lists.  The tiles left a lower bound of the query's k-th best key in gthr (the largest
+// k-th key any tile found); entries below it cannot be in the top-k, and what is left -- normally k .. a few k entries --
+// is ranked by counting.  Without a published bound (no tile had more than k matches) the k-th largest per-thread maximum
+// serves.  A query with more than HSEL_CAP survivors (a wall of equal scores) is handed to the radix select.
+#define HSEL_CAP 2048
+__global__ void __launch_bounds__(1024) hybrid_select_kernel(const double* __restrict__ xkey,
+                                                             const uint32_t* __restrict__ xrow, size_t entries, int k,
+                                                             const uint32_t* __restrict__ gthr, RowMap rmap,
+                                                             int64_t* __restrict__ out_rows,
+                                                             float* __restrict__ out_scores,
+                                                             double* __restrict__ out_keys, int* __restrict__ fallback) {
+  __shared__ uint32_t ck[HSEL_CAP], cr[HSEL_CAP];
+  __shared__ int s_n;
+  const int tid = threadIdx.x, q = blockIdx.x;
+  const double* key = xkey + (size_t)q * entries;
+  const uint32_t* row = xrow + (size_t)q * entries;
+  if (tid == 0) s_n = 0;
+  uint32_t thr = gthr[q];
+  if (thr == 0) {
+    uint32_t mx = 0;
+    for (size_t i = tid; i < entries; i += blockDim.x)
+      if (row[i] != 0xffffffffu) mx = max(mx, ord32((float)key[i]));
+    uint32_t bp = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = bp | (1u << bit);
+      if (__syncthreads_count(mx >= cand) >= k) bp = cand;
+    }
+    thr = bp;
+  }
+  __syncthreads();
+  for (size_t i = tid; i < entries; i += blockDim.x) {
+    const uint32_t r = row[i];
+    if (r == 0xffffffffu) continue;
+    const uint32_t o = ord32((float)key[i]);
+    if (o >= thr) {
+      const int pos = atomicAdd(&s_n, 1);
+      if (pos < HSEL_CAP) { ck[pos] = o; cr[pos] = r; }
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n > HSEL_CAP) {
+    if (tid == 0) fallback[q] = 1;
+    return;
+  }
+  if (tid == 0) fallback[q] = 0;
+  for (int c = tid; c < n; c += blockDim.x) {
+    const uint32_t mk = ck[c], mr = cr[c];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (ck[j] > mk) || (ck[j] == mk && cr[j] < mr);
+    if (rank < k) {
+      const size_t o = (size_t)q * k + rank;
+      const float v = unord32(mk);
+      out_rows[o] = row_local_to_global(rmap, (int64_t)mr);
+      out_scores[o] = v;
+      if (out_keys) out_keys[o] = (double)v;
+    }
+  }
+  for (int r = n + tid; r < k; r += blockDim.x) {
+    const size_t o = (size_t)q * k + r;
+    out_rows[o] = -1;
+    out_scores[o] = 0.f;
+    if (out_keys) out_keys[o] = 0.0;
+  }
+}
+
 int launch_select_batch(rass_engine* h, size_t entries, int B, int k, int64_t* out_rows, float* out_scores,
-                        double* out_keys, cudaStream_t st);
+                        double* out_keys, cudaStream_t st, const int* only_if);
 
 static int ensure_hybrid_workspace(rass_engine* h, size_t n_terms_cap, int B) {
   Bm25State& b = h->bm25;
@@ -459,10 +885,13 @@ static int ensure_hybrid_workspace(rass_engine* h, size_t n_terms_cap, int B) {
     CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
     const size_t tc = std::max<size_t>(n_terms_cap * 2, 1024), qc = std::max<size_t>((size_t)B * 2 + 2, 256);
     // one pinned + one device block:
-    // [t_lo i64 x tc][t_len u32 x tc][t_w f32 x tc][t_row i32 x tc][indptr i32 x qc][t_field u8 x tc][t_flag u8 x tc]
-    const size_t bytes = tc * (8 + 4 + 4 + 4 + 1 + 1) + qc * 4;
+    // [t_lo i64 x tc][t_len u32 x tc][t_w f32 x tc][t_row i32 x tc][t_bound f32 x tc][indptr i32 x qc][t_field u8 x tc]
+    // [t_flag u8 x tc]
+    const size_t bytes = tc * (8 + 4 + 4 + 4 + 4 + 1 + 1) + qc * 4;
     cudaFree(b.hyb_gthr); b.hyb_gthr = nullptr;
     CUDA_TRY(h, cudaMalloc(&b.hyb_gthr, qc * sizeof(uint32_t)));
+    cudaFree(b.sel_fallback); b.sel_fallback = nullptr;
+    CUDA_TRY(h, cudaMalloc(&b.sel_fallback, qc * sizeof(int)));
     cudaFreeHost(b.qt_host); b.qt_host = nullptr;
     cudaFree(b.qt_dev); b.qt_dev = nullptr;
     CUDA_TRY(h, cudaMallocHost(&b.qt_host, bytes));
@@ -477,20 +906,12 @@ static int ensure_hybrid_workspace(rass_engine* h, size_t n_terms_cap, int B) {
 // qweights == null: weight of a term = float(w_text) * idf(term); otherwise the caller's per-term weights
 // (fuzzy expansions carry their own boost and blended idf)
 // Row-sharded corpora fuse against the GLOBAL k nearest (all-gathered and merged by the caller) and leave their local
-// top-k on the device for the next all-gather.
-struct HybridExt {
-  const int64_t* knn_rows_dev;   // [B, k] global rows (-1 = none); rows outside this shard are ignored
-  const float* knn_scores_dev;   // [B, k]
-  int64_t* out_rows_dev;         // [B, k] global rows
-  float* out_scores_dev;         // [B, k] fused float scores
-  double* out_keys_dev;          // [B, k] the same as double (what rass_merge_topk_dev ranks by), nullable
-};
-
+// top-k on the device for the next exchange (HybridExt, common.cuh).
 // qflags (nullable): per term, bit 0 = last term of its field group, bit 1 = last term of its clause; the clause score is
 // the maximum over its field groups (multi_match best_fields), the query's text score the sum over clauses.
-static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr, const int32_t* qterms,
-                       const float* qweights, const uint8_t* qflags, float w_text, float w_knn, int k,
-                       int64_t* out_rows, float* out_scores, rass_stats* stats, const HybridExt* ext = nullptr) {
+int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr, const int32_t* qterms,
+                const float* qweights, const uint8_t* qflags, float w_text, float w_knn, int k,
+                int64_t* out_rows, float* out_scores, rass_stats* stats, const HybridExt* ext) {
   if (!h) return RASS_E_INVALID;
   cudaSetDevice(h->device);
   if (B < 1 || (!ext && (!out_rows || !out_scores))) return rass_fail(h, RASS_E_INVALID, "bad arguments");
@@ -523,6 +944,8 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
   const bool have_text = qterm_indptr != nullptr;
   size_t n_terms = 0;
   bool multi = false;
+  static const bool force_ordered = getenv("RASS_DEBUG_HYBRID_ORDERED") != nullptr;   // A/B and test switch
+  bool order_free = !force_ordered && !h->bm25.force_ordered;
   if (have_text) {
     if ((rc = ensure_hybrid_workspace(h, (size_t)(qterm_indptr[B] - qterm_indptr[0]), B))) return rc;
     unsigned char* base = b.qt_host;
@@ -530,13 +953,20 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
     uint32_t* t_len = reinterpret_cast<uint32_t*>(base + b.qt_cap * 8);
     float* t_w = reinterpret_cast<float*>(base + b.qt_cap * 12);
     int32_t* t_row = reinterpret_cast<int32_t*>(base + b.qt_cap * 16);
-    int32_t* indptr = reinterpret_cast<int32_t*>(base + b.qt_cap * 20);
-    uint8_t* t_field = base + b.qt_cap * 20 + b.qt_q_cap * 4;
+    float* t_bound = reinterpret_cast<float*>(base + b.qt_cap * 20);
+    int32_t* indptr = reinterpret_cast<int32_t*>(base + b.qt_cap * 24);
+    uint8_t* t_field = base + b.qt_cap * 24 + b.qt_q_cap * 4;
     uint8_t* t_flag = t_field + b.qt_cap;
+    std::vector<std::pair<float, size_t>> by_bound;
     const float bo = w_text;
     for (int q = 0; q < B; ++q) {
       indptr[q] = (int32_t)n_terms;
       int in_query = 0;
+      // order-free check (hybrid_tile_fast_kernel): sum of the largest scores, smallest score, one field
+      double q_sum_max = 0.0;
+      float q_min = INFINITY;
+      int q_field = -1;
+      bool q_ok = true;
       for (int32_t j = qterm_indptr[q]; j < qterm_indptr[q + 1]; ++j) {
         const int32_t t = qterms[j];
         const uint8_t fl = qflags ? qflags[j] : 0;
@@ -559,8 +989,39 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
         t_field[n_terms] = b.term_field_host[(size_t)t];
         t_flag[n_terms] = fl;
         if (fl && j + 1 < qterm_indptr[q + 1]) multi = true;     // a group or clause ends before the query does
+        {
+          volatile float wq = t_w[n_terms], one = 1.0f;
+          volatile float lo_d = one + b.xmin_host[(size_t)t], hi_d = one + b.xmax_host[(size_t)t];
+          volatile float lo_q = wq / lo_d, hi_q = wq / hi_d;
+          volatile float s_lo = wq - lo_q, s_hi = wq - hi_q;
+          if (s_hi > 0.f) {                       // a term whose scores are all <= 0 never adds anything
+            if (!(s_lo > 0.f)) q_ok = false;
+            q_sum_max += (double)s_hi;
+            q_min = std::min(q_min, (float)s_lo);
+          }
+          t_bound[n_terms] = s_hi > 0.f ? (float)s_hi : 0.f;     // the term's largest score; summed below
+          if (q_field < 0) q_field = t_field[n_terms];
+          else if (q_field != t_field[n_terms]) q_ok = false;
+        }
         s.bytes_streamed += len * 6;
         ++n_terms;
+      }
+      if (q_ok && q_sum_max > 0.0) {
+        // every addend is a multiple of 2^(ilogb(q_min) - 23); every partial sum is < 2^(ilogb(q_sum_max) + 1)
+        if ((ilogb(q_sum_max) + 1) - (ilogb((double)q_min) - 23) > 53) q_ok = false;
+      }
+      if (!q_ok) order_free = false;
+      // MaxScore bounds: terms by ascending largest score; t_bound = the sum up to and including the term, rounded UP
+      // to float -- no doc matching only those terms scores more (its float score is the rounded sum of smaller addends)
+      by_bound.clear();
+      for (size_t j = (size_t)indptr[q]; j < n_terms; ++j) by_bound.emplace_back(t_bound[j], j);
+      std::sort(by_bound.begin(), by_bound.end());
+      double cum = 0.0;
+      for (const auto& e : by_bound) {
+        cum += (double)e.first;
+        float f = (float)cum;
+        if ((double)f < cum) f = nextafterf(f, INFINITY);
+        t_bound[e.second] = f;
       }
     }
     indptr[B] = (int32_t)n_terms;
@@ -582,8 +1043,10 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
     a.t_len = reinterpret_cast<const uint32_t*>(base + b.qt_cap * 8);
     a.t_w = reinterpret_cast<const float*>(base + b.qt_cap * 12);
     a.t_row = reinterpret_cast<const int32_t*>(base + b.qt_cap * 16);
-    a.qt_indptr = reinterpret_cast<const int32_t*>(base + b.qt_cap * 20);
-    a.t_field = base + b.qt_cap * 20 + b.qt_q_cap * 4;
+    static const bool no_prune = getenv("RASS_DEBUG_NO_MAXSCORE") != nullptr;       // A/B switch
+    a.t_bound = no_prune ? nullptr : reinterpret_cast<const float*>(base + b.qt_cap * 20);
+    a.qt_indptr = reinterpret_cast<const int32_t*>(base + b.qt_cap * 24);
+    a.t_field = base + b.qt_cap * 24 + b.qt_q_cap * 4;
     a.t_flag = a.t_field + b.qt_cap;
   }
   a.norm_rows = b.N;
@@ -591,7 +1054,7 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
   a.knn_scores = knn_scores;
   a.row_filter = h->row_filter;
   a.filter_rows = h->row_filter_rows;
-  a.row_base = h->row_base;
+  a.rmap = h->rmap;
   a.n_docs = n_docs;
   a.n_tiles = n_tiles;
   a.table_tiles = b.built ? b.n_tiles : 0;
@@ -604,23 +1067,31 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
   CUDA_TRY(h, cudaMemsetAsync(b.hyb_gthr, 0, (size_t)B * sizeof(uint32_t), st));
   const size_t smem_single = (size_t)HYB_TILE * 8, smem_multi = (size_t)HYB_TILE * (8 + 8 + 4);
   CUDA_TRY(h, cudaFuncSetAttribute(hybrid_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi));
-  for (int q0 = 0; q0 < B; q0 += 32768) {
-    const int nq = std::min(B - q0, 32768);
-    HybridArgs aq = a;
-    if (aq.qt_indptr) aq.qt_indptr += q0;
-    if (aq.knn_rows) { aq.knn_rows += (size_t)q0 * k; aq.knn_scores += (size_t)q0 * k; }
-    aq.xkey += (size_t)q0 * a.n_tiles * k;
-    aq.xrow += (size_t)q0 * a.n_tiles * k;
-    aq.gthr += q0;
-    if (multi) hybrid_tile_kernel<true><<<dim3((unsigned)a.n_tiles, (unsigned)nq), HYB_THREADS, smem_multi, st>>>(aq);
-    else hybrid_tile_kernel<false><<<dim3((unsigned)a.n_tiles, (unsigned)nq), HYB_THREADS, smem_single, st>>>(aq);
+  if (a.n_tiles > 65535) return rass_fail(h, RASS_E_UNSUPPORTED, "more than 65535 tiles of %d documents", HYB_TILE);
+  const bool fast = order_free && !multi;
+  if (fast) s.path |= RASS_PATH_HYBRID_ORDER_FREE;
+  {
+    // grid = (queries, tiles): queries are the fast index, so the CTAs in flight cover a few tiles of every query and
+    // a query's cross-tile pruning bound exists after its first tiles
+    const dim3 grid((unsigned)B, (unsigned)a.n_tiles);
+    if (multi) hybrid_tile_kernel<true><<<grid, HYB_THREADS, smem_multi, st>>>(a);
+    else if (fast && a.row_filter) hybrid_tile_fast_kernel<true><<<grid, HYB_THREADS, 0, st>>>(a);
+    else if (fast) hybrid_tile_fast_kernel<false><<<grid, HYB_THREADS, 0, st>>>(a);
+    else hybrid_tile_kernel<false><<<grid, HYB_THREADS, smem_single, st>>>(a);
     CUDA_TRY(h, cudaGetLastError());
     s.launches++;
   }
-  if ((rc = launch_select_batch(h, (size_t)a.n_tiles * k, B, k, ext ? ext->out_rows_dev : h->out_rows,
-                                ext ? ext->out_scores_dev : h->out_scores, ext ? ext->out_keys_dev : nullptr, st)))
-    return rc;
-  s.launches++;
+  {
+    int64_t* o_rows = ext ? ext->out_rows_dev : h->out_rows;
+    float* o_scores = ext ? ext->out_scores_dev : h->out_scores;
+    double* o_keys = ext ? ext->out_keys_dev : nullptr;
+    hybrid_select_kernel<<<B, 1024, 0, st>>>(h->xlist_key, h->xlist_row, (size_t)a.n_tiles * k, k, b.hyb_gthr,
+                                             h->rmap, o_rows, o_scores, o_keys, b.sel_fallback);
+    CUDA_TRY(h, cudaGetLastError());
+    if ((rc = launch_select_batch(h, (size_t)a.n_tiles * k, B, k, o_rows, o_scores, o_keys, st, b.sel_fallback)))
+      return rc;
+    s.launches += 2;
+  }
   CUDA_TRY(h, cudaEventRecord(e1, st));
   if (!ext) {
     CUDA_TRY(h, cudaMemcpyAsync(h->out_rows_host, h->out_rows, n_out * 8, cudaMemcpyDeviceToHost, st));
@@ -635,6 +1106,7 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
   CUDA_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
   s.finish_ms += ms;
   s.total_ms += ms;
+  h->last_stats = s;
   if (stats) *stats = s;
   return RASS_OK;
 }
@@ -642,6 +1114,7 @@ static int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t
 extern "C" int rass_search_hybrid(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr,
                                   const int32_t* qterms, float w_text, float w_knn, int k, int64_t* out_rows,
                                   float* out_scores, rass_stats* stats) {
+  SHARDED(h, sharded_search_hybrid(h, q_host, B, qterm_indptr, qterms, nullptr, nullptr, w_text, w_knn, k, out_rows, out_scores, stats));
   return hybrid_core(h, q_host, B, qterm_indptr, qterms, nullptr, nullptr, w_text, w_knn, k, out_rows, out_scores,
                      stats);
 }
@@ -650,6 +1123,7 @@ extern "C" int rass_search_hybrid_weighted(rass_engine* h, const float* q_host, 
                                            const int32_t* qterms, const float* qweights, const uint8_t* qflags,
                                            float w_knn, int k, int64_t* out_rows, float* out_scores,
                                            rass_stats* stats) {
+  SHARDED(h, (qterm_indptr && !qweights) ? rass_fail(h, RASS_E_INVALID, "null weights") : sharded_search_hybrid(h, q_host, B, qterm_indptr, qterms, qweights, qflags, 0.f, w_knn, k, out_rows, out_scores, stats));
   if (h && qterm_indptr && !qweights) return rass_fail(h, RASS_E_INVALID, "null weights");
   return hybrid_core(h, q_host, B, qterm_indptr, qterms, qweights, qflags, 0.f, w_knn, k, out_rows, out_scores,
                      stats);
@@ -659,6 +1133,7 @@ extern "C" int rass_fuse_hybrid_dev(rass_engine* h, int B, const int32_t* qterm_
                                     const float* qweights, const uint8_t* qflags, float w_text,
                                     const int64_t* knn_rows_dev, const float* knn_scores_dev, float w_knn, int k,
                                     int64_t* out_rows_dev, float* out_scores_dev, double* out_keys_dev) {
+  SHARDED(h, rass_fail(h, RASS_E_UNSUPPORTED, "rass_fuse_hybrid_dev is the per-shard step; a sharded handle fuses through rass_search_hybrid / rass_fuse_hybrid"));
   if (!h) return RASS_E_INVALID;
   if (!out_rows_dev || !out_scores_dev || (knn_rows_dev && !knn_scores_dev))
     return rass_fail(h, RASS_E_INVALID, "null buffer");
@@ -673,6 +1148,7 @@ extern "C" int rass_fuse_hybrid(rass_engine* h, int B, const int32_t* qterm_indp
                                 const float* qweights, const uint8_t* qflags, float w_text,
                                 const int64_t* knn_rows_host, const float* knn_scores_host, float w_knn, int k,
                                 int64_t* out_rows, float* out_scores) {
+  SHARDED(h, sharded_fuse_hybrid(h, B, qterm_indptr, qterms, qweights, qflags, w_text, knn_rows_host, knn_scores_host, w_knn, k, out_rows, out_scores));
   if (!h) return RASS_E_INVALID;
   cudaSetDevice(h->device);
   if (B < 1 || k < 1 || k > RASS_MAX_K || !out_rows || !out_scores || (knn_rows_host && !knn_scores_host))
@@ -772,6 +1248,7 @@ __global__ void __launch_bounds__(256) fuzzy_scan_kernel(const uint32_t* __restr
 }
 
 extern "C" int rass_text_set_vocab(rass_engine* h, const char* blob, const int64_t* offsets, int64_t V) {
+  SHARDED(h, rass_text_set_vocab(sharded_first(h), blob, offsets, V));
   if (!h) return RASS_E_INVALID;
   cudaSetDevice(h->device);
   if (V < 0 || !offsets || (offsets[V] > 0 && !blob)) return rass_fail(h, RASS_E_INVALID, "bad vocabulary");
@@ -801,6 +1278,7 @@ extern "C" int rass_text_set_vocab(rass_engine* h, const char* blob, const int64
 extern "C" int rass_fuzzy_expand(rass_engine* h, const char* token, int token_len, int max_edits, int64_t term_lo,
                                  int64_t term_hi, int64_t max_out, int32_t* out_terms, int32_t* out_edits,
                                  int64_t* out_n) {
+  SHARDED(h, rass_fuzzy_expand(sharded_first(h), token, token_len, max_edits, term_lo, term_hi, max_out, out_terms, out_edits, out_n));
   if (!h) return RASS_E_INVALID;
   cudaSetDevice(h->device);
   Bm25State& b = h->bm25;

@@ -23,6 +23,29 @@ __host__ __device__ constexpr int rass_tc_keep(int seg) { return seg == 512 ? 12
 #define RASS_EXACT_NQ 4        // queries per pass of the fp64 scan
 #define RASS_FINISH_THREADS 1024
 
+// Where a shard's local rows sit among the global rows.  One shard: global = base + local.  A shard g of G inside a
+// single-process sharded handle (sharded.cu) owns every G-th block of 2^blk_log2 consecutive global rows, so an index
+// that grows by bulk appends stays balanced: global = base + (((local >> s) * G + g) << s) + (local & (2^s - 1)).
+struct RowMap {
+  int64_t base;
+  int32_t g, G, blk_log2;
+};
+#define RASS_SHARD_BLOCK_LOG2 10
+__host__ __device__ inline int64_t row_local_to_global(const RowMap& m, int64_t local) {
+  if (m.G <= 1) return m.base + local;
+  const int64_t b = local >> m.blk_log2, in = local & ((int64_t(1) << m.blk_log2) - 1);
+  return m.base + (((b * m.G + m.g) << m.blk_log2) | in);
+}
+// -1: the row belongs to another shard (or lies below the base)
+__host__ __device__ inline int64_t row_global_to_local(const RowMap& m, int64_t global) {
+  const int64_t r = global - m.base;
+  if (r < 0) return -1;
+  if (m.G <= 1) return r;
+  const int64_t b = r >> m.blk_log2;
+  if ((int32_t)(b % m.G) != m.g) return -1;
+  return ((b / m.G) << m.blk_log2) | (r & ((int64_t(1) << m.blk_log2) - 1));
+}
+
 struct Bm25State {
   bool built = false;
   int64_t V = 0, N = 0, nnz = 0;
@@ -50,6 +73,9 @@ struct Bm25State {
   int64_t doc_count = 0;
   std::vector<int64_t> indptr_host;
   std::vector<float> idf_host;   // (float) ln(1 + (docCount - df + .5) / (df + .5))
+  std::vector<float> xmin_host, xmax_host;   // per term: range of tf * inv[norm] over its postings (term_xrange_kernel)
+  bool force_ordered = false;    // RASS_OPT_HYBRID_ORDERED: always take the ordered tile kernel (tests, A/B)
+  int* sel_fallback = nullptr;   // device [qt_q_cap]: queries hybrid_select_kernel hands to the radix select
 };
 
 // device-resident scalars the kernels update / read without a host round trip
@@ -68,7 +94,9 @@ struct rass_engine {
   uint32_t flags = 0;
   int num_sms = 0;
   int path = RASS_PATH_AUTO;
-  int64_t cap = 0, n_rows = 0, n_live = 0, row_base = 0;
+  int64_t cap = 0, n_rows = 0, n_live = 0;
+  RowMap rmap = {0, 0, 1, RASS_SHARD_BLOCK_LOG2};     // local row -> global row (rass_set_row_base, sharded handles)
+  struct ShardSet* shards = nullptr;                  // non-null: a coordinator over several single-device engines
   float* x32 = nullptr;             // [cap, dim_pad] fp32 (null when BF16_ONLY)
   __nv_bfloat16* x16 = nullptr;     // [cap, dim_pad] bf16 shadow / corpus
   double* norm64 = nullptr;         // [cap] ||x|| accumulated in fp64 from the stored values
@@ -153,6 +181,7 @@ struct rass_engine {
   int64_t row_filter_rows = 0;
   size_t row_filter_cap = 0;
   Bm25State bm25;
+  rass_stats last_stats = {};       // of the last search / hybrid / fuse call (rass_last_stats)
   std::string err;
 };
 
@@ -424,6 +453,60 @@ int launch_exact(rass_engine* h, int k, const int* qids_host, int n_q, int64_t* 
 int launch_merge_topk(rass_engine* h, const double* keys, const int64_t* rows, int64_t shard_stride, int G, int B,
                       int k, int64_t* out_rows, float* out_scores, double* out_keys, cudaStream_t st,
                       bool raw_score = false);
+// blocking (async_slot < 0) or enqueue-only search of prepared device queries (engine.cu)
+int search_core_ex(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
+                   double* out_keys, rass_stats* stats, int async_slot, int64_t* async_flag_dev);
+int stage_queries(rass_engine* h, const float* q_host, int B, float** q_dev_out);
+// Row-sharded hybrid: fuse against an EXTERNAL (global) knn list and leave this shard's top-k on the device
+struct HybridExt {
+  const int64_t* knn_rows_dev;   // [B, k] global rows (-1 = none); rows outside this shard are ignored
+  const float* knn_scores_dev;   // [B, k]
+  int64_t* out_rows_dev;         // [B, k] global rows
+  float* out_scores_dev;         // [B, k] fused float scores
+  double* out_keys_dev;          // [B, k] the same as double (what the shard merge ranks by), nullable
+};
+int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr, const int32_t* qterms,
+                const float* qweights, const uint8_t* qflags, float w_text, float w_knn, int k, int64_t* out_rows,
+                float* out_scores, rass_stats* stats, const HybridExt* ext = nullptr);
+// g_doc_count / g_sum_ttf: [F] corpus-wide statistics, g_df: [V] (all nullable: taken from the arrays given)
+int bm25_build_impl(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
+                    const int32_t* term_field, const uint32_t* doclen, int64_t V, int64_t N, int F,
+                    const int64_t* g_doc_count, const int64_t* g_sum_ttf, const int64_t* g_df);
+// ---- single-process multi-GPU handles (sharded.cu): the public entry points forward to these when h->shards is set ----
+int sharded_destroy(rass_engine* h);
+int sharded_set_option(rass_engine* h, int opt, int64_t value);
+int sharded_set_row_base(rass_engine* h, int64_t base);
+int sharded_sync(rass_engine* h);
+int sharded_append(rass_engine* h, const float* rows_host, int64_t n, int64_t* out_first_row);
+int sharded_append_dev(rass_engine* h, const float* rows_dev, int64_t n, int64_t* out_first_row);
+int sharded_overwrite(rass_engine* h, int64_t row, const float* v_host);
+int sharded_tombstone(rass_engine* h, int64_t row);
+int sharded_read_rows(rass_engine* h, int64_t first_row, int64_t n, float* out_host);
+int sharded_read_rows_list(rass_engine* h, const int64_t* rows_host, int64_t n, float* out_host);
+int sharded_set_row_filter(rass_engine* h, const uint8_t* mask_host, int64_t n);
+int sharded_set_row_filter_rows(rass_engine* h, const int64_t* rows_host, int64_t n, int64_t total_rows);
+int sharded_search_knn(rass_engine* h, const float* q_host, int B, int k, int64_t* out_rows, float* out_scores,
+                       double* out_keys, rass_stats* stats);
+int sharded_search_knn_dev(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows_dev,
+                           float* out_scores_dev, double* out_keys_dev, rass_stats* stats);
+int sharded_search_knn_dev_async(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows_dev,
+                                 float* out_scores_dev, double* out_keys_dev, int slot, int64_t* flag_out_dev);
+int sharded_search_knn_dev_wait(rass_engine* h, int slot, rass_stats* stats);
+int sharded_bm25_build(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
+                       const int32_t* term_field, const uint32_t* doclen, int64_t V, int64_t N, int F);
+int sharded_search_hybrid(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr, const int32_t* qterms,
+                          const float* qweights, const uint8_t* qflags, float w_text, float w_knn, int k,
+                          int64_t* out_rows, float* out_scores, rass_stats* stats);
+int sharded_fuse_hybrid(rass_engine* h, int B, const int32_t* qterm_indptr, const int32_t* qterms,
+                        const float* qweights, const uint8_t* qflags, float w_text, const int64_t* knn_rows_host,
+                        const float* knn_scores_host, float w_knn, int k, int64_t* out_rows, float* out_scores);
+int sharded_save(rass_engine* h, const char* path);
+rass_engine* sharded_first(rass_engine* h);      // the shard on the coordinator device (dictionary scans run there)
+#define SHARDED(h, call)                 \
+  do {                                   \
+    if ((h) && (h)->shards) return call; \
+  } while (0)
+
 int ensure_query_workspace(rass_engine* h, int B);
 int ensure_pool(rass_engine* h, size_t entries_per_query, size_t segs_per_query, size_t n_queries = RASS_GROUP_Q);
 int ensure_xlist_workspace(rass_engine* h, size_t entries);

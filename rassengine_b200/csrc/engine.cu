@@ -125,6 +125,7 @@ extern "C" int rass_create(int dim, int metric, int device, int64_t capacity_row
 }
 
 extern "C" int rass_destroy(rass_engine* h) {
+  SHARDED(h, sharded_destroy(h));
   if (!h) return RASS_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
@@ -149,7 +150,7 @@ extern "C" int rass_destroy(rass_engine* h) {
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   Bm25State& b = h->bm25;
   cudaFree(b.indptr); cudaFree(b.doc); cudaFree(b.tf); cudaFree(b.norm); cudaFree(b.inv_dev);
-  cudaFree(b.tile_off); cudaFree(b.qt_dev); cudaFreeHost(b.qt_host); cudaFree(b.hyb_gthr);
+  cudaFree(b.tile_off); cudaFree(b.qt_dev); cudaFreeHost(b.qt_host); cudaFree(b.hyb_gthr); cudaFree(b.sel_fallback);
   cudaFree(b.vocab_blob); cudaFree(b.vocab_off); cudaFree(b.fz_terms); cudaFree(b.fz_edits); cudaFree(b.fz_n);
   free(h->tmap_x); free(h->tmap_q); free(h->tmap_q2);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -159,10 +160,14 @@ extern "C" int rass_destroy(rass_engine* h) {
 }
 
 extern "C" int rass_set_option(rass_engine* h, int opt, int64_t value) {
+  SHARDED(h, sharded_set_option(h, opt, value));
   CHECK_HANDLE(h);
   switch (opt) {
     case RASS_OPT_KNN_PREFILTER:
       h->knn_prefilter = value != 0;
+      return RASS_OK;
+    case RASS_OPT_HYBRID_ORDERED:
+      h->bm25.force_ordered = value != 0;
       return RASS_OK;
     case RASS_OPT_PATH:
       if (value < RASS_PATH_AUTO || value > RASS_PATH_GEMM) return rass_fail(h, RASS_E_INVALID, "bad path %lld", (long long)value);
@@ -183,8 +188,9 @@ extern "C" int rass_set_option(rass_engine* h, int opt, int64_t value) {
 }
 
 extern "C" int rass_set_row_base(rass_engine* h, int64_t base) {
+  SHARDED(h, sharded_set_row_base(h, base));
   CHECK_HANDLE(h);
-  h->row_base = base;
+  h->rmap.base = base;
   return RASS_OK;
 }
 
@@ -200,7 +206,14 @@ extern "C" int rass_rows(const rass_engine* h, int64_t* out) {
   return RASS_OK;
 }
 
+extern "C" int rass_last_stats(const rass_engine* h, rass_stats* out) {
+  if (!h || !out) return RASS_E_INVALID;
+  *out = h->last_stats;
+  return RASS_OK;
+}
+
 extern "C" int rass_sync(rass_engine* h) {
+  SHARDED(h, sharded_sync(h));
   CHECK_HANDLE(h);
   CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
   return RASS_OK;
@@ -231,6 +244,7 @@ static int append_from_device(rass_engine* h, const float* rows_dev, int64_t fir
 }
 
 extern "C" int rass_append_dev(rass_engine* h, const float* rows_dev, int64_t n, int64_t* out_first_row) {
+  SHARDED(h, sharded_append_dev(h, rows_dev, n, out_first_row));
   CHECK_HANDLE(h);
   if (n < 0 || (n > 0 && !rows_dev)) return rass_fail(h, RASS_E_INVALID, "bad rows");
   int rc = ensure_capacity(h, h->n_rows + n);
@@ -273,6 +287,7 @@ static int upload_rows(rass_engine* h, const float* rows_host, int64_t first, in
 }
 
 extern "C" int rass_append(rass_engine* h, const float* rows_host, int64_t n, int64_t* out_first_row) {
+  SHARDED(h, sharded_append(h, rows_host, n, out_first_row));
   CHECK_HANDLE(h);
   if (n < 0 || (n > 0 && !rows_host)) return rass_fail(h, RASS_E_INVALID, "bad rows");
   int rc = ensure_capacity(h, h->n_rows + n);
@@ -289,6 +304,7 @@ extern "C" int rass_append(rass_engine* h, const float* rows_host, int64_t n, in
 }
 
 extern "C" int rass_overwrite(rass_engine* h, int64_t row, const float* v_host) {
+  SHARDED(h, sharded_overwrite(h, row, v_host));
   CHECK_HANDLE(h);
   if (row < 0 || row >= h->n_rows || !v_host) return rass_fail(h, RASS_E_NOTFOUND, "row %lld out of range", (long long)row);
   cudaStream_t st = eng_stream(h);
@@ -300,6 +316,7 @@ extern "C" int rass_overwrite(rass_engine* h, int64_t row, const float* v_host) 
 }
 
 extern "C" int rass_tombstone(rass_engine* h, int64_t row) {
+  SHARDED(h, sharded_tombstone(h, row));
   CHECK_HANDLE(h);
   if (row < 0 || row >= h->n_rows) return rass_fail(h, RASS_E_NOTFOUND, "row %lld out of range", (long long)row);
   if (h->dead[(size_t)row]) return RASS_OK;
@@ -323,6 +340,7 @@ __global__ void widen_rows_kernel(const __nv_bfloat16* __restrict__ x16, int dim
 }
 
 extern "C" int rass_read_rows(rass_engine* h, int64_t first_row, int64_t n, float* out_host) {
+  SHARDED(h, sharded_read_rows(h, first_row, n, out_host));
   CHECK_HANDLE(h);
   if (first_row < 0 || n < 0 || first_row + n > h->n_rows || (n && !out_host))
     return rass_fail(h, RASS_E_NOTFOUND, "rows [%lld, +%lld) out of range", (long long)first_row, (long long)n);
@@ -361,6 +379,7 @@ struct SnapHeader {
 // File = header, tombstone bytes [n_rows], stored values [n_rows, dim] fp32 (the bf16 values widened for a bf16
 // corpus).  Restore re-ingests through the normal append path, so shadow, norms and bounds are rebuilt, not trusted.
 extern "C" int rass_save(rass_engine* h, const char* path) {
+  SHARDED(h, sharded_save(h, path));
   CHECK_HANDLE(h);
   if (!path) return rass_fail(h, RASS_E_INVALID, "null path");
   FILE* f = fopen(path, "wb");
@@ -405,7 +424,8 @@ extern "C" int rass_load(rass_engine* h, const char* path) {
     if (hd.n_rows && fread(dead.data(), 1, dead.size(), f) != dead.size())
       rc = rass_fail(h, RASS_E_INVALID, "%s is truncated", path);
   }
-  const int64_t chunk = std::max<int64_t>(1, (int64_t)(h->stage_bytes / ((size_t)h->dim * 4)));
+  const size_t stage = h->stage_bytes ? h->stage_bytes : ((size_t)64 << 20);     // a sharded coordinator has no staging
+  const int64_t chunk = std::max<int64_t>(1, (int64_t)(stage / ((size_t)h->dim * 4)));
   std::vector<float> buf;
   if (!rc) buf.resize((size_t)std::min<int64_t>(chunk, std::max<int64_t>(hd.n_rows, 1)) * h->dim);
   for (int64_t off = 0; !rc && off < hd.n_rows; off += chunk) {
@@ -582,6 +602,12 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
 int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
                 double* out_keys, rass_stats* stats) {
   return search_core_impl(h, q_dev, B, k, out_rows, out_scores, out_keys, stats, false, -1, nullptr);
+}
+
+// the same with the async form exposed (sharded.cu drives one of these per shard)
+int search_core_ex(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
+                   double* out_keys, rass_stats* stats, int async_slot, int64_t* async_flag_dev) {
+  return search_core_impl(h, q_dev, B, k, out_rows, out_scores, out_keys, stats, false, async_slot, async_flag_dev);
 }
 
 // robust = false: 256-entry segments (a compaction keeps 32..64 entries): fastest, and every pivot has >= 32 >= k
@@ -785,6 +811,7 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
   }
   s.scan_ms = scan + retry_scan_ms;
   s.finish_ms = s.total_ms - s.scan_ms;
+  h->last_stats = s;
   if (stats) *stats = s;
   return RASS_OK;
 }
@@ -792,6 +819,7 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
 extern "C" int rass_search_knn_dev_async(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows_dev,
                                          float* out_scores_dev, double* out_keys_dev, int slot,
                                          int64_t* flag_out_dev) {
+  SHARDED(h, sharded_search_knn_dev_async(h, q_dev, B, k, out_rows_dev, out_scores_dev, out_keys_dev, slot, flag_out_dev));
   CHECK_HANDLE(h);
   if (!q_dev || !out_rows_dev || !out_scores_dev) return rass_fail(h, RASS_E_INVALID, "null buffer");
   if (slot < 0 || slot > 1) return rass_fail(h, RASS_E_INVALID, "slot must be 0 or 1");
@@ -800,6 +828,7 @@ extern "C" int rass_search_knn_dev_async(rass_engine* h, const float* q_dev, int
 }
 
 extern "C" int rass_search_knn_dev_wait(rass_engine* h, int slot, rass_stats* stats) {
+  SHARDED(h, sharded_search_knn_dev_wait(h, slot, stats));
   CHECK_HANDLE(h);
   if (slot < 0 || slot > 1) return rass_fail(h, RASS_E_INVALID, "slot must be 0 or 1");
   rass_engine::AsyncSlot& a = h->aslot[slot];
@@ -828,6 +857,7 @@ extern "C" int rass_search_knn_dev_wait(rass_engine* h, int slot, rass_stats* st
 
 extern "C" int rass_search_knn_dev(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows_dev,
                                    float* out_scores_dev, double* out_keys_dev, rass_stats* stats) {
+  SHARDED(h, sharded_search_knn_dev(h, q_dev, B, k, out_rows_dev, out_scores_dev, out_keys_dev, stats));
   CHECK_HANDLE(h);
   if (!q_dev || !out_rows_dev || !out_scores_dev) return rass_fail(h, RASS_E_INVALID, "null buffer");
   return search_core(h, q_dev, B, k, out_rows_dev, out_scores_dev, out_keys_dev, stats);
@@ -851,6 +881,7 @@ int stage_queries(rass_engine* h, const float* q_host, int B, float** q_dev_out)
 
 extern "C" int rass_search_knn(rass_engine* h, const float* q_host, int B, int k, int64_t* out_rows,
                                float* out_scores, double* out_keys, rass_stats* stats) {
+  SHARDED(h, sharded_search_knn(h, q_host, B, k, out_rows, out_scores, out_keys, stats));
   CHECK_HANDLE(h);
   if (!q_host || !out_rows || !out_scores) return rass_fail(h, RASS_E_INVALID, "null buffer");
   if (B < 1) return rass_fail(h, RASS_E_INVALID, "B must be >= 1");
@@ -899,6 +930,7 @@ extern "C" int rass_merge_scores_dev(rass_engine* h, const double* scores_dev, c
 
 // bool.filter of the next hybrid queries as a per-row pass mask (NULL clears it)
 extern "C" int rass_set_row_filter(rass_engine* h, const uint8_t* mask_host, int64_t n) {
+  SHARDED(h, sharded_set_row_filter(h, mask_host, n));
   CHECK_HANDLE(h);
   cudaStream_t st = eng_stream(h);
   if (!mask_host) {
@@ -934,6 +966,7 @@ __global__ void set_mask_rows_kernel(const int64_t* __restrict__ rows, int64_t n
 }
 
 extern "C" int rass_set_row_filter_rows(rass_engine* h, const int64_t* rows_host, int64_t n, int64_t total_rows) {
+  SHARDED(h, sharded_set_row_filter_rows(h, rows_host, n, total_rows));
   CHECK_HANDLE(h);
   if (n < 0 || total_rows < 0 || (n && !rows_host)) return rass_fail(h, RASS_E_INVALID, "bad filter rows");
   cudaStream_t st = eng_stream(h);
@@ -975,6 +1008,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ x32, const __nv_bfl
 }
 
 extern "C" int rass_read_rows_list(rass_engine* h, const int64_t* rows_host, int64_t n, float* out_host) {
+  SHARDED(h, sharded_read_rows_list(h, rows_host, n, out_host));
   CHECK_HANDLE(h);
   if (n < 0 || (n && (!rows_host || !out_host))) return rass_fail(h, RASS_E_INVALID, "bad arguments");
   if (n == 0) return RASS_OK;
@@ -1005,6 +1039,7 @@ extern "C" int rass_read_rows_list(rass_engine* h, const int64_t* rows_host, int
 // Debug entry (not part of the reference surface): raw tcgen05 dot products of <= 64 queries against every row,
 // out_host [n_rows, 64].  Lets the tests check the TMA/UMMA descriptors in isolation.
 extern "C" int rass_debug_gemm_scores(rass_engine* h, const float* q_host, int B, float* out_host) {
+  SHARDED(h, rass_fail(h, RASS_E_UNSUPPORTED, "debug entry points take a single-device handle"));
   CHECK_HANDLE(h);
   if (!q_host || !out_host || B < 1 || B > RASS_QPAD) return rass_fail(h, RASS_E_INVALID, "bad arguments");
   if (h->n_rows == 0) return RASS_OK;
@@ -1019,6 +1054,7 @@ extern "C" int rass_debug_gemm_scores(rass_engine* h, const float* q_host, int B
 }
 
 extern "C" int rass_debug_umma_scores(rass_engine* h, const float* q_host, int B, float* out_host) {
+  SHARDED(h, rass_fail(h, RASS_E_UNSUPPORTED, "debug entry points take a single-device handle"));
   CHECK_HANDLE(h);
   if (!q_host || !out_host || B < 1 || B > RASS_GROUP_Q) return rass_fail(h, RASS_E_INVALID, "bad arguments");
   if (h->n_rows == 0) return RASS_OK;

@@ -34,7 +34,7 @@ struct FinishArgs {
   int* flagged;
   int dim_pad, metric, k, g0;
   float acc_eps;
-  int64_t row_base;
+  RowMap rmap;
   int64_t* out_rows;
   float* out_scores;
   double* out_keys;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(RASS_FINISH_THREADS, 1) finish_kernel(FinishAr
     for (int j = 0; j < ncand; ++j) rank += entry_better<double>(ckey[j], crow[j], key, row);
     if (rank < kk) {
       const size_t o = (size_t)q * kk + rank;
-      a.out_rows[o] = a.row_base + (int64_t)row;
+      a.out_rows[o] = row_local_to_global(a.rmap, (int64_t)row);
       a.out_scores[o] = score_from_key(key, a.metric);
       if (a.out_keys) a.out_keys[o] = a.metric == RASS_METRIC_COSINE ? key : -key;
       if (rank == kk - 1) { s_sk = key; s_have = 1; }
@@ -233,7 +233,7 @@ int launch_finish(rass_engine* h, int g0, int ng, int k, int n_segs, int seg_siz
   a.k = k;
   a.g0 = g0;
   a.acc_eps = acc_allowance(h->dim_pad);
-  a.row_base = h->row_base;
+  a.rmap = h->rmap;
   a.out_rows = out_rows;
   a.out_scores = out_scores;
   a.out_keys = out_keys;
@@ -310,9 +310,11 @@ __global__ void __launch_bounds__(1024, 1) exact_select_kernel(const double* __r
                                                                const uint32_t* __restrict__ xrow, size_t xlist_entries,
                                                                int n, int k, const int* __restrict__ qids, int q_fixed,
                                                                int raw_score, int metric,
-                                                               int64_t row_base, int64_t* __restrict__ out_rows,
+                                                               RowMap rmap, int64_t* __restrict__ out_rows,
                                                                float* __restrict__ out_scores,
-                                                               double* __restrict__ out_keys) {
+                                                               double* __restrict__ out_keys,
+                                                               const int* __restrict__ only_if) {
+  if (only_if && !only_if[blockIdx.x]) return;     // hybrid_select_kernel already ranked this query
   __shared__ int hist[256];
   __shared__ int s_bucket, s_remaining, s_nsel, s_nvalid;
   __shared__ double selk[RASS_MAX_K];
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(1024, 1) exact_select_kernel(const double* __r
     for (int j = 0; j < nsel; ++j) rank += entry_better<double>(selk[j], selr[j], selk[c], selr[c]);
     if (rank < k) {
       const size_t o = (size_t)q * k + rank;
-      out_rows[o] = row_base + (int64_t)selr[c];
+      out_rows[o] = row_local_to_global(rmap, (int64_t)selr[c]);
       out_scores[o] = raw_score ? (float)selk[c] : score_from_key(selk[c], metric);
       if (out_keys) out_keys[o] = metric == RASS_METRIC_COSINE ? selk[c] : -selk[c];
     }
@@ -437,7 +439,7 @@ int launch_exact(rass_engine* h, int k, const int* qids_host, int n_q, int64_t* 
 #undef RASS_EX
     CUDA_TRY(h, cudaGetLastError());
     exact_select_kernel<<<nq, 1024, 0, st>>>(h->xlist_key, h->xlist_row, entries, (int)entries, k, qids_dev + p, 0, 0,
-                                             h->metric, h->row_base, out_rows, out_scores, out_keys);
+                                             h->metric, h->rmap, out_rows, out_scores, out_keys, nullptr);
     CUDA_TRY(h, cudaGetLastError());
     if (launches) *launches += 2;
   }
@@ -446,10 +448,10 @@ int launch_exact(rass_engine* h, int k, const int* qids_host, int n_q, int64_t* 
 
 // top-k of B queries' fused (score, row) lists of `entries` entries each; the score is emitted as is (bm25.cu)
 int launch_select_batch(rass_engine* h, size_t entries, int B, int k, int64_t* out_rows, float* out_scores,
-                        double* out_keys, cudaStream_t st) {
+                        double* out_keys, cudaStream_t st, const int* only_if) {
   // raw scores: "larger is better" whatever the vector metric of the engine is
   exact_select_kernel<<<B, 1024, 0, st>>>(h->xlist_key, h->xlist_row, entries, (int)entries, k, nullptr, 0, 1,
-                                          RASS_METRIC_COSINE, h->row_base, out_rows, out_scores, out_keys);
+                                          RASS_METRIC_COSINE, h->rmap, out_rows, out_scores, out_keys, only_if);
   CUDA_TRY(h, cudaGetLastError());
   return RASS_OK;
 }

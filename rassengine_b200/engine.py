@@ -14,18 +14,45 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _pack_terms(qterms, B: int):
+    """qterms: B term-id lists, or an already packed (indptr int32 [B+1], terms int32 [nnz]) pair."""
+    if isinstance(qterms, tuple) and len(qterms) == 2 and isinstance(qterms[0], np.ndarray):
+        indptr = np.ascontiguousarray(qterms[0], dtype=np.int32)
+        terms = np.ascontiguousarray(qterms[1], dtype=np.int32)
+        if indptr.size != B + 1:
+            raise ValueError("packed qterms: indptr must have B + 1 entries")
+        return indptr, (terms if terms.size else np.zeros(1, dtype=np.int32))
+    if len(qterms) != B:
+        raise ValueError("qterms must hold one list per query")
+    indptr = np.zeros(B + 1, dtype=np.int32)
+    indptr[1:] = np.cumsum([len(t) for t in qterms])
+    terms = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int32) for t in qterms])
+                                 if indptr[-1] else np.zeros(1, dtype=np.int32), dtype=np.int32)
+    return indptr, terms
+
+
 class Engine:
     """One device-resident shard of the vector store + its postings (rass_create ... rass_destroy)."""
 
     def __init__(self, dim: int = 1024, metric: int = capi.METRIC_COSINE, device: int = 0, capacity_rows: int = 0,
-                 flags: int = 0):
+                 flags: int = 0, devices=None):
+        """devices: a list of CUDA ordinals -> ONE handle whose rows are spread over those GPUs (rass_create_sharded;
+        devices[0] is the coordinator).  Every method below works unchanged on such a handle."""
         self._lib = capi.lib()
         self._h = C.c_void_p()
-        rc = self._lib.rass_create(dim, metric, device, capacity_rows, flags, C.byref(self._h))
+        if devices is not None and len(devices) > 1:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self._lib.rass_create_sharded(dim, metric, len(devices), ids, capacity_rows, flags, C.byref(self._h))
+            device = int(devices[0])
+        else:
+            if devices:
+                device = int(devices[0])
+            rc = self._lib.rass_create(dim, metric, device, capacity_rows, flags, C.byref(self._h))
         if rc:
             msg = self._lib.rass_last_error(None).decode()
             self._h = None
             raise RassError(rc, msg)
+        self.devices = [int(d) for d in devices] if devices else [device]
         self.dim, self.metric, self.device, self.flags = dim, metric, device, flags or capi.KEEP_FP32
         self.last_stats: dict = {}
 
@@ -60,6 +87,10 @@ class Engine:
     def set_knn_prefilter(self, on: bool):
         """When on, search_knn returns the exact top-k of the rows passing set_row_filter (pre-filter)."""
         self._check(self._lib.rass_set_option(self._h, capi.OPT_KNN_PREFILTER, 1 if on else 0))
+
+    def set_hybrid_ordered(self, on: bool):
+        """Force the ordered (one barrier per term) text kernel for hybrid calls; results are bit-identical either way."""
+        self._check(self._lib.rass_set_option(self._h, capi.OPT_HYBRID_ORDERED, 1 if on else 0))
 
     def set_row_base(self, base: int):
         self._check(self._lib.rass_set_row_base(self._h, base))
@@ -238,19 +269,15 @@ class Engine:
         """q: [B, dim] fp32 or None (text only); qterms: list of B term-id lists or None (vector only); qweights:
         optional list of B float32 lists, the weight of every term occurrence (replaces w_text * idf); qflags:
         optional list of B uint8 lists (bit 0 = last term of its field group, bit 1 = last term of its clause)."""
+        packed = isinstance(qterms, tuple)
         if q is not None:
             q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
             B = q.shape[0]
         else:
-            B = len(qterms)
+            B = qterms[0].size - 1 if packed else len(qterms)
         indptr = terms = None
         if qterms is not None:
-            if len(qterms) != B:
-                raise ValueError("qterms must hold one list per query")
-            indptr = np.zeros(B + 1, dtype=np.int32)
-            indptr[1:] = np.cumsum([len(t) for t in qterms])
-            terms = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int32) for t in qterms])
-                                         if indptr[-1] else np.zeros(1, dtype=np.int32), dtype=np.int32)
+            indptr, terms = _pack_terms(qterms, B)
         rows = np.empty((B, k), dtype=np.int64)
         scores = np.empty((B, k), dtype=np.float32)
         st = RassStats()
@@ -310,13 +337,9 @@ class Engine:
         """Text clauses fused with an external (global) knn list; this shard's top-k stays on the device."""
         indptr = terms = w = fl = None
         if qterms is not None:
-            if len(qterms) != B:
-                raise ValueError("qterms must hold one list per query")
-            indptr = np.zeros(B + 1, dtype=np.int32)
-            indptr[1:] = np.cumsum([len(t) for t in qterms])
+            indptr, terms = _pack_terms(qterms, B)
             cat = lambda xs, dt: np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=dt) for x in xs])
                                                       if indptr[-1] else np.zeros(1, dtype=dt), dtype=dt)
-            terms = cat(qterms, np.int32)
             w = cat(qweights, np.float32) if qweights is not None else None
             fl = cat(qflags, np.uint8) if qflags is not None else None
         vp = lambda p: C.c_void_p(p) if p else None
@@ -324,6 +347,13 @@ class Engine:
             self._h, B, _ptr(indptr) if indptr is not None else None, _ptr(terms) if terms is not None else None,
             _ptr(w) if w is not None else None, _ptr(fl) if fl is not None else None, w_text, vp(knn_rows_ptr),
             vp(knn_scores_ptr), w_knn, k, vp(out_rows_ptr), vp(out_scores_ptr), vp(out_keys_ptr)))
+        self.last_hybrid_stats = self.stats()
+
+    def stats(self) -> dict:
+        """rass_last_stats: of the last blocking search / hybrid / fuse call."""
+        st = RassStats()
+        self._check(self._lib.rass_last_stats(self._h, C.byref(st)))
+        return st.as_dict()
 
     def debug_umma_scores(self, q: np.ndarray) -> np.ndarray:
         """Raw tensor-core dot products bf16(q_hat) . bf16(x) of up to 64 queries against every row: [rows, 64]."""

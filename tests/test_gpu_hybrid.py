@@ -499,3 +499,86 @@ def test_hybrid_degenerate_queries():
         rows_v, scores_v = e.search_hybrid(Q, None, 0.0, 2.0, k)           # vector-only bool.should
         assert np.array_equal(rows_v, knn_rows)
         np.testing.assert_allclose(scores_v, np.float32(2.0) * knn_scores, rtol=1e-6)
+
+
+def test_order_free_text_kernel_equals_the_ordered_walk():
+    """hybrid_tile_fast_kernel takes all postings of a tile as one flat list with shared-memory atomics; it only runs for
+    queries whose clause sums are exact in double whatever the order (checked per query from the per-term score ranges),
+    so its scores must be BIT-identical to the ordered kernel's -- and to the oracle's.  10 tiles, 40 queries, k = 10 and
+    100, with and without the knn clause, with a row filter."""
+    idx, X, Q, qterms = _text_case(n_docs=40000, vocab=3000, dim=64, nq=40)
+    alive = (np.arange(40000) % 5 != 1)
+    with _engine(dim=64) as e:
+        e.append(X)
+        e.bm25_build(idx.indptr, idx.doc, idx.tf, idx.doclen)
+        for k in (10, 100):
+            for q in (Q, None):
+                for mask in (None, alive):
+                    e.set_row_filter(mask)
+                    e.set_hybrid_ordered(False)
+                    rows_f, scores_f = e.search_hybrid(q, qterms, 4.5, 2.0, k)
+                    assert e.last_stats["path"] & 0x100, "the order-free kernel should have run"
+                    e.set_hybrid_ordered(True)
+                    rows_o, scores_o = e.search_hybrid(q, qterms, 4.5, 2.0, k)
+                    assert not (e.last_stats["path"] & 0x100)
+                    assert np.array_equal(rows_f, rows_o)
+                    assert np.array_equal(scores_f.view(np.uint32), scores_o.view(np.uint32))
+        e.set_row_filter(None)
+        e.set_hybrid_ordered(False)
+        rows_t, scores_t = e.search_hybrid(None, qterms[:6], 4.5, 0.0, 10)
+        for b in range(6):
+            qt = [t for t in qterms[b] if 0 <= t < idx.vocab]
+            wr, ws = bm25.topk(idx.score(qt, boost=4.5), 10)
+            assert rows_t[b, :len(wr)].tolist() == wr.tolist() and scores_t[b, :len(wr)].tolist() == ws.tolist()
+
+
+def test_sums_that_could_round_take_the_ordered_kernel():
+    """A query mixing a weight of 1e-12 with a weight of 50 has addends 2^45 apart: a double sum of such floats may round,
+    so its result depends on the order and the engine must walk the terms in query order (no order-free bit in
+    stats.path).  Scores still bit-identical to the oracle's ordered sum."""
+    idx, X, Q, qterms = _text_case(n_docs=9000, vocab=800, dim=64, nq=4)
+    with _engine(dim=64) as e:
+        e.append(X)
+        e.bm25_build(idx.indptr, idx.doc, idx.tf, idx.doclen)
+        terms = [[5, 40, 200, 7], [3, 9]]
+        weights = [np.array([50.0, 1e-12, 3.0, 1e-12], dtype=np.float32), np.array([2.0, 1.0], dtype=np.float32)]
+        rows, scores = e.search_hybrid(None, terms, 0.0, 0.0, 10, qweights=weights)
+        assert not (e.last_stats["path"] & 0x100)
+        for b in range(2):
+            wr, ws = bm25.topk(fuzzy.score(idx, terms[b], weights[b]), 10)
+            assert rows[b, :len(wr)].tolist() == wr.tolist() and scores[b, :len(wr)].tolist() == ws.tolist()
+        rows, scores = e.search_hybrid(None, terms[1:], 0.0, 0.0, 10, qweights=weights[1:])     # this one alone is order-free
+        assert e.last_stats["path"] & 0x100
+        wr, ws = bm25.topk(fuzzy.score(idx, terms[1], weights[1]), 10)
+        assert rows[0, :len(wr)].tolist() == wr.tolist() and scores[0, :len(wr)].tolist() == ws.tolist()
+
+
+def test_maxscore_pruning_keeps_results_exact():
+    """147 tiles x 64 queries is ten times what the GPU holds at once, so most tiles start with a pruning bound and
+    score the postings of the frequent (non-essential) terms for marked docs only.  The emitted ids and float32 scores
+    must still be the oracle's -- text-only, fused with the knn clause, top-10 and top-100 -- and identical to the ordered
+    kernel's, which never prunes."""
+    n_docs, vocab, dim, nq = 600_000, 8000, 64, 64
+    indptr, doc, tf, doclen = synth.text_corpus(n_docs, vocab=vocab, seed=81, median_len=50, max_len=200)
+    idx = bm25.BM25Index(indptr, doc, tf, doclen)
+    X = synth.embeddings(n_docs, dim, 82)
+    Q = synth.embeddings(nq, dim, 83)
+    qterms = synth.text_queries(nq, vocab=vocab, seed=84)
+    with _engine(dim=dim, capacity_rows=n_docs) as e:
+        e.append(X)
+        e.bm25_build(indptr, doc, tf, doclen)
+        for k in (10, 100):
+            knn_rows, _, knn_scores = knn.knn_exact(X, Q, k)
+            rows_b, scores_b = e.search_hybrid(Q, qterms, 4.5, 2.0, k)
+            assert e.last_stats["path"] & 0x100
+            rows_t, scores_t = e.search_hybrid(None, qterms, 4.5, 0.0, k)
+            e.set_hybrid_ordered(True)
+            rows_o, scores_o = e.search_hybrid(Q, qterms, 4.5, 2.0, k)
+            e.set_hybrid_ordered(False)
+            assert np.array_equal(rows_b, rows_o) and np.array_equal(scores_b.view(np.uint32), scores_o.view(np.uint32))
+            for b in range(0, nq, 1 if k == 10 else 8):
+                wr, ws = fusion.hybrid(idx, qterms[b], knn_rows[b], knn_scores[b], 4.5, 2.0, k)
+                assert rows_b[b, :len(wr)].tolist() == wr.tolist(), (k, b)
+                np.testing.assert_allclose(scores_b[b, :len(wr)], ws, rtol=2e-6, atol=0)
+                tr, ts = bm25.topk(idx.score(qterms[b], boost=4.5), k)
+                assert rows_t[b, :len(tr)].tolist() == tr.tolist() and scores_t[b, :len(tr)].tolist() == ts.tolist(), (k, b)
