@@ -39,10 +39,11 @@ def _early_env():
         n = str(os.cpu_count() or 1)
         for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
             os.environ[v] = n
-    elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and "NCCL_DEBUG" not in os.environ:
-        # communicator setup (rank / nranks lines) to stderr, so stdout stays the one JSON line
-        os.environ["NCCL_DEBUG"] = "INFO"
-        os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # communicator setup (rank / nranks lines) to stderr, so stdout stays the one JSON line -- whatever level the
+        # environment asked for (at WARN / VERSION NCCL prints its version banner on stdout); RASS_NCCL_DEBUG overrides
+        os.environ["NCCL_DEBUG"] = os.environ.get("RASS_NCCL_DEBUG", "INFO")
+        os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("RASS_NCCL_DEBUG_SUBSYS", "INIT")
         os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 
 

@@ -85,6 +85,10 @@ enum {
   RASS_OPT_HYBRID_ORDERED = 4,  /* 1: the text clauses of hybrid calls always walk the query terms in order (one barrier
                             per term); 0 (default): queries whose clause sums are exact in double in ANY order take the
                             order-free kernel.  Both give bit-identical scores; the switch exists for tests and A/B runs */
+  RASS_OPT_HYBRID_MAXSCORE = 5, /* 1: the order-free text kernel splits a query's terms the way Lucene's MaxScore scorer
+                            does once a pruning bound exists: terms whose summed score bounds stay below the bound are only
+                            scored for docs an essential term (or the knn clause) already touched.  Results are identical
+                            (tests/test_gpu_hybrid.py); off by default because it measures slower at the current tile size */
   RASS_OPT_KNN_PREFILTER = 3  /* 1: rass_search_knn honours rass_set_row_filter as an exact PRE-filter (top-k of
                             the rows that pass); 0 (default): the filter only applies to rass_search_hybrid and
                             the host post-filters the k nearest, which is what OpenSearch's nmslib engine does
@@ -242,6 +246,25 @@ int rass_set_row_filter(rass_engine* h, const uint8_t* mask_host, int64_t n);
 /* The same filter given as the list of rows that pass (a term filter on patientId selects a few hundred rows of
  * millions): the mask over [0, total_rows) is built on the device, the host moves n * 8 bytes. */
 int rass_set_row_filter_rows(rass_engine* h, const int64_t* rows_host, int64_t n, int64_t total_rows);
+
+/* Per-query filters in ONE call (every production query carries its own `term patientId` filter, app/main.py:1543-1550,
+ * 1599-1604, :2884; a window of coalesced requests holds as many filters as requests).  Query b brings the rows that pass
+ * ITS bool.filter: frows[frow_indptr[b] .. frow_indptr[b+1]) (engine rows, any order, no duplicates).  The listed rows are
+ * scored directly -- no corpus pass for them, no pass mask.
+ *   rass_search_knn_filtered     exact top-k among each query's listed rows (the pre-filter semantics of
+ *                                RASS_OPT_KNN_PREFILTER: same keys, ranking and scores)
+ *   rass_search_hybrid_filtered  bool.should of the text clauses + knn over each query's listed rows, as rass_search_hybrid
+ *                                (_weighted when qweights != NULL; qflags as there) computes it under that filter.  knn_mode
+ *                                0: the knn clause is the k nearest of the WHOLE corpus -- one scan pass shared by the batch,
+ *                                OpenSearch/nmslib's post-filter behaviour and this engine's default; 1: the k nearest among
+ *                                the listed rows.
+ * Single-device handles only. */
+int rass_search_knn_filtered(rass_engine* h, const float* q_host, int B, int k, const int64_t* frow_indptr,
+                             const int64_t* frows, int64_t* out_rows, float* out_scores, double* out_keys);
+int rass_search_hybrid_filtered(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr,
+                                const int32_t* qterms, const float* qweights, const uint8_t* qflags, float w_text,
+                                float w_knn, int k, const int64_t* frow_indptr, const int64_t* frows, int knn_mode,
+                                int64_t* out_rows, float* out_scores, rass_stats* stats);
 
 int rass_sync(rass_engine* h);
 /* statistics of the last blocking search / hybrid / fuse call on the handle (the entry points without a stats argument,

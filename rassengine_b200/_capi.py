@@ -20,7 +20,7 @@ ERR_NAMES = {-1: "RASS_E_INVALID", -2: "RASS_E_OOM", -3: "RASS_E_CUDA", -4: "RAS
 METRIC_COSINE, METRIC_L2 = 0, 1
 KEEP_FP32, BF16_ONLY = 1, 2
 PATH_AUTO, PATH_STREAM, PATH_UMMA, PATH_EXACT, PATH_GEMM = 0, 1, 2, 3, 4
-OPT_PATH, OPT_STREAM, OPT_KNN_PREFILTER, OPT_HYBRID_ORDERED = 1, 2, 3, 4
+OPT_PATH, OPT_STREAM, OPT_KNN_PREFILTER, OPT_HYBRID_ORDERED, OPT_HYBRID_MAXSCORE = 1, 2, 3, 4, 5
 PATH_HYBRID_ORDER_FREE = 0x100
 
 
@@ -78,6 +78,9 @@ PROTOTYPES = {
     "rass_fuzzy_expand": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _P, _P,
                                     C.POINTER(C.c_int64)]),
     "rass_set_row_filter": (C.c_int, [_P, _P, C.c_int64]),
+    "rass_search_knn_filtered": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "rass_search_hybrid_filtered": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int, _P, _P,
+                                              C.c_int, _P, _P, C.POINTER(RassStats)]),
     "rass_sync": (C.c_int, [_P]),
     "rass_last_stats": (C.c_int, [_P, C.POINTER(RassStats)]),
     "rass_save": (C.c_int, [_P, C.c_char_p]),

@@ -32,6 +32,7 @@ TEXT_FIELD = "unstructuredText"      # the only analysed field chunk documents c
 FILTER_FIELDS = ("patientId", "doc_type", "resourceType", "doc_id")   # keyword fields the hot path filters on
 _SPACE = {"cosinesimil": capi.METRIC_COSINE, "l2": capi.METRIC_L2}
 MAX_K = 128                          # RASS_MAX_K: the largest top-k one engine call returns
+FILTER_LIST_MAX = 1 << 17            # filters passing at most this many rows are scored row by row (rass_search_*_filtered)
 
 
 class NotFoundError(KeyError):
@@ -357,8 +358,14 @@ class _Index:
         if plan.kind == "knn":
             k = max(plan.knn_k, 1)
             if has_filter and self.knn_filter == "pre":
-                # exact filtered kNN: the scan itself skips rows failing the term filters, so the
-                # k best rows OF THE PATIENT come back instead of whichever of the global k nearest happen to pass
+                # exact filtered kNN: the k best rows OF THE PATIENT come back instead of whichever
+                # of the global k nearest happen to pass.  A selective filter (a patient's few hundred rows) is scored
+                # row by row, no corpus pass; a broad one is folded into the scan as a pass mask.
+                frows = self._filter_rows(plan.filters, plan.host_filters)
+                if frows.size <= FILTER_LIST_MAX and len(eng.devices) == 1:
+                    rows, scores = eng.search_knn_filtered(q, k, [frows])
+                    hits = [(int(r), float(s) * plan.knn_boost) for r, s in zip(rows[0], scores[0]) if r >= 0]
+                    return self._hits(hits[: plan.size])
                 self._apply_filter(plan)
                 eng.set_knn_prefilter(True)
                 try:
@@ -415,7 +422,16 @@ class _Index:
             raise NotImplementedError("knn k different from size in a hybrid query")
         if q is None and qterms is None:
             return []
-        # bool.filter: only rows that satisfy every term filter may score (device-side pass mask)
+        # bool.filter: only rows that satisfy every filter may score.  A selective filter (every production query carries
+        # its own `term patientId`, app/main.py:1599-1604) travels as the list of passing rows and those rows are scored
+        # directly -- text clauses by posting lookups, the knn clause still the k nearest of the whole corpus; a broad
+        # filter becomes a device-side pass mask for the tile kernel.
+        if has_filter and self.batch_window_s is None and len(eng.devices) == 1:
+            frows = self._filter_rows(plan.filters, plan.host_filters)
+            if frows.size <= FILTER_LIST_MAX:
+                rows, scores = eng.search_hybrid_filtered(q, qterms, w_text, plan.knn_boost, k, [frows],
+                                                          qweights=qweights, qflags=qflags)
+                return self._hits([(int(r), float(s)) for r, s in zip(rows[0], scores[0]) if r >= 0][: plan.size])
         if has_filter:
             self._apply_filter(plan)
         else:

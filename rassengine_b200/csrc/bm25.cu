@@ -907,46 +907,20 @@ static int ensure_hybrid_workspace(rass_engine* h, size_t n_terms_cap, int B) {
 // (fuzzy expansions carry their own boost and blended idf)
 // Row-sharded corpora fuse against the GLOBAL k nearest (all-gathered and merged by the caller) and leave their local
 // top-k on the device for the next exchange (HybridExt, common.cuh).
-// qflags (nullable): per term, bit 0 = last term of its field group, bit 1 = last term of its clause; the clause score is
-// the maximum over its field groups (multi_match best_fields), the query's text score the sum over clauses.
-int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr, const int32_t* qterms,
-                const float* qweights, const uint8_t* qflags, float w_text, float w_knn, int k,
-                int64_t* out_rows, float* out_scores, rass_stats* stats, const HybridExt* ext) {
-  if (!h) return RASS_E_INVALID;
-  cudaSetDevice(h->device);
-  if (B < 1 || (!ext && (!out_rows || !out_scores))) return rass_fail(h, RASS_E_INVALID, "bad arguments");
-  if (k < 1 || k > RASS_MAX_K) return rass_fail(h, RASS_E_INVALID, "k must be in [1, %d], got %d", RASS_MAX_K, k);
-  if (!q_host && !qterm_indptr && !(ext && ext->knn_rows_dev))
-    return rass_fail(h, RASS_E_INVALID, "neither a vector nor a text clause");
+// The query terms of a batch in the layout the text kernels read (one pinned + one device block, see
+// ensure_hybrid_workspace): posting ranges, float(boost) * idf weights (or the caller's), structure flags, MaxScore bounds;
+// plus what the host decides from them -- whether the batch needs the multi-clause kernel, and whether every query's
+// clause sums are exact in double in any order.
+int stage_hybrid_terms(rass_engine* h, int B, const int32_t* qterm_indptr, const int32_t* qterms, const float* qweights,
+                       const uint8_t* qflags, float w_text, HybridTerms* out, cudaStream_t st) {
   Bm25State& b = h->bm25;
-  if (qterm_indptr && (!b.built || !qterms)) return rass_fail(h, RASS_E_INVALID, "text clause without rass_bm25_build");
-  cudaStream_t st = eng_stream(h);
   int rc;
-  const size_t n_out = (size_t)B * k;
-  if ((rc = ensure_out_workspace(h, 2 * n_out))) return rc;
-  rass_stats s;
-  memset(&s, 0, sizeof(s));
-  s.n_queries = B;
-  // 1. the knn clause: exact top-k per query (results stay on the device in the second half of the staging)
-  const int64_t* knn_rows = h->out_rows + n_out;
-  const float* knn_scores = h->out_scores + n_out;
-  bool have_vec = q_host != nullptr && h->n_rows > 0;
-  if (ext && ext->knn_rows_dev) {
-    knn_rows = ext->knn_rows_dev;
-    knn_scores = ext->knn_scores_dev;
-    have_vec = true;
-  } else if (have_vec) {
-    float* q_dev = nullptr;
-    if ((rc = stage_queries(h, q_host, B, &q_dev))) return rc;
-    if ((rc = search_core(h, q_dev, B, k, h->out_rows + n_out, h->out_scores + n_out, nullptr, &s))) return rc;
-  }
-  // 2. the query terms: posting ranges and float(boost) * idf weights, in query order
-  const bool have_text = qterm_indptr != nullptr;
   size_t n_terms = 0;
   bool multi = false;
   static const bool force_ordered = getenv("RASS_DEBUG_HYBRID_ORDERED") != nullptr;   // A/B and test switch
   bool order_free = !force_ordered && !h->bm25.force_ordered;
-  if (have_text) {
+  int64_t postings = 0;
+  {
     if ((rc = ensure_hybrid_workspace(h, (size_t)(qterm_indptr[B] - qterm_indptr[0]), B))) return rc;
     unsigned char* base = b.qt_host;
     int64_t* t_lo = reinterpret_cast<int64_t*>(base);
@@ -1003,7 +977,7 @@ int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm
           if (q_field < 0) q_field = t_field[n_terms];
           else if (q_field != t_field[n_terms]) q_ok = false;
         }
-        s.bytes_streamed += len * 6;
+        postings += len;
         ++n_terms;
       }
       if (q_ok && q_sum_max > 0.0) {
@@ -1027,6 +1001,64 @@ int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm
     indptr[B] = (int32_t)n_terms;
     CUDA_TRY(h, cudaMemcpyAsync(b.qt_dev, b.qt_host, b.qt_bytes, cudaMemcpyHostToDevice, st));
   }
+  unsigned char* base = b.qt_dev;
+  out->t_lo = reinterpret_cast<const int64_t*>(base);
+  out->t_len = reinterpret_cast<const uint32_t*>(base + b.qt_cap * 8);
+  out->t_w = reinterpret_cast<const float*>(base + b.qt_cap * 12);
+  out->t_row = reinterpret_cast<const int32_t*>(base + b.qt_cap * 16);
+  out->t_bound = reinterpret_cast<const float*>(base + b.qt_cap * 20);
+  out->qt_indptr = reinterpret_cast<const int32_t*>(base + b.qt_cap * 24);
+  out->t_field = base + b.qt_cap * 24 + b.qt_q_cap * 4;
+  out->t_flag = out->t_field + b.qt_cap;
+  out->multi = multi;
+  out->order_free = order_free;
+  out->n_terms = n_terms;
+  out->postings = postings;
+  return RASS_OK;
+}
+
+// qflags (nullable): per term, bit 0 = last term of its field group, bit 1 = last term of its clause; the clause score is
+// the maximum over its field groups (multi_match best_fields), the query's text score the sum over clauses.
+int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr, const int32_t* qterms,
+                const float* qweights, const uint8_t* qflags, float w_text, float w_knn, int k,
+                int64_t* out_rows, float* out_scores, rass_stats* stats, const HybridExt* ext) {
+  if (!h) return RASS_E_INVALID;
+  cudaSetDevice(h->device);
+  if (B < 1 || (!ext && (!out_rows || !out_scores))) return rass_fail(h, RASS_E_INVALID, "bad arguments");
+  if (k < 1 || k > RASS_MAX_K) return rass_fail(h, RASS_E_INVALID, "k must be in [1, %d], got %d", RASS_MAX_K, k);
+  if (!q_host && !qterm_indptr && !(ext && ext->knn_rows_dev))
+    return rass_fail(h, RASS_E_INVALID, "neither a vector nor a text clause");
+  Bm25State& b = h->bm25;
+  if (qterm_indptr && (!b.built || !qterms)) return rass_fail(h, RASS_E_INVALID, "text clause without rass_bm25_build");
+  cudaStream_t st = eng_stream(h);
+  int rc;
+  const size_t n_out = (size_t)B * k;
+  if ((rc = ensure_out_workspace(h, 2 * n_out))) return rc;
+  rass_stats s;
+  memset(&s, 0, sizeof(s));
+  s.n_queries = B;
+  // 1. the knn clause: exact top-k per query (results stay on the device in the second half of the staging)
+  const int64_t* knn_rows = h->out_rows + n_out;
+  const float* knn_scores = h->out_scores + n_out;
+  bool have_vec = q_host != nullptr && h->n_rows > 0;
+  if (ext && ext->knn_rows_dev) {
+    knn_rows = ext->knn_rows_dev;
+    knn_scores = ext->knn_scores_dev;
+    have_vec = true;
+  } else if (have_vec) {
+    float* q_dev = nullptr;
+    if ((rc = stage_queries(h, q_host, B, &q_dev))) return rc;
+    if ((rc = search_core(h, q_dev, B, k, h->out_rows + n_out, h->out_scores + n_out, nullptr, &s))) return rc;
+  }
+  // 2. the query terms: posting ranges and float(boost) * idf weights, in query order
+  const bool have_text = qterm_indptr != nullptr;
+  HybridTerms ta;
+  memset(&ta, 0, sizeof(ta));
+  ta.order_free = true;
+  if (have_text && (rc = stage_hybrid_terms(h, B, qterm_indptr, qterms, qweights, qflags, w_text, &ta, st))) return rc;
+  const bool multi = ta.multi;
+  const bool order_free = ta.order_free;
+  s.bytes_streamed += ta.postings * 6;
   // 3. one fused kernel over (tile, query), then the per-query top-k of the tile lists
   const int64_t n_docs = std::max<int64_t>(std::max<int64_t>(b.built ? b.N : 0, h->n_rows), 1);
   const int n_tiles = (int)((n_docs + HYB_TILE - 1) / HYB_TILE);
@@ -1038,16 +1070,13 @@ int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm
   memset(&a, 0, sizeof(a));
   a.doc = b.doc; a.tf = b.tf; a.norm = b.norm; a.inv = b.inv_dev; a.tile_off = b.tile_off;
   if (have_text) {
-    unsigned char* base = b.qt_dev;
-    a.t_lo = reinterpret_cast<const int64_t*>(base);
-    a.t_len = reinterpret_cast<const uint32_t*>(base + b.qt_cap * 8);
-    a.t_w = reinterpret_cast<const float*>(base + b.qt_cap * 12);
-    a.t_row = reinterpret_cast<const int32_t*>(base + b.qt_cap * 16);
-    static const bool no_prune = getenv("RASS_DEBUG_NO_MAXSCORE") != nullptr;       // A/B switch
-    a.t_bound = no_prune ? nullptr : reinterpret_cast<const float*>(base + b.qt_cap * 20);
-    a.qt_indptr = reinterpret_cast<const int32_t*>(base + b.qt_cap * 24);
-    a.t_field = base + b.qt_cap * 24 + b.qt_q_cap * 4;
-    a.t_flag = a.t_field + b.qt_cap;
+    a.t_lo = ta.t_lo; a.t_len = ta.t_len; a.t_w = ta.t_w; a.t_row = ta.t_row;
+    // MaxScore marks are opt-in (RASS_OPT_HYBRID_MAXSCORE / RASS_HYBRID_MAXSCORE=1): on the cfg4 corpus they remove 88 % of
+    // the scoring work but add a barrier-separated phase to a CTA that is latency-bound, not work-bound, and measure
+    // 10 % slower (1.69 ms against 1.53 ms per 64-query batch at 5M docs, profiles/r2_hybrid_kernel_ncu.md)
+    static const bool env_prune = getenv("RASS_HYBRID_MAXSCORE") != nullptr;
+    a.t_bound = (env_prune || h->bm25.maxscore) ? ta.t_bound : nullptr;
+    a.qt_indptr = ta.qt_indptr; a.t_field = ta.t_field; a.t_flag = ta.t_flag;
   }
   a.norm_rows = b.N;
   a.knn_rows = have_vec ? knn_rows : nullptr;

@@ -75,6 +75,7 @@ struct Bm25State {
   std::vector<float> idf_host;   // (float) ln(1 + (docCount - df + .5) / (df + .5))
   std::vector<float> xmin_host, xmax_host;   // per term: range of tf * inv[norm] over its postings (term_xrange_kernel)
   bool force_ordered = false;    // RASS_OPT_HYBRID_ORDERED: always take the ordered tile kernel (tests, A/B)
+  bool maxscore = false;         // RASS_OPT_HYBRID_MAXSCORE: essential / non-essential term split in the order-free kernel
   int* sel_fallback = nullptr;   // device [qt_q_cap]: queries hybrid_select_kernel hands to the radix select
 };
 
@@ -170,6 +171,8 @@ struct rass_engine {
     size_t n_ev = 0;
     rass_stats stats;
   } aslot[2];
+  int64_t* flist_dev = nullptr;     // per-query filter row lists of the running call (filtered.cu): [B + 1] offsets + rows
+  size_t flist_cap = 0;
   uint8_t* row_filter = nullptr;    // device [row_filter_rows] 1 = row passes the bool.filter of the running query
   int64_t* filter_rows_dev = nullptr;   // staging of row lists (rass_set_row_filter_rows, rass_read_rows_list)
   size_t filter_rows_cap = 0;
@@ -465,6 +468,23 @@ struct HybridExt {
   float* out_scores_dev;         // [B, k] fused float scores
   double* out_keys_dev;          // [B, k] the same as double (what the shard merge ranks by), nullable
 };
+// device views of a batch's staged query terms (stage_hybrid_terms, bm25.cu)
+struct HybridTerms {
+  const int32_t* qt_indptr;
+  const int64_t* t_lo;
+  const uint32_t* t_len;
+  const float* t_w;
+  const int32_t* t_row;
+  const float* t_bound;
+  const uint8_t* t_field;
+  const uint8_t* t_flag;
+  bool multi, order_free;
+  size_t n_terms;
+  int64_t postings;
+};
+typedef HybridTerms FilteredTermArrays;
+int stage_hybrid_terms(rass_engine* h, int B, const int32_t* qterm_indptr, const int32_t* qterms, const float* qweights,
+                       const uint8_t* qflags, float w_text, HybridTerms* out, cudaStream_t st);
 int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr, const int32_t* qterms,
                 const float* qweights, const uint8_t* qflags, float w_text, float w_knn, int k, int64_t* out_rows,
                 float* out_scores, rass_stats* stats, const HybridExt* ext = nullptr);

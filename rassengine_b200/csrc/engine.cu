@@ -142,6 +142,7 @@ extern "C" int rass_destroy(rass_engine* h) {
   cudaFree(h->q_stage_dev);
   cudaFree(h->row_filter);
   cudaFree(h->filter_rows_dev);
+  cudaFree(h->flist_dev);
   cudaFree(h->sb_filtered);
   cudaFree(h->retry_ids); cudaFree(h->retry_q); cudaFree(h->retry_rows); cudaFree(h->retry_scores); cudaFree(h->retry_keys);
   for (cudaEvent_t e : h->ev_pool) if (e) cudaEventDestroy(e);
@@ -168,6 +169,9 @@ extern "C" int rass_set_option(rass_engine* h, int opt, int64_t value) {
       return RASS_OK;
     case RASS_OPT_HYBRID_ORDERED:
       h->bm25.force_ordered = value != 0;
+      return RASS_OK;
+    case RASS_OPT_HYBRID_MAXSCORE:
+      h->bm25.maxscore = value != 0;
       return RASS_OK;
     case RASS_OPT_PATH:
       if (value < RASS_PATH_AUTO || value > RASS_PATH_GEMM) return rass_fail(h, RASS_E_INVALID, "bad path %lld", (long long)value);

@@ -446,6 +446,15 @@ int launch_exact(rass_engine* h, int k, const int* qids_host, int n_q, int64_t* 
   return RASS_OK;
 }
 
+// exact top-k of B queries' (fp64 key, row) lists of `entries` entries each, scores translated by the engine's metric
+int launch_exact_select(rass_engine* h, size_t entries, int B, int k, int64_t* out_rows, float* out_scores,
+                        double* out_keys, cudaStream_t st) {
+  exact_select_kernel<<<B, 1024, 0, st>>>(h->xlist_key, h->xlist_row, entries, (int)entries, k, nullptr, 0, 0, h->metric,
+                                          h->rmap, out_rows, out_scores, out_keys, nullptr);
+  CUDA_TRY(h, cudaGetLastError());
+  return RASS_OK;
+}
+
 // top-k of B queries' fused (score, row) lists of `entries` entries each; the score is emitted as is (bm25.cu)
 int launch_select_batch(rass_engine* h, size_t entries, int B, int k, int64_t* out_rows, float* out_scores,
                         double* out_keys, cudaStream_t st, const int* only_if) {

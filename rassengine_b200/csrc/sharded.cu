@@ -133,6 +133,14 @@ static int64_t shard_rows_below(const rass_engine* h, int g, int64_t total) {
   return n;
 }
 
+// cudaMemcpyPeer is asynchronous with respect to the host and is not ordered against cudaStreamNonBlocking streams, which
+// is what every engine runs on: copy on the shard's own stream and wait for it.
+static cudaError_t peer_copy_sync(void* dst, int dst_dev, const void* src, int src_dev, size_t bytes, cudaStream_t st) {
+  cudaError_t e = cudaMemcpyPeerAsync(dst, dst_dev, src, src_dev, bytes, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  return e;
+}
+
 static int run_all(rass_engine* h, const std::function<int(int)>& fn) {
   ShardSet* S = h->shards;
   for (int g = 0; g < S->G; ++g) S->workers[g]->post([&fn, g] { return fn(g); });
@@ -375,7 +383,7 @@ static int sharded_append_impl(rass_engine* h, const float* rows, bool on_device
       // device rows of the coordinator -> this shard's device (peer copy), then the ordinary device append
       float* tmp = nullptr;
       CUDA_TRY(sh, cudaMalloc(&tmp, (size_t)run * h->dim * 4));
-      cudaError_t e = cudaMemcpyPeer(tmp, S->dev[g], src, h->device, (size_t)run * h->dim * 4);
+      cudaError_t e = peer_copy_sync(tmp, S->dev[g], src, h->device, (size_t)run * h->dim * 4, eng_stream(sh));
       int rc2 = e == cudaSuccess ? rass_append_dev(sh, tmp, run, nullptr)
                                  : rass_fail(sh, RASS_E_NCCL, "peer copy of appended rows: %s", cudaGetErrorString(e));
       cudaFree(tmp);
@@ -528,8 +536,9 @@ static int knn_to_coordinator(rass_engine* h, const float* q_host, int B, int k,
     // blocking form: certificate failures are retried / re-scanned exactly before it returns (stream synchronised)
     if ((r = search_core_ex(sh, qd, B, k, o_rows, sh->out_scores, o_keys, &S->st[g], -1, nullptr))) return r;
     if (o_rows == S->l_rows[g]) {
-      cudaError_t e = cudaMemcpyPeer(S->g_rows[0] + (size_t)g * S->cap, h->device, o_rows, S->dev[g], n * 8);
-      if (e == cudaSuccess) e = cudaMemcpyPeer(S->g_keys[0] + (size_t)g * S->cap, h->device, o_keys, S->dev[g], n * 8);
+      cudaError_t e = peer_copy_sync(S->g_rows[0] + (size_t)g * S->cap, h->device, o_rows, S->dev[g], n * 8, eng_stream(sh));
+      if (e == cudaSuccess)
+        e = peer_copy_sync(S->g_keys[0] + (size_t)g * S->cap, h->device, o_keys, S->dev[g], n * 8, eng_stream(sh));
       if (e != cudaSuccess) return rass_fail(sh, RASS_E_NCCL, "list exchange: %s", cudaGetErrorString(e));
     }
     return (int)RASS_OK;
@@ -758,8 +767,8 @@ static int fuse_on_shards(rass_engine* h, int B, const int32_t* qterm_indptr, co
     if (knn_rows_c) {
       if (S->dev[g] == h->device) { kr = knn_rows_c; ks = knn_scores_c; }
       else {
-        cudaError_t e = cudaMemcpyPeer(S->knn_rows[g], S->dev[g], knn_rows_c, h->device, n * 8);
-        if (e == cudaSuccess) e = cudaMemcpyPeer(S->knn_scores[g], S->dev[g], knn_scores_c, h->device, n * 4);
+        cudaError_t e = peer_copy_sync(S->knn_rows[g], S->dev[g], knn_rows_c, h->device, n * 8, eng_stream(sh));
+        if (e == cudaSuccess) e = peer_copy_sync(S->knn_scores[g], S->dev[g], knn_scores_c, h->device, n * 4, eng_stream(sh));
         if (e != cudaSuccess) return rass_fail(sh, RASS_E_NCCL, "knn list broadcast: %s", cudaGetErrorString(e));
         kr = S->knn_rows[g];
         ks = S->knn_scores[g];
@@ -772,8 +781,9 @@ static int fuse_on_shards(rass_engine* h, int B, const int32_t* qterm_indptr, co
                          &S->st[g], &ext)))
       return r;
     if (!direct) {
-      cudaError_t e = cudaMemcpyPeer(S->g_rows[0] + (size_t)g * S->cap, h->device, S->l_rows[g], S->dev[g], n * 8);
-      if (e == cudaSuccess) e = cudaMemcpyPeer(S->g_keys[0] + (size_t)g * S->cap, h->device, S->l_keys[g], S->dev[g], n * 8);
+      cudaError_t e = peer_copy_sync(S->g_rows[0] + (size_t)g * S->cap, h->device, S->l_rows[g], S->dev[g], n * 8, eng_stream(sh));
+      if (e == cudaSuccess)
+        e = peer_copy_sync(S->g_keys[0] + (size_t)g * S->cap, h->device, S->l_keys[g], S->dev[g], n * 8, eng_stream(sh));
       if (e != cudaSuccess) return rass_fail(sh, RASS_E_NCCL, "fused list exchange: %s", cudaGetErrorString(e));
     }
     return (int)RASS_OK;

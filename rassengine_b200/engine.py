@@ -92,6 +92,10 @@ class Engine:
         """Force the ordered (one barrier per term) text kernel for hybrid calls; results are bit-identical either way."""
         self._check(self._lib.rass_set_option(self._h, capi.OPT_HYBRID_ORDERED, 1 if on else 0))
 
+    def set_hybrid_maxscore(self, on: bool):
+        """MaxScore-style essential / non-essential term split in the order-free text kernel (identical results)."""
+        self._check(self._lib.rass_set_option(self._h, capi.OPT_HYBRID_MAXSCORE, 1 if on else 0))
+
     def set_row_base(self, base: int):
         self._check(self._lib.rass_set_row_base(self._h, base))
 
@@ -302,6 +306,59 @@ class Engine:
                                                  _ptr(indptr) if indptr is not None else None,
                                                  _ptr(terms) if terms is not None else None,
                                                  w_text, w_knn, k, _ptr(rows), _ptr(scores), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return rows, scores
+
+    @staticmethod
+    def _pack_rows(row_lists):
+        """B lists of passing rows -> (indptr int64 [B + 1], rows int64 [total])."""
+        indptr = np.zeros(len(row_lists) + 1, dtype=np.int64)
+        indptr[1:] = np.cumsum([len(r) for r in row_lists])
+        rows = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.int64).reshape(-1) for r in row_lists])
+                                    if indptr[-1] else np.zeros(1, dtype=np.int64), dtype=np.int64)
+        return indptr, rows
+
+    def search_knn_filtered(self, q: np.ndarray, k: int, row_lists, want_keys: bool = False):
+        """Exact top-k among each query's OWN list of passing rows (per-query bool.filter, one call for the batch)."""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
+        B = q.shape[0]
+        if len(row_lists) != B:
+            raise ValueError("row_lists must hold one list per query")
+        fip, frows = self._pack_rows(row_lists)
+        rows = np.empty((B, k), dtype=np.int64)
+        scores = np.empty((B, k), dtype=np.float32)
+        keys = np.empty((B, k), dtype=np.float64) if want_keys else None
+        self._check(self._lib.rass_search_knn_filtered(self._h, _ptr(q), B, k, _ptr(fip), _ptr(frows), _ptr(rows),
+                                                       _ptr(scores), _ptr(keys) if want_keys else None))
+        return (rows, scores, keys) if want_keys else (rows, scores)
+
+    def search_hybrid_filtered(self, q, qterms, w_text: float, w_knn: float, k: int, row_lists, knn_pre: bool = False,
+                               qweights=None, qflags=None):
+        """search_hybrid with a DIFFERENT bool.filter per query, given as each query's list of passing rows; the knn
+        clause is the k nearest of the whole corpus (one shared pass) unless knn_pre (k nearest among the list)."""
+        if q is not None:
+            q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
+            B = q.shape[0]
+        else:
+            B = len(row_lists)
+        if len(row_lists) != B:
+            raise ValueError("row_lists must hold one list per query")
+        fip, frows = self._pack_rows(row_lists)
+        indptr = terms = w = fl = None
+        if qterms is not None:
+            indptr, terms = _pack_terms(qterms, B)
+            cat = lambda xs, dt: np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=dt) for x in xs])
+                                                      if indptr[-1] else np.zeros(1, dtype=dt), dtype=dt)
+            w = cat(qweights, np.float32) if qweights is not None else None
+            fl = cat(qflags, np.uint8) if qflags is not None else None
+        rows = np.empty((B, k), dtype=np.int64)
+        scores = np.empty((B, k), dtype=np.float32)
+        st = RassStats()
+        self._check(self._lib.rass_search_hybrid_filtered(
+            self._h, _ptr(q) if q is not None else None, B, _ptr(indptr) if indptr is not None else None,
+            _ptr(terms) if terms is not None else None, _ptr(w) if w is not None else None,
+            _ptr(fl) if fl is not None else None, w_text, w_knn, k, _ptr(fip), _ptr(frows), 1 if knn_pre else 0,
+            _ptr(rows), _ptr(scores), C.byref(st)))
         self.last_stats = st.as_dict()
         return rows, scores
 

@@ -567,11 +567,16 @@ def test_maxscore_pruning_keeps_results_exact():
     with _engine(dim=dim, capacity_rows=n_docs) as e:
         e.append(X)
         e.bm25_build(indptr, doc, tf, doclen)
+        e.set_hybrid_maxscore(True)
         for k in (10, 100):
             knn_rows, _, knn_scores = knn.knn_exact(X, Q, k)
             rows_b, scores_b = e.search_hybrid(Q, qterms, 4.5, 2.0, k)
             assert e.last_stats["path"] & 0x100
             rows_t, scores_t = e.search_hybrid(None, qterms, 4.5, 0.0, k)
+            e.set_hybrid_maxscore(False)
+            rows_n, scores_n = e.search_hybrid(Q, qterms, 4.5, 2.0, k)            # the default: no term split
+            assert np.array_equal(rows_b, rows_n) and np.array_equal(scores_b.view(np.uint32), scores_n.view(np.uint32))
+            e.set_hybrid_maxscore(True)
             e.set_hybrid_ordered(True)
             rows_o, scores_o = e.search_hybrid(Q, qterms, 4.5, 2.0, k)
             e.set_hybrid_ordered(False)
@@ -582,3 +587,60 @@ def test_maxscore_pruning_keeps_results_exact():
                 np.testing.assert_allclose(scores_b[b, :len(wr)], ws, rtol=2e-6, atol=0)
                 tr, ts = bm25.topk(idx.score(qterms[b], boost=4.5), k)
                 assert rows_t[b, :len(tr)].tolist() == tr.tolist() and scores_t[b, :len(tr)].tolist() == ts.tolist(), (k, b)
+
+
+def test_64_different_patient_filters_in_one_call_equal_64_filtered_calls():
+    """Every production query carries its own `term patientId` filter (app/main.py:1599-1604).  One batched call with a row
+    list per query must return exactly what 64 single calls with that filter set return -- kNN (pre-filter) and hybrid
+    (knn clause = the global k nearest, post-filter, and the pre-filter variant) -- and what the oracle returns."""
+    n_docs, vocab, dim, nq, k = 30000, 2000, 128, 64, 10
+    indptr, doc, tf, doclen = synth.text_corpus(n_docs, vocab=vocab, seed=91, median_len=40, max_len=160)
+    idx = bm25.BM25Index(indptr, doc, tf, doclen)
+    X = synth.embeddings(n_docs, dim, 92)
+    Q = synth.embeddings(nq, dim, 93)
+    qterms = synth.text_queries(nq, vocab=vocab, seed=94)
+    rng = np.random.default_rng(95)
+    patient = rng.integers(0, 200, size=n_docs)                      # ~150 rows per patient
+    lists = [np.flatnonzero(patient == (b * 3) % 200) for b in range(nq)]
+    lists[5] = lists[5][:4]                                          # fewer rows than k
+    lists[6] = np.zeros(0, dtype=np.int64)                           # a patient without documents
+    lists[7] = rng.permutation(lists[7])                             # the list need not be sorted
+    not_tomb = np.ones(n_docs, dtype=bool)
+    not_tomb[int(lists[0][0])] = False
+    knn_g, _, knn_gs = knn.knn_exact(X, Q, k, alive=not_tomb)
+    with _engine(dim=dim, capacity_rows=n_docs) as e:
+        e.append(X)
+        e.bm25_build(indptr, doc, tf, doclen)
+        e.tombstone(int(lists[0][0]))
+        r_knn, s_knn, key_knn = e.search_knn_filtered(Q, k, lists, want_keys=True)
+        r_post, s_post = e.search_hybrid_filtered(Q, qterms, 4.5, 2.0, k, lists)
+        r_pre, s_pre = e.search_hybrid_filtered(Q, qterms, 4.5, 2.0, k, lists, knn_pre=True)
+        r_txt, s_txt = e.search_hybrid_filtered(None, qterms, 4.5, 0.0, k, lists)
+        for b in range(nq):
+            mask = np.zeros(n_docs, dtype=bool)
+            mask[lists[b]] = True
+            alive = mask.copy()
+            alive[int(lists[0][0])] = False                           # the tombstoned vector never matches a knn clause
+            # single calls with the same filter set for the whole call
+            e.set_row_filter(mask)
+            e.set_knn_prefilter(True)
+            r1, s1, k1 = e.search_knn(Q[b:b + 1], k, want_keys=True)
+            e.set_knn_prefilter(False)
+            h1, hs1 = e.search_hybrid(Q[b:b + 1], [qterms[b]], 4.5, 2.0, k)
+            t1, ts1 = e.search_hybrid(None, [qterms[b]], 4.5, 0.0, k)
+            e.set_row_filter(None)
+            assert r_knn[b].tolist() == r1[0].tolist() and s_knn[b].tolist() == s1[0].tolist(), b
+            nv = int((r1[0] >= 0).sum())
+            assert key_knn[b, :nv].tolist() == k1[0, :nv].tolist()
+            assert r_post[b].tolist() == h1[0].tolist() and s_post[b].tolist() == hs1[0].tolist(), b
+            assert r_txt[b].tolist() == t1[0].tolist() and s_txt[b].tolist() == ts1[0].tolist(), b
+            # the oracle: kNN restricted to the list; fusion with the global / the restricted k nearest
+            wr, _, ws = knn.knn_exact(X, Q[b:b + 1], k, alive=alive)
+            kk = wr.shape[1]
+            assert r_knn[b, :kk].tolist() == wr[0].tolist() and (r_knn[b, kk:] == -1).all()
+            fr, fs = fusion.hybrid(idx, qterms[b], knn_g[b], knn_gs[b], 4.5, 2.0, k, alive=mask)
+            assert r_post[b, :len(fr)].tolist() == fr.tolist(), b
+            np.testing.assert_allclose(s_post[b, :len(fr)], fs, rtol=2e-6, atol=0)
+            pr, ps = fusion.hybrid(idx, qterms[b], wr[0], ws[0], 4.5, 2.0, k, alive=mask)
+            assert r_pre[b, :len(pr)].tolist() == pr.tolist(), b
+            np.testing.assert_allclose(s_pre[b, :len(pr)], ps, rtol=2e-6, atol=0)

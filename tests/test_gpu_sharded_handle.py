@@ -105,7 +105,10 @@ def test_sharded_async_device_path(devices):
     want, _, want_scores = knn.knn_exact(X, Q, k)
     dev = torch.device("cuda", devices[0])
     with _engine(dim=D, devices=devices) as e:
-        e.append_dev(torch.from_numpy(X).to(dev).data_ptr(), N)          # device rows of the coordinator, spread by peer copies
+        Xd = torch.from_numpy(X).to(dev)
+        torch.cuda.synchronize(dev)              # the rows are complete before another stream / device reads them
+        e.append_dev(Xd.data_ptr(), N)           # device rows of the coordinator, spread by peer copies
+        del Xd
         qd = [torch.from_numpy(Q[:B]).to(dev), torch.from_numpy(Q[B:]).to(dev)]
         rows = [torch.empty((B, k), dtype=torch.int64, device=dev) for _ in range(2)]
         scores = [torch.empty((B, k), dtype=torch.float32, device=dev) for _ in range(2)]
