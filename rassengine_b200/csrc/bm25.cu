@@ -255,9 +255,11 @@ struct HybridArgs {
 // The rest of a (tile, query) CTA once the text clauses are summed in `fused` (double per doc, 0 = no match): the knn
 // clause, then the tile's top-k by (fused float score desc, row asc) into the query's list.  MULTI: `fused` holds clause
 // sums in double (the knn score is one more clause); otherwise the single text clause is rounded to float first.
+// pre_g (nullable): the query's pruning bound already sitting in shared memory (the caller read it while the tile was
+// being scored), which saves the tail a global round trip and two barriers.
 template <bool MULTI>
 __device__ __forceinline__ void hybrid_tile_tail(const HybridArgs& a, double* fused, int q, int tile, int64_t d0,
-                                                 int64_t d1, bool knn_done = false) {
+                                                 int64_t d1, bool knn_done = false, const uint32_t* pre_g = nullptr) {
   __shared__ __align__(16) int s_cnt[2][HYB_THREADS / 32];
   __shared__ uint32_t s_list[HYB_LIST];
   __shared__ int s_nout, s_nmatch, s_ns;
@@ -289,9 +291,11 @@ __device__ __forceinline__ void hybrid_tile_tail(const HybridArgs& a, double* fu
     key[i] = v != 0.0 ? ord32((float)v) : 0u;
     nm += v != 0.0;
   }
-  if (nm) atomicAdd(&s_nmatch, nm);
-  __syncthreads();
-  const int n_match = s_nmatch;
+  if (!pre_g) {
+    if (nm) atomicAdd(&s_nmatch, nm);
+    __syncthreads();
+  }
+  const int n_match = pre_g ? HYB_TILE : s_nmatch;      // with a bound at hand the survivors are counted below
   double* xk = a.xkey + ((size_t)q * a.n_tiles + tile) * a.k;
   uint32_t* xr = a.xrow + ((size_t)q * a.n_tiles + tile) * a.k;
   int buf = 0;
@@ -306,11 +310,13 @@ __device__ __forceinline__ void hybrid_tile_tail(const HybridArgs& a, double* fu
   // Cross-tile pruning: some other tile of this query already holds k rows with key >= g, so keys below g cannot
   // reach the query's top-k.  Most tiles of a batched launch then keep a handful of keys and skip the selection.
   // (read once per CTA: other tiles raise the bound concurrently, and the branches below must be uniform)
-  if (tid == 0) s_g = n_match > a.k ? __ldcg(a.gthr + q) : 0u;
-  __syncthreads();
-  const uint32_t g = s_g;
+  if (!pre_g) {
+    if (tid == 0) s_g = n_match > a.k ? __ldcg(a.gthr + q) : 0u;
+    __syncthreads();
+  }
+  const uint32_t g = pre_g ? *pre_g : s_g;
   int n_live = n_match;
-  if (g) {
+  if (g || pre_g) {
     int c = 0;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
@@ -547,18 +553,20 @@ __device__ __forceinline__ bool hyb_score_add(double* acc, const float* s_inv, i
   return sc > 0.f;
 }
 
-template <bool FILTER>
-__global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_fast_kernel(const __grid_constant__ HybridArgs a) {
+// PRUNE = false (the default) leaves the MaxScore machinery out: 40 registers and 36.6 KB of shared memory, six CTAs per SM
+// instead of five (1.53 -> 1.36 ms per 64-query batch at 5M docs).
+template <bool FILTER, bool PRUNE>
+__global__ void __launch_bounds__(HYB_THREADS, PRUNE ? 5 : 6) hybrid_tile_fast_kernel(const __grid_constant__ HybridArgs a) {
   __shared__ double acc[HYB_TILE];
-  __shared__ uint32_t s_bits[HYB_TILE / 32];      // docs touched by an essential term or named by the knn clause
+  __shared__ uint32_t s_bits[PRUNE ? HYB_TILE / 32 : 1];   // docs touched by an essential term or named by the knn clause
   __shared__ float s_inv[256];
   __shared__ int64_t s_lo[HYB_FAST_TERMS];
   __shared__ uint32_t s_n[HYB_FAST_TERMS];
   __shared__ uint32_t s_cpre[2][HYB_FAST_TERMS + 1];   // chunk prefix of the essential [0] / non-essential [1] terms
   __shared__ float s_w[HYB_FAST_TERMS];
-  __shared__ int s_qrel[HYB_THREADS / 32][HYB_QUEUE];      // per-warp queue: doc slot, posting, weight
-  __shared__ uint32_t s_qtf[HYB_THREADS / 32][HYB_QUEUE];
-  __shared__ float s_qw[HYB_THREADS / 32][HYB_QUEUE];
+  __shared__ int s_qrel[HYB_THREADS / 32][PRUNE ? HYB_QUEUE : 1];      // per-warp queue: doc slot, posting, weight
+  __shared__ uint32_t s_qtf[HYB_THREADS / 32][PRUNE ? HYB_QUEUE : 1];
+  __shared__ float s_qw[HYB_THREADS / 32][PRUNE ? HYB_QUEUE : 1];
   __shared__ int s_cn;
   __shared__ uint32_t s_go;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -572,16 +580,16 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_fast_kernel(const __g
     const int j_begin = a.qt_indptr[q], j_end = a.qt_indptr[q + 1];
     const uint8_t* norm_t = a.norm + d0;    // the tile's slice of the norm plane
     // MaxScore needs all essential terms done before the first non-essential one: one staging round only
-    const bool may_prune = a.t_bound != nullptr && j_end - j_begin <= HYB_FAST_TERMS;
+    const bool may_prune = PRUNE && a.t_bound != nullptr && j_end - j_begin <= HYB_FAST_TERMS;
     // The bound is read ONCE per CTA (other tiles raise it while this one runs, and every branch on it must be
     // uniform): warp 0 reads it and stages the first round right away, the other warps clear the tile meanwhile.
     float g0 = neg_inf<float>();
     if (warp == 0) {
       uint32_t v = 0;
-      if (lane == 0 && may_prune) v = __ldcg(a.gthr + q);
+      if (lane == 0) v = __ldcg(a.gthr + q);             // the tail uses it as well (hybrid_tile_tail pre_g)
       v = __shfl_sync(0xffffffffu, v, 0);
       if (lane == 0) s_go = v;
-      if (v) g0 = unord32(v);
+      if (v && may_prune) g0 = unord32(v);
     }
     if (j_begin < j_end) {                  // every term of the query is of one field (hybrid_core checked)
       const int field = a.t_field[j_begin];
@@ -592,7 +600,7 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_fast_kernel(const __g
       for (int i = tid - (j_begin == j_end ? 0 : 32); i < HYB_TILE; i += HYB_THREADS - (j_begin == j_end ? 0 : 32))
         acc[i] = 0.0;
     }
-    if (warp == 1) {
+    if (PRUNE && warp == 1) {
       for (int i = lane; i < HYB_TILE / 32; i += 32) s_bits[i] = 0u;
       if (lane == 0) s_cn = 0;
     }
@@ -646,7 +654,7 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_fast_kernel(const __g
       __syncthreads();                      // (first round: the tile is cleared, s_go / s_inv are set as well)
       if (j0 == j_begin) {
         go = s_go;
-        pruned = go != 0;
+        pruned = may_prune && go != 0;
         if (pruned && a.knn_rows) {         // the knn rows of the tile can reach the top-k whatever their text score
           if (tid < a.k) {
             const int64_t r = a.knn_rows[(size_t)q * a.k + tid];
@@ -682,13 +690,13 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_fast_kernel(const __g
 #pragma unroll
           for (int u = 0; u < HYB_CHUNK / 32; ++u) {
             if (rel[u] < 0) continue;
-            if (hyb_score_add(acc, s_inv, rel[u], tfv[u], nb[u], w) && pruned)
+            if (hyb_score_add(acc, s_inv, rel[u], tfv[u], nb[u], w) && PRUNE && pruned)
               atomicOr(&s_bits[rel[u] >> 5], 1u << (rel[u] & 31));
           }
         }
       }
       // ---- non-essential terms: a doc id per posting, scored for marked docs only ----
-      if (s_cpre[1][nt] != 0) {                                // uniform over the CTA
+      if (PRUNE && s_cpre[1][nt] != 0) {                       // uniform over the CTA
         __syncthreads();                                       // the marks are complete
         const uint32_t n_chunks = s_cpre[1][nt];
         int j = 0;
@@ -747,14 +755,15 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_fast_kernel(const __g
     }
   } else {
     for (int i = tid; i < HYB_TILE; i += HYB_THREADS) acc[i] = 0.0;      // vector-only: nothing but the knn clause
+    if (tid == 0) s_go = __ldcg(a.gthr + q);
   }
   __syncthreads();
-  if (!pruned) {
-    hybrid_tile_tail<false>(a, acc, q, tile, d0, d1);
+  if (!PRUNE || !pruned) {
+    hybrid_tile_tail<false>(a, acc, q, tile, d0, d1, false, &s_go);
     return;
   }
   // ---- sparse tail: only marked docs can have a score; rank those at or above the bound ----
-  static_assert(HYB_SPARSE_CAP == (HYB_THREADS / 32) * HYB_QUEUE, "the candidate list reuses the warps' queues");
+  static_assert(!PRUNE || HYB_SPARSE_CAP == (HYB_THREADS / 32) * HYB_QUEUE, "the candidate list reuses the warps' queues");
   uint32_t* c_key = reinterpret_cast<uint32_t*>(&s_qrel[0][0]);      // the queues are drained: reuse their memory
   uint32_t* c_doc = &s_qtf[0][0];
   if (a.knn_rows && tid < a.k) {            // the knn clause (see hybrid_tile_tail)
@@ -1104,8 +1113,13 @@ int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm
     // a query's cross-tile pruning bound exists after its first tiles
     const dim3 grid((unsigned)B, (unsigned)a.n_tiles);
     if (multi) hybrid_tile_kernel<true><<<grid, HYB_THREADS, smem_multi, st>>>(a);
-    else if (fast && a.row_filter) hybrid_tile_fast_kernel<true><<<grid, HYB_THREADS, 0, st>>>(a);
-    else if (fast) hybrid_tile_fast_kernel<false><<<grid, HYB_THREADS, 0, st>>>(a);
+    else if (fast && a.t_bound) {
+      if (a.row_filter) hybrid_tile_fast_kernel<true, true><<<grid, HYB_THREADS, 0, st>>>(a);
+      else hybrid_tile_fast_kernel<false, true><<<grid, HYB_THREADS, 0, st>>>(a);
+    } else if (fast) {
+      if (a.row_filter) hybrid_tile_fast_kernel<true, false><<<grid, HYB_THREADS, 0, st>>>(a);
+      else hybrid_tile_fast_kernel<false, false><<<grid, HYB_THREADS, 0, st>>>(a);
+    }
     else hybrid_tile_kernel<false><<<grid, HYB_THREADS, smem_single, st>>>(a);
     CUDA_TRY(h, cudaGetLastError());
     s.launches++;
