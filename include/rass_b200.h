@@ -89,6 +89,15 @@ enum {
                             does once a pruning bound exists: terms whose summed score bounds stay below the bound are only
                             scored for docs an essential term (or the knn clause) already touched.  Results are identical
                             (tests/test_gpu_hybrid.py); off by default because it measures slower at the current tile size */
+  RASS_OPT_ASYNC_OVERLAP = 6,   /* 1: each slot of rass_search_knn_dev_async runs on an engine-owned stream of its own,
+                            forked from the engine stream when the search is enqueued, and slot 1 has a second search
+                            workspace: the fixed costs of batch i (query preparation, threshold seed, merge + rerank) run
+                            under the corpus pass of batch i+1.  Results are ordered by rass_search_knn_dev_wait (host) or
+                            rass_async_join (a stream), no longer by the engine stream.  0 (default): both slots are
+                            enqueued on the engine stream, back to back */
+  RASS_OPT_SCAN_RESERVE_SMS = 7, /* value = SMs the 64-query corpus pass leaves free (default 0).  A row-sharded index
+                            sets a few so the exchange of batch i (NCCL all-gather + merge, which cannot share an SM with a
+                            scan CTA) runs during the pass of batch i+1 instead of after it */
   RASS_OPT_KNN_PREFILTER = 3  /* 1: rass_search_knn honours rass_set_row_filter as an exact PRE-filter (top-k of
                             the rows that pass); 0 (default): the filter only applies to rass_search_hybrid and
                             the host post-filters the k nearest, which is what OpenSearch's nmslib engine does
@@ -163,6 +172,10 @@ int rass_search_knn_dev(rass_engine* h, const float* q_dev, int B, int k,
 int rass_search_knn_dev_async(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows_dev,
                               float* out_scores_dev, double* out_keys_dev, int slot, int64_t* flag_out_dev);
 int rass_search_knn_dev_wait(rass_engine* h, int slot, rass_stats* stats);
+/* Makes `stream` (a cudaStream_t; 0 = the legacy default stream) wait for the search enqueued in `slot`: what a caller
+ * needs before it reads the outputs on a stream of its own (the all-gather of a row-sharded index) when
+ * RASS_OPT_ASYNC_OVERLAP is on.  No host synchronisation. */
+int rass_async_join(rass_engine* h, int slot, void* stream);
 
 /* Merge G per-shard top-k lists (what each rank all-gathers) into the global top-k, (key desc, row asc).
  * keys_dev / rows_dev point at shard 0's [B, k] fp64 keys / int64 rows (-1 = empty); shard g's lists start

@@ -20,7 +20,8 @@ ERR_NAMES = {-1: "RASS_E_INVALID", -2: "RASS_E_OOM", -3: "RASS_E_CUDA", -4: "RAS
 METRIC_COSINE, METRIC_L2 = 0, 1
 KEEP_FP32, BF16_ONLY = 1, 2
 PATH_AUTO, PATH_STREAM, PATH_UMMA, PATH_EXACT, PATH_GEMM = 0, 1, 2, 3, 4
-OPT_PATH, OPT_STREAM, OPT_KNN_PREFILTER, OPT_HYBRID_ORDERED, OPT_HYBRID_MAXSCORE = 1, 2, 3, 4, 5
+OPT_PATH, OPT_STREAM, OPT_KNN_PREFILTER, OPT_HYBRID_ORDERED, OPT_HYBRID_MAXSCORE, OPT_ASYNC_OVERLAP, \
+    OPT_SCAN_RESERVE_SMS = 1, 2, 3, 4, 5, 6, 7
 PATH_HYBRID_ORDER_FREE = 0x100
 
 
@@ -64,6 +65,7 @@ PROTOTYPES = {
     "rass_search_knn_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.POINTER(RassStats)]),
     "rass_search_knn_dev_async": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P]),
     "rass_search_knn_dev_wait": (C.c_int, [_P, C.c_int, C.POINTER(RassStats)]),
+    "rass_async_join": (C.c_int, [_P, C.c_int, _P]),
     "rass_merge_topk_dev": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "rass_merge_scores_dev": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "rass_bm25_build": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),

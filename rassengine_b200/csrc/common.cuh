@@ -87,7 +87,8 @@ struct DevScalars {
   int max_cand;       // largest rerank candidate set in the running search
   int n_certified;
   int finish_done;    // CTAs of the running finish launch that are through (the last one publishes flagged_n, resets this)
-  int pad[2];
+  int tile_ctr[2];    // scan_umma_kernel's tile scheduler: tiles handed out beyond the first per CTA, CTAs through (the
+                      // last one zeroes both)
 };
 
 struct rass_engine {
@@ -163,6 +164,34 @@ struct rass_engine {
   double* retry_keys = nullptr;
   size_t retry_cap = 0;
   int retry_k = 0;
+  // RASS_OPT_ASYNC_OVERLAP: each async slot runs on its own stream (forked from the engine stream when the search is
+  // enqueued) and slot 1 owns a second search workspace, so the fixed costs of batch i (query prep, threshold seed,
+  // finish) run under the scan of batch i+1.  While slot 1's search is being enqueued the workspace fields of the handle
+  // are swapped with `ws_alt` (kernels capture the pointers at launch).
+  struct SearchWs {
+    DevScalars* scal = nullptr;
+    int q_cap = 0;
+    float *q_raw = nullptr, *q_hat = nullptr;
+    __nv_bfloat16* q16 = nullptr;
+    double* q_norm = nullptr;
+    float* q_rho = nullptr;
+    uint32_t* q_gthr = nullptr;
+    size_t pool_entries = 0, pool_alloc_entries = 0;
+    float* pool_key = nullptr;
+    uint32_t* pool_row = nullptr;
+    size_t pool_segs = 0, pool_alloc_segs = 0;
+    float* pool_thr = nullptr;
+    int* pool_cnt = nullptr;
+    int *flagged = nullptr, *flagged_host = nullptr;
+    void *tmap_q = nullptr, *tmap_q2 = nullptr;
+    const void *tmap_q2base = nullptr, *tmap_qbase = nullptr;
+  } ws_alt;
+  bool async_overlap = false;
+  int scan_reserve_sms = 0;         // RASS_OPT_SCAN_RESERVE_SMS
+  cudaStream_t slot_stream[2] = {nullptr, nullptr};
+  cudaEvent_t slot_fork[2] = {nullptr, nullptr};
+  uint64_t store_version = 1;       // bumped whenever rho_x / max_xnorm may have changed (store_convert launches)
+  uint64_t alt_store_version = 0;   // the version ws_alt.scal mirrors
   // two searches may be in flight through rass_search_knn_dev_async (one slot each)
   struct AsyncSlot {
     bool pending = false, trivial = false;
@@ -201,6 +230,11 @@ int rass_fail(rass_engine* h, int code, const char* fmt, ...);
   } while (0)
 
 static inline cudaStream_t eng_stream(const rass_engine* h) { return h->has_user_stream ? h->user_stream : h->stream; }
+// the stream an async slot's search was (or will be) enqueued on
+static inline cudaStream_t slot_stream_of(const rass_engine* h, int slot) {
+  return h->async_overlap && h->slot_stream[slot] ? h->slot_stream[slot] : eng_stream(h);
+}
+void swap_search_ws(rass_engine* h);
 
 // fp32 accumulation allowance of a length-d dot product with |x||q| <= 1 (gamma_d, doubled for the tensor
 // pipe's unspecified summation order)
@@ -512,6 +546,7 @@ int sharded_search_knn_dev(rass_engine* h, const float* q_dev, int B, int k, int
 int sharded_search_knn_dev_async(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows_dev,
                                  float* out_scores_dev, double* out_keys_dev, int slot, int64_t* flag_out_dev);
 int sharded_search_knn_dev_wait(rass_engine* h, int slot, rass_stats* stats);
+int sharded_async_join(rass_engine* h, int slot, void* stream);
 int sharded_bm25_build(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
                        const int32_t* term_field, const uint32_t* doclen, int64_t V, int64_t N, int F);
 int sharded_search_hybrid(rass_engine* h, const float* q_host, int B, const int32_t* qterm_indptr, const int32_t* qterms,

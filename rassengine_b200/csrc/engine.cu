@@ -145,6 +145,18 @@ extern "C" int rass_destroy(rass_engine* h) {
   cudaFree(h->flist_dev);
   cudaFree(h->sb_filtered);
   cudaFree(h->retry_ids); cudaFree(h->retry_q); cudaFree(h->retry_rows); cudaFree(h->retry_scores); cudaFree(h->retry_keys);
+  {
+    rass_engine::SearchWs& w = h->ws_alt;
+    cudaFree(w.scal);
+    cudaFree(w.q_raw); cudaFree(w.q_hat); cudaFree(w.q16); cudaFree(w.q_norm); cudaFree(w.q_rho); cudaFree(w.q_gthr);
+    cudaFree(w.pool_key); cudaFree(w.pool_row); cudaFree(w.pool_thr); cudaFree(w.pool_cnt);
+    cudaFree(w.flagged); cudaFreeHost(w.flagged_host);
+    free(w.tmap_q); free(w.tmap_q2);
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (h->slot_stream[i]) cudaStreamDestroy(h->slot_stream[i]);
+    if (h->slot_fork[i]) cudaEventDestroy(h->slot_fork[i]);
+  }
   for (cudaEvent_t e : h->ev_pool) if (e) cudaEventDestroy(e);
   for (auto& a : h->aslot) { cudaFreeHost(a.scal_host); if (a.done) cudaEventDestroy(a.done); }
   for (int i = 0; i < 2; ++i) { cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
@@ -176,6 +188,15 @@ extern "C" int rass_set_option(rass_engine* h, int opt, int64_t value) {
     case RASS_OPT_PATH:
       if (value < RASS_PATH_AUTO || value > RASS_PATH_GEMM) return rass_fail(h, RASS_E_INVALID, "bad path %lld", (long long)value);
       h->path = (int)value;
+      return RASS_OK;
+    case RASS_OPT_ASYNC_OVERLAP:
+      for (auto& a : h->aslot)
+        if (a.pending) return rass_fail(h, RASS_E_INVALID, "RASS_OPT_ASYNC_OVERLAP cannot change while a search is in flight");
+      h->async_overlap = value != 0;
+      return RASS_OK;
+    case RASS_OPT_SCAN_RESERVE_SMS:
+      if (value < 0 || value >= h->num_sms) return rass_fail(h, RASS_E_INVALID, "bad SM reserve %lld", (long long)value);
+      h->scan_reserve_sms = (int)value;
       return RASS_OK;
     case RASS_OPT_STREAM:
       if (value == -1) {
@@ -462,9 +483,43 @@ extern "C" int rass_load(rass_engine* h, const char* path) {
     CUDA_TRY(h, cudaMallocHost(&(p), (n) * sizeof(*(p))));      \
   } while (0)
 
+// a workspace is about to be freed: nothing enqueued may still use it
+static int sync_for_realloc(rass_engine* h) {
+  CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+  for (int i = 0; i < 2; ++i)
+    if (h->slot_stream[i]) CUDA_TRY(h, cudaStreamSynchronize(h->slot_stream[i]));
+  return RASS_OK;
+}
+
+void swap_search_ws(rass_engine* h) {
+  rass_engine::SearchWs& w = h->ws_alt;
+  std::swap(h->scal, w.scal);
+  std::swap(h->q_cap, w.q_cap);
+  std::swap(h->q_raw, w.q_raw);
+  std::swap(h->q_hat, w.q_hat);
+  std::swap(h->q16, w.q16);
+  std::swap(h->q_norm, w.q_norm);
+  std::swap(h->q_rho, w.q_rho);
+  std::swap(h->q_gthr, w.q_gthr);
+  std::swap(h->pool_entries, w.pool_entries);
+  std::swap(h->pool_alloc_entries, w.pool_alloc_entries);
+  std::swap(h->pool_key, w.pool_key);
+  std::swap(h->pool_row, w.pool_row);
+  std::swap(h->pool_segs, w.pool_segs);
+  std::swap(h->pool_alloc_segs, w.pool_alloc_segs);
+  std::swap(h->pool_thr, w.pool_thr);
+  std::swap(h->pool_cnt, w.pool_cnt);
+  std::swap(h->flagged, w.flagged);
+  std::swap(h->flagged_host, w.flagged_host);
+  std::swap(h->tmap_q, w.tmap_q);
+  std::swap(h->tmap_q2, w.tmap_q2);
+  std::swap(h->tmap_q2base, w.tmap_q2base);
+  std::swap(h->tmap_qbase, w.tmap_qbase);
+}
+
 int ensure_query_workspace(rass_engine* h, int B) {
   if (B <= h->q_cap) return RASS_OK;
-  CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+  { const int rc_ = sync_for_realloc(h); if (rc_) return rc_; }
   const size_t cap = (size_t)(B + RASS_QPAD - 1) / RASS_QPAD * RASS_QPAD, d = (size_t)h->dim_pad;
   REALLOC_DEV(h, h->q_raw, cap * d);
   REALLOC_DEV(h, h->q_hat, cap * d);
@@ -483,14 +538,14 @@ int ensure_query_workspace(rass_engine* h, int B) {
 int ensure_pool(rass_engine* h, size_t entries_per_query, size_t segs_per_query, size_t n_queries) {
   const size_t need_e = entries_per_query * n_queries, need_s = segs_per_query * n_queries;
   if (need_e > h->pool_alloc_entries) {
-    CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+    { const int rc_ = sync_for_realloc(h); if (rc_) return rc_; }
     h->pool_alloc_entries = 0;
     REALLOC_DEV(h, h->pool_key, need_e);
     REALLOC_DEV(h, h->pool_row, need_e);
     h->pool_alloc_entries = need_e;
   }
   if (need_s > h->pool_alloc_segs) {
-    CUDA_TRY(h, cudaStreamSynchronize(eng_stream(h)));
+    { const int rc_ = sync_for_realloc(h); if (rc_) return rc_; }
     h->pool_alloc_segs = 0;
     REALLOC_DEV(h, h->pool_thr, need_s);
     REALLOC_DEV(h, h->pool_cnt, need_s);
@@ -621,11 +676,60 @@ int search_core_ex(rass_engine* h, const float* q_dev, int B, int k, int64_t* ou
 //
 // async_slot >= 0: enqueue only -- no host synchronisation, no fallback; the certificate outcome lands in the slot's
 // pinned scalars (and, for row-sharded callers, in *async_flag_dev, which travels with the all-gathered candidates).
+static int search_core_body(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
+                            double* out_keys, rass_stats* stats, bool robust, int async_slot, int64_t* async_flag_dev,
+                            cudaStream_t st);
+
 static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
                             double* out_keys, rass_stats* stats, bool robust, int async_slot, int64_t* async_flag_dev) {
   if (B < 1) return rass_fail(h, RASS_E_INVALID, "B must be >= 1");
   if (k < 1 || k > RASS_MAX_K) return rass_fail(h, RASS_E_INVALID, "k must be in [1, %d], got %d", RASS_MAX_K, k);
   cudaStream_t st = eng_stream(h);
+  int rc;
+  if (!h->async_overlap)
+    return search_core_body(h, q_dev, B, k, out_rows, out_scores, out_keys, stats, robust, async_slot, async_flag_dev, st);
+  if (async_slot < 0) {
+    // a blocking search shares slot 0's workspace (and must see everything enqueued so far): order it behind the
+    // searches in flight
+    for (auto& a : h->aslot)
+      if (a.pending && a.done) CUDA_TRY(h, cudaStreamWaitEvent(st, a.done, 0));
+    return search_core_body(h, q_dev, B, k, out_rows, out_scores, out_keys, stats, robust, async_slot, async_flag_dev, st);
+  }
+  if (h->aslot[async_slot].pending)
+    return rass_fail(h, RASS_E_INVALID, "async slot %d still has a search in flight", async_slot);
+  if (!h->slot_stream[async_slot]) {
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->slot_stream[async_slot], cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->slot_fork[async_slot], cudaEventDisableTiming));
+  }
+  // the folded filter offsets are shared by both slots: (re)build them ahead of the fork, on the engine stream
+  if ((rc = select_scan_offsets(h, st))) return rc;
+  cudaStream_t ss = h->slot_stream[async_slot];
+  CUDA_TRY(h, cudaEventRecord(h->slot_fork[async_slot], st));
+  CUDA_TRY(h, cudaStreamWaitEvent(ss, h->slot_fork[async_slot], 0));
+  if (async_slot == 0)
+    return search_core_body(h, q_dev, B, k, out_rows, out_scores, out_keys, stats, robust, async_slot, async_flag_dev, ss);
+  swap_search_ws(h);
+  rc = RASS_OK;
+  if (!h->scal) {
+    cudaError_t e = cudaMalloc(&h->scal, sizeof(DevScalars));
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->scal, 0, sizeof(DevScalars), ss);
+    if (e != cudaSuccess) rc = rass_fail(h, RASS_E_CUDA, "second search workspace: %s", cudaGetErrorString(e));
+    h->alt_store_version = 0;
+  }
+  if (!rc && h->alt_store_version != h->store_version) {       // rho_x / max_xnorm of the store, as of this search
+    cudaError_t e = cudaMemcpyAsync(h->scal, h->ws_alt.scal, 2 * sizeof(float), cudaMemcpyDeviceToDevice, ss);
+    if (e != cudaSuccess) rc = rass_fail(h, RASS_E_CUDA, "second search workspace: %s", cudaGetErrorString(e));
+    h->alt_store_version = h->store_version;
+  }
+  if (!rc)
+    rc = search_core_body(h, q_dev, B, k, out_rows, out_scores, out_keys, stats, robust, async_slot, async_flag_dev, ss);
+  swap_search_ws(h);
+  return rc;
+}
+
+static int search_core_body(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
+                            double* out_keys, rass_stats* stats, bool robust, int async_slot, int64_t* async_flag_dev,
+                            cudaStream_t st) {
   int rc;
   if ((rc = ensure_query_workspace(h, B))) return rc;
   rass_stats s;
@@ -665,10 +769,9 @@ static int search_core_impl(rass_engine* h, const float* q_dev, int B, int k, in
   int64_t* flag_out = as ? async_flag_dev : nullptr;   // published by the last CTA of the last finish launch
   if (robust && path == RASS_PATH_STREAM) path = RASS_PATH_UMMA;    // the streaming scan keeps 32 per warp only
   s.path = path;
-  if ((rc = select_scan_offsets(h, st))) return rc;
-  // reset the per-search device counters (keeps rho_x / max_xnorm)
-  CUDA_TRY(h, cudaMemsetAsync(&h->scal->flagged_n, 0, sizeof(int) * 3, st));
-  CUDA_TRY(h, cudaEventRecord(h->ev[0], st));
+  if (!(as && h->async_overlap) && (rc = select_scan_offsets(h, st))) return rc;
+  // (query_prep_kernel resets the per-search device counters; rho_x / max_xnorm stay)
+  if (!as) CUDA_TRY(h, cudaEventRecord(h->ev[0], st));
   if ((rc = launch_query_prep(h, q_dev, B, st))) return rc;
   s.launches = 1;
   size_t n_ev = 0;
@@ -857,6 +960,16 @@ extern "C" int rass_search_knn_dev_wait(rass_engine* h, int slot, rass_stats* st
   s.n_fallback = nf;          // queries whose outputs are NOT final: the caller repeats the search with the blocking call
   if (stats) *stats = s;
   return nf > 0 ? RASS_E_AGAIN : RASS_OK;
+}
+
+extern "C" int rass_async_join(rass_engine* h, int slot, void* stream) {
+  SHARDED(h, sharded_async_join(h, slot, stream));
+  CHECK_HANDLE(h);
+  if (slot < 0 || slot > 1) return rass_fail(h, RASS_E_INVALID, "slot must be 0 or 1");
+  rass_engine::AsyncSlot& a = h->aslot[slot];
+  if (!a.pending || !a.done) return rass_fail(h, RASS_E_INVALID, "no search in flight in slot %d", slot);
+  CUDA_TRY(h, cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), a.done, 0));
+  return RASS_OK;
 }
 
 extern "C" int rass_search_knn_dev(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows_dev,

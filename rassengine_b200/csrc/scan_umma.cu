@@ -24,6 +24,7 @@
 #define UMMA_ACC 4                          // TMEM accumulator stages (64 columns each)
 #define UMMA_TMEM_COLS 256
 #define UMMA_THREADS 256
+#define UMMA_RING 8                         // tile ids in flight between the producer and the other roles
 
 namespace {
 
@@ -36,6 +37,8 @@ struct UmmaSmem {
   uint64_t acc_full[UMMA_ACC];
   uint64_t acc_empty[UMMA_ACC];
   uint64_t q_full;
+  uint64_t ring_full[UMMA_RING];
+  int ring[UMMA_RING];
   uint32_t tmem_base;
   uint32_t pad;
   float thr[UMMA_NQ];
@@ -53,8 +56,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
                      const float* __restrict__ sa, const float* __restrict__ sb, int64_t n_rows, int n_tiles,
                      int k_blocks, int q_row0, float* __restrict__ pool_key, uint32_t* __restrict__ pool_row,
                      float* __restrict__ pool_thr, int* __restrict__ pool_cnt, size_t pool_entries, int n_segs,
-                     uint32_t* __restrict__ gthr, float* __restrict__ dbg_out, int relaxed_wait,
-                     unsigned long long* __restrict__ dbg_t) {
+                     uint32_t* __restrict__ gthr, int* __restrict__ tile_ctr, float* __restrict__ dbg_out,
+                     int relaxed_wait, unsigned long long* __restrict__ dbg_t) {
   extern __shared__ unsigned char smem_dyn[];
   // 128B-swizzled tiles need 1024-byte alignment: [ Q: k_blocks * 8 KB ][ stages: UMMA_STAGES * 16 KB ][ UmmaSmem ]
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -70,6 +73,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
     for (int i = 0; i < UMMA_STAGES; ++i) { mbar_init(&ss->full[i], 1); mbar_init(&ss->empty[i], 1); }
     for (int i = 0; i < UMMA_ACC; ++i) { mbar_init(&ss->acc_full[i], 1); mbar_init(&ss->acc_empty[i], 4); }
     mbar_init(&ss->q_full, 1);
+    for (int i = 0; i < UMMA_RING; ++i) mbar_init(&ss->ring_full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -98,7 +102,18 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
         tma_load_2d(&map_q, &ss->q_full, q_smem + (size_t)kb * UMMA_QBLK_BYTES, kb * UMMA_KBLK, q_row0, kEvictLast);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cta; tile < n_tiles; tile += gridDim.x) {
+      // Tiles are drawn from a device-wide counter (the first one is the CTA's own): a CTA that starts late -- the
+      // previous batch's finish kernel may still hold its SM -- or meets more compactions simply takes fewer tiles,
+      // and all CTAs end within one tile of each other.  The id of the tile after this one is requested before this
+      // tile's loads are issued, so the L2 round trip of the atomic is never waited for.  Ids travel to the MMA and
+      // epilogue roles through a ring in shared memory; the roles are at most 5 tiles apart (4 accumulator stages +
+      // the smem stages), so UMMA_RING slots never wrap onto a live entry.
+      int tile = cta;
+      for (int it = 0;; ++it) {
+        ss->ring[it & (UMMA_RING - 1)] = tile;
+        mbar_arrive(&ss->ring_full[it & (UMMA_RING - 1)]);
+        if (tile >= n_tiles) break;
+        const int next = tile_ctr ? (int)gridDim.x + atomicAdd(tile_ctr, 1) : tile + (int)gridDim.x;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&ss->empty[stage], phase ^ 1);
           mbar_expect_tx(&ss->full[stage], UMMA_STAGE_BYTES);
@@ -106,6 +121,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
                       tile * UMMA_ROWS, kEvictFirst);
           if (++stage == UMMA_STAGES) { stage = 0; phase ^= 1; }
         }
+        tile = next;
       }
     }
   } else if (warp == 1) {
@@ -116,7 +132,9 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       const uint32_t q_base = smem_u32(q_smem), x_base = smem_u32(x_smem);
-      for (int tile = cta; tile < n_tiles; tile += gridDim.x) {
+      for (int it = 0;; ++it) {
+        mbar_wait(&ss->ring_full[it & (UMMA_RING - 1)], (uint32_t)(it / UMMA_RING) & 1u);
+        if (*(volatile int*)&ss->ring[it & (UMMA_RING - 1)] >= n_tiles) break;
         mbar_wait(&ss->acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * UMMA_NQ;
@@ -142,7 +160,10 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
     const int et = threadIdx.x - 128;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cta; tile < n_tiles; tile += gridDim.x) {
+    for (int it = 0;; ++it) {
+      mbar_wait(&ss->ring_full[it & (UMMA_RING - 1)], (uint32_t)(it / UMMA_RING) & 1u);
+      const int tile = *(volatile int*)&ss->ring[it & (UMMA_RING - 1)];
+      if (tile >= n_tiles) break;
       const int64_t row = (int64_t)tile * UMMA_ROWS + ew * 32 + lane;
       float a = 0.f, b = neg_inf<float>();
       if (row < n_rows) { a = __ldg(sa + row); b = __ldg(sb + row); }
@@ -156,7 +177,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
       else if (lane == 0) mbar_wait_relaxed(&ss->acc_full[acc], acc_phase);
       __syncwarp();
       tc_fence_after();
-      if (dbg_t && et == 0 && tile == cta) dbg_t[cta * 4 + 1] = globaltimer_ns();
+      if (dbg_t && et == 0 && it == 0) dbg_t[cta * 4 + 1] = globaltimer_ns();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * UMMA_NQ;
 #pragma unroll
       for (int c = 0; c < UMMA_NQ; c += 16) {
@@ -251,7 +272,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
         q_cur = q_next;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (dbg_t && et == 0 && cta == 0 && tile / (int)gridDim.x < 64) dbg_t[1024 + tile / (int)gridDim.x] = globaltimer_ns();
+      if (dbg_t && et == 0 && cta == 0 && it < 64) dbg_t[1024 + it] = globaltimer_ns();
     }
     if (dbg_t && et == 0) dbg_t[cta * 4 + 2] = globaltimer_ns();
     // publish the segment sizes and bounds
@@ -264,6 +285,11 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
   tc_fence_before();
   __syncthreads();
   if (dbg_t && threadIdx.x == 0) dbg_t[cta * 4 + 3] = globaltimer_ns();
+  // the last CTA through leaves the tile counter at zero for the next pass (every producer has drawn its last id)
+  if (tile_ctr && threadIdx.x == 0 && atomicAdd(tile_ctr + 1, 1) == (int)gridDim.x - 1) {
+    tile_ctr[0] = 0;
+    tile_ctr[1] = 0;
+  }
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)UMMA_TMEM_COLS)
                  : "memory");
@@ -360,9 +386,14 @@ static int umma_launch(rass_engine* h, int q0, int64_t n_rows, int seg, float* d
     h->tmap_qbase = h->q16;
   }
   const int n_tiles = (int)((n_rows + UMMA_ROWS - 1) / UMMA_ROWS);
-  const int grid = n_tiles < h->num_sms ? n_tiles : h->num_sms;
+  // RASS_OPT_SCAN_RESERVE_SMS: leave a few SMs to the kernels that run beside the pass (the other slot's finish, the
+  // NCCL all-gather and the merge of a row-sharded index); the tile counter spreads the tiles over whatever runs
+  const int ctas = std::max(1, h->num_sms - h->scan_reserve_sms);
+  const int grid = n_tiles < ctas ? n_tiles : ctas;
   // q_gthr[q0 .. q0 + 64) was initialised by launch_seed_thresholds (or cleared by the self-test)
   static const int relaxed_wait = getenv("RASS_DEBUG_RELAXED_WAIT") != nullptr;
+  // RASS_DEBUG_STATIC_TILES: tile = cta + i * grid instead of the device-wide counter (the A/B switch of the measurement)
+  static const bool static_tiles = getenv("RASS_DEBUG_STATIC_TILES") != nullptr;
   const size_t smem = umma_smem_bytes(h);
   // timing experiment only (RASS_DEBUG_TIMES): per-CTA timestamps, printed after a blocking wait
   static const bool want_times = getenv("RASS_DEBUG_TIMES") != nullptr;
@@ -374,7 +405,7 @@ static int umma_launch(rass_engine* h, int q0, int64_t n_rows, int seg, float* d
     scan_umma_kernel<S><<<grid, UMMA_THREADS, smem, st>>>(                                                           \
         *(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q, h->sa, h->sb_scan, n_rows, n_tiles, h->dim_pad / UMMA_KBLK, \
         q0, h->pool_key, h->pool_row, h->pool_thr, h->pool_cnt, h->pool_entries, scan_umma_segs(h), h->q_gthr + q0,  \
-        dbg_out, relaxed_wait, dbg_t);                                                                                 \
+        static_tiles ? nullptr : &h->scal->tile_ctr[0], dbg_out, relaxed_wait, dbg_t);                                                                                 \
   } while (0)
   if (seg == 512) RASS_UMMA_LAUNCH(512); else RASS_UMMA_LAUNCH(256);
 #undef RASS_UMMA_LAUNCH

@@ -633,6 +633,7 @@ int sharded_search_knn_dev_async(rass_engine* h, const float* q_dev, int B, int 
     int64_t* o_flag = S->g_flag[slot] + g;               // 8 bytes: always a peer store or a small copy below
     int64_t* flag_dst = direct ? o_flag : reinterpret_cast<int64_t*>(sh->out_rows + n);   // spare local word
     if ((r = search_core_ex(sh, qd, B, k, o_rows, sh->out_scores, o_keys, nullptr, slot, flag_dst))) return r;
+    sg = slot_stream_of(sh, slot);             // RASS_OPT_ASYNC_OVERLAP: the search ran on the slot's own stream
     if (!direct) {
       CUDA_TRY(sh, cudaMemcpyPeerAsync(S->g_rows[slot] + (size_t)g * S->cap, h->device, o_rows, S->dev[g], n * 8, sg));
       CUDA_TRY(sh, cudaMemcpyPeerAsync(S->g_keys[slot] + (size_t)g * S->cap, h->device, o_keys, S->dev[g], n * 8, sg));
@@ -652,6 +653,14 @@ int sharded_search_knn_dev_async(rass_engine* h, const float* q_dev, int B, int 
   }
   CUDA_TRY(h, cudaEventRecord(S->ev_done[slot], st));
   S->pending[slot] = true;
+  return RASS_OK;
+}
+
+int sharded_async_join(rass_engine* h, int slot, void* stream) {
+  ShardSet* S = h->shards;
+  if (slot < 0 || slot > 1) return rass_fail(h, RASS_E_INVALID, "slot must be 0 or 1");
+  if (!S->pending[slot]) return rass_fail(h, RASS_E_INVALID, "no search in flight in slot %d", slot);
+  CUDA_TRY(h, cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), S->ev_done[slot], 0));
   return RASS_OK;
 }
 

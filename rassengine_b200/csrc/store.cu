@@ -67,6 +67,7 @@ int launch_store_convert(rass_engine* h, const float* src_dev, int64_t src_strid
                          cudaStream_t st) {
   if (n <= 0) return RASS_OK;
   h->sb_filtered_dirty = true;
+  h->store_version++;
   const bool bf16_only = (h->flags & RASS_BF16_ONLY) != 0;
   const bool in_place = !bf16_only && src_dev == h->x32 + (size_t)first_row * h->dim_pad;
   const int warps = 8;
@@ -83,9 +84,15 @@ int launch_store_convert(rass_engine* h, const float* src_dev, int64_t src_strid
 __global__ void __launch_bounds__(128) query_prep_kernel(const float* __restrict__ q, int dim, int dim_pad, int metric,
                                                          int B, int B_pad, float* __restrict__ q_raw,
                                                          float* __restrict__ q_hat, __nv_bfloat16* __restrict__ q16,
-                                                         double* __restrict__ q_norm, float* __restrict__ q_rho) {
+                                                         double* __restrict__ q_norm, float* __restrict__ q_rho,
+                                                         DevScalars* __restrict__ scal) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {      // the per-search counters (rho_x / max_xnorm stay)
+    scal->flagged_n = 0;
+    scal->max_cand = 0;
+    scal->n_certified = 0;
+  }
   if (b >= B_pad) return;
   if (b >= B) {
     for (int j = lane; j < dim_pad; j += 32) q16[(size_t)b * dim_pad + j] = __float2bfloat16_rn(0.f);
@@ -122,7 +129,7 @@ int launch_query_prep(rass_engine* h, const float* q_dev, int B, cudaStream_t st
   const int warps = 4;
   query_prep_kernel<<<(B_pad + warps - 1) / warps, warps * 32, 0, st>>>(q_dev, h->dim, h->dim_pad, h->metric, B, B_pad,
                                                                         h->q_raw, h->q_hat, h->q16, h->q_norm,
-                                                                        h->q_rho);
+                                                                        h->q_rho, h->scal);
   CUDA_TRY(h, cudaGetLastError());
   return RASS_OK;
 }

@@ -190,6 +190,19 @@ class Engine:
                                                         C.c_void_p(keys_ptr) if keys_ptr else None, slot,
                                                         C.c_void_p(flag_ptr) if flag_ptr else None))
 
+    def set_async_overlap(self, on: bool = True):
+        """Each async slot on its own stream and workspace (RASS_OPT_ASYNC_OVERLAP): the fixed costs of batch i run
+        under the corpus pass of batch i+1.  Order readers of the outputs with async_join / search_knn_dev_wait."""
+        self._check(self._lib.rass_set_option(self._h, capi.OPT_ASYNC_OVERLAP, 1 if on else 0))
+
+    def set_scan_reserve_sms(self, n: int):
+        """SMs the 64-query corpus pass leaves to the kernels beside it (RASS_OPT_SCAN_RESERVE_SMS)."""
+        self._check(self._lib.rass_set_option(self._h, capi.OPT_SCAN_RESERVE_SMS, int(n)))
+
+    def async_join(self, slot: int, cuda_stream: int):
+        """Make `cuda_stream` wait (on the device) for the search enqueued in `slot`."""
+        self._check(self._lib.rass_async_join(self._h, slot, C.c_void_p(cuda_stream) if cuda_stream else None))
+
     def search_knn_dev_wait(self, slot: int = 0) -> tuple[bool, dict]:
         """(final, stats): final is False when some query failed its certificate and the batch must be repeated with
         the blocking call."""

@@ -8,6 +8,9 @@ the merged top-k is the top-k of the union, bit-identical to a single-shard sear
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -57,6 +60,10 @@ class _DeviceOps:
     def search_wait(self, slot):
         return self.engine.search_knn_dev_wait(slot)
 
+    def join(self, slot, stream):
+        """`stream` waits (on the device) for the search enqueued in `slot` (RASS_OPT_ASYNC_OVERLAP)."""
+        self.engine.async_join(slot, stream)
+
     def bm25_build(self, indptr, doc, tf, doclen, doc_count, sum_ttf, df):
         self.engine.bm25_build(indptr, doc, tf, doclen, global_doc_count=doc_count, global_sum_ttf=sum_ttf,
                                global_df=df)
@@ -83,6 +90,14 @@ class ShardedIndex:
             engine = Engine(dim=dim, metric=metric, device=device, capacity_rows=capacity_rows, flags=flags)
             # run on torch's current stream so NCCL and the engine's kernels are ordered by the stream
             engine.set_stream(torch.cuda.current_stream().cuda_stream)
+            # pipelined searches: each of the two batches in flight on its own stream and workspace
+            # (RASS_B200_NO_OVERLAP=1: both on the main stream, back to back -- the A/B switch of the measurement)
+            self._overlap = os.environ.get("RASS_B200_NO_OVERLAP") != "1"
+            engine.set_async_overlap(self._overlap)
+            # the all-gather and the merge of batch i need an SM of their own while batch i+1 is being scanned (measured
+            # at 2 x 1.25M rows, batch 64: 0.461 ms per step with none, 0.441 with 1 or 2, 0.448 with 8 reserved)
+            reserve = os.environ.get("RASS_B200_SCAN_RESERVE")
+            engine.set_scan_reserve_sms(int(reserve) if reserve is not None else (2 if self.world > 1 else 0))
         self.engine = engine
         self.ops = ops if ops is not None else _DeviceOps(
             engine, torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else 0)
@@ -91,6 +106,7 @@ class ShardedIndex:
         self._pending = [None, None]   # search_dev_async tickets
         self._next_slot = 0
         self._side = None              # side stream of the pipelined exchange
+        self._overlap = getattr(self, "_overlap", False)
 
     def _buffers(self, B: int, k: int, dev):
         key = (B, k, str(dev))
@@ -143,21 +159,32 @@ class ShardedIndex:
             b["scores_host"] = torch.empty((B, k), dtype=torch.float32, pin_memory=pin)
             b["ev_out"] = torch.cuda.Event() if pin else None
         self.ops.search_async(q, k, b["packed"], b["scores"], slot, b["flat"][-1:])
-        if self.world == 1 and to_host:
-            b["rows_host"].copy_(b["packed"][1], non_blocking=True)        # behind the search, ahead of the next batch
-            b["scores_host"].copy_(b["scores"], non_blocking=True)
-            if b["ev_out"] is not None:
-                b["ev_out"].record(torch.cuda.current_stream())
-        if self.world > 1:
-            cuda = dev.type == "cuda"
-            if cuda:
-                if self._side is None:
-                    self._side = torch.cuda.Stream(device=dev)
-                b["ev_main"].record(torch.cuda.current_stream())
-                ctx = torch.cuda.stream(self._side)
-                self._side.wait_event(b["ev_main"])
+        cuda = dev.type == "cuda"
+        if cuda and self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+
+        def side_after_search():
+            # the side stream picks up behind this batch's search: behind the slot's own stream when the slots overlap
+            # (the main stream must not wait for it: the next batch forks from there), else behind the main stream
+            if self._overlap:
+                self.ops.join(slot, self._side.cuda_stream)
             else:
-                import contextlib
+                b["ev_main"].record(torch.cuda.current_stream())
+                self._side.wait_event(b["ev_main"])
+
+        if self.world == 1 and to_host:
+            if cuda:
+                side_after_search()
+            with (torch.cuda.stream(self._side) if cuda else contextlib.nullcontext()):
+                b["rows_host"].copy_(b["packed"][1], non_blocking=True)    # behind the search, beside the next batch
+                b["scores_host"].copy_(b["scores"], non_blocking=True)
+                if b["ev_out"] is not None:
+                    b["ev_out"].record(self._side)
+        if self.world > 1:
+            if cuda:
+                side_after_search()
+                ctx = torch.cuda.stream(self._side)
+            else:
                 ctx = contextlib.nullcontext()
             with ctx:
                 dist.all_gather_into_tensor(b["gathered"], b["flat"], group=self.group)

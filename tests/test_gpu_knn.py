@@ -359,6 +359,61 @@ def test_async_search_publishes_the_certificate_outcome():
             assert st["n_certified"] == B - st["n_fallback"], (path, st)
 
 
+@pytest.mark.parametrize("path,B,k", [("umma", 64, 10), ("umma", 70, 10), ("gemm", 300, 10), ("stream", 1, 10),
+                                      ("umma", 33, 100)])
+def test_overlapped_async_slots_equal_the_oracle(path, B, k):
+    """RASS_OPT_ASYNC_OVERLAP: both slots in flight on their own streams and workspaces, a different batch in each, many
+    rounds back to back, a blocking search in between -- every batch's ids are the oracle's.  A workspace shared by
+    mistake, a missing stream dependency or a tile-counter left dirty by the scan's scheduler shows up here as a wrong
+    or torn list."""
+    import torch
+    n_batches = 12
+    X = synth.embeddings(150000, 1024, 71)
+    Qs = [synth.embeddings(B, 1024, 72 + i) for i in range(n_batches)]
+    want = [knn.knn_exact(X, Q, k)[0] for Q in Qs]
+    with _engine(dim=1024) as e:
+        e.append(X)
+        e.set_path(_paths()[path])
+        e.set_async_overlap(True)
+        side = torch.cuda.Stream()
+        Qd = [torch.from_numpy(Q).cuda() for Q in Qs]
+        rows = [torch.full((B, k), -7, dtype=torch.int64, device="cuda") for _ in range(2)]
+        scores = [torch.empty((B, k), dtype=torch.float32, device="cuda") for _ in range(2)]
+        flags = [torch.empty(1, dtype=torch.int64, device="cuda") for _ in range(2)]
+        joined = [torch.empty((B, k), dtype=torch.int64, device="cuda") for _ in range(2)]
+        torch.cuda.synchronize()
+        got = [None] * n_batches
+
+        def collect(i):
+            slot = i & 1
+            final, st = e.search_knn_dev_wait(slot)
+            assert final and int(flags[slot].item()) == 0, (i, st)
+            side.synchronize()
+            # the copy made on the side stream behind rass_async_join sees the finished list as well
+            assert torch.equal(joined[slot], rows[slot]), i
+            got[i] = rows[slot].cpu().numpy().copy()
+
+        for i in range(n_batches):
+            slot = i & 1
+            if i >= 2:
+                collect(i - 2)
+            e.search_knn_dev_async(Qd[i].data_ptr(), B, k, rows[slot].data_ptr(), scores[slot].data_ptr(), 0, slot,
+                                   flags[slot].data_ptr())
+            e.async_join(slot, side.cuda_stream)
+            with torch.cuda.stream(side):
+                joined[slot].copy_(rows[slot])
+            if i == 5:          # a blocking search while both slots are busy: ordered behind them, same answer
+                r, _ = e.search_knn(Qs[0], k)
+                assert np.array_equal(r, want[0])
+        collect(n_batches - 2)
+        collect(n_batches - 1)
+        for i in range(n_batches):
+            assert np.array_equal(got[i], want[i]), (path, i)
+        e.set_async_overlap(False)
+        r, _ = e.search_knn(Qs[1], k)
+        assert np.array_equal(r, want[1])
+
+
 def test_properties_at_2m_rows_all_paths_agree():
     """Larger than the oracle can check in seconds: size-independent properties instead.  On 2M device-generated
     rows every scan path returns the same ids for the same queries, the fp64 scan (the definition) agrees on a
