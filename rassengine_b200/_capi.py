@@ -74,6 +74,13 @@ PROTOTYPES = {
     "rass_search_hybrid_weighted": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P, _P,
                                               C.POINTER(RassStats)]),
     "rass_bm25_build_fields": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int]),
+    "rass_text_add_rows": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P, _P]),
+    "rass_text_add_rows_dev": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P, _P]),
+    "rass_text_commit": (C.c_int, [_P, _P, C.c_int, C.c_int64]),
+    "rass_text_size": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                 C.POINTER(C.c_int)]),
+    "rass_text_export": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "rass_text_stats": (C.c_int, [_P, _P, _P, _P]),
     "rass_fuse_hybrid": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_float, _P, _P, C.c_float, C.c_int, _P, _P]),
     "rass_fuse_hybrid_dev": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_float, _P, _P, C.c_float, C.c_int, _P, _P, _P]),
     "rass_text_set_vocab": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),

@@ -291,10 +291,8 @@ class _Index:
 
     def _sync_text(self):
         if self.text.dirty and self.engine is not None:
-            indptr, doc, tf, term_field, doclen = self.text.postings(len(self.sources))
-            self.engine.bm25_build_fields(indptr, doc, tf, term_field, doclen)
+            self.text.sync_device(self.engine, len(self.sources))
             self.engine.set_vocab(self.text.terms_in_id_order())
-            self.text.dirty = False
 
     # -- search ------------------------------------------------------------------------------------------
     def _hits(self, pairs, with_vectors: bool = True) -> list[dict]:

@@ -20,84 +20,6 @@
 int search_core(rass_engine* h, const float* q_dev, int B, int k, int64_t* out_rows, float* out_scores,
                 double* out_keys, rass_stats* stats);
 
-// ---- Lucene SmallFloat.intToByte4 / byte4ToInt (restated from the published algorithm) --------------------
-static int long_to_int4(int64_t v) {
-  int nb = v == 0 ? 0 : 64 - __builtin_clzll((unsigned long long)v);
-  if (nb < 4) return (int)v;
-  int shift = nb - 4;
-  int enc = (int)((v >> shift) & 7);
-  enc |= (shift + 1) << 3;
-  return enc;
-}
-static int64_t int4_to_long(int e) {
-  int bits = e & 7, shift = (e >> 3) - 1;
-  return shift == -1 ? bits : (int64_t)(bits | 8) << shift;
-}
-static const int kNumFree = 24;  // 255 - longToInt4(Integer.MAX_VALUE)
-static uint8_t int_to_byte4(uint32_t i) { return (uint8_t)(i < (uint32_t)kNumFree ? i : kNumFree + long_to_int4((int64_t)i - kNumFree)); }
-static int64_t byte4_to_int(int b) { return b < kNumFree ? b : kNumFree + int4_to_long(b - kNumFree); }
-
-#define BM25_MAX_TERMS 1024      // term queries per query string: 12 tokens x <= 50 fuzzy expansions and then some
-#define HYB_TILE 4096            // docs per tile: the fused clause sums of a tile live in shared memory (32 KB)
-#define HYB_THREADS 256
-#define HYB_LIST 512             // keys that survive the tile's top-k pre-filter (2 per thread)
-#define HYB_TABLE_MIN_DF 512     // terms at least this frequent get a row of per-tile posting offsets
-
-// Per-tile posting offsets of the frequent terms, built once per rass_bm25_build:
-// tile_off[row * (n_tiles + 1) + t] = number of postings of the term whose doc is < t * HYB_TILE.
-__global__ void tile_offsets_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ doc,
-                                    const int32_t* __restrict__ table_terms, int n_table, int n_tiles,
-                                    uint32_t* __restrict__ tile_off) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)n_table * (n_tiles + 1)) return;
-  const int row = (int)(i / (n_tiles + 1)), t = (int)(i % (n_tiles + 1));
-  const int32_t term = table_terms[row];
-  const int64_t lo = indptr[term], hi = indptr[term + 1];
-  const int64_t bound = (int64_t)t * HYB_TILE;
-  int64_t a = lo, b = hi;                 // first posting with doc >= bound
-  while (a < b) {
-    const int64_t m = (a + b) >> 1;
-    if ((int64_t)doc[m] < bound) a = m + 1; else b = m;
-  }
-  tile_off[i] = (uint32_t)(a - lo);
-}
-
-// Per-term range of x = tf * inv[norm] over the term's postings (one CTA per term), computed with the scoring kernel's
-// own float ops.  s(x) = w - w / (1 + x) is non-decreasing in x under round-to-nearest, so s(xmin) / s(xmax) bound every
-// score the term can contribute -- what hybrid_core needs to decide whether a query's clause sums are exact in double
-// whatever the order of the additions (see hybrid_tile_fast_kernel).
-__global__ void __launch_bounds__(256) term_xrange_kernel(const int64_t* __restrict__ indptr,
-                                                          const int32_t* __restrict__ doc,
-                                                          const uint16_t* __restrict__ tf,
-                                                          const uint8_t* __restrict__ norm, const float* __restrict__ inv,
-                                                          const uint8_t* __restrict__ term_field, int64_t norm_rows,
-                                                          float* __restrict__ xmin, float* __restrict__ xmax) {
-  const int64_t t = blockIdx.x;
-  const int64_t lo = indptr[t], hi = indptr[t + 1];
-  const int f = term_field[t];
-  const uint8_t* nf = norm + (size_t)f * norm_rows;
-  const float* iv = inv + f * 256;
-  float mn = __int_as_float(0x7f800000), mx = 0.f;
-  for (int64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
-    const float x = __fmul_rn((float)tf[p], iv[nf[doc[p]]]);
-    mn = fminf(mn, x);
-    mx = fmaxf(mx, x);
-  }
-  __shared__ float smn[8], smx[8];
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, m));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-  }
-  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; ++i) { mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
-    xmin[t] = mn;
-    xmax[t] = mx;
-  }
-}
-
 template <typename T>
 static int upload(rass_engine* h, T** dst, const T* src, size_t n) {
   cudaFree(*dst);
@@ -107,120 +29,10 @@ static int upload(rass_engine* h, T** dst, const T* src, size_t n) {
   return RASS_OK;
 }
 
-// F analysed fields share one CSR: term t belongs to field term_field[t]; doclen is [F][N] (tokens of the field per
-// row, 0 = the row does not have the field).  Statistics (docCount, avgdl, idf) are per field, as in Lucene.
-int bm25_build_impl(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
-                    const int32_t* term_field, const uint32_t* doclen, int64_t V, int64_t N, int F,
-                    const int64_t* g_doc_count, const int64_t* g_sum_ttf, const int64_t* global_df) {
-  if (!h) return RASS_E_INVALID;
-  cudaSetDevice(h->device);
-  if (V < 0 || N < 0 || F < 1 || F > 255 || !indptr || (N && !doclen)) return rass_fail(h, RASS_E_INVALID, "bad postings");
-  const int64_t nnz = indptr[V];
-  if (nnz < 0 || (nnz && (!doc || !tf))) return rass_fail(h, RASS_E_INVALID, "bad postings");
-  if (N > 0xfffffff0LL) return rass_fail(h, RASS_E_INVALID, "too many documents");
-  if (term_field)
-    for (int64_t t = 0; t < V; ++t)
-      if (term_field[t] < 0 || term_field[t] >= F) return rass_fail(h, RASS_E_INVALID, "term %lld: bad field", (long long)t);
-  Bm25State& b = h->bm25;
-  b.V = V; b.N = N; b.nnz = nnz; b.F = F;
-  std::vector<uint8_t> norm((size_t)N * F);
-  std::vector<float> inv((size_t)256 * F);
-  std::vector<int64_t> doc_count((size_t)F, 0);
-  const float k1 = 1.2f, bb = 0.75f, one = 1.0f;
-  for (int f = 0; f < F; ++f) {
-    int64_t dc = 0, sum_ttf = 0;
-    const uint32_t* dl = doclen + (size_t)f * N;
-    for (int64_t i = 0; i < N; ++i) {
-      dc += dl[i] != 0;
-      sum_ttf += dl[i];
-      norm[(size_t)f * N + i] = int_to_byte4(dl[i]);
-    }
-    if (g_doc_count && g_sum_ttf && g_doc_count[f] > 0) { dc = g_doc_count[f]; sum_ttf = g_sum_ttf[f]; }
-    doc_count[(size_t)f] = dc;
-    const float avgdl = dc ? (float)((double)sum_ttf / (double)dc) : 0.f;
-    if (f == 0) { b.doc_count = dc; b.avgdl = avgdl; }
-    for (int i = 0; i < 256; ++i) {
-      if (!dc) { inv[(size_t)f * 256 + i] = 0.f; continue; }
-      volatile float t = bb * (float)byte4_to_int(i);   // volatile: every step rounds to float, no contraction
-      t = t / avgdl;
-      t = (one - bb) + t;
-      t = k1 * t;
-      inv[(size_t)f * 256 + i] = one / t;
-    }
-  }
-  b.indptr_host.assign(indptr, indptr + V + 1);
-  b.idf_host.resize((size_t)V);
-  b.term_field_host.assign((size_t)V, 0);
-  for (int64_t t = 0; t < V; ++t) {
-    const int f = term_field ? term_field[t] : 0;
-    b.term_field_host[(size_t)t] = (uint8_t)f;
-    const int64_t df = global_df ? global_df[t] : indptr[t + 1] - indptr[t];
-    const double dc = (double)doc_count[(size_t)f];
-    b.idf_host[(size_t)t] = (float)log(1.0 + (dc - (double)df + 0.5) / ((double)df + 0.5));
-  }
-  int rc;
-  if ((rc = upload(h, &b.indptr, indptr, (size_t)V + 1))) return rc;
-  if ((rc = upload(h, &b.doc, doc, (size_t)nnz))) return rc;
-  if ((rc = upload(h, &b.tf, tf, (size_t)nnz))) return rc;
-  if ((rc = upload(h, &b.norm, norm.data(), norm.size()))) return rc;
-  if ((rc = upload(h, &b.inv_dev, inv.data(), inv.size()))) return rc;
-  // per-tile posting offsets of the frequent terms (hybrid_tile_kernel jumps straight to a tile's postings)
-  b.n_tiles = (int)((std::max<int64_t>(N, 1) + HYB_TILE - 1) / HYB_TILE);
-  b.table_row_host.assign((size_t)V, -1);
-  std::vector<int32_t> table_terms;
-  for (int64_t t = 0; t < V; ++t)
-    if (indptr[t + 1] - indptr[t] >= HYB_TABLE_MIN_DF) {
-      b.table_row_host[(size_t)t] = (int32_t)table_terms.size();
-      table_terms.push_back((int32_t)t);
-    }
-  cudaFree(b.tile_off); b.tile_off = nullptr;
-  const size_t n_off = table_terms.size() * (size_t)(b.n_tiles + 1);
-  CUDA_TRY(h, cudaMalloc(&b.tile_off, std::max<size_t>(n_off, 1) * sizeof(uint32_t)));
-  if (n_off) {
-    int32_t* tt_dev = nullptr;
-    if ((rc = upload(h, &tt_dev, table_terms.data(), table_terms.size()))) return rc;
-    tile_offsets_kernel<<<(unsigned)((n_off + 255) / 256), 256>>>(b.indptr, b.doc, tt_dev, (int)table_terms.size(),
-                                                                  b.n_tiles, b.tile_off);
-    cudaError_t e = cudaDeviceSynchronize();
-    cudaFree(tt_dev);
-    if (e != cudaSuccess) return rass_fail(h, RASS_E_CUDA, "tile_offsets_kernel: %s", cudaGetErrorString(e));
-  }
-  // per-term score ranges (order-free fast path of hybrid_core)
-  b.xmin_host.assign((size_t)V, 0.f);
-  b.xmax_host.assign((size_t)V, 0.f);
-  if (V > 0) {
-    uint8_t* tfield_dev = nullptr;
-    float *xmin_dev = nullptr, *xmax_dev = nullptr;
-    if ((rc = upload(h, &tfield_dev, b.term_field_host.data(), (size_t)V))) return rc;
-    cudaError_t e = cudaMalloc(&xmin_dev, (size_t)V * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&xmax_dev, (size_t)V * 4);
-    if (e == cudaSuccess) {
-      term_xrange_kernel<<<(unsigned)V, 256>>>(b.indptr, b.doc, b.tf, b.norm, b.inv_dev, tfield_dev, N, xmin_dev, xmax_dev);
-      e = cudaMemcpy(b.xmin_host.data(), xmin_dev, (size_t)V * 4, cudaMemcpyDeviceToHost);
-      if (e == cudaSuccess) e = cudaMemcpy(b.xmax_host.data(), xmax_dev, (size_t)V * 4, cudaMemcpyDeviceToHost);
-    }
-    cudaFree(tfield_dev); cudaFree(xmin_dev); cudaFree(xmax_dev);
-    if (e != cudaSuccess) return rass_fail(h, RASS_E_CUDA, "term_xrange_kernel: %s", cudaGetErrorString(e));
-  }
-  b.built = true;
-  return RASS_OK;
-}
+#define BM25_MAX_TERMS 1024      // term queries per query string: 12 tokens x <= 50 fuzzy expansions and then some
+#define HYB_THREADS 256
+#define HYB_LIST 512             // keys that survive the tile's top-k pre-filter (2 per thread)
 
-extern "C" int rass_bm25_build(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
-                               const uint32_t* doclen, int64_t V, int64_t N, int64_t global_doc_count,
-                               int64_t global_sum_ttf, const int64_t* global_df) {
-  SHARDED(h, sharded_bm25_build(h, indptr, doc, tf, nullptr, doclen, V, N, 1));
-  const bool global = global_doc_count > 0;
-  return bm25_build_impl(h, indptr, doc, tf, nullptr, doclen, V, N, 1, global ? &global_doc_count : nullptr,
-                         global ? &global_sum_ttf : nullptr, global_df);
-}
-
-extern "C" int rass_bm25_build_fields(rass_engine* h, const int64_t* indptr, const int32_t* doc, const uint16_t* tf,
-                                      const int32_t* term_field, const uint32_t* doclen, int64_t V, int64_t N, int F) {
-  SHARDED(h, sharded_bm25_build(h, indptr, doc, tf, term_field, doclen, V, N, F));
-  if (h && !term_field) return rass_fail(h, RASS_E_INVALID, "null term_field");
-  return bm25_build_impl(h, indptr, doc, tf, term_field, doclen, V, N, F, nullptr, nullptr, nullptr);
-}
 
 // ---- kernels ------------------------------------------------------------------------------------------------
 struct HybridArgs {

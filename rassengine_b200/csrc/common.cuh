@@ -46,6 +46,19 @@ __host__ __device__ inline int64_t row_global_to_local(const RowMap& m, int64_t 
   return ((b / m.G) << m.blk_log2) | (r & ((int64_t(1) << m.blk_log2) - 1));
 }
 
+#define HYB_TILE 4096            // docs per tile of the hybrid kernels: a tile's fused clause sums live in shared memory
+#define HYB_TABLE_MIN_DF 512     // terms at least this frequent get a row of per-tile posting offsets
+
+// the postings of one bulk of new rows of one field, sorted by (term, doc): what a commit folds into the CSR (postings.cu)
+struct TextSegment {
+  int field = 0;
+  int64_t n_post = 0, n_uniq = 0;
+  int32_t* uterm = nullptr;      // device [n_uniq] distinct local term ids, ascending
+  int64_t* uptr = nullptr;       // device [n_uniq + 1] where each one's run starts
+  int32_t* doc = nullptr;        // device [n_post]
+  uint16_t* tf = nullptr;        // device [n_post]
+};
+
 struct Bm25State {
   bool built = false;
   int64_t V = 0, N = 0, nnz = 0;
@@ -77,6 +90,15 @@ struct Bm25State {
   bool force_ordered = false;    // RASS_OPT_HYBRID_ORDERED: always take the ordered tile kernel (tests, A/B)
   bool maxscore = false;         // RASS_OPT_HYBRID_MAXSCORE: essential / non-essential term split in the order-free kernel
   int* sel_fallback = nullptr;   // device [qt_q_cap]: queries hybrid_select_kernel hands to the radix select
+  // device-side ingest (postings.cu)
+  std::vector<TextSegment> pending;      // segments rass_text_commit has not folded in yet
+  uint32_t* doclen_dev = nullptr;        // device [doclen_F][doclen_stride] tokens of the field per row
+  int doclen_F = 0;
+  int64_t doclen_stride = 0;
+  std::vector<int64_t> field_vocab;      // terms per field as of the last build / commit (field f owns one block of ids)
+  std::vector<int64_t> field_last_row;   // highest row each field holds (segments included)
+  bool contiguous_fields = true;
+  std::vector<int64_t> field_doc_count, field_sum_ttf;   // per field, as of the last build / commit
 };
 
 // device-resident scalars the kernels update / read without a host round trip

@@ -253,6 +253,56 @@ class Engine:
         self._check(self._lib.rass_bm25_build_fields(self._h, _ptr(indptr), _ptr(doc), _ptr(tf), _ptr(term_field),
                                                      _ptr(doclen), indptr.size - 1, doclen.shape[1], doclen.shape[0]))
 
+    def text_add_rows(self, field: int, rows, tok_indptr, tok_terms):
+        """Device-side ingest of one field of a bulk of NEW rows (rass_text_add_rows): rows int64 [n] ascending,
+        tok_indptr int64 [n + 1], tok_terms int32 term ids local to the field, token order, repeats included.
+        Searchable after text_commit."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        tok_indptr = np.ascontiguousarray(tok_indptr, dtype=np.int64)
+        tok_terms = np.ascontiguousarray(tok_terms, dtype=np.int32)
+        if tok_indptr.size != rows.size + 1:
+            raise ValueError("tok_indptr must have len(rows) + 1 entries")
+        self._check(self._lib.rass_text_add_rows(self._h, int(field), _ptr(rows), rows.size, _ptr(tok_indptr),
+                                                 _ptr(tok_terms) if tok_terms.size else None))
+
+    def text_add_rows_dev(self, field: int, rows_ptr: int, n_rows: int, tok_indptr_ptr: int, tok_terms_ptr: int):
+        """The same with device pointers (int64 rows, int64 offsets, int32 term ids)."""
+        self._check(self._lib.rass_text_add_rows_dev(self._h, int(field), C.c_void_p(rows_ptr), int(n_rows),
+                                                     C.c_void_p(tok_indptr_ptr), C.c_void_p(tok_terms_ptr)))
+
+    def text_commit(self, field_vocab, n_rows: int):
+        """Fold the pending segments into the searchable CSR (rass_text_commit): field_vocab = terms per field now."""
+        fv = np.ascontiguousarray(field_vocab, dtype=np.int64)
+        self._check(self._lib.rass_text_commit(self._h, _ptr(fv), fv.size, int(n_rows)))
+
+    def text_size(self) -> dict:
+        V, N, nnz, F = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        self._check(self._lib.rass_text_size(self._h, C.byref(V), C.byref(N), C.byref(nnz), C.byref(F)))
+        return {"V": V.value, "N": N.value, "nnz": nnz.value, "F": F.value}
+
+    def text_stats(self):
+        """(indptr int64 [V + 1], doc_count int64 [F]) of the committed index -- host copies, no device traffic."""
+        sz = self.text_size()
+        indptr = np.zeros(sz["V"] + 1, dtype=np.int64)
+        dc = np.zeros(max(sz["F"], 1), dtype=np.int64)
+        self._check(self._lib.rass_text_stats(self._h, _ptr(indptr), _ptr(dc), None))
+        return indptr, dc[:sz["F"]]
+
+    def text_export(self, postings: bool = True):
+        """The committed index read back: (indptr int64 [V+1], doc int32 [nnz], tf uint16 [nnz], doclen uint32 [F, N],
+        norm uint8 [F, N]); doc / tf are None with postings=False."""
+        sz = self.text_size()
+        indptr = np.zeros(sz["V"] + 1, dtype=np.int64)
+        doc = np.zeros(sz["nnz"], dtype=np.int32) if postings else None
+        tf = np.zeros(sz["nnz"], dtype=np.uint16) if postings else None
+        doclen = np.zeros((sz["F"], sz["N"]), dtype=np.uint32)
+        norm = np.zeros((sz["F"], sz["N"]), dtype=np.uint8)
+        self._check(self._lib.rass_text_export(self._h, _ptr(indptr), _ptr(doc) if postings and doc.size else None,
+                                               _ptr(tf) if postings and tf.size else None,
+                                               _ptr(doclen) if doclen.size else None,
+                                               _ptr(norm) if norm.size else None))
+        return indptr, doc, tf, doclen, norm
+
     def set_row_filter(self, mask):
         """mask: uint8/bool [rows] (1 = passes the query's bool.filter) or None to clear."""
         if mask is None:

@@ -23,6 +23,12 @@ class TextField:
         self._terms: list[str] = []                  # id -> term, rebuilt when the vocabulary grew
         self.df = np.zeros(0, dtype=np.int64)        # document frequency per term, as of the last postings()
         self.doc_count = 0                           # documents with at least one token, as of the last postings()
+        # device-side ingest (TextIndex.sync_device): rows added since the last sync, in ascending row order; a change
+        # to a row at or below `last_row` cannot be appended and asks for a rebuild from host arrays
+        self.pending_rows: list[int] = []
+        self.pending_ids: list[np.ndarray] = []
+        self.last_row = -1
+        self.rebuild = False
 
     def set_row(self, row: int, text: str | None):
         self.set_row_tokens(row, analyze(text) if text else [])
@@ -30,17 +36,35 @@ class TextField:
     def set_row_tokens(self, row: int, toks: list[str]):
         if not toks:
             if self.row_terms.pop(row, None) is not None:
-                self.dirty = True
+                self.dirty = self.rebuild = True
             return
         v = self.vocab
         ids = np.fromiter((v.setdefault(t, len(v)) for t in toks), dtype=np.int32, count=len(toks))
-        self.row_terms[row] = ids
-        self.dirty = True
+        self._store(row, ids)
 
     def set_row_ids(self, row: int, ids: np.ndarray):
         """Pre-tokenised input (synthetic corpora): term ids must be < declare_vocab()."""
-        self.row_terms[row] = np.asarray(ids, dtype=np.int32)
+        self._store(row, np.asarray(ids, dtype=np.int32))
+
+    def _store(self, row: int, ids: np.ndarray):
+        self.row_terms[row] = ids
         self.dirty = True
+        if row > self.last_row:
+            self.pending_rows.append(row)
+            self.pending_ids.append(ids)
+            self.last_row = row
+        else:
+            self.rebuild = True              # a rewrite (or a late first value) of an older row
+
+    def take_pending(self):
+        """(rows int64 [n], tok_indptr int64 [n + 1], tok_terms int32) of the rows added since the last call."""
+        rows = np.asarray(self.pending_rows, dtype=np.int64)
+        indptr = np.zeros(rows.size + 1, dtype=np.int64)
+        if rows.size:
+            indptr[1:] = np.cumsum([a.size for a in self.pending_ids])
+        terms = np.concatenate(self.pending_ids).astype(np.int32) if rows.size else np.zeros(0, np.int32)
+        self.pending_rows, self.pending_ids = [], []
+        return rows, indptr, terms
 
     def query_terms(self, text: str) -> list[int]:
         """Term ids of the query tokens; unknown tokens map to -1 (the kernel ignores them)."""
@@ -156,6 +180,8 @@ class TextIndex:
         self.order: list[str] = []                # field id -> name
         self.base: dict[str, int] = {}            # as of the last postings()
         self.dirty = True
+        self.device_commits = 0                   # syncs that went through the device-side ingest / a host rebuild
+        self.host_rebuilds = 0
 
     def field_id(self, name: str) -> int:
         return self.order.index(name)
@@ -215,6 +241,39 @@ class TextIndex:
             return z(1, np.int64), z(0, np.int32), z(0, np.uint16), z(0, np.int32), z((1, n_rows), np.uint32)
         indptr = np.concatenate(indptrs + [np.array([nnz], dtype=np.int64)]).astype(np.int64)
         return (indptr, np.concatenate(docs), np.concatenate(tfs), np.concatenate(fields), np.stack(lens))
+
+    def sync_device(self, engine, n_rows: int):
+        """Bring the engine's postings up to date with the rows indexed so far.  New rows travel as token-id streams
+        and are inverted on the device (rass_text_add_rows + rass_text_commit: a segment per bulk, one merge pass);
+        a rewrite of an indexed row, a keyword field with several values in one document (omitted norms: its length
+        must read 1), or a handle spread over several GPUs takes the rebuild from host arrays instead."""
+        flds = [self.fields[n] for n in self.order]
+        kw_multi = any(self.types.get(n) == "keyword" and any(a.size > 1 for a in self.fields[n].pending_ids)
+                       for n in self.order)
+        if any(f.rebuild for f in flds) or kw_multi or len(getattr(engine, "devices", [0])) > 1 or not self.order:
+            indptr, doc, tf, term_field, doclen = self.postings(n_rows)
+            engine.bm25_build_fields(indptr, doc, tf, term_field, doclen)
+            for f in flds:
+                f.pending_rows, f.pending_ids, f.rebuild = [], [], False
+            self.host_rebuilds += 1
+        else:
+            for fid, f in enumerate(flds):
+                if f.pending_rows:
+                    engine.text_add_rows(fid, *f.take_pending())
+            engine.text_commit([len(f.vocab) for f in flds], n_rows)
+            # the host-side statistics the query rewriting needs (df per term, docCount per field)
+            indptr, doc_count = engine.text_stats()
+            base = 0
+            self.base = {}
+            for fid, (name, f) in enumerate(zip(self.order, flds)):
+                V = len(f.vocab)
+                self.base[name] = base
+                f.df = np.diff(indptr[base:base + V + 1])
+                f.doc_count = int(doc_count[fid])
+                f._fuzzy = {}
+                base += V
+            self.device_commits += 1
+        self.dirty = False
 
     def terms_in_id_order(self) -> list[str]:
         out: list[str] = []
