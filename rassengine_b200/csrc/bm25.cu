@@ -38,6 +38,7 @@ static int upload(rass_engine* h, T** dst, const T* src, size_t n) {
 struct HybridArgs {
   const int32_t* doc;
   const uint16_t* tf;
+  const float* xq;               // per posting: tf * inv[norm of the doc] (the impact the order-free kernel scores from)
   const uint8_t* norm;
   const float* inv;
   const uint32_t* tile_off;
@@ -97,11 +98,24 @@ __device__ __forceinline__ void hybrid_tile_tail(const HybridArgs& a, double* fu
   constexpr int PER = HYB_TILE / HYB_THREADS;
   uint32_t key[PER];
   int nm = 0;
+  // With a positive bound at hand only sums that can round to a float >= the bound need a key.  For positive doubles
+  // the high words order like the values, so one 32-bit load and an integer compare per doc decide it: thr_hi = high
+  // word of the next float BELOW the bound (every double that rounds to the bound or above is larger than that).
+  // Without a bound (or a bound <= 0) every doc passes, as before.
+  int thr_hi = (int)0x80000000;
+  if (pre_g && *pre_g > 0x80000000u) {
+    const float gf = unord32(*pre_g);
+    thr_hi = __double2hiint((double)__uint_as_float(__float_as_uint(gf) - 1u));
+  }
+  const int* acc_hi = reinterpret_cast<const int*>(acc) + 1;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
-    const double v = acc[i * HYB_THREADS + tid];          // doc = d0 + i * HYB_THREADS + tid
-    key[i] = v != 0.0 ? ord32((float)v) : 0u;
-    nm += v != 0.0;
+    key[i] = 0u;
+    if (acc_hi[2 * (i * HYB_THREADS + tid)] >= thr_hi) {
+      const double v = acc[i * HYB_THREADS + tid];          // doc = d0 + i * HYB_THREADS + tid
+      key[i] = v != 0.0 ? ord32((float)v) : 0u;
+      nm += v != 0.0;
+    }
   }
   if (!pre_g) {
     if (nm) atomicAdd(&s_nmatch, nm);
@@ -358,6 +372,13 @@ __global__ void __launch_bounds__(HYB_THREADS) hybrid_tile_kernel(const __grid_c
 
 // one scored posting: s = w - w / (1 + tf * inv[norm]) with every float op rounded (Lucene's BM25Similarity), added to
 // the doc's clause sum
+// the same from the posting's precomputed impact x = tf * inv[norm] (Bm25State::xq, written by term_xrange_kernel with
+// this very multiplication)
+__device__ __forceinline__ bool hyb_score_add_x(double* acc, int rel, float x, float w) {
+  const float sc = __fsub_rn(w, __fdiv_rn(w, __fadd_rn(1.0f, x)));
+  if (sc > 0.f) atomicAdd(&acc[rel], (double)sc);
+  return sc > 0.f;
+}
 __device__ __forceinline__ bool hyb_score_add(double* acc, const float* s_inv, int rel, uint32_t tfv, uint32_t nb, float w) {
   const float x = __fmul_rn((float)tfv, s_inv[nb]);
   const float sc = __fsub_rn(w, __fdiv_rn(w, __fadd_rn(1.0f, x)));
@@ -371,7 +392,7 @@ template <bool FILTER, bool PRUNE>
 __global__ void __launch_bounds__(HYB_THREADS, PRUNE ? 5 : 6) hybrid_tile_fast_kernel(const __grid_constant__ HybridArgs a) {
   __shared__ double acc[HYB_TILE];
   __shared__ uint32_t s_bits[PRUNE ? HYB_TILE / 32 : 1];   // docs touched by an essential term or named by the knn clause
-  __shared__ float s_inv[256];
+  __shared__ float s_inv[PRUNE ? 256 : 1];        // (the MaxScore phases score from tf and norm bytes)
   __shared__ int64_t s_lo[HYB_FAST_TERMS];
   __shared__ uint32_t s_n[HYB_FAST_TERMS];
   __shared__ uint32_t s_cpre[2][HYB_FAST_TERMS + 1];   // chunk prefix of the essential [0] / non-essential [1] terms
@@ -405,7 +426,7 @@ __global__ void __launch_bounds__(HYB_THREADS, PRUNE ? 5 : 6) hybrid_tile_fast_k
     }
     if (j_begin < j_end) {                  // every term of the query is of one field (hybrid_core checked)
       const int field = a.t_field[j_begin];
-      s_inv[tid] = a.inv[field * 256 + tid];
+      if (PRUNE) s_inv[tid] = a.inv[field * 256 + tid];
       norm_t = a.norm + (size_t)field * a.norm_rows + d0;
     }
     if (warp != 0 || j_begin == j_end) {
@@ -480,14 +501,16 @@ __global__ void __launch_bounds__(HYB_THREADS, PRUNE ? 5 : 6) hybrid_tile_fast_k
       {
         const uint32_t n_chunks = s_cpre[0][nt];
         int j = 0;
+        uint32_t c_lo = 0, c_hi = s_cpre[0][1];                // chunk range of term j
         for (uint32_t c = warp; c < n_chunks; c += HYB_THREADS / 32) {
-          while (c >= s_cpre[0][j + 1]) ++j;                   // warp-uniform: once per chunk
-          const uint32_t first = (c - s_cpre[0][j]) * HYB_CHUNK, n_rem = s_n[j] - first;
-          const int32_t* pd = a.doc + s_lo[j] + first;
-          const uint16_t* pt = a.tf + s_lo[j] + first;
+          while (c >= c_hi) { ++j; c_lo = c_hi; c_hi = s_cpre[0][j + 1]; }    // warp-uniform: the chunk's term
+          const uint32_t first = (c - c_lo) * HYB_CHUNK, n_rem = s_n[j] - first;
+          const int64_t p0 = s_lo[j] + first;
+          const int32_t* pd = a.doc + p0;
+          const float* px = a.xq + p0;
           const float w = s_w[j];
           int rel[HYB_CHUNK / 32];
-          uint32_t tfv[HYB_CHUNK / 32], nb[HYB_CHUNK / 32];
+          float xv[HYB_CHUNK / 32];
 #pragma unroll
           for (int u = 0; u < HYB_CHUNK / 32; ++u) {
             const uint32_t i = u * 32 + lane;
@@ -495,14 +518,12 @@ __global__ void __launch_bounds__(HYB_THREADS, PRUNE ? 5 : 6) hybrid_tile_fast_k
             rel[u] = dd - (int)d0;                             // in the tile iff 0 <= rel < tile_len (rare terms scan
             if ((uint32_t)rel[u] >= tile_len) rel[u] = -1;     // their whole list); -1 and out-of-range ids fall out
             if (FILTER && rel[u] >= 0 && (dd >= a.filter_rows || !a.row_filter[dd])) rel[u] = -1;      // bool.filter
-            if (rel[u] >= 0) tfv[u] = __ldg(pt + i);
+            xv[u] = rel[u] >= 0 ? __ldg(px + i) : 0.f;
           }
-#pragma unroll
-          for (int u = 0; u < HYB_CHUNK / 32; ++u) nb[u] = rel[u] >= 0 ? norm_t[rel[u]] : 0u;
 #pragma unroll
           for (int u = 0; u < HYB_CHUNK / 32; ++u) {
             if (rel[u] < 0) continue;
-            if (hyb_score_add(acc, s_inv, rel[u], tfv[u], nb[u], w) && PRUNE && pruned)
+            if (hyb_score_add_x(acc, rel[u], xv[u], w) && PRUNE && pruned)
               atomicOr(&s_bits[rel[u] >> 5], 1u << (rel[u] & 31));
           }
         }
@@ -889,7 +910,7 @@ int hybrid_core(rass_engine* h, const float* q_host, int B, const int32_t* qterm
   CUDA_TRY(h, cudaEventRecord(e0, st));
   HybridArgs a;
   memset(&a, 0, sizeof(a));
-  a.doc = b.doc; a.tf = b.tf; a.norm = b.norm; a.inv = b.inv_dev; a.tile_off = b.tile_off;
+  a.doc = b.doc; a.tf = b.tf; a.xq = b.xq; a.norm = b.norm; a.inv = b.inv_dev; a.tile_off = b.tile_off;
   if (have_text) {
     a.t_lo = ta.t_lo; a.t_len = ta.t_len; a.t_w = ta.t_w; a.t_row = ta.t_row;
     // MaxScore marks are opt-in (RASS_OPT_HYBRID_MAXSCORE / RASS_HYBRID_MAXSCORE=1): on the cfg4 corpus they remove 88 % of

@@ -67,6 +67,7 @@ struct Bm25State {
   int64_t* indptr = nullptr;     // device [V+1]
   int32_t* doc = nullptr;        // device [nnz]
   uint16_t* tf = nullptr;        // device [nnz]
+  float* xq = nullptr;           // device [nnz] tf * inv[norm of the doc]: the posting's impact (term_xrange_kernel)
   uint8_t* norm = nullptr;       // device [F][N]  SmallFloat byte4 of the field length of the doc
   float* inv_dev = nullptr;      // device [F][256] 1 / (k1 * ((1-b) + b * len/avgdl))
   int n_tiles = 0;               // tiles of 4096 docs

@@ -162,7 +162,7 @@ extern "C" int rass_destroy(rass_engine* h) {
   for (int i = 0; i < 2; ++i) { cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   Bm25State& b = h->bm25;
-  cudaFree(b.indptr); cudaFree(b.doc); cudaFree(b.tf); cudaFree(b.norm); cudaFree(b.inv_dev);
+  cudaFree(b.indptr); cudaFree(b.doc); cudaFree(b.tf); cudaFree(b.xq); cudaFree(b.norm); cudaFree(b.inv_dev);
   cudaFree(b.tile_off); cudaFree(b.qt_dev); cudaFreeHost(b.qt_host); cudaFree(b.hyb_gthr); cudaFree(b.sel_fallback);
   for (TextSegment& sg : b.pending) { cudaFree(sg.uterm); cudaFree(sg.uptr); cudaFree(sg.doc); cudaFree(sg.tf); }
   cudaFree(b.doclen_dev);

@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(256) term_xrange_kernel(const int64_t* __restr
                                                           const uint16_t* __restrict__ tf,
                                                           const uint8_t* __restrict__ norm, const float* __restrict__ inv,
                                                           const uint8_t* __restrict__ term_field, int64_t norm_rows,
-                                                          float* __restrict__ xmin, float* __restrict__ xmax) {
+                                                          float* __restrict__ xmin, float* __restrict__ xmax,
+                                                          float* __restrict__ xq) {
   const int64_t t = blockIdx.x;
   const int64_t lo = indptr[t], hi = indptr[t + 1];
   const int f = term_field[t];
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(256) term_xrange_kernel(const int64_t* __restr
   float mn = __int_as_float(0x7f800000), mx = 0.f;
   for (int64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
     const float x = __fmul_rn((float)tf[p], iv[nf[doc[p]]]);
+    xq[p] = x;                        // the posting's impact, what hybrid_tile_fast_kernel scores from
     mn = fminf(mn, x);
     mx = fmaxf(mx, x);
   }
@@ -241,10 +243,13 @@ static int text_finalize(rass_engine* h, int64_t V, int64_t N, int F, const int6
     uint8_t* tfield_dev = nullptr;
     float *xmin_dev = nullptr, *xmax_dev = nullptr;
     if ((rc = upload(h, &tfield_dev, b.term_field_host.data(), (size_t)V))) return rc;
+    cudaFree(b.xq); b.xq = nullptr;
     cudaError_t e = cudaMalloc(&xmin_dev, (size_t)V * 4);
     if (e == cudaSuccess) e = cudaMalloc(&xmax_dev, (size_t)V * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&b.xq, std::max<size_t>((size_t)b.nnz, 1) * 4);
     if (e == cudaSuccess) {
-      term_xrange_kernel<<<(unsigned)V, 256>>>(b.indptr, b.doc, b.tf, b.norm, b.inv_dev, tfield_dev, N, xmin_dev, xmax_dev);
+      term_xrange_kernel<<<(unsigned)V, 256>>>(b.indptr, b.doc, b.tf, b.norm, b.inv_dev, tfield_dev, N, xmin_dev, xmax_dev,
+                                              b.xq);
       e = cudaMemcpy(b.xmin_host.data(), xmin_dev, (size_t)V * 4, cudaMemcpyDeviceToHost);
       if (e == cudaSuccess) e = cudaMemcpy(b.xmax_host.data(), xmax_dev, (size_t)V * 4, cudaMemcpyDeviceToHost);
     }
