@@ -292,7 +292,7 @@ class _Index:
     def _sync_text(self):
         if self.text.dirty and self.engine is not None:
             self.text.sync_device(self.engine, len(self.sources))
-            self.engine.set_vocab(self.text.terms_in_id_order())
+            self.engine.set_vocab_raw(*self.text.vocab_blob())
 
     # -- search ------------------------------------------------------------------------------------------
     def _hits(self, pairs, with_vectors: bool = True) -> list[dict]:

@@ -342,18 +342,42 @@ extern "C" int rass_overwrite(rass_engine* h, int64_t row, const float* v_host) 
   return RASS_OK;
 }
 
+// sb = -inf for one row (row >= 0) or for the listed rows: stream-ordered, nothing for the host to wait for
+__global__ void tombstone_kernel(float* __restrict__ sb, int64_t row, const int64_t* __restrict__ rows, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sb[rows ? rows[i] : row] = __int_as_float(0xff800000);
+}
+
 extern "C" int rass_tombstone(rass_engine* h, int64_t row) {
   SHARDED(h, sharded_tombstone(h, row));
   CHECK_HANDLE(h);
   if (row < 0 || row >= h->n_rows) return rass_fail(h, RASS_E_NOTFOUND, "row %lld out of range", (long long)row);
   if (h->dead[(size_t)row]) return RASS_OK;
-  cudaStream_t st = eng_stream(h);
-  const uint32_t ninf = 0xff800000u;
-  CUDA_TRY(h, cudaMemcpyAsync(h->sb + row, &ninf, 4, cudaMemcpyHostToDevice, st));
+  tombstone_kernel<<<1, 32, 0, eng_stream(h)>>>(h->sb, row, nullptr, 1);     // ordered before the next search, no sync
+  CUDA_TRY(h, cudaGetLastError());
   h->sb_filtered_dirty = true;
-  CUDA_TRY(h, cudaStreamSynchronize(st));
   h->dead[(size_t)row] = 1;
   h->n_live--;
+  return RASS_OK;
+}
+
+// the tombstones of a snapshot in one launch
+static int tombstone_many(rass_engine* h, const std::vector<int64_t>& rows) {
+  if (rows.empty()) return RASS_OK;
+  cudaStream_t st = eng_stream(h);
+  int64_t* dev = nullptr;
+  CUDA_TRY(h, cudaMalloc(&dev, rows.size() * 8));
+  cudaError_t e = cudaMemcpyAsync(dev, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    tombstone_kernel<<<(unsigned)((rows.size() + 255) / 256), 256, 0, st>>>(h->sb, -1, dev, (int64_t)rows.size());
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(dev);
+  if (e != cudaSuccess) return rass_fail(h, RASS_E_CUDA, "tombstones: %s", cudaGetErrorString(e));
+  for (int64_t r : rows)
+    if (!h->dead[(size_t)r]) { h->dead[(size_t)r] = 1; h->n_live--; }
+  h->sb_filtered_dirty = true;
   return RASS_OK;
 }
 
@@ -464,8 +488,15 @@ extern "C" int rass_load(rass_engine* h, const char* path) {
     rc = rass_append(h, buf.data(), m, nullptr);
   }
   fclose(f);
-  for (int64_t r = 0; !rc && r < hd.n_rows; ++r)
-    if (dead[(size_t)r]) rc = rass_tombstone(h, r);
+  if (!rc) {
+    std::vector<int64_t> gone;
+    for (int64_t r = 0; r < hd.n_rows; ++r)
+      if (dead[(size_t)r]) gone.push_back(r);
+    if (h->shards)                                    // a sharded handle routes every row to its shard
+      for (size_t i = 0; !rc && i < gone.size(); ++i) rc = rass_tombstone(h, gone[i]);
+    else
+      rc = tombstone_many(h, gone);
+  }
   return rc;
 }
 

@@ -320,6 +320,12 @@ class Engine:
         self._check(self._lib.rass_text_set_vocab(self._h, b"".join(enc), _ptr(off), len(enc)))
         self._vocab_size = len(enc)
 
+    def set_vocab_raw(self, blob: bytes, offsets):
+        """set_vocab from prepared arrays: the terms' utf-8 bytes back to back, int64 byte offsets [V + 1]."""
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._check(self._lib.rass_text_set_vocab(self._h, blob, _ptr(off), off.size - 1))
+        self._vocab_size = off.size - 1
+
     def fuzzy_expand(self, token: str, max_edits: int, term_lo: int = 0, term_hi: int = -1):
         """Dictionary terms of [term_lo, term_hi) within max_edits (optimal string alignment) of the token:
         (term ids, edits), unordered."""

@@ -20,7 +20,9 @@ class TextField:
         self.row_terms: dict[int, np.ndarray] = {}   # row -> int32 term ids (with repeats)
         self.dirty = True
         self._fuzzy: dict = {}                       # token -> ranked expansion, as of the last postings()
-        self._terms: list[str] = []                  # id -> term, rebuilt when the vocabulary grew
+        self._terms: list[str] = []                  # id -> term, extended when the vocabulary grew
+        self._enc_blob = bytearray()                 # the terms' utf-8 bytes, back to back (encoded_terms)
+        self._enc_lens: list[int] = []
         self.df = np.zeros(0, dtype=np.int64)        # document frequency per term, as of the last postings()
         self.doc_count = 0                           # documents with at least one token, as of the last postings()
         # device-side ingest (TextIndex.sync_device): rows added since the last sync, in ascending row order; a change
@@ -90,12 +92,26 @@ class TextField:
         return indptr, d_of, tf, doclen
 
     def terms_in_id_order(self) -> list[str]:
-        if len(self._terms) != len(self.vocab):
-            out = [""] * len(self.vocab)
-            for t, i in self.vocab.items():
-                out[i] = t
-            self._terms = out
+        if len(self._terms) > len(self.vocab):
+            self._terms = []
+        if len(self._terms) < len(self.vocab):
+            # ids are handed out in insertion order (vocab.setdefault(t, len(vocab))), which is the dict's own order
+            import itertools
+            self._terms.extend(itertools.islice(self.vocab, len(self._terms), None))
         return self._terms
+
+    def encoded_terms(self):
+        """(utf-8 bytes of all terms back to back, int64 byte length per term), extended by the terms that are new
+        since the last call -- what the device dictionary of the fuzzy scan is uploaded from."""
+        terms = self.terms_in_id_order()
+        n_old = len(self._enc_lens)
+        if n_old > len(terms):
+            self._enc_blob, self._enc_lens, n_old = bytearray(), [], 0
+        if n_old < len(terms):
+            enc = [t.encode("utf-8", "replace") for t in terms[n_old:]]
+            self._enc_blob += b"".join(enc)
+            self._enc_lens.extend(len(e) for e in enc)
+        return self._enc_blob, np.asarray(self._enc_lens, dtype=np.int64)
 
     @staticmethod
     def auto_max_edits(n_chars: int) -> int:
@@ -274,6 +290,24 @@ class TextIndex:
                 base += V
             self.device_commits += 1
         self.dirty = False
+
+    def vocab_blob(self):
+        """The device dictionary in global term-id order: (bytes, int64 offsets [V + 1]).  Only analysed fields are
+        ever scanned (fuzziness applies to their tokens; a keyword field's whole value is matched exactly), so keyword
+        terms are uploaded as empty strings -- a `doc_id` field alone has one term per document."""
+        blobs, lens = [], []
+        for name in self.order:
+            f = self.fields[name]
+            if self.types.get(name) == "keyword":
+                lens.append(np.zeros(len(f.vocab), dtype=np.int64))
+            else:
+                b, ln = f.encoded_terms()
+                blobs.append(bytes(b))
+                lens.append(ln)
+        off = np.zeros(sum(l.size for l in lens) + 1, dtype=np.int64)
+        if lens:
+            off[1:] = np.cumsum(np.concatenate(lens))
+        return b"".join(blobs), off
 
     def terms_in_id_order(self) -> list[str]:
         out: list[str] = []

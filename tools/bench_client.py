@@ -32,6 +32,22 @@ t_ingest = time.perf_counter() - t0
 idxr = ix.B200Indexer(client, name)
 q = rng.standard_normal((1, D)).astype(np.float32)
 out = {"docs": N, "ingest_docs_per_s": N / t_ingest}
+# refresh: the first hybrid query after the last bulk makes the new rows' text searchable (device-side segments + one
+# commit, rassengine_b200/csrc/postings.cu); then one more bulk and the query after it
+t0 = time.perf_counter()
+idxr.hybrid_search("w0001 w0500 w2999 w1234", q, k=3)
+out["first_hybrid_after_ingest_ms"] = (time.perf_counter() - t0) * 1e3
+m = 10_000
+emb = rng.standard_normal((m, D), dtype=np.float32)
+tok = rng.integers(0, len(words), size=(m, 24))
+docs = [{"doc_id": f"x{i}", "doc_type": "unstructured", "patientId": f"p{i % 500}",
+         "unstructuredText": " ".join(words[j] for j in tok[i])} for i in range(m)]
+ix.store_chunks(client, name, docs, emb, as_lists=False, flush=m)
+t0 = time.perf_counter()
+idxr.hybrid_search("w0001 w0500 w2999 w1234", q, k=3)
+out["first_hybrid_after_a_10k_bulk_ms"] = (time.perf_counter() - t0) * 1e3
+ti = client._indices[name].text
+out["text_syncs"] = {"device_commits": ti.device_commits, "host_rebuilds": ti.host_rebuilds}
 
 
 def lat(fn, n=100):
