@@ -204,12 +204,12 @@ int rass_bm25_build_fields(rass_engine* h, const int64_t* indptr, const int32_t*
                            const int32_t* term_field, const uint32_t* doclen, int64_t V, int64_t N, int F);
 
 /* ---- text ingest on the device (what a bulk request does to the `text` / `keyword` fields, app/main.py:1258-1269) ----
- * rass_text_add_rows hands over the analysed tokens of n_rows NEW rows of one field: rows[n_rows] ascending row ids, all
- * above every row the field already holds; tok_indptr[n_rows + 1] (starting at 0) into tok_terms, the rows' token
- * sequences as term ids LOCAL to the field (repeats included; only the counts matter to BM25).  The bulk becomes a
- * segment on the device (stable radix sort by term, repeats folded into term frequencies); nothing is searchable
- * until rass_text_commit -- OpenSearch's refresh.  The _dev flavour takes device pointers.
- * RASS_E_UNSUPPORTED: a row at or below one the field already holds (a rewrite): rebuild with rass_bm25_build_fields. */
+ * rass_text_add_rows hands over the analysed tokens of n_rows rows of one field: rows[n_rows] ascending, distinct row
+ * ids; tok_indptr[n_rows + 1] (starting at 0) into tok_terms, the rows' token sequences as term ids LOCAL to the field
+ * (repeats included; only the counts matter to BM25).  The bulk becomes a segment on the device (stable radix sort by
+ * term, repeats folded into term frequencies); nothing is searchable until rass_text_commit -- OpenSearch's refresh.
+ * A row the field already holds is REWRITTEN (an index request with a known _id): what it held is dropped at the
+ * commit, like Lucene's delete-then-add; a row with no tokens loses the field.  The _dev flavour takes device pointers. */
 int rass_text_add_rows(rass_engine* h, int field, const int64_t* rows, int64_t n_rows, const int64_t* tok_indptr,
                        const int32_t* tok_terms);
 int rass_text_add_rows_dev(rass_engine* h, int field, const int64_t* rows_dev, int64_t n_rows,
@@ -217,8 +217,9 @@ int rass_text_add_rows_dev(rass_engine* h, int field, const int64_t* rows_dev, i
 /* Folds the pending segments into the CSR the hybrid kernels walk and recomputes lengths, norm bytes, statistics, idf
  * and the kernels' side tables on the device.  field_vocab[F] = terms of each field NOW (vocabularies only grow); the
  * global id of (field f, local term t) is sum(field_vocab[:f]) + t, the layout rass_bm25_build_fields is given by the
- * client.  N = rows of the index.  One copy pass over the postings: rows only grow, so a term's merged list is its old
- * list followed by each segment's. */
+ * client.  N = rows of the index.  When the segments only add rows above the ones indexed, a term's merged list is its
+ * old list followed by each segment's: one copy pass over the postings.  When some row was rewritten, the live postings
+ * of every source (a per-(field, row) generation word says which source owns the row) are re-sorted by (term, doc). */
 int rass_text_commit(rass_engine* h, const int64_t* field_vocab, int F, int64_t N);
 /* Sizes of the committed index, and its arrays read back (tests, host-side evaluation); every pointer nullable:
  * indptr [V + 1], doc / tf [nnz], doclen [F][N], norm [F][N] (Lucene's SmallFloat.intToByte4 of doclen). */

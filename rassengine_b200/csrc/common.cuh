@@ -94,12 +94,17 @@ struct Bm25State {
   // device-side ingest (postings.cu)
   std::vector<TextSegment> pending;      // segments rass_text_commit has not folded in yet
   uint32_t* doclen_dev = nullptr;        // device [doclen_F][doclen_stride] tokens of the field per row
+  uint32_t* gen_dev = nullptr;           // device [doclen_F][doclen_stride] which source owns the (field, row): 0 = the
+                                         // committed CSR, s = the s-th pending segment (rewrites, postings.cu)
+  bool has_rewrite = false;              // a pending segment rewrites rows the index held: the commit re-sorts
   int doclen_F = 0;
   int64_t doclen_stride = 0;
   std::vector<int64_t> field_vocab;      // terms per field as of the last build / commit (field f owns one block of ids)
   std::vector<int64_t> field_last_row;   // highest row each field holds (segments included)
   bool contiguous_fields = true;
   std::vector<int64_t> field_doc_count, field_sum_ttf;   // per field, as of the last build / commit
+  void* scratch = nullptr;               // arena of the segment builds, kept between bulks, released by the commit
+  size_t scratch_bytes = 0;
 };
 
 // device-resident scalars the kernels update / read without a host round trip

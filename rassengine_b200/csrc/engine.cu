@@ -166,6 +166,8 @@ extern "C" int rass_destroy(rass_engine* h) {
   cudaFree(b.tile_off); cudaFree(b.qt_dev); cudaFreeHost(b.qt_host); cudaFree(b.hyb_gthr); cudaFree(b.sel_fallback);
   for (TextSegment& sg : b.pending) { cudaFree(sg.uterm); cudaFree(sg.uptr); cudaFree(sg.doc); cudaFree(sg.tf); }
   cudaFree(b.doclen_dev);
+  cudaFree(b.gen_dev);
+  cudaFree(b.scratch);
   cudaFree(b.vocab_blob); cudaFree(b.vocab_off); cudaFree(b.fz_terms); cudaFree(b.fz_edits); cudaFree(b.fz_n);
   free(h->tmap_x); free(h->tmap_q); free(h->tmap_q2);
   if (h->stream) cudaStreamDestroy(h->stream);

@@ -149,14 +149,21 @@ static int ensure_doclen(rass_engine* h, int F, int64_t N) {
   int64_t stride = b.doclen_stride;
   if (N > stride) stride = std::max<int64_t>(N, stride + stride / 2);
   stride = std::max<int64_t>(stride, 1024);
-  uint32_t* p = nullptr;
+  uint32_t *p = nullptr, *g = nullptr;
   TEXT_TRY(h, cudaMalloc(&p, (size_t)nF * stride * sizeof(uint32_t)));
   TEXT_TRY(h, cudaMemset(p, 0, (size_t)nF * stride * sizeof(uint32_t)));
-  if (b.doclen_dev && b.doclen_F > 0 && b.doclen_stride > 0)
+  TEXT_TRY(h, cudaMalloc(&g, (size_t)nF * stride * sizeof(uint32_t)));
+  TEXT_TRY(h, cudaMemset(g, 0, (size_t)nF * stride * sizeof(uint32_t)));
+  if (b.doclen_dev && b.doclen_F > 0 && b.doclen_stride > 0) {
     TEXT_TRY(h, cudaMemcpy2D(p, (size_t)stride * 4, b.doclen_dev, (size_t)b.doclen_stride * 4, (size_t)b.doclen_stride * 4,
                              (size_t)b.doclen_F, cudaMemcpyDeviceToDevice));
+    TEXT_TRY(h, cudaMemcpy2D(g, (size_t)stride * 4, b.gen_dev, (size_t)b.doclen_stride * 4, (size_t)b.doclen_stride * 4,
+                             (size_t)b.doclen_F, cudaMemcpyDeviceToDevice));
+  }
   cudaFree(b.doclen_dev);
+  cudaFree(b.gen_dev);
   b.doclen_dev = p;
+  b.gen_dev = g;
   b.doclen_F = nF;
   b.doclen_stride = stride;
   return RASS_OK;
@@ -302,6 +309,8 @@ int bm25_build_impl(rass_engine* h, const int64_t* indptr, const int32_t* doc, c
   if ((rc = upload(h, &b.doc, doc, (size_t)nnz))) return rc;
   if ((rc = upload(h, &b.tf, tf, (size_t)nnz))) return rc;
   cudaFree(b.doclen_dev); b.doclen_dev = nullptr; b.doclen_F = 0; b.doclen_stride = 0;
+  cudaFree(b.gen_dev); b.gen_dev = nullptr;
+  b.has_rewrite = false;
   if ((rc = ensure_doclen(h, F, N))) return rc;
   if (N)
     TEXT_TRY(h, cudaMemcpy2D(b.doclen_dev, (size_t)b.doclen_stride * 4, doclen, (size_t)N * 4, (size_t)N * 4, (size_t)F,
@@ -341,10 +350,16 @@ __global__ void token_keys_kernel(const int64_t* __restrict__ tok_indptr, const 
 }
 
 // the lengths of the bulk's rows go into the field's plane (once the token stream has been validated)
+// ... and the segment's number into its generation plane: a posting of a source (0 = the committed CSR, s = the s-th
+// pending segment) is live iff the generation of its (field, doc) still names that source
 __global__ void doclen_scatter_kernel(const int64_t* __restrict__ tok_indptr, const int64_t* __restrict__ rows,
-                                      int64_t n_rows, uint32_t* __restrict__ doclen_plane) {
+                                      int64_t n_rows, uint32_t* __restrict__ doclen_plane,
+                                      uint32_t* __restrict__ gen_plane, uint32_t seg_id) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n_rows) doclen_plane[rows[r]] = (uint32_t)(tok_indptr[r + 1] - tok_indptr[r]);
+  if (r < n_rows) {
+    doclen_plane[rows[r]] = (uint32_t)(tok_indptr[r + 1] - tok_indptr[r]);
+    gen_plane[rows[r]] = seg_id;
+  }
 }
 
 // unique (term, row position) keys + repeat counts -> doc ids, term frequencies, "first posting of a new term" marks
@@ -359,22 +374,37 @@ __global__ void split_runs_kernel(const uint64_t* __restrict__ ukeys, const int*
   term_of[i] = (int32_t)(k >> 32);
 }
 
+// scratch of the segment builds: grow-only between commits (a cudaMalloc / cudaFree pair per buffer and bulk costs
+// more than the sort), released by rass_text_commit
+static int ensure_scratch(rass_engine* h, size_t bytes) {
+  Bm25State& b = h->bm25;
+  if (bytes <= b.scratch_bytes) return RASS_OK;
+  cudaFree(b.scratch);
+  b.scratch = nullptr;
+  b.scratch_bytes = 0;
+  bytes += bytes / 4;
+  TEXT_TRY(h, cudaMalloc(&b.scratch, bytes));
+  b.scratch_bytes = bytes;
+  return RASS_OK;
+}
+
 static int seg_build(rass_engine* h, int field, const int64_t* rows_dev, int64_t n_rows, const int64_t* indptr_dev,
                      const int32_t* terms_dev, int64_t T, int32_t max_term, cudaStream_t st) {
   Bm25State& b = h->bm25;
   TextSegment seg;
   seg.field = field;
-  if (T == 0) return RASS_OK;
+  const uint32_t seg_id = (uint32_t)b.pending.size() + 1;
+  if (T == 0) {                  // rows without tokens: lengths 0, whatever they held before is dropped at the commit
+    doclen_scatter_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(
+        indptr_dev, rows_dev, n_rows, b.doclen_dev + (size_t)field * b.doclen_stride,
+        b.gen_dev + (size_t)field * b.doclen_stride, seg_id);
+    TEXT_TRY(h, cudaGetLastError());
+    b.pending.push_back(seg);
+    return RASS_OK;
+  }
   int term_bits = 1;
   while (term_bits < 31 && ((int64_t)1 << term_bits) <= (int64_t)max_term) ++term_bits;
-  uint64_t *k0 = nullptr, *k1 = nullptr;
-  int *cnt = nullptr, *n_runs_dev = nullptr, *bad_dev = nullptr;
-  int32_t* term_of = nullptr;
-  void* tmp = nullptr;
-  int rc = RASS_OK;
   auto done = [&](int code) {
-    cudaFree(k0); cudaFree(k1); cudaFree(cnt); cudaFree(n_runs_dev); cudaFree(bad_dev); cudaFree(term_of);
-    cudaFree(tmp);
     if (code) { cudaFree(seg.uterm); cudaFree(seg.uptr); cudaFree(seg.doc); cudaFree(seg.tf); }
     return code;
   };
@@ -385,59 +415,66 @@ static int seg_build(rass_engine* h, int field, const int64_t* rows_dev, int64_t
       return done(rass_fail(h, e_ == cudaErrorMemoryAllocation ? RASS_E_OOM : RASS_E_CUDA, "%s failed: %s (%s:%d)", \
                             #call, cudaGetErrorString(e_), __FILE__, __LINE__));                               \
   } while (0)
-  SEG_TRY(cudaMalloc(&k0, (size_t)T * 8));
-  SEG_TRY(cudaMalloc(&k1, (size_t)T * 8));
-  SEG_TRY(cudaMalloc(&bad_dev, sizeof(int)));
+  // temporary storage of the four CUB calls (host-side size queries), then one arena:
+  // [k0 u64 x T][k1 u64 x T][cnt i32 x T][term_of i32 x T][uterm i32 x T][n_runs, bad][cub temp]
+  size_t tmp_bytes = 0;
+  {
+    cub::DoubleBuffer<uint64_t> kq(nullptr, nullptr);
+    size_t t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+    SEG_TRY(cub::DeviceRadixSort::SortKeys(nullptr, t1, kq, (int)T, 32, 32 + term_bits, st));
+    SEG_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, t2, (uint64_t*)nullptr, (uint64_t*)nullptr, (int*)nullptr,
+                                               (int*)nullptr, (int)T, st));
+    SEG_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, t3, (int32_t*)nullptr, (int32_t*)nullptr, (int*)nullptr,
+                                               (int*)nullptr, (int)T, st));
+    SEG_TRY(cub::DeviceScan::InclusiveSum(nullptr, t4, (int*)nullptr, (int64_t*)nullptr, (int)T, st));
+    tmp_bytes = std::max(std::max(t1, t2), std::max(t3, t4));
+  }
+  const size_t Tp = ((size_t)T + 63) & ~(size_t)63;      // keeps every sub-array 256-byte aligned
+  int rc;
+  if ((rc = ensure_scratch(h, Tp * 28 + 256 + tmp_bytes + 256))) return done(rc);
+  unsigned char* base = static_cast<unsigned char*>(b.scratch);
+  uint64_t* k0 = reinterpret_cast<uint64_t*>(base);
+  uint64_t* k1 = reinterpret_cast<uint64_t*>(base + Tp * 8);
+  int* cnt = reinterpret_cast<int*>(base + Tp * 16);
+  int32_t* term_of = reinterpret_cast<int32_t*>(base + Tp * 20);
+  int32_t* uterm_tmp = reinterpret_cast<int32_t*>(base + Tp * 24);
+  int* n_runs_dev = reinterpret_cast<int*>(base + Tp * 28);
+  int* bad_dev = n_runs_dev + 1;
+  void* tmp = base + Tp * 28 + 256;
   SEG_TRY(cudaMemsetAsync(bad_dev, 0, sizeof(int), st));
   token_keys_kernel<<<(unsigned)n_rows, 128, 0, st>>>(indptr_dev, terms_dev, n_rows, k0, bad_dev);
   SEG_TRY(cudaGetLastError());
   // stable sort by the term bits only: a term's run keeps the bulk's row order, which is ascending
   cub::DoubleBuffer<uint64_t> keys(k0, k1);
-  size_t tmp_bytes = 0;
-  SEG_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, (int)T, 32, 32 + term_bits, st));
-  SEG_TRY(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
   SEG_TRY(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys, (int)T, 32, 32 + term_bits, st));
-  cudaFree(tmp); tmp = nullptr;
   // repeats of (term, row) fold into a term frequency
   uint64_t* sorted = keys.Current();
   uint64_t* uk = keys.Alternate();            // the other buffer is free again: the unique keys go there
-  SEG_TRY(cudaMalloc(&cnt, (size_t)T * sizeof(int)));
-  SEG_TRY(cudaMalloc(&n_runs_dev, sizeof(int)));
-  tmp_bytes = 0;
-  SEG_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, sorted, uk, cnt, n_runs_dev, (int)T, st));
-  SEG_TRY(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
   SEG_TRY(cub::DeviceRunLengthEncode::Encode(tmp, tmp_bytes, sorted, uk, cnt, n_runs_dev, (int)T, st));
   int n_post = 0, bad = 0;
   SEG_TRY(cudaMemcpyAsync(&n_post, n_runs_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
   SEG_TRY(cudaMemcpyAsync(&bad, bad_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
   SEG_TRY(cudaStreamSynchronize(st));
-  cudaFree(tmp); tmp = nullptr;
   if (bad) return done(rass_fail(h, RASS_E_INVALID, "negative term id in the token stream"));
-  doclen_scatter_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(indptr_dev, rows_dev, n_rows,
-                                                                         b.doclen_dev + (size_t)field * b.doclen_stride);
+  doclen_scatter_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(
+      indptr_dev, rows_dev, n_rows, b.doclen_dev + (size_t)field * b.doclen_stride,
+      b.gen_dev + (size_t)field * b.doclen_stride, seg_id);
   seg.n_post = n_post;
   SEG_TRY(cudaMalloc(&seg.doc, (size_t)n_post * 4));
   SEG_TRY(cudaMalloc(&seg.tf, (size_t)n_post * 2));
-  SEG_TRY(cudaMalloc(&term_of, (size_t)n_post * 4));
   split_runs_kernel<<<(unsigned)((n_post + 255) / 256), 256, 0, st>>>(uk, cnt, n_post, rows_dev, seg.doc, seg.tf, term_of);
   SEG_TRY(cudaGetLastError());
   // the segment's own term directory: distinct terms + where each one's run starts
   int* ucnt = cnt;                             // reuse: run lengths of the term sequence
-  SEG_TRY(cudaMalloc(&seg.uterm, (size_t)n_post * 4));
-  tmp_bytes = 0;
-  SEG_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, term_of, seg.uterm, ucnt, n_runs_dev, n_post, st));
-  SEG_TRY(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
-  SEG_TRY(cub::DeviceRunLengthEncode::Encode(tmp, tmp_bytes, term_of, seg.uterm, ucnt, n_runs_dev, n_post, st));
+  SEG_TRY(cub::DeviceRunLengthEncode::Encode(tmp, tmp_bytes, term_of, uterm_tmp, ucnt, n_runs_dev, n_post, st));
   int n_uniq = 0;
   SEG_TRY(cudaMemcpyAsync(&n_uniq, n_runs_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
   SEG_TRY(cudaStreamSynchronize(st));
-  cudaFree(tmp); tmp = nullptr;
   seg.n_uniq = n_uniq;
+  SEG_TRY(cudaMalloc(&seg.uterm, std::max<size_t>((size_t)n_uniq, 1) * 4));
+  SEG_TRY(cudaMemcpyAsync(seg.uterm, uterm_tmp, (size_t)n_uniq * 4, cudaMemcpyDeviceToDevice, st));
   SEG_TRY(cudaMalloc(&seg.uptr, ((size_t)n_uniq + 1) * 8));
   SEG_TRY(cudaMemsetAsync(seg.uptr, 0, 8, st));
-  tmp_bytes = 0;
-  SEG_TRY(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, ucnt, seg.uptr + 1, n_uniq, st));
-  SEG_TRY(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
   SEG_TRY(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, ucnt, seg.uptr + 1, n_uniq, st));
   SEG_TRY(cudaStreamSynchronize(st));
 #undef SEG_TRY
@@ -473,12 +510,14 @@ static int text_add_rows_impl(rass_engine* h, int field, const int64_t* rows, in
   const int64_t last = (size_t)field < b.field_last_row.size() ? b.field_last_row[(size_t)field] : -1;
   for (int64_t i = 0; i < n_rows; ++i) {
     if (ip[(size_t)i + 1] < ip[(size_t)i]) return rass_fail(h, RASS_E_INVALID, "token offsets must not decrease");
-    if (rw[(size_t)i] <= (i ? rw[(size_t)i - 1] : last))
-      return rass_fail(h, RASS_E_UNSUPPORTED,
-                       "row %lld of field %d is not above the rows already indexed (%lld): rewrites need a rebuild from "
-                       "host arrays", (long long)rw[(size_t)i], field, (long long)(i ? rw[(size_t)i - 1] : last));
+    if (rw[(size_t)i] < 0 || (i && rw[(size_t)i] <= rw[(size_t)i - 1]))
+      return rass_fail(h, RASS_E_INVALID, "the rows of a bulk must be ascending and distinct (row %lld after %lld)",
+                       (long long)rw[(size_t)i], (long long)(i ? rw[(size_t)i - 1] : -1));
   }
   if (rw[(size_t)n_rows - 1] > 0x7ffffff0LL) return rass_fail(h, RASS_E_INVALID, "too many documents");
+  // a row at or below one the field already holds is a REWRITE: the commit drops what the row held before (its
+  // generation no longer names the old source) and re-sorts instead of concatenating
+  const bool rewrites = rw[0] <= last;
   int rc;
   if ((rc = ensure_doclen(h, std::max(field + 1, std::max(b.F, b.doclen_F)), rw[(size_t)n_rows - 1] + 1))) return rc;
   int64_t *rows_dev = nullptr, *ip_dev = nullptr;
@@ -511,7 +550,8 @@ static int text_add_rows_impl(rass_engine* h, int field, const int64_t* rows, in
   if (rc) return rc;
   if (e != cudaSuccess) return rass_fail(h, RASS_E_CUDA, "text ingest: %s", cudaGetErrorString(e));
   if (b.field_last_row.size() <= (size_t)field) b.field_last_row.resize((size_t)field + 1, -1);
-  b.field_last_row[(size_t)field] = rw[(size_t)n_rows - 1];
+  b.field_last_row[(size_t)field] = std::max(b.field_last_row[(size_t)field], rw[(size_t)n_rows - 1]);
+  if (rewrites) b.has_rewrite = true;
   return RASS_OK;
 }
 
@@ -590,6 +630,157 @@ __global__ void cursor_seg_kernel(const int32_t* __restrict__ uterm, const int64
   if (u < n_uniq) cursor[base + uterm[u]] += uptr[u + 1] - uptr[u];
 }
 
+// ---- the re-sort commit: some pending segment rewrites rows the index already held ----
+// Every source's live postings (generation of (field, doc) == the source) become keys `new term << db | doc`, dead ones
+// the sentinel `V_new << db`; one radix sort of (key, tf) pairs IS the new CSR order.
+__global__ void gather_old_kernel(const int64_t* __restrict__ old_indptr, const int32_t* __restrict__ remap,
+                                  const uint8_t* __restrict__ tfield_old, int64_t V_old, int64_t nnz_old,
+                                  const int32_t* __restrict__ doc_old, const uint16_t* __restrict__ tf_old,
+                                  const uint32_t* __restrict__ gen, int64_t stride, int db, uint64_t sentinel,
+                                  uint64_t* __restrict__ keys, uint16_t* __restrict__ vals,
+                                  unsigned long long* __restrict__ n_live) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = false;
+  if (p < nnz_old) {
+    int64_t a = 0, b = V_old;
+    while (b - a > 1) {
+      const int64_t m = (a + b) >> 1;
+      if (old_indptr[m] <= p) a = m; else b = m;
+    }
+    const int32_t d = doc_old[p];
+    live = gen[(size_t)tfield_old[a] * stride + d] == 0u;
+    keys[p] = live ? (((uint64_t)(uint32_t)remap[a] << db) | (uint64_t)(uint32_t)d) : sentinel;
+    vals[p] = tf_old[p];
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, live);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_live, (unsigned long long)__popc(bal));
+}
+
+__global__ void gather_seg_kernel(const int32_t* __restrict__ uterm, const int64_t* __restrict__ uptr, int64_t n_uniq,
+                                  int64_t n_post, int64_t base, const int32_t* __restrict__ doc,
+                                  const uint16_t* __restrict__ tf, const uint32_t* __restrict__ gen_plane, uint32_t seg_id,
+                                  int db, uint64_t sentinel, uint64_t* __restrict__ keys, uint16_t* __restrict__ vals,
+                                  unsigned long long* __restrict__ n_live) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = false;
+  if (j < n_post) {
+    int64_t a = 0, b = n_uniq;
+    while (b - a > 1) {
+      const int64_t m = (a + b) >> 1;
+      if (uptr[m] <= j) a = m; else b = m;
+    }
+    const int32_t d = doc[j];
+    live = gen_plane[d] == seg_id;
+    keys[j] = live ? (((uint64_t)(base + uterm[a]) << db) | (uint64_t)(uint32_t)d) : sentinel;
+    vals[j] = tf[j];
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, live);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_live, (unsigned long long)__popc(bal));
+}
+
+__global__ void split_sorted_kernel(const uint64_t* __restrict__ keys, const uint16_t* __restrict__ vals, int64_t n,
+                                    uint64_t doc_mask, int32_t* __restrict__ doc, uint16_t* __restrict__ tf) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { doc[i] = (int32_t)(keys[i] & doc_mask); tf[i] = vals[i]; }
+}
+
+// indptr[t] = number of sorted keys below `t << db`
+__global__ void term_bounds_kernel(const uint64_t* __restrict__ keys, int64_t n, int db, int64_t V,
+                                   int64_t* __restrict__ indptr) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > V) return;
+  const uint64_t want = (uint64_t)t << db;
+  int64_t a = 0, b = n;
+  while (a < b) {
+    const int64_t m = (a + b) >> 1;
+    if (keys[m] < want) a = m + 1; else b = m;
+  }
+  indptr[t] = a;
+}
+
+static int commit_resort(rass_engine* h, const std::vector<int64_t>& base_new, const int32_t* remap_dev, int64_t V_old,
+                         int64_t nnz_old, int64_t V_new, int64_t N, cudaStream_t st, int64_t** indptr_out,
+                         int32_t** doc_out, uint16_t** tf_out) {
+  Bm25State& b = h->bm25;
+  int64_t total = nnz_old;
+  for (const TextSegment& s : b.pending) total += s.n_post;
+  if (total > 0x7fffffffLL) return rass_fail(h, RASS_E_UNSUPPORTED, "a re-sorting commit handles at most 2^31 - 1 postings");
+  int db = 1, tb = 1;
+  while (db < 32 && ((int64_t)1 << db) < std::max<int64_t>(N, 2)) ++db;
+  while (tb < 32 && ((int64_t)1 << tb) <= V_new) ++tb;          // the sentinel term V_new must be representable
+  const uint64_t sentinel = (uint64_t)V_new << db;
+  uint64_t *k0 = nullptr, *k1 = nullptr;
+  uint16_t *v0 = nullptr, *v1 = nullptr;
+  uint8_t* tfield_dev = nullptr;
+  unsigned long long* n_live_dev = nullptr;
+  void* tmp = nullptr;
+  int64_t* indptr_new = nullptr;
+  int32_t* doc_new = nullptr;
+  uint16_t* tf_new = nullptr;
+  auto done = [&](int code) {
+    cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(tfield_dev); cudaFree(n_live_dev); cudaFree(tmp);
+    if (code) { cudaFree(indptr_new); cudaFree(doc_new); cudaFree(tf_new); }
+    return code;
+  };
+#define RESORT_TRY(call)                                                                                       \
+  do {                                                                                                         \
+    cudaError_t e_ = (call);                                                                                   \
+    if (e_ != cudaSuccess)                                                                                     \
+      return done(rass_fail(h, e_ == cudaErrorMemoryAllocation ? RASS_E_OOM : RASS_E_CUDA, "%s failed: %s (%s:%d)", \
+                            #call, cudaGetErrorString(e_), __FILE__, __LINE__));                               \
+  } while (0)
+  const size_t n = std::max<size_t>((size_t)total, 1);
+  RESORT_TRY(cudaMalloc(&k0, n * 8));
+  RESORT_TRY(cudaMalloc(&k1, n * 8));
+  RESORT_TRY(cudaMalloc(&v0, n * 2));
+  RESORT_TRY(cudaMalloc(&v1, n * 2));
+  RESORT_TRY(cudaMalloc(&n_live_dev, 8));
+  RESORT_TRY(cudaMemsetAsync(n_live_dev, 0, 8, st));
+  RESORT_TRY(cudaMalloc(&tfield_dev, std::max<size_t>((size_t)V_old, 1)));
+  if (V_old)
+    RESORT_TRY(cudaMemcpyAsync(tfield_dev, b.term_field_host.data(), (size_t)V_old, cudaMemcpyHostToDevice, st));
+  const unsigned TB = 256;
+  auto blocks = [&](int64_t m) { return (unsigned)std::max<int64_t>((m + TB - 1) / TB, 1); };
+  if (nnz_old)
+    gather_old_kernel<<<blocks(nnz_old), TB, 0, st>>>(b.indptr, remap_dev, tfield_dev, V_old, nnz_old, b.doc, b.tf, b.gen_dev,
+                                                     b.doclen_stride, db, sentinel, k0, v0, n_live_dev);
+  int64_t off = nnz_old;
+  for (size_t i = 0; i < b.pending.size(); ++i) {
+    const TextSegment& s = b.pending[i];
+    if (!s.n_post) continue;
+    gather_seg_kernel<<<blocks(s.n_post), TB, 0, st>>>(s.uterm, s.uptr, s.n_uniq, s.n_post, base_new[(size_t)s.field], s.doc,
+                                                      s.tf, b.gen_dev + (size_t)s.field * b.doclen_stride, (uint32_t)i + 1,
+                                                      db, sentinel, k0 + off, v0 + off, n_live_dev);
+    off += s.n_post;
+  }
+  RESORT_TRY(cudaGetLastError());
+  cub::DoubleBuffer<uint64_t> keys(k0, k1);
+  cub::DoubleBuffer<uint16_t> vals(v0, v1);
+  size_t tmp_bytes = 0;
+  RESORT_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, vals, (int)total, 0, db + tb, st));
+  RESORT_TRY(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
+  if (total) RESORT_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, vals, (int)total, 0, db + tb, st));
+  unsigned long long n_live = 0;
+  RESORT_TRY(cudaMemcpyAsync(&n_live, n_live_dev, 8, cudaMemcpyDeviceToHost, st));
+  RESORT_TRY(cudaStreamSynchronize(st));
+  RESORT_TRY(cudaMalloc(&indptr_new, ((size_t)V_new + 1) * 8));
+  RESORT_TRY(cudaMalloc(&doc_new, std::max<size_t>((size_t)n_live, 1) * 4));
+  RESORT_TRY(cudaMalloc(&tf_new, std::max<size_t>((size_t)n_live, 1) * 2));
+  if (n_live)
+    split_sorted_kernel<<<blocks((int64_t)n_live), TB, 0, st>>>(keys.Current(), vals.Current(), (int64_t)n_live,
+                                                               ((uint64_t)1 << db) - 1, doc_new, tf_new);
+  term_bounds_kernel<<<blocks(V_new + 1), TB, 0, st>>>(keys.Current(), (int64_t)n_live, db, V_new, indptr_new);
+  RESORT_TRY(cudaGetLastError());
+  b.indptr_host.assign((size_t)V_new + 1, 0);
+  RESORT_TRY(cudaMemcpyAsync(b.indptr_host.data(), indptr_new, ((size_t)V_new + 1) * 8, cudaMemcpyDeviceToHost, st));
+  RESORT_TRY(cudaStreamSynchronize(st));
+#undef RESORT_TRY
+  *indptr_out = indptr_new;
+  *doc_out = doc_new;
+  *tf_out = tf_new;
+  return done(RASS_OK);
+}
+
 extern "C" int rass_text_commit(rass_engine* h, const int64_t* field_vocab, int F, int64_t N) {
   if (!h) return RASS_E_INVALID;
   if (h->shards) return rass_fail(h, RASS_E_UNSUPPORTED, "device-side text ingest runs on single-device handles");
@@ -645,6 +836,11 @@ extern "C" int rass_text_commit(rass_engine* h, const int64_t* field_vocab, int 
   auto blocks = [&](int64_t n) { return (unsigned)std::max<int64_t>((n + TB - 1) / TB, 1); };
   COMMIT_TRY(cudaMalloc(&remap_dev, std::max<size_t>((size_t)V_old, 1) * 4));
   if (V_old) COMMIT_TRY(cudaMemcpyAsync(remap_dev, remap.data(), (size_t)V_old * 4, cudaMemcpyHostToDevice, st));
+  if (b.has_rewrite) {
+    // rows were rewritten: drop what they held, re-sort everything that is live
+    if ((rc = commit_resort(h, base_new, remap_dev, V_old, nnz_old, V_new, N, st, &indptr_new, &doc_new, &tf_new)))
+      return done(rc);
+  } else {
   COMMIT_TRY(cudaMalloc(&df_new, ((size_t)V_new + 1) * 8));
   COMMIT_TRY(cudaMemsetAsync(df_new, 0, ((size_t)V_new + 1) * 8, st));
   if (V_old) old_df_kernel<<<blocks(V_old), TB, 0, st>>>(b.indptr, remap_dev, V_old, df_new);
@@ -678,10 +874,16 @@ extern "C" int rass_text_commit(rass_engine* h, const int64_t* field_vocab, int 
   }
   COMMIT_TRY(cudaGetLastError());
   COMMIT_TRY(cudaStreamSynchronize(st));
+  }
+  // every (field, doc) is the committed index's again
+  if (b.gen_dev)
+    COMMIT_TRY(cudaMemsetAsync(b.gen_dev, 0, (size_t)b.doclen_F * b.doclen_stride * sizeof(uint32_t), st));
+  b.has_rewrite = false;
 #undef COMMIT_TRY
   cudaFree(b.indptr); cudaFree(b.doc); cudaFree(b.tf);
   b.indptr = indptr_new; b.doc = doc_new; b.tf = tf_new;
   drop_segments(b);
+  cudaFree(b.scratch); b.scratch = nullptr; b.scratch_bytes = 0;
   b.field_vocab.assign(field_vocab, field_vocab + F);
   b.contiguous_fields = true;
   b.term_field_host.assign((size_t)V_new, 0);

@@ -25,20 +25,20 @@ class TextField:
         self._enc_lens: list[int] = []
         self.df = np.zeros(0, dtype=np.int64)        # document frequency per term, as of the last postings()
         self.doc_count = 0                           # documents with at least one token, as of the last postings()
-        # device-side ingest (TextIndex.sync_device): rows added since the last sync, in ascending row order; a change
-        # to a row at or below `last_row` cannot be appended and asks for a rebuild from host arrays
+        # device-side ingest (TextIndex.sync_device): rows added, rewritten or cleared since the last sync
         self.pending_rows: list[int] = []
         self.pending_ids: list[np.ndarray] = []
-        self.last_row = -1
-        self.rebuild = False
+        self.rebuild = False                         # set by whoever needs the rebuild from host arrays instead
 
     def set_row(self, row: int, text: str | None):
         self.set_row_tokens(row, analyze(text) if text else [])
 
     def set_row_tokens(self, row: int, toks: list[str]):
         if not toks:
-            if self.row_terms.pop(row, None) is not None:
-                self.dirty = self.rebuild = True
+            if self.row_terms.pop(row, None) is not None:       # the row loses the field: an empty rewrite
+                self.dirty = True
+                self.pending_rows.append(row)
+                self.pending_ids.append(np.zeros(0, dtype=np.int32))
             return
         v = self.vocab
         ids = np.fromiter((v.setdefault(t, len(v)) for t in toks), dtype=np.int32, count=len(toks))
@@ -51,20 +51,25 @@ class TextField:
     def _store(self, row: int, ids: np.ndarray):
         self.row_terms[row] = ids
         self.dirty = True
-        if row > self.last_row:
-            self.pending_rows.append(row)
-            self.pending_ids.append(ids)
-            self.last_row = row
-        else:
-            self.rebuild = True              # a rewrite (or a late first value) of an older row
+        self.pending_rows.append(row)
+        self.pending_ids.append(ids)
 
     def take_pending(self):
-        """(rows int64 [n], tok_indptr int64 [n + 1], tok_terms int32) of the rows added since the last call."""
+        """(rows int64 [n] ascending and distinct, tok_indptr int64 [n + 1], tok_terms int32) of the rows added,
+        rewritten or cleared since the last call (the last write to a row wins)."""
         rows = np.asarray(self.pending_rows, dtype=np.int64)
+        ids = self.pending_ids
+        if rows.size > 1 and not np.all(rows[1:] > rows[:-1]):
+            last = {}
+            for i, r in enumerate(self.pending_rows):
+                last[r] = i
+            keep = sorted(last.values(), key=lambda i: self.pending_rows[i])
+            rows = rows[keep]
+            ids = [self.pending_ids[i] for i in keep]
         indptr = np.zeros(rows.size + 1, dtype=np.int64)
         if rows.size:
-            indptr[1:] = np.cumsum([a.size for a in self.pending_ids])
-        terms = np.concatenate(self.pending_ids).astype(np.int32) if rows.size else np.zeros(0, np.int32)
+            indptr[1:] = np.cumsum([a.size for a in ids])
+        terms = np.concatenate(ids).astype(np.int32) if rows.size else np.zeros(0, np.int32)
         self.pending_rows, self.pending_ids = [], []
         return rows, indptr, terms
 
@@ -259,10 +264,11 @@ class TextIndex:
         return (indptr, np.concatenate(docs), np.concatenate(tfs), np.concatenate(fields), np.stack(lens))
 
     def sync_device(self, engine, n_rows: int):
-        """Bring the engine's postings up to date with the rows indexed so far.  New rows travel as token-id streams
-        and are inverted on the device (rass_text_add_rows + rass_text_commit: a segment per bulk, one merge pass);
-        a rewrite of an indexed row, a keyword field with several values in one document (omitted norms: its length
-        must read 1), or a handle spread over several GPUs takes the rebuild from host arrays instead."""
+        """Bring the engine's postings up to date with the rows indexed so far.  New, rewritten and cleared rows travel
+        as token-id streams and are inverted on the device (rass_text_add_rows + rass_text_commit: a segment per bulk,
+        one merge pass, or a re-sort when rows were rewritten); a keyword field with several values in one document
+        (omitted norms: its length must read 1) or a handle spread over several GPUs takes the rebuild from host arrays
+        instead."""
         flds = [self.fields[n] for n in self.order]
         kw_multi = any(self.types.get(n) == "keyword" and any(a.size > 1 for a in self.fields[n].pending_ids)
                        for n in self.order)

@@ -134,7 +134,56 @@ def test_incremental_index_scores_like_a_host_built_one():
             assert np.array_equal(sa.view(np.uint32), sb.view(np.uint32))
 
 
-def test_ingest_continues_a_host_built_index_and_rejects_rewrites():
+def test_rewritten_and_cleared_rows_are_replaced_at_the_commit():
+    """Index requests with a known _id: rows rewritten with other text, rows that lose the field, rows rewritten twice
+    before one commit, all mixed with fresh rows and a growing vocabulary, in two fields.  After every commit the index
+    equals the from-scratch build of the rows' CURRENT contents (the re-sorting commit)."""
+    rng = np.random.default_rng(29)
+    with _engine(dim=256) as e:
+        state = [dict(), dict()]
+        vocab = [300, 40]
+        n_rows = 0
+
+        def send(f, changes):
+            rows = sorted(changes)
+            indptr = np.zeros(len(rows) + 1, dtype=np.int64)
+            indptr[1:] = np.cumsum([changes[r].size for r in rows])
+            cat = np.concatenate([changes[r] for r in rows]) if indptr[-1] else np.zeros(0, np.int32)
+            e.text_add_rows(f, rows, indptr, cat)
+            for r in rows:
+                if changes[r].size:
+                    state[f][r] = changes[r]
+                else:
+                    state[f].pop(r, None)
+
+        for step in range(6):
+            vocab = [vocab[0] + 150, vocab[1] + 5]
+            fresh = int(rng.integers(200, 900))
+            for f in range(2):
+                ch = {r: _zipf_tokens(rng, vocab[f], int(rng.integers(1, 50))) for r in range(n_rows, n_rows + fresh)
+                      if not (f == 1 and r % 2)}
+                send(f, ch)
+            n_rows += fresh
+            if step >= 1:
+                for f in range(2):
+                    old = rng.choice(n_rows - fresh, size=60, replace=False)
+                    ch = {}
+                    for i, r in enumerate(old):
+                        ch[int(r)] = (np.zeros(0, np.int32) if i % 5 == 0
+                                      else _zipf_tokens(rng, vocab[f], int(rng.integers(1, 50))))
+                    send(f, ch)
+                    if step == 3:      # the same rows once more before the commit: the later segment wins
+                        send(f, {int(r): _zipf_tokens(rng, vocab[f], 7) for r in old[:20]})
+            e.text_commit(vocab, n_rows)
+            _check_export(e, state, vocab, n_rows)
+        # and the plain appending commit still follows a re-sorting one
+        send(0, {n_rows: np.array([1, 1, 2], np.int32), n_rows + 1: np.array([5], np.int32)})
+        n_rows += 2
+        e.text_commit(vocab, n_rows)
+        _check_export(e, state, vocab, n_rows)
+
+
+def test_ingest_continues_a_host_built_index_and_rejects_bad_streams():
     rng = np.random.default_rng(17)
     V0, n0 = 500, 2000
     toks = {r: _zipf_tokens(rng, V0, int(rng.integers(1, 40))) for r in range(n0)}
@@ -152,19 +201,25 @@ def test_ingest_continues_a_host_built_index_and_rejects_rewrites():
         toks.update(new)
         _check_export(e, [toks], [V1], n1)
         one = np.array([0, 3], dtype=np.int64)
-        with pytest.raises(rb.RassError) as err:             # row 100 is already indexed
-            e.text_add_rows(0, [100], one, np.array([1, 2, 3], np.int32))
-        assert "rebuild" in str(err.value)
+        with pytest.raises(rb.RassError) as err:             # rows of a bulk are ascending and distinct
+            e.text_add_rows(0, [n1 + 5, n1 + 5], np.array([0, 1, 2], np.int64), np.array([1, 2], np.int32))
+        assert "ascending" in str(err.value)
         with pytest.raises(rb.RassError):                    # negative term id
             e.text_add_rows(0, [n1], one, np.array([1, -2, 3], np.int32))
         with pytest.raises(rb.RassError):                    # vocabularies only grow
             e.text_commit([V1 - 1], n1)
         _check_export(e, [toks], [V1], n1)                   # nothing of that stuck
+        # a rewrite of a row the host-built index holds
+        toks[100] = np.array([3, 3, 9], np.int32)
+        e.text_add_rows(0, [100], one, toks[100])
+        e.text_commit([V1], n1)
+        _check_export(e, [toks], [V1], n1)
 
 
 def test_client_bulks_go_through_the_device_ingest():
-    """B200Client: bulks of chunk documents become searchable through device-side segments (no host CSR rebuild);
-    rewriting a document takes the rebuild path; both give the hits of a client that indexed everything at once."""
+    """B200Client: bulks of chunk documents become searchable through device-side segments (no host CSR rebuild),
+    a re-indexed document through the re-sorting commit; both give the hits of a client that indexed everything at
+    once."""
     from rassengine_b200.client import B200Client
     from rassengine_b200 import indexer as ix
     rng = np.random.default_rng(23)
@@ -197,7 +252,7 @@ def test_client_bulks_go_through_the_device_ingest():
     assert once == many
     t2 = c2._indices[n2].text
     assert t2.device_commits == 5 and t2.host_rebuilds == 0
-    c3, n3, again = make([(0, 300), (300, n_docs)], rewrite=7)  # same content rewritten: same hits, via the rebuild
+    c3, n3, again = make([(0, 300), (300, n_docs)], rewrite=7)  # same content rewritten: same hits
     assert again == once
     t3 = c3._indices[n3].text
-    assert t3.device_commits == 2 and t3.host_rebuilds == 1
+    assert t3.device_commits == 3 and t3.host_rebuilds == 0

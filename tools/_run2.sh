@@ -1,12 +1,16 @@
 cd /root/repo
-python -m pytest tests -m gpu -x -q > gpurun_out/r2w_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2w_pytest.log
-python tools/bench_client.py 300000 > gpurun_out/r2w_client.json 2> gpurun_out/r2w_client.err; echo "client rc=$?"; tail -2 gpurun_out/r2w_client.err; cat gpurun_out/r2w_client.json
-( time python bench.py > gpurun_out/r2w_bench.json 2> gpurun_out/r2w_bench.err ) 2> gpurun_out/r2w_time.txt; echo "bench rc=$?"; cat gpurun_out/r2w_time.txt
-( time python bench.py --impl reference > gpurun_out/r2w_ref.json 2> gpurun_out/r2w_ref.err ) 2>> gpurun_out/r2w_time.txt; echo "ref rc=$?"; tail -4 gpurun_out/r2w_time.txt
+python -m pytest tests/test_gpu_text_ingest.py -x -q > gpurun_out/r2x_ingest.log 2>&1; echo "ingest rc=$?"; tail -25 gpurun_out/r2x_ingest.log
+python -m pytest tests/test_gpu_hybrid.py tests/test_gpu_hostquery.py tests/test_gpu_lifecycle.py -x -q 2>&1 | tail -3
+python bench.py --workload cfg4 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2x_cfg4.json 2> gpurun_out/r2x_cfg4.err; echo "cfg4 rc=$?"; tail -2 gpurun_out/r2x_cfg4.err
+python -c "
+import json; d=json.loads(open('gpurun_out/r2x_cfg4.json').read().strip().splitlines()[-1]); print(d['value'], d['ingest'], d['parity']['fused_ids_equal_cpu_oracle'])"
+B="python bench.py --no-extras --no-cpu-parity --no-cpu-baseline --steps 300 --warmup 20"
+for rep in 1 2; do
+$B > gpurun_out/rw_poll_$rep.json 2>/dev/null
+RASS_DEBUG_RELAXED_WAIT=1 $B > gpurun_out/rw_relaxed_$rep.json 2>/dev/null
+done
 python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2w_bench.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','e2e','gpu_launches','clocks')})
-print(d['roofline']); print(d['parity']); print(d['sustained']); print(d['batch1']); print({k:(v if not isinstance(v,dict) else {kk:vv for kk,vv in v.items() if kk in ('qps','frac_of_tensor_peak','scan_tflops_per_gpu')}) for k,v in d['batched'].items()}); print({k:d['hybrid'][k] for k in ('qps','qps_e2e','ms_per_batch','knn_scan_ms','bm25_fusion_ms','frac_of_knn_ceiling','parity','ingest')}); print(d['cpu_baseline'])
-r=json.loads(open('gpurun_out/r2w_ref.json').read().strip().splitlines()[-1]); print(r)
+import json,glob
+for f in sorted(glob.glob('gpurun_out/rw_*.json')):
+    d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, round(d['value']), round(d['ms_per_step'],4), 'sust', round(d['sustained']['qps']), d['clocks']['sm_mhz'])
 PY
