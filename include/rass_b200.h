@@ -150,6 +150,10 @@ int rass_overwrite(rass_engine* h, int64_t row, const float* v_host);
 int rass_tombstone(rass_engine* h, int64_t row);
 int rass_count(const rass_engine* h, int64_t* out_live_rows);
 int rass_rows(const rass_engine* h, int64_t* out_total_rows);
+/* How the store is held: *capacity_rows = rows the mapped memory holds; *grows_in_place = 1 when the arrays live in
+ * reserved virtual address ranges and grow by mapping more physical chunks (no copy, no second resident array:
+ * csrc/vmm.cu), 0 when they are cudaMalloc'ed and grow by copy (a driver without the virtual-memory API). */
+int rass_store_info(const rass_engine* h, int64_t* capacity_rows, int* grows_in_place);
 /* stored values (fp32, or the bf16 values widened when RASS_BF16_ONLY) back to the host: [n, dim] */
 int rass_read_rows(rass_engine* h, int64_t first_row, int64_t n, float* out_host);
 /* same for a list of rows (the `_source.embedding` of the hits of one search): one gather, one copy */

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "rass_tombstone": (C.c_int, [_P, C.c_int64]),
     "rass_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "rass_rows": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "rass_store_info": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "rass_read_rows": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     "rass_read_rows_list": (C.c_int, [_P, _P, C.c_int64, _P]),
     "rass_set_row_filter_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),

@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["engine.cu", "store.cu", "scan_stream.cu", "scan_umma.cu", "scan_gemm.cu", "finish.cu", "bm25.cu", "postings.cu", "sharded.cu", "filtered.cu"]
+SOURCES = ["engine.cu", "vmm.cu", "store.cu", "scan_stream.cu", "scan_umma.cu", "scan_gemm.cu", "finish.cu", "bm25.cu", "postings.cu", "sharded.cu", "filtered.cu"]
 LIB = os.path.join(HERE, "librass_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -119,6 +119,18 @@ struct DevScalars {
                       // last one zeroes both)
 };
 
+// a device array that grows in place (vmm.cu): reserved address range, physical chunks mapped on demand
+struct VmArray {
+  void* base = nullptr;
+  size_t reserved = 0, mapped = 0, chunk = 0;
+  int device = 0;
+  std::vector<unsigned long long> handles;   // CUmemGenericAllocationHandle of every mapped chunk
+};
+bool vm_available();
+bool vm_reserve(VmArray* a, int device, size_t max_bytes, size_t chunk_hint);
+int vm_grow(VmArray* a, size_t bytes);       // 0 ok, 1 out of memory, 2 other failure
+void vm_free(VmArray* a);
+
 struct rass_engine {
   int dim = 0, dim_pad = 0, metric = 0, device = 0;
   uint32_t flags = 0;
@@ -132,6 +144,10 @@ struct rass_engine {
   double* norm64 = nullptr;         // [cap] ||x|| accumulated in fp64 from the stored values
   float* sa = nullptr;              // [cap] scan scale:  cosine 1/||x|| (0 for zero rows), L2 1
   float* sb = nullptr;              // [cap] scan offset: cosine 0, L2 -0.5||x||^2; -inf = tombstone
+  // the five arrays above live in growable virtual-memory arrays when the driver offers them (vm[i].base == the
+  // pointer); otherwise they are cudaMalloc'ed and grow by copy
+  VmArray vm[5];
+  bool use_vm = false;
   DevScalars* scal = nullptr;       // device
   DevScalars* scal_host = nullptr;  // pinned mirror
   cudaStream_t stream = nullptr, user_stream = nullptr, copy_stream = nullptr;

@@ -48,12 +48,59 @@ static int dev_realloc(rass_engine* h, T** p, size_t old_n, size_t new_n, cudaSt
 
 static int ensure_capacity(rass_engine* h, int64_t rows) {
   if (rows <= h->cap) return RASS_OK;
-  int64_t ncap = std::max<int64_t>(rows, std::max<int64_t>(h->cap * 2, 1024));
-  if (ncap > 0xfffffff0LL) return rass_fail(h, RASS_E_INVALID, "a shard holds at most 2^32-16 rows");
+  if (rows > 0xfffffff0LL) return rass_fail(h, RASS_E_INVALID, "a shard holds at most 2^32-16 rows");
   cudaStream_t st = eng_stream(h);
-  const size_t o = (size_t)h->n_rows, n = (size_t)ncap, d = (size_t)h->dim_pad;
+  const size_t d = (size_t)h->dim_pad;
+  const bool bf16_only = (h->flags & RASS_BF16_ONLY) != 0;
+  // bytes per row of x32, x16, norm64, sa, sb
+  const size_t per_row[5] = {bf16_only ? 0 : d * 4, d * 2, 8, 4, 4};
+  if (h->cap == 0 && !h->use_vm && vm_available()) {
+    // first allocation: reserve address space for as many rows as the device could ever hold of each array
+    size_t free_b = 0, total_b = 0;
+    bool ok = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess;
+    for (int i = 0; ok && i < 5; ++i)
+      if (per_row[i]) {
+        const size_t max_rows = std::min<size_t>(0xfffffff0ULL, total_b / per_row[i] + 1);
+        ok = vm_reserve(&h->vm[i], h->device, std::max<size_t>(max_rows, (size_t)rows) * per_row[i], 32768 * per_row[i]);
+      }
+    if (!ok) for (int i = 0; i < 5; ++i) vm_free(&h->vm[i]);
+    h->use_vm = ok;
+  }
+  if (h->use_vm) {
+    // grow in place: map enough chunks for `rows` (plus head room: an eighth, at least 64k rows) behind the same
+    // pointers -- no copy, no second resident array
+    // (none on the first allocation: a caller that passes capacity_rows has sized the store)
+    int64_t ncap = std::max<int64_t>(h->cap == 0 ? rows : rows + std::max<int64_t>(rows / 8, 65536), 1024);
+    ncap = std::min<int64_t>(ncap, 0xfffffff0LL);
+    for (int pass = 0; pass < 2; ++pass) {
+      int bad = 0;
+      for (int i = 0; i < 5 && !bad; ++i)
+        if (per_row[i]) {
+          if ((size_t)ncap * per_row[i] > h->vm[i].reserved) ncap = (int64_t)(h->vm[i].reserved / per_row[i]);
+          bad = vm_grow(&h->vm[i], (size_t)ncap * per_row[i]);
+        }
+      if (!bad) break;
+      if (pass == 1 || ncap == rows)
+        return rass_fail(h, bad == 1 ? RASS_E_OOM : RASS_E_CUDA, "cannot map device memory for %lld rows", (long long)rows);
+      ncap = rows;                 // out of memory with the head room: retry with exactly what is needed
+    }
+    if (ncap < rows) return rass_fail(h, RASS_E_OOM, "%lld rows exceed the address range reserved for the store", (long long)rows);
+    // the arrays' capacity in rows is what the smallest mapping holds (chunks are not row-aligned)
+    for (int i = 0; i < 5; ++i)
+      if (per_row[i]) ncap = std::min<int64_t>(ncap, (int64_t)(h->vm[i].mapped / per_row[i]));
+    h->x32 = bf16_only ? nullptr : (float*)h->vm[0].base;
+    h->x16 = (__nv_bfloat16*)h->vm[1].base;
+    h->norm64 = (double*)h->vm[2].base;
+    h->sa = (float*)h->vm[3].base;
+    h->sb = (float*)h->vm[4].base;
+    h->cap = ncap;
+    return RASS_OK;
+  }
+  int64_t ncap = std::max<int64_t>(rows, std::max<int64_t>(h->cap * 2, 1024));
+  if (ncap > 0xfffffff0LL) ncap = 0xfffffff0LL;
+  const size_t o = (size_t)h->n_rows, n = (size_t)ncap;
   int rc;
-  if (!(h->flags & RASS_BF16_ONLY))
+  if (!bf16_only)
     if ((rc = dev_realloc(h, &h->x32, o * d, n * d, st))) return rc;
   if ((rc = dev_realloc(h, &h->x16, o * d, n * d, st))) return rc;
   if ((rc = dev_realloc(h, &h->norm64, o, n, st))) return rc;
@@ -129,7 +176,11 @@ extern "C" int rass_destroy(rass_engine* h) {
   if (!h) return RASS_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  cudaFree(h->x32); cudaFree(h->x16); cudaFree(h->norm64); cudaFree(h->sa); cudaFree(h->sb);
+  if (h->use_vm) {
+    for (int i = 0; i < 5; ++i) vm_free(&h->vm[i]);
+  } else {
+    cudaFree(h->x32); cudaFree(h->x16); cudaFree(h->norm64); cudaFree(h->sa); cudaFree(h->sb);
+  }
   cudaFree(h->scal); cudaFreeHost(h->scal_host);
   cudaFree(h->dev_stage);
   cudaFree(h->q_raw); cudaFree(h->q_hat); cudaFree(h->q16); cudaFree(h->q_norm); cudaFree(h->q_rho); cudaFree(h->q_gthr);
@@ -232,6 +283,14 @@ extern "C" int rass_count(const rass_engine* h, int64_t* out) {
 extern "C" int rass_rows(const rass_engine* h, int64_t* out) {
   if (!h || !out) return RASS_E_INVALID;
   *out = h->n_rows;
+  return RASS_OK;
+}
+
+extern "C" int rass_store_info(const rass_engine* h, int64_t* capacity_rows, int* grows_in_place) {
+  if (!h) return RASS_E_INVALID;
+  const rass_engine* e = h->shards ? sharded_first(const_cast<rass_engine*>(h)) : h;
+  if (capacity_rows) *capacity_rows = e->cap;
+  if (grows_in_place) *grows_in_place = e->use_vm ? 1 : 0;
   return RASS_OK;
 }
 

@@ -111,6 +111,12 @@ class Engine:
         self._check(self._lib.rass_load(self._h, path.encode()))
 
     # -- store ------------------------------------------------------------------------------------------
+    def store_info(self) -> dict:
+        """{"capacity_rows", "grows_in_place"}: see rass_store_info."""
+        cap, vm = C.c_int64(), C.c_int()
+        self._check(self._lib.rass_store_info(self._h, C.byref(cap), C.byref(vm)))
+        return {"capacity_rows": cap.value, "grows_in_place": bool(vm.value)}
+
     def append(self, rows: np.ndarray) -> int:
         rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, self.dim)
         first = C.c_int64(-1)

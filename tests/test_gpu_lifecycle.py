@@ -180,3 +180,41 @@ def test_hybrid_requests_share_the_knn_pass_under_a_batch_window():
     assert mb is not None and mb.requests == 10 and mb.batches < 10
     plain.close()
     windowed.close()
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_store_grows_in_place_across_many_appends(bf16):
+    """The store's arrays grow by mapping more physical chunks behind the same pointers (csrc/vmm.cu; cudaMalloc + copy
+    where the driver lacks the API): rows appended in uneven batches across several chunk boundaries read back unchanged,
+    tombstones and overwrites made before a growth survive it, and searches in between and at the end equal the oracle."""
+    import rassengine_b200 as rb
+    flags = rb.BF16_ONLY if bf16 else 0
+    n, dim = 150_000, 1024                       # x32 chunks hold 32k rows, so the store grows several times
+    X = synth.embeddings(n, dim, 51)
+    Q = synth.embeddings(5, dim, 52)
+    with rb.Engine(dim=dim, flags=flags) as e:
+        cuts = [0, 1, 700, 33_000, 33_001, 70_000, 131_073, n]
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            assert e.append(X[lo:hi]) == lo
+            if hi == 700:
+                e.tombstone(5)
+                e.overwrite(9, X[100])
+            if hi in (33_001, n):
+                stored = e.read_rows(0, hi)
+                Xs = stored.copy()
+                rows, scores = e.search_knn(Q, 10)
+                alive = np.ones(hi, dtype=bool)
+                alive[5] = False
+                want_rows, _, want_scores = knn.knn_exact(Xs, Q, 10, alive=alive)
+                assert np.array_equal(rows, want_rows)
+                np.testing.assert_allclose(scores, want_scores, rtol=1e-5)
+        stored = e.read_rows(0, n)
+        if not bf16:
+            keep = np.ones(n, dtype=bool)
+            keep[9] = False
+            assert np.array_equal(stored[keep], X[keep]) and np.array_equal(stored[9], X[100])
+        assert e.rows() == n and e.count() == n - 1
+        info = e.store_info()
+        assert info["capacity_rows"] >= n
+        import os
+        assert info["grows_in_place"] == ("RASS_DEBUG_NO_VMM" not in os.environ)      # the B200 driver has the API
