@@ -1,7 +1,7 @@
 cd /root/repo
-python -m pytest tests/test_gpu_lifecycle.py -x -q > gpurun_out/r2z_life.log 2>&1; echo "lifecycle rc=$?"; tail -15 gpurun_out/r2z_life.log
-python -m pytest tests -m gpu -x -q > gpurun_out/r2z_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2z_pytest.log
-python bench.py --steps 20 --warmup 5 --no-extras --no-cpu-baseline > gpurun_out/r2z_bench.json 2> gpurun_out/r2z_bench.err; echo "bench rc=$?"; tail -2 gpurun_out/r2z_bench.err
-python -c "
-import json; d=json.loads(open('gpurun_out/r2z_bench.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['parity'].get('ids_equal_cpu_oracle'))"
-nvidia-smi --query-gpu=memory.used --format=csv
+for rows in 2500000 10000000; do
+for ov in 1 0 1 0; do
+python tools/bench_sharded.py --rows $rows --overlap $ov --steps 400 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print($rows, 'overlap', d['async_overlap'], round(d['qps']), round(d['ms_per_step'],4), d['ids_equal_cpu_oracle'], d['batches_repeated'])"
+done
+done

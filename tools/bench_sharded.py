@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--overlap", type=int, default=1, help="1: every shard runs its two async slots on their own streams")
     ap.add_argument("--check", type=int, default=8, help="queries compared with the fp64 exact scan of every shard")
     a = ap.parse_args()
     D, CH = 1024, 500_000
@@ -49,6 +50,7 @@ def main():
         del x
     fill_s = time.time() - t0
     e.set_stream(torch.cuda.current_stream().cuda_stream)
+    e.set_async_overlap(bool(a.overlap))
     gq = torch.Generator(device=dev).manual_seed(5678)
     B, k = a.batch, a.k
     qs = [torch.randn((B, D), generator=gq, device=dev) for _ in range(8)]
@@ -115,7 +117,7 @@ def main():
            "ids_equal_cpu_oracle": bool(np.array_equal(r_fast, o_rows) and np.array_equal(r_async, o_rows)),
            "queries_checked_cpu": int(n_chk),
            "max_score_rel_err": float(np.max(np.abs(s_fast - oknn.score_from_cos(o_cos)) / oknn.score_from_cos(o_cos))),
-           "fill_s": round(fill_s, 1), "exchange": "peer stores into the coordinator's gather buffer + one merge kernel"}
+           "fill_s": round(fill_s, 1), "async_overlap": bool(a.overlap), "exchange": "peer stores into the coordinator's gather buffer + one merge kernel"}
     print(json.dumps(out), flush=True)
     e.close()
 
