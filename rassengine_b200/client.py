@@ -81,7 +81,8 @@ def _gpu_count() -> int:
 
 
 class _Index:
-    def __init__(self, name: str, body: dict | None, device: int, knn_filter: str = "post", devices=None):
+    def __init__(self, name: str, body: dict | None, device: int, knn_filter: str = "post", devices=None,
+                 sim_boost=1.0):
         self.name = name
         self.body = body or {}
         self.device = device
@@ -111,7 +112,7 @@ class _Index:
         types = {f: spec["type"] for f, spec in props.items()
                  if isinstance(spec, dict) and spec.get("type") in ("text", "keyword")}
         types.setdefault(TEXT_FIELD, "text")
-        self.text = TextIndex(types)
+        self.text = TextIndex(types, sim_boost)
         self.n_docs = 0
         self.host_views: dict = {}               # hostquery.FieldView cache (N4 host-side queries)
         self.kw: dict[str, dict[object, list[int]]] = {f: {} for f in FILTER_FIELDS}   # field -> value -> rows
@@ -468,7 +469,7 @@ class IndicesClient:
     def create(self, index: str, body: dict | None = None, **_) -> dict:
         if index in self._c._indices:
             raise RequestError(f"resource_already_exists_exception: index [{index}] already exists")
-        idx = _Index(index, body, self._c.device, self._c.knn_filter, self._c.devices)
+        idx = _Index(index, body, self._c.device, self._c.knn_filter, self._c.devices, self._c.sim_boost)
         idx.batch_window_s = self._c.batch_window_s
         self._c._indices[index] = idx
         return {"acknowledged": True, "shards_acknowledged": True, "index": index}
@@ -488,9 +489,12 @@ class B200Client:
     """Drop-in for `OpenSearch(hosts=[...], ...)`; connection arguments are accepted and ignored."""
 
     def __init__(self, hosts=None, device: int = 0, knn_filter: str = "post", batch_window_ms: float | None = None,
-                 devices=None, **_ignored):
+                 devices=None, bm25_legacy_boost: bool = False, **_ignored):
         """knn_filter: "post" (default) applies bool.filter to the k nearest neighbours, as OpenSearch's nmslib engine
-        does; "pre" returns the exact top-k among the rows passing the filter (device-side pass mask in the scan)."""
+        does; "pre" returns the exact top-k among the rows passing the filter (device-side pass mask in the scan).
+        bm25_legacy_boost: score text clauses the way Lucene's LegacyBM25Similarity does -- every boost times
+        float32(1 + k1) = 2.2f before the scorer is built, otherwise the same arithmetic (oracle/SEMANTICS.md: which of
+        the two a given OpenSearch release ships is part of what is unpinned; the default is the form SURVEY.md states)."""
         if knn_filter not in ("post", "pre"):
             raise ValueError("knn_filter must be 'post' or 'pre'")
         self.device = device
@@ -498,6 +502,7 @@ class B200Client:
         # RASS_B200_DEVICES or the create body's settings.index.number_of_shards decide (resolve_devices)
         self.devices = list(devices) if devices else None
         self.knn_filter = knn_filter
+        self.sim_boost = np.float32(1.0) + np.float32(1.2) if bm25_legacy_boost else np.float32(1.0)
         # batch_window_ms: concurrent knn searches (threads) wait up to this long to share one corpus pass
         self.batch_window_s = None if batch_window_ms is None else batch_window_ms / 1e3
         self._indices: dict[str, _Index] = {}
@@ -616,7 +621,7 @@ class B200Client:
             name = meta["name"]
             if name in self._indices:
                 raise RequestError(f"resource_already_exists_exception: index [{name}] already exists")
-            idx = _Index(name, meta["body"], self.device, self.knn_filter, self.devices)
+            idx = _Index(name, meta["body"], self.device, self.knn_filter, self.devices, self.sim_boost)
             idx.batch_window_s = self.batch_window_s
             idx.ids, idx.sources, idx.has_vec = meta["ids"], meta["sources"], meta["has_vec"]
             idx.n_docs = meta["n_docs"]

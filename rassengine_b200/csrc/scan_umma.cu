@@ -20,7 +20,7 @@
 #define UMMA_KBLK 64                       // bf16 elements per k-block (128 bytes: one swizzle row)
 #define UMMA_STAGE_BYTES (UMMA_ROWS * 128)  // 16 KB
 #define UMMA_QBLK_BYTES (UMMA_NQ * 128)     // 8 KB
-#define UMMA_STAGES 6
+#define UMMA_STAGES 6                       // smem stages of the ring (run-time: 2..UMMA_STAGES, see umma_launch)
 #define UMMA_ACC 4                          // TMEM accumulator stages (64 columns each)
 #define UMMA_TMEM_COLS 256
 #define UMMA_THREADS 256
@@ -57,13 +57,13 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
                      int k_blocks, int q_row0, float* __restrict__ pool_key, uint32_t* __restrict__ pool_row,
                      float* __restrict__ pool_thr, int* __restrict__ pool_cnt, size_t pool_entries, int n_segs,
                      uint32_t* __restrict__ gthr, int* __restrict__ tile_ctr, float* __restrict__ dbg_out,
-                     int relaxed_wait, unsigned long long* __restrict__ dbg_t) {
+                     int relaxed_wait, unsigned long long* __restrict__ dbg_t, int n_stages) {
   extern __shared__ unsigned char smem_dyn[];
   // 128B-swizzled tiles need 1024-byte alignment: [ Q: k_blocks * 8 KB ][ stages: UMMA_STAGES * 16 KB ][ UmmaSmem ]
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* q_smem = smem;
   unsigned char* x_smem = smem + (size_t)k_blocks * UMMA_QBLK_BYTES;
-  UmmaSmem* ss = reinterpret_cast<UmmaSmem*>(x_smem + (size_t)UMMA_STAGES * UMMA_STAGE_BYTES);
+  UmmaSmem* ss = reinterpret_cast<UmmaSmem*>(x_smem + (size_t)n_stages * UMMA_STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
           mbar_expect_tx(&ss->full[stage], UMMA_STAGE_BYTES);
           tma_load_2d(&map_x, &ss->full[stage], x_smem + (size_t)stage * UMMA_STAGE_BYTES, kb * UMMA_KBLK,
                       tile * UMMA_ROWS, kEvictFirst);
-          if (++stage == UMMA_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         tile = next;
       }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1)
             umma_bf16(d_tmem, smem_desc_sw128(a_addr + k * 32), smem_desc_sw128(b_addr + k * 32), kIdesc,
                       (uint32_t)((kb | k) != 0));
           umma_commit(&ss->empty[stage]);   // frees the smem stage once these MMAs have read it
-          if (++stage == UMMA_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&ss->acc_full[acc]);    // accumulator complete
         if (++acc == UMMA_ACC) { acc = 0; acc_phase ^= 1; }
@@ -332,8 +332,19 @@ int encode_rows_map(rass_engine* h, void* map_out, const void* base, int64_t row
   return RASS_OK;
 }
 
+// stages of the TMA ring: UMMA_STAGES by default; RASS_DEBUG_UMMA_STAGES=n (2..UMMA_STAGES) for the measurement of what
+// a smaller ring costs (a ring of 5 would leave room for the seed / finish kernels next to a scan CTA)
+static int umma_stages() {
+  static const int n = [] {
+    const char* e = getenv("RASS_DEBUG_UMMA_STAGES");
+    const int v = e ? atoi(e) : UMMA_STAGES;
+    return v < 2 ? 2 : (v > UMMA_STAGES ? UMMA_STAGES : v);
+  }();
+  return n;
+}
+
 static size_t umma_smem_bytes(const rass_engine* h) {
-  return (size_t)(h->dim_pad / UMMA_KBLK) * UMMA_QBLK_BYTES + (size_t)UMMA_STAGES * UMMA_STAGE_BYTES +
+  return (size_t)(h->dim_pad / UMMA_KBLK) * UMMA_QBLK_BYTES + (size_t)umma_stages() * UMMA_STAGE_BYTES +
          sizeof(UmmaSmem) + 1024;
 }
 
@@ -405,7 +416,7 @@ static int umma_launch(rass_engine* h, int q0, int64_t n_rows, int seg, float* d
     scan_umma_kernel<S><<<grid, UMMA_THREADS, smem, st>>>(                                                           \
         *(CUtensorMap*)h->tmap_x, *(CUtensorMap*)h->tmap_q, h->sa, h->sb_scan, n_rows, n_tiles, h->dim_pad / UMMA_KBLK, \
         q0, h->pool_key, h->pool_row, h->pool_thr, h->pool_cnt, h->pool_entries, scan_umma_segs(h), h->q_gthr + q0,  \
-        static_tiles ? nullptr : &h->scal->tile_ctr[0], dbg_out, relaxed_wait, dbg_t);                                                                                 \
+        static_tiles ? nullptr : &h->scal->tile_ctr[0], dbg_out, relaxed_wait, dbg_t, umma_stages());                                                                                 \
   } while (0)
   if (seg == 512) RASS_UMMA_LAUNCH(512); else RASS_UMMA_LAUNCH(256);
 #undef RASS_UMMA_LAUNCH

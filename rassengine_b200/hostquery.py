@@ -228,10 +228,11 @@ class HostSearcher:
             positions.append(ids)
         if len(positions) == 1:
             # one position: a plain disjunction of term queries
-            groups = [(positions[0], [np.float32(boost * v.idf(int(v.df[t]))) for t in positions[0]])]
+            bo = np.float32(np.float32(boost) * v.fld.sim_boost)
+            groups = [(positions[0], [np.float32(bo * v.idf(int(v.df[t]))) for t in positions[0]])]
             return self._field_terms_score(v, groups, "or")
         idf = np.float32(sum(float(v.idf(int(v.df[t]))) for ids in positions for t in ids))
-        w = np.float32(boost * idf)
+        w = np.float32(np.float32(np.float32(boost) * v.fld.sim_boost) * idf)
         cand = None
         for ids in positions:
             rows = np.unique(np.concatenate([v.doc[v.indptr[t]:v.indptr[t + 1]] for t in ids]))

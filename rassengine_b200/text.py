@@ -29,6 +29,9 @@ class TextField:
         self.pending_rows: list[int] = []
         self.pending_ids: list[np.ndarray] = []
         self.rebuild = False                         # set by whoever needs the rebuild from host arrays instead
+        # what the similarity multiplies every query boost by before it builds the scorer: 1 (Lucene's BM25Similarity,
+        # what SURVEY.md 8c states) or float32(1 + k1) = 2.2f (LegacyBM25Similarity: B200Client(bm25_legacy_boost=True))
+        self.sim_boost = np.float32(1.0)
 
     def set_row(self, row: int, text: str | None):
         self.set_row_tokens(row, analyze(text) if text else [])
@@ -127,7 +130,7 @@ class TextField:
         """Plain term queries (no fuzziness): (term ids, float32 weights = float(boost) * idf), query order."""
         import math
         ids, ws = [], []
-        bo = np.float32(boost)
+        bo = np.float32(np.float32(boost) * self.sim_boost)
         for tok in tokens:
             t = self.vocab.get(tok, -1)
             if t < 0 or t >= self.df.size or self.df[t] == 0:
@@ -147,7 +150,7 @@ class TextField:
         import math
         ids: list[int] = []
         ws: list[np.float32] = []
-        bo = np.float32(boost)
+        bo = np.float32(np.float32(boost) * self.sim_boost)
         for tok in (analyze(text) if isinstance(text, str) else text):
             hit = self._fuzzy.get(tok)
             if hit is None:
@@ -195,7 +198,8 @@ class TextIndex:
     term ids [base[f], base[f] + V_f).  A keyword field is a field whose "analyzer" emits the whole value as one token
     (no lower-casing), which is how Lucene indexes it; its norms are omitted, i.e. every value counts as length 1."""
 
-    def __init__(self, field_types: dict[str, str]):
+    def __init__(self, field_types: dict[str, str], sim_boost=1.0):
+        self.sim_boost = np.float32(sim_boost)    # handed to every field (TextField.sim_boost)
         self.types = dict(field_types)            # field name -> "text" | "keyword"
         self.fields: dict[str, TextField] = {}    # created when the first document carries the field
         self.order: list[str] = []                # field id -> name
@@ -231,6 +235,7 @@ class TextIndex:
                 if not toks:
                     continue
                 fld = self.fields[name] = TextField()
+                fld.sim_boost = self.sim_boost
                 self.order.append(name)
             before = fld.dirty
             fld.dirty = False

@@ -238,3 +238,66 @@ def test_phrase_longer_than_the_field_value_is_no_match_not_an_error(setup):
     assert client.search(index=name, body=body)["hits"]["hits"] == []
     body["query"]["multi_match"]["query"] = "chest pain"
     assert {h["_id"] for h in client.search(index=name, body=body)["hits"]["hits"]} == {"c1", "c2", "c3"}
+
+
+def test_legacy_bm25_boost_is_the_same_scorer_with_the_boost_times_one_plus_k1():
+    """B200Client(bm25_legacy_boost=True): Lucene-misc's LegacyBM25Similarity (what Elasticsearch 7 kept its old scores
+    with) multiplies every query boost by float32(1 + k1) = 2.2f before the BM25 scorer is built; everything after is
+    the same arithmetic.  So the phrase and the fuzzy best_fields searches of such a client equal the oracle called with
+    that boost -- and the ranking of a pure text query does not move (oracle/SEMANTICS.md)."""
+    from rassengine_b200.client import B200Client
+    from rassengine_b200 import indexer as ix
+    f22 = np.float32(1.0) + np.float32(1.2)
+    client = B200Client(bm25_legacy_boost=True)
+    name = ix.get_index_name("legacy")
+    ix.ensure_index_exists(client, name, ix.index_body(16))
+    idx = client._get(name)
+    with idx.lock:
+        for row, d in enumerate(DOCS):
+            idx.sources.append(dict(d))
+            idx.has_vec.append(False)
+            idx.ids.append(d["doc_id"])
+            idx.row_of[d["doc_id"]] = row
+            idx.text.set_doc(row, d, fresh=True)
+            idx._kw_add(row, d)
+        idx.n_docs = len(DOCS)
+    types = {f.split("^")[0]: "text" for f in ix.TEXT_FIELDS}
+    types.update({f.split("^")[0]: "keyword" for f in ix.KEYWORD_FIELDS})
+    types["patientId"] = "keyword"
+    fields = multifield.build(DOCS, types)
+    idxr = ix.B200Indexer(client, name)
+
+    def phrase(specs, cb):
+        best = np.zeros(len(DOCS), dtype=np.float32)
+        for fname, fb in specs:
+            f = fields.get(fname)
+            if f is not None:
+                toks = multifield.field_tokens(DOCS, fname, f.kind)
+                bo = np.float32(np.float32(np.float32(cb) * np.float32(fb)) * f22)
+                best = np.maximum(best, multifield.phrase_score(f, toks, "chest pain", bo, prefix=False))
+        return best
+
+    total = phrase(_spec(ix.TEXT_FIELDS), 2.0).astype(np.float64) + phrase(_spec(ix.KEYWORD_FIELDS), 1.0).astype(np.float64)
+    want = _ranked(total.astype(np.float32))[:10]
+    hits = idxr.exact_match_search("chest pain", k=10)
+    assert [h[0]["doc_id"] for h in hits] == [DOCS[r]["doc_id"] for r in want] and len(hits) >= 4
+    np.testing.assert_allclose([h[1] for h in hits], total.astype(np.float32)[want], rtol=1e-6)
+    # against the default client: same order, scores 2.2 times larger (up to the rounding of the boost product)
+    base = B200Client()
+    ix.ensure_index_exists(base, name, ix.index_body(16))
+    bidx = base._get(name)
+    with bidx.lock:
+        for row, d in enumerate(DOCS):
+            bidx.sources.append(dict(d))
+            bidx.has_vec.append(False)
+            bidx.ids.append(d["doc_id"])
+            bidx.row_of[d["doc_id"]] = row
+            bidx.text.set_doc(row, d, fresh=True)
+            bidx._kw_add(row, d)
+        bidx.n_docs = len(DOCS)
+    ref = ix.B200Indexer(base, name).comparison_search("diabetis chest", k=10)
+    got = idxr.comparison_search("diabetis chest", k=10)
+    assert [h[0]["doc_id"] for h in got] == [h[0]["doc_id"] for h in ref] and len(got) == 4
+    np.testing.assert_allclose([h[1] for h in got], [float(f22) * h[1] for h in ref], rtol=1e-6)
+    client.close()
+    base.close()

@@ -1,5 +1,15 @@
 cd /root/repo
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --no-cpu-parity > gpurun_out/r3b_plain.json 2> gpurun_out/r3b_plain.err; echo "plain rc=$?"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2_cfg2.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --no-cpu-parity > gpurun_out/r3b_ncu_l.log 2>&1; echo "launch list rc=$?"
-ncu --set full --import-source on --clock-control none -k regex:scan_umma -s 4 -c 1 -o gpurun_out/prof_r2_umma -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --no-cpu-parity > gpurun_out/r3b_ncu_f.log 2>&1; echo "full rc=$?"
-ls -la gpurun_out/prof_r2_umma.ncu-rep gpurun_out/launches_r2_cfg2.csv
+B="python bench.py --no-extras --no-cpu-parity --no-cpu-baseline"
+for rep in 1 2; do
+for st in 6 5 4; do
+RASS_DEBUG_UMMA_STAGES=$st $B --rows 10000000 --steps 100 --warmup 10 > gpurun_out/st_10M_${st}_$rep.json 2>/dev/null
+RASS_DEBUG_UMMA_STAGES=$st $B --rows 1250000 --steps 800 --warmup 20 > gpurun_out/st_1M_${st}_$rep.json 2>/dev/null
+done
+done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/st_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, round(d['value']), round(d['ms_per_step'],4), 'kernel_ms', round(d['roofline']['kernel_ms'],4), 'sust', round(d['sustained']['qps']), d['clocks']['sm_mhz'], d['parity']['fast_path_ids_equal_fp64_scan'])
+    except Exception as e: print(f, 'ERR', e)
+PY
