@@ -213,7 +213,8 @@ int rass_bm25_build_fields(rass_engine* h, const int64_t* indptr, const int32_t*
  * (repeats included; only the counts matter to BM25).  The bulk becomes a segment on the device (stable radix sort by
  * term, repeats folded into term frequencies); nothing is searchable until rass_text_commit -- OpenSearch's refresh.
  * A row the field already holds is REWRITTEN (an index request with a known _id): what it held is dropped at the
- * commit, like Lucene's delete-then-add; a row with no tokens loses the field.  The _dev flavour takes device pointers. */
+ * commit, like Lucene's delete-then-add; a row with no tokens loses the field.  The _dev flavour takes device pointers
+ * (single-device handles; a handle over several GPUs takes the host flavour and splits the stream by its row map). */
 int rass_text_add_rows(rass_engine* h, int field, const int64_t* rows, int64_t n_rows, const int64_t* tok_indptr,
                        const int32_t* tok_terms);
 int rass_text_add_rows_dev(rass_engine* h, int field, const int64_t* rows_dev, int64_t n_rows,

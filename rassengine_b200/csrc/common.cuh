@@ -103,6 +103,7 @@ struct Bm25State {
   std::vector<int64_t> field_last_row;   // highest row each field holds (segments included)
   bool contiguous_fields = true;
   std::vector<int64_t> field_doc_count, field_sum_ttf;   // per field, as of the last build / commit
+  int64_t pending_V = 0;                 // terms of the CSR text_commit_merge left for the finalisation
   void* scratch = nullptr;               // arena of the segment builds, kept between bulks, released by the commit
   size_t scratch_bytes = 0;
 };
@@ -600,6 +601,16 @@ int sharded_fuse_hybrid(rass_engine* h, int B, const int32_t* qterm_indptr, cons
                         const float* qweights, const uint8_t* qflags, float w_text, const int64_t* knn_rows_host,
                         const float* knn_scores_host, float w_knn, int k, int64_t* out_rows, float* out_scores);
 int sharded_save(rass_engine* h, const char* path);
+int sharded_text_add_rows(rass_engine* h, int field, const int64_t* rows, int64_t n_rows, const int64_t* tok_indptr,
+                          const int32_t* tok_terms);
+int sharded_text_commit(rass_engine* h, const int64_t* field_vocab, int F, int64_t N);
+int sharded_text_size(rass_engine* h, int64_t* V, int64_t* N, int64_t* nnz, int* F);
+int sharded_text_stats(rass_engine* h, int64_t* indptr, int64_t* doc_count, int64_t* sum_ttf);
+// the two halves of rass_text_commit and the statistics a sharded handle sums in between (postings.cu)
+int text_commit_merge(rass_engine* h, const int64_t* field_vocab, int F, int64_t N);
+int text_local_stats(rass_engine* h, int F, int64_t N, int64_t* doc_count, int64_t* sum_ttf);
+int text_finalize_global(rass_engine* h, int64_t N, int F, const int64_t* g_doc_count, const int64_t* g_sum_ttf,
+                         const int64_t* global_df);
 rass_engine* sharded_first(rass_engine* h);      // the shard on the coordinator device (dictionary scans run there)
 #define SHARDED(h, call)                 \
   do {                                   \

@@ -171,13 +171,9 @@ static int ensure_doclen(rass_engine* h, int F, int64_t N) {
 
 // Everything derived from the CSR (b.indptr / b.doc / b.tf on the device, b.indptr_host) and the length planes:
 // norm bytes, per-field statistics and length tables, idf, the tile-offset table, the per-term score ranges.
-static int text_finalize(rass_engine* h, int64_t V, int64_t N, int F, const int64_t* g_doc_count,
-                         const int64_t* g_sum_ttf, const int64_t* global_df) {
+// norm bytes of the [F][N] planes (b.norm) + per-field docCount / sumTotalTermFreq of THIS handle's rows
+static int text_norms_and_stats(rass_engine* h, int64_t N, int F, std::vector<unsigned long long>* stats_out) {
   Bm25State& b = h->bm25;
-  const int64_t* indptr = b.indptr_host.data();
-  b.V = V; b.N = N; b.nnz = indptr[V]; b.F = F;
-  int rc;
-  // norm planes + statistics
   cudaFree(b.norm); b.norm = nullptr;
   TEXT_TRY(h, cudaMalloc(&b.norm, std::max<size_t>((size_t)N * F, 1)));
   std::vector<unsigned long long> stats((size_t)2 * F, 0);
@@ -193,6 +189,29 @@ static int text_finalize(rass_engine* h, int64_t V, int64_t N, int F, const int6
     cudaFree(stats_dev);
     if (e != cudaSuccess) return rass_fail(h, RASS_E_CUDA, "norm_stats_kernel: %s", cudaGetErrorString(e));
   }
+  *stats_out = stats;
+  return RASS_OK;
+}
+
+// what a sharded handle sums over its shards between the merge and the finalisation of a commit
+int text_local_stats(rass_engine* h, int F, int64_t N, int64_t* doc_count, int64_t* sum_ttf) {
+  cudaSetDevice(h->device);
+  std::vector<unsigned long long> stats;
+  const int rc = text_norms_and_stats(h, N, F, &stats);
+  if (rc) return rc;
+  for (int f = 0; f < F; ++f) { doc_count[f] = (int64_t)stats[(size_t)2 * f]; sum_ttf[f] = (int64_t)stats[(size_t)2 * f + 1]; }
+  return RASS_OK;
+}
+
+static int text_finalize(rass_engine* h, int64_t V, int64_t N, int F, const int64_t* g_doc_count,
+                         const int64_t* g_sum_ttf, const int64_t* global_df) {
+  Bm25State& b = h->bm25;
+  const int64_t* indptr = b.indptr_host.data();
+  b.V = V; b.N = N; b.nnz = indptr[V]; b.F = F;
+  int rc;
+  // norm planes + statistics
+  std::vector<unsigned long long> stats;
+  if ((rc = text_norms_and_stats(h, N, F, &stats))) return rc;
   std::vector<float> inv((size_t)256 * F);
   std::vector<int64_t> doc_count((size_t)F, 0);
   const float k1 = 1.2f, bb = 0.75f, one = 1.0f;
@@ -485,7 +504,8 @@ static int seg_build(rass_engine* h, int field, const int64_t* rows_dev, int64_t
 static int text_add_rows_impl(rass_engine* h, int field, const int64_t* rows, int64_t n_rows, const int64_t* tok_indptr,
                               const int32_t* tok_terms, bool on_device) {
   if (!h) return RASS_E_INVALID;
-  if (h->shards) return rass_fail(h, RASS_E_UNSUPPORTED, "device-side text ingest runs on single-device handles");
+  if (h->shards)
+    return rass_fail(h, RASS_E_UNSUPPORTED, "a handle over several GPUs takes token streams from host memory (rass_text_add_rows)");
   cudaSetDevice(h->device);
   Bm25State& b = h->bm25;
   if (field < 0 || field > 254) return rass_fail(h, RASS_E_INVALID, "bad field %d", field);
@@ -557,6 +577,7 @@ static int text_add_rows_impl(rass_engine* h, int field, const int64_t* rows, in
 
 extern "C" int rass_text_add_rows(rass_engine* h, int field, const int64_t* rows, int64_t n_rows,
                                   const int64_t* tok_indptr, const int32_t* tok_terms) {
+  SHARDED(h, sharded_text_add_rows(h, field, rows, n_rows, tok_indptr, tok_terms));
   return text_add_rows_impl(h, field, rows, n_rows, tok_indptr, tok_terms, false);
 }
 
@@ -781,9 +802,10 @@ static int commit_resort(rass_engine* h, const std::vector<int64_t>& base_new, c
   return done(RASS_OK);
 }
 
-extern "C" int rass_text_commit(rass_engine* h, const int64_t* field_vocab, int F, int64_t N) {
+// The merge half of a commit: new CSR, length planes and b.indptr_host in place; nothing derived from corpus statistics yet
+// (text_finalize / text_finalize_global does that, with this handle's statistics or a sharded handle's sums).
+int text_commit_merge(rass_engine* h, const int64_t* field_vocab, int F, int64_t N) {
   if (!h) return RASS_E_INVALID;
-  if (h->shards) return rass_fail(h, RASS_E_UNSUPPORTED, "device-side text ingest runs on single-device handles");
   cudaSetDevice(h->device);
   Bm25State& b = h->bm25;
   if (!field_vocab || F < 1 || F > 255 || N < 0 || N > 0x7ffffff0LL) return rass_fail(h, RASS_E_INVALID, "bad commit");
@@ -890,13 +912,26 @@ extern "C" int rass_text_commit(rass_engine* h, const int64_t* field_vocab, int 
   for (int f = 0; f < F; ++f)
     std::fill(b.term_field_host.begin() + base_new[(size_t)f], b.term_field_host.begin() + base_new[(size_t)f + 1], (uint8_t)f);
   if (b.field_last_row.size() < (size_t)F) b.field_last_row.resize((size_t)F, -1);
-  done(RASS_OK);
-  return text_finalize(h, V_new, N, F, nullptr, nullptr, nullptr);
+  b.pending_V = V_new;
+  return done(RASS_OK);
+}
+
+int text_finalize_global(rass_engine* h, int64_t N, int F, const int64_t* g_doc_count, const int64_t* g_sum_ttf,
+                         const int64_t* global_df) {
+  cudaSetDevice(h->device);
+  return text_finalize(h, h->bm25.pending_V, N, F, g_doc_count, g_sum_ttf, global_df);
+}
+
+extern "C" int rass_text_commit(rass_engine* h, const int64_t* field_vocab, int F, int64_t N) {
+  SHARDED(h, sharded_text_commit(h, field_vocab, F, N));
+  const int rc = text_commit_merge(h, field_vocab, F, N);
+  if (rc) return rc;
+  return text_finalize(h, h->bm25.pending_V, N, F, nullptr, nullptr, nullptr);
 }
 
 extern "C" int rass_text_size(rass_engine* h, int64_t* V, int64_t* N, int64_t* nnz, int* F) {
   if (!h) return RASS_E_INVALID;
-  if (h->shards) return rass_fail(h, RASS_E_UNSUPPORTED, "device-side text ingest runs on single-device handles");
+  SHARDED(h, sharded_text_size(h, V, N, nnz, F));
   const Bm25State& b = h->bm25;
   if (V) *V = b.built ? b.V : 0;
   if (N) *N = b.built ? b.N : 0;
@@ -907,7 +942,7 @@ extern "C" int rass_text_size(rass_engine* h, int64_t* V, int64_t* N, int64_t* n
 
 extern "C" int rass_text_stats(rass_engine* h, int64_t* indptr, int64_t* doc_count, int64_t* sum_ttf) {
   if (!h) return RASS_E_INVALID;
-  if (h->shards) return rass_fail(h, RASS_E_UNSUPPORTED, "device-side text ingest runs on single-device handles");
+  SHARDED(h, sharded_text_stats(h, indptr, doc_count, sum_ttf));
   const Bm25State& b = h->bm25;
   if (!b.built) return rass_fail(h, RASS_E_NOTFOUND, "no postings");
   if (indptr) memcpy(indptr, b.indptr_host.data(), ((size_t)b.V + 1) * 8);

@@ -757,6 +757,94 @@ int sharded_bm25_build(rass_engine* h, const int64_t* indptr, const int32_t* doc
   return RASS_OK;
 }
 
+// ---- device-side text ingest on a sharded handle: token streams split by the row map, every shard inverts and merges its
+// own rows, the corpus-wide statistics are summed between the merge and the finalisation of the commit ----
+int sharded_text_add_rows(rass_engine* h, int field, const int64_t* rows, int64_t n_rows, const int64_t* tok_indptr,
+                          const int32_t* tok_terms) {
+  ShardSet* S = h->shards;
+  if (n_rows < 0 || (n_rows && (!rows || !tok_indptr))) return rass_fail(h, RASS_E_INVALID, "bad token stream");
+  if (n_rows == 0) return RASS_OK;
+  if (tok_indptr[0] != 0) return rass_fail(h, RASS_E_INVALID, "token offsets start at 0");
+  for (int64_t i = 0; i < n_rows; ++i) {
+    if (tok_indptr[i + 1] < tok_indptr[i]) return rass_fail(h, RASS_E_INVALID, "token offsets must not decrease");
+    if (rows[i] < h->rmap.base || (i && rows[i] <= rows[i - 1]))
+      return rass_fail(h, RASS_E_INVALID, "the rows of a bulk must be ascending and distinct");
+  }
+  if (tok_indptr[n_rows] && !tok_terms) return rass_fail(h, RASS_E_INVALID, "bad token stream");
+  return run_all(h, [&](int g) {
+    const RowMap rm = shard_map(h, g);
+    std::vector<int64_t> lr, ip(1, 0);
+    std::vector<int32_t> tk;
+    for (int64_t i = 0; i < n_rows; ++i) {
+      const int64_t l = row_global_to_local(rm, rows[i]);
+      if (l < 0) continue;
+      lr.push_back(l);                                        // ascending: the map is monotone inside a shard
+      tk.insert(tk.end(), tok_terms + tok_indptr[i], tok_terms + tok_indptr[i + 1]);
+      ip.push_back((int64_t)tk.size());
+    }
+    if (lr.empty()) return (int)RASS_OK;
+    return rass_text_add_rows(S->sh[g], field, lr.data(), (int64_t)lr.size(), ip.data(), tk.empty() ? nullptr : tk.data());
+  });
+}
+
+int sharded_text_commit(rass_engine* h, const int64_t* field_vocab, int F, int64_t N) {
+  ShardSet* S = h->shards;
+  if (!field_vocab || F < 1 || F > 255 || N < 0) return rass_fail(h, RASS_E_INVALID, "bad commit");
+  int64_t V = 0;
+  for (int f = 0; f < F; ++f) V += field_vocab[f];
+  std::vector<std::vector<int64_t>> dc((size_t)S->G, std::vector<int64_t>((size_t)F, 0)), ttf = dc;
+  int rc = run_all(h, [&](int g) {
+    rass_engine* sh = S->sh[g];
+    const int64_t n_local = shard_rows_below(h, g, N);
+    int r = text_commit_merge(sh, field_vocab, F, n_local);
+    if (r) return r;
+    return text_local_stats(sh, F, n_local, dc[(size_t)g].data(), ttf[(size_t)g].data());
+  });
+  if (rc) return rc;
+  // corpus-wide statistics: scores must not depend on how the rows are spread
+  std::vector<int64_t> g_dc((size_t)F, 0), g_ttf((size_t)F, 0), g_df((size_t)V, 0);
+  int64_t nnz = 0;
+  for (int g = 0; g < S->G; ++g) {
+    for (int f = 0; f < F; ++f) { g_dc[(size_t)f] += dc[(size_t)g][(size_t)f]; g_ttf[(size_t)f] += ttf[(size_t)g][(size_t)f]; }
+    const std::vector<int64_t>& ip = S->sh[g]->bm25.indptr_host;
+    for (int64_t t = 0; t < V; ++t) g_df[(size_t)t] += ip[(size_t)t + 1] - ip[(size_t)t];
+    nnz += ip[(size_t)V];
+  }
+  rc = run_all(h, [&](int g) {
+    return text_finalize_global(S->sh[g], shard_rows_below(h, g, N), F, g_dc.data(), g_ttf.data(), g_df.data());
+  });
+  if (rc) return rc;
+  Bm25State& b = h->bm25;
+  b.built = true;
+  b.V = V; b.N = N; b.F = F; b.nnz = nnz;
+  b.indptr_host.assign((size_t)V + 1, 0);                     // corpus-wide document frequencies, as offsets
+  for (int64_t t = 0; t < V; ++t) b.indptr_host[(size_t)t + 1] = b.indptr_host[(size_t)t] + g_df[(size_t)t];
+  b.field_doc_count = g_dc;
+  b.field_sum_ttf = g_ttf;
+  return RASS_OK;
+}
+
+int sharded_text_size(rass_engine* h, int64_t* V, int64_t* N, int64_t* nnz, int* F) {
+  const Bm25State& b = h->bm25;
+  const bool have = b.built && !b.indptr_host.empty();
+  if (V) *V = have ? b.V : 0;
+  if (N) *N = have ? b.N : 0;
+  if (nnz) *nnz = have ? b.nnz : 0;
+  if (F) *F = have ? b.F : 0;
+  return RASS_OK;
+}
+
+int sharded_text_stats(rass_engine* h, int64_t* indptr, int64_t* doc_count, int64_t* sum_ttf) {
+  const Bm25State& b = h->bm25;
+  if (!b.built || b.indptr_host.empty()) return rass_fail(h, RASS_E_NOTFOUND, "no committed text index on this handle");
+  if (indptr) memcpy(indptr, b.indptr_host.data(), ((size_t)b.V + 1) * 8);
+  for (int f = 0; f < b.F; ++f) {
+    if (doc_count) doc_count[f] = b.field_doc_count[(size_t)f];
+    if (sum_ttf) sum_ttf[f] = b.field_sum_ttf[(size_t)f];
+  }
+  return RASS_OK;
+}
+
 // knn list (global rows) on the coordinator device -> fused top-k: every shard fuses its own rows against the list and
 // stores its fused list into the gather buffer; raw-score merge on the coordinator.  Leaves S->m_rows / m_scores.
 static int fuse_on_shards(rass_engine* h, int B, const int32_t* qterm_indptr, const int32_t* qterms,

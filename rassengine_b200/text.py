@@ -271,13 +271,13 @@ class TextIndex:
     def sync_device(self, engine, n_rows: int):
         """Bring the engine's postings up to date with the rows indexed so far.  New, rewritten and cleared rows travel
         as token-id streams and are inverted on the device (rass_text_add_rows + rass_text_commit: a segment per bulk,
-        one merge pass, or a re-sort when rows were rewritten); a keyword field with several values in one document
-        (omitted norms: its length must read 1) or a handle spread over several GPUs takes the rebuild from host arrays
-        instead."""
+        one merge pass, or a re-sort when rows were rewritten; a handle spread over several GPUs splits the streams by
+        its row map); a keyword field with several values in one document (omitted norms: its length must read 1) takes
+        the rebuild from host arrays instead."""
         flds = [self.fields[n] for n in self.order]
         kw_multi = any(self.types.get(n) == "keyword" and any(a.size > 1 for a in self.fields[n].pending_ids)
                        for n in self.order)
-        if any(f.rebuild for f in flds) or kw_multi or len(getattr(engine, "devices", [0])) > 1 or not self.order:
+        if any(f.rebuild for f in flds) or kw_multi or not self.order:
             indptr, doc, tf, term_field, doclen = self.postings(n_rows)
             engine.bm25_build_fields(indptr, doc, tf, term_field, doclen)
             for f in flds:

@@ -223,3 +223,58 @@ print("ok")
     env = dict(os.environ, RASS_DEBUG_NO_PEER="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("devices", _device_sets())
+def test_sharded_text_ingest_equals_single_device(devices):
+    """rass_text_add_rows / rass_text_commit on a handle over several GPUs: the token streams are split by the row map,
+    every shard inverts and merges its own rows, the corpus-wide statistics are summed between the merge and the
+    finalisation.  Same bulks (fresh rows, rewrites, a cleared row, a growing vocabulary) into a single-device handle:
+    the statistics agree and hybrid / text-only searches return the same rows with bit-identical scores."""
+    rng = np.random.default_rng(71)
+    n_docs, dim = 9000, 256
+
+    def zipf(vocab, n):
+        p = 1.0 / np.arange(1, vocab + 1) ** 1.07
+        return rng.choice(vocab, size=n, p=p / p.sum()).astype(np.int32)
+
+    X = synth.embeddings(n_docs, dim, 72)
+    Q = synth.embeddings(12, dim, 73)
+    bulks = []                                         # (field, {row: ids}), vocab sizes after the bulk
+    vocab = [800, 50]
+    cuts = [0, 1, 1023, 1025, 4100, n_docs]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        vocab = [vocab[0] + 100, vocab[1] + 3]
+        for f in range(2):
+            ch = {r: zipf(vocab[f], int(rng.integers(1, 40))) for r in range(lo, hi) if not (f == 1 and r % 3)}
+            bulks.append((f, ch, list(vocab), hi))
+    # rewrites of rows on different shards, one of them cleared
+    bulks.append((0, {5: zipf(vocab[0], 9), 1024: np.zeros(0, np.int32), 2047: zipf(vocab[0], 30), 8999: zipf(vocab[0], 3)},
+                  list(vocab), n_docs))
+
+    def feed(e):
+        out = []
+        for i, (f, ch, vs, n) in enumerate(bulks):
+            rows = sorted(ch)
+            indptr = np.zeros(len(rows) + 1, dtype=np.int64)
+            indptr[1:] = np.cumsum([ch[r].size for r in rows])
+            cat = np.concatenate([ch[r] for r in rows]) if indptr[-1] else np.zeros(0, np.int32)
+            e.text_add_rows(f, rows, indptr, cat)
+            if f == 1 or i == len(bulks) - 1:          # a commit per bulk of rows, and one after the rewrites
+                e.text_commit(vs, n)
+                out.append(e.text_stats())
+        return out
+
+    qterms = [[int(t) for t in zipf(vocab[0], int(rng.integers(2, 8)))] for _ in range(12)]
+    with _engine(dim=dim) as a, _engine(dim=dim, devices=devices) as b:
+        a.append(X)
+        b.append(X)
+        sa, sb = feed(a), feed(b)
+        for (ia, da), (ib, db) in zip(sa, sb):
+            assert np.array_equal(ia, ib) and np.array_equal(da, db)
+        assert a.text_size() == b.text_size()
+        for w_text, w_knn in ((4.5, 2.0), (1.0, 0.0)):
+            ra, xa = a.search_hybrid(Q if w_knn else None, qterms, w_text, w_knn, 10)
+            rb_, xb = b.search_hybrid(Q if w_knn else None, qterms, w_text, w_knn, 10)
+            assert np.array_equal(ra, rb_)
+            assert np.array_equal(xa.view(np.uint32), xb.view(np.uint32))
