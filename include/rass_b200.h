@@ -226,6 +226,10 @@ int rass_text_add_rows_dev(rass_engine* h, int field, const int64_t* rows_dev, i
  * old list followed by each segment's: one copy pass over the postings.  When some row was rewritten, the live postings
  * of every source (a per-(field, row) generation word says which source owns the row) are re-sorted by (term, doc). */
 int rass_text_commit(rass_engine* h, const int64_t* field_vocab, int F, int64_t N);
+/* omit = 1: the field omits norms, like a `keyword` field of the mapping -- every document that has a value counts as
+ * length 1 however many values (tokens) it sent; takes effect at the next commit.  The host-array path expresses the
+ * same by passing lengths of 0 / 1 to rass_bm25_build_fields. */
+int rass_text_omit_norms(rass_engine* h, int field, int omit);
 /* Sizes of the committed index, and its arrays read back (tests, host-side evaluation); every pointer nullable:
  * indptr [V + 1], doc / tf [nnz], doclen [F][N], norm [F][N] (Lucene's SmallFloat.intToByte4 of doclen). */
 int rass_text_size(rass_engine* h, int64_t* V, int64_t* N, int64_t* nnz, int* F);

@@ -78,6 +78,7 @@ PROTOTYPES = {
     "rass_text_add_rows": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P, _P]),
     "rass_text_add_rows_dev": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P, _P]),
     "rass_text_commit": (C.c_int, [_P, _P, C.c_int, C.c_int64]),
+    "rass_text_omit_norms": (C.c_int, [_P, C.c_int, C.c_int]),
     "rass_text_size": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                  C.POINTER(C.c_int)]),
     "rass_text_export": (C.c_int, [_P, _P, _P, _P, _P, _P]),

@@ -103,6 +103,7 @@ struct Bm25State {
   std::vector<int64_t> field_last_row;   // highest row each field holds (segments included)
   bool contiguous_fields = true;
   std::vector<int64_t> field_doc_count, field_sum_ttf;   // per field, as of the last build / commit
+  std::vector<uint8_t> field_omit_norms; // rass_text_omit_norms: the field's documents all count as length 1 (`keyword`)
   int64_t pending_V = 0;                 // terms of the CSR text_commit_merge left for the finalisation
   void* scratch = nullptr;               // arena of the segment builds, kept between bulks, released by the commit
   size_t scratch_bytes = 0;
@@ -611,6 +612,7 @@ int text_commit_merge(rass_engine* h, const int64_t* field_vocab, int F, int64_t
 int text_local_stats(rass_engine* h, int F, int64_t N, int64_t* doc_count, int64_t* sum_ttf);
 int text_finalize_global(rass_engine* h, int64_t N, int F, const int64_t* g_doc_count, const int64_t* g_sum_ttf,
                          const int64_t* global_df);
+const std::vector<rass_engine*>& sharded_shards(rass_engine* h);
 rass_engine* sharded_first(rass_engine* h);      // the shard on the coordinator device (dictionary scans run there)
 #define SHARDED(h, call)                 \
   do {                                   \

@@ -85,7 +85,9 @@ static int ensure_capacity(rass_engine* h, int64_t rows) {
       ncap = rows;                 // out of memory with the head room: retry with exactly what is needed
     }
     if (ncap < rows) return rass_fail(h, RASS_E_OOM, "%lld rows exceed the address range reserved for the store", (long long)rows);
-    // the arrays' capacity in rows is what the smallest mapping holds (chunks are not row-aligned)
+    // the capacity in rows is what the smallest mapping holds: chunks are not row-aligned, and the last one mapped is
+    // usually only partly asked for
+    ncap = 0xfffffff0LL;
     for (int i = 0; i < 5; ++i)
       if (per_row[i]) ncap = std::min<int64_t>(ncap, (int64_t)(h->vm[i].mapped / per_row[i]));
     h->x32 = bf16_only ? nullptr : (float*)h->vm[0].base;

@@ -102,13 +102,17 @@ __global__ void __launch_bounds__(256) term_xrange_kernel(const int64_t* __restr
 }
 
 // norm bytes of the [F][N] length planes + per-field docCount / sumTotalTermFreq
+// (omit_mask bit f: the field omits norms -- a `keyword` field: every document that has a value counts as length 1)
 __global__ void __launch_bounds__(256) norm_stats_kernel(const uint32_t* __restrict__ doclen, int64_t stride, int64_t N,
                                                          uint8_t* __restrict__ norm,
-                                                         unsigned long long* __restrict__ stats) {
+                                                         unsigned long long* __restrict__ stats,
+                                                         const uint8_t* __restrict__ omit) {
   const int f = blockIdx.y;
+  const bool om = omit[f] != 0;
   unsigned long long dc = 0, ttf = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t l = doclen[(size_t)f * stride + i];
+    uint32_t l = doclen[(size_t)f * stride + i];
+    if (om) l = l != 0;
     norm[(size_t)f * N + i] = int_to_byte4(l);
     dc += l != 0;
     ttf += l;
@@ -123,6 +127,22 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const uint32_t* __restr
     atomicAdd(stats + 2 * f + 1, ttf);
   }
 }
+
+// RASS_DEBUG_TEXT_TIMES: wall-clock marks of the ingest / commit phases on stderr (measurement switch)
+#include <chrono>
+struct TextTimer {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  const char* what;
+  explicit TextTimer(const char* w) : on(getenv("RASS_DEBUG_TEXT_TIMES") != nullptr), t0(std::chrono::steady_clock::now()), what(w) {}
+  void mark(const char* label) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[text times] %s: %s %.2f ms\n", what, label, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 #define TEXT_TRY(h, call)                                                                                     \
   do {                                                                                                        \
@@ -179,14 +199,20 @@ static int text_norms_and_stats(rass_engine* h, int64_t N, int F, std::vector<un
   std::vector<unsigned long long> stats((size_t)2 * F, 0);
   if (N > 0) {
     unsigned long long* stats_dev = nullptr;
+    uint8_t* omit_dev = nullptr;
+    std::vector<uint8_t> omit((size_t)F, 0);
+    for (int f = 0; f < F && f < (int)b.field_omit_norms.size(); ++f) omit[(size_t)f] = b.field_omit_norms[(size_t)f];
     TEXT_TRY(h, cudaMalloc(&stats_dev, stats.size() * 8));
-    cudaError_t e = cudaMemset(stats_dev, 0, stats.size() * 8);
+    cudaError_t e = cudaMalloc(&omit_dev, (size_t)F);
+    if (e == cudaSuccess) e = cudaMemcpy(omit_dev, omit.data(), (size_t)F, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(stats_dev, 0, stats.size() * 8);
     if (e == cudaSuccess) {
       const dim3 grid((unsigned)std::min<int64_t>((N + 255) / 256, 1024), (unsigned)F);
-      norm_stats_kernel<<<grid, 256>>>(b.doclen_dev, b.doclen_stride, N, b.norm, stats_dev);
+      norm_stats_kernel<<<grid, 256>>>(b.doclen_dev, b.doclen_stride, N, b.norm, stats_dev, omit_dev);
       e = cudaMemcpy(stats.data(), stats_dev, stats.size() * 8, cudaMemcpyDeviceToHost);
     }
     cudaFree(stats_dev);
+    cudaFree(omit_dev);
     if (e != cudaSuccess) return rass_fail(h, RASS_E_CUDA, "norm_stats_kernel: %s", cudaGetErrorString(e));
   }
   *stats_out = stats;
@@ -210,8 +236,10 @@ static int text_finalize(rass_engine* h, int64_t V, int64_t N, int F, const int6
   b.V = V; b.N = N; b.nnz = indptr[V]; b.F = F;
   int rc;
   // norm planes + statistics
+  TextTimer tt("finalize");
   std::vector<unsigned long long> stats;
   if ((rc = text_norms_and_stats(h, N, F, &stats))) return rc;
+  tt.mark("norms + stats");
   std::vector<float> inv((size_t)256 * F);
   std::vector<int64_t> doc_count((size_t)F, 0);
   const float k1 = 1.2f, bb = 0.75f, one = 1.0f;
@@ -241,6 +269,7 @@ static int text_finalize(rass_engine* h, int64_t V, int64_t N, int F, const int6
     b.idf_host[(size_t)t] = (float)log(1.0 + (dc - (double)df + 0.5) / ((double)df + 0.5));
   }
   if ((rc = upload(h, &b.inv_dev, inv.data(), inv.size()))) return rc;
+  tt.mark("idf + length tables");
   // per-tile posting offsets of the frequent terms (the tile kernels jump straight to a tile's postings)
   b.n_tiles = (int)((std::max<int64_t>(N, 1) + HYB_TILE - 1) / HYB_TILE);
   b.table_row_host.assign((size_t)V, -1);
@@ -262,6 +291,7 @@ static int text_finalize(rass_engine* h, int64_t V, int64_t N, int F, const int6
     cudaFree(tt_dev);
     if (e != cudaSuccess) return rass_fail(h, RASS_E_CUDA, "tile_offsets_kernel: %s", cudaGetErrorString(e));
   }
+  tt.mark("tile offsets");
   // per-term score ranges (order-free fast path of hybrid_core)
   b.xmin_host.assign((size_t)V, 0.f);
   b.xmax_host.assign((size_t)V, 0.f);
@@ -282,6 +312,7 @@ static int text_finalize(rass_engine* h, int64_t V, int64_t N, int F, const int6
     cudaFree(tfield_dev); cudaFree(xmin_dev); cudaFree(xmax_dev);
     if (e != cudaSuccess) return rass_fail(h, RASS_E_CUDA, "term_xrange_kernel: %s", cudaGetErrorString(e));
   }
+  tt.mark("impacts + term ranges");
   b.built = true;
   return RASS_OK;
 }
@@ -828,8 +859,10 @@ int text_commit_merge(rass_engine* h, const int64_t* field_vocab, int F, int64_t
     if (b.field_last_row[f] >= N) return rass_fail(h, RASS_E_INVALID, "field %d holds row %lld >= N", (int)f,
                                                    (long long)b.field_last_row[f]);
   int rc;
+  TextTimer tt("commit");
   if ((rc = ensure_doclen(h, F, N))) return rc;
   cudaStream_t st = eng_stream(h);
+  tt.mark("planes");
   // old term -> new term (the blocks of the fields move apart as vocabularies grow)
   std::vector<int32_t> remap((size_t)V_old);
   {
@@ -897,6 +930,7 @@ int text_commit_merge(rass_engine* h, const int64_t* field_vocab, int F, int64_t
   COMMIT_TRY(cudaGetLastError());
   COMMIT_TRY(cudaStreamSynchronize(st));
   }
+  tt.mark(b.has_rewrite ? "re-sort" : "merge copy");
   // every (field, doc) is the committed index's again
   if (b.gen_dev)
     COMMIT_TRY(cudaMemsetAsync(b.gen_dev, 0, (size_t)b.doclen_F * b.doclen_stride * sizeof(uint32_t), st));
@@ -913,6 +947,7 @@ int text_commit_merge(rass_engine* h, const int64_t* field_vocab, int F, int64_t
     std::fill(b.term_field_host.begin() + base_new[(size_t)f], b.term_field_host.begin() + base_new[(size_t)f + 1], (uint8_t)f);
   if (b.field_last_row.size() < (size_t)F) b.field_last_row.resize((size_t)F, -1);
   b.pending_V = V_new;
+  tt.mark("swap in");
   return done(RASS_OK);
 }
 
@@ -927,6 +962,22 @@ extern "C" int rass_text_commit(rass_engine* h, const int64_t* field_vocab, int 
   const int rc = text_commit_merge(h, field_vocab, F, N);
   if (rc) return rc;
   return text_finalize(h, h->bm25.pending_V, N, F, nullptr, nullptr, nullptr);
+}
+
+extern "C" int rass_text_omit_norms(rass_engine* h, int field, int omit) {
+  if (!h) return RASS_E_INVALID;
+  if (field < 0 || field > 254) return rass_fail(h, RASS_E_INVALID, "bad field %d", field);
+  if (h->shards) {
+    for (rass_engine* sh : sharded_shards(h)) {
+      const int rc = rass_text_omit_norms(sh, field, omit);
+      if (rc) return rc;
+    }
+    return RASS_OK;
+  }
+  Bm25State& b = h->bm25;
+  if (b.field_omit_norms.size() <= (size_t)field) b.field_omit_norms.resize((size_t)field + 1, 0);
+  b.field_omit_norms[(size_t)field] = omit ? 1 : 0;
+  return RASS_OK;
 }
 
 extern "C" int rass_text_size(rass_engine* h, int64_t* V, int64_t* N, int64_t* nnz, int* F) {

@@ -121,6 +121,7 @@ struct ShardSet {
 };
 
 rass_engine* sharded_first(rass_engine* h) { return h->shards->sh[0]; }
+const std::vector<rass_engine*>& sharded_shards(rass_engine* h) { return h->shards->sh; }
 
 static RowMap shard_map(const rass_engine* h, int g) { return RowMap{h->rmap.base, g, h->shards->G, RASS_SHARD_BLOCK_LOG2}; }
 static int shard_of(const rass_engine* h, int64_t row) { return (int)((row >> RASS_SHARD_BLOCK_LOG2) % h->shards->G); }

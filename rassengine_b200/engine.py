@@ -276,6 +276,10 @@ class Engine:
         self._check(self._lib.rass_text_add_rows_dev(self._h, int(field), C.c_void_p(rows_ptr), int(n_rows),
                                                      C.c_void_p(tok_indptr_ptr), C.c_void_p(tok_terms_ptr)))
 
+    def text_omit_norms(self, field: int, omit: bool = True):
+        """The field's documents all count as length 1 (a `keyword` field): rass_text_omit_norms."""
+        self._check(self._lib.rass_text_omit_norms(self._h, int(field), 1 if omit else 0))
+
     def text_commit(self, field_vocab, n_rows: int):
         """Fold the pending segments into the searchable CSR (rass_text_commit): field_vocab = terms per field now."""
         fv = np.ascontiguousarray(field_vocab, dtype=np.int64)

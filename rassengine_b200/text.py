@@ -272,19 +272,19 @@ class TextIndex:
         """Bring the engine's postings up to date with the rows indexed so far.  New, rewritten and cleared rows travel
         as token-id streams and are inverted on the device (rass_text_add_rows + rass_text_commit: a segment per bulk,
         one merge pass, or a re-sort when rows were rewritten; a handle spread over several GPUs splits the streams by
-        its row map); a keyword field with several values in one document (omitted norms: its length must read 1) takes
-        the rebuild from host arrays instead."""
+        its row map; keyword fields omit norms).  The rebuild from host arrays (rass_bm25_build_fields) remains for a
+        caller that sets `rebuild` on a field."""
         flds = [self.fields[n] for n in self.order]
-        kw_multi = any(self.types.get(n) == "keyword" and any(a.size > 1 for a in self.fields[n].pending_ids)
-                       for n in self.order)
-        if any(f.rebuild for f in flds) or kw_multi or not self.order:
+        if any(f.rebuild for f in flds) or not self.order:
             indptr, doc, tf, term_field, doclen = self.postings(n_rows)
             engine.bm25_build_fields(indptr, doc, tf, term_field, doclen)
             for f in flds:
                 f.pending_rows, f.pending_ids, f.rebuild = [], [], False
             self.host_rebuilds += 1
         else:
-            for fid, f in enumerate(flds):
+            for fid, (name, f) in enumerate(zip(self.order, flds)):
+                if self.types.get(name) == "keyword":
+                    engine.text_omit_norms(fid, True)      # however many values: a document counts as length 1
                 if f.pending_rows:
                     engine.text_add_rows(fid, *f.take_pending())
             engine.text_commit([len(f.vocab) for f in flds], n_rows)

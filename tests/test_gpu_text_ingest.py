@@ -256,3 +256,33 @@ def test_client_bulks_go_through_the_device_ingest():
     assert again == once
     t3 = c3._indices[n3].text
     assert t3.device_commits == 3 and t3.host_rebuilds == 0
+
+
+def test_keyword_fields_omit_norms_on_the_device():
+    """A `keyword` field counts every document that has a value as length 1, however many values it sent
+    (rass_text_omit_norms): norm bytes, docCount / sumTotalTermFreq and the scores equal a host-built index that was
+    handed lengths of 0 / 1 (what the client's rebuild path passes)."""
+    rng = np.random.default_rng(31)
+    n, V = 4000, 60
+    toks = {r: rng.integers(0, V, size=int(rng.integers(1, 4))).astype(np.int32) for r in range(n) if r % 4}
+    indptr, doc, tf, doclen = _host_csr([toks], [V], n)
+    dl01 = (doclen > 0).astype(np.uint32)
+    rows = sorted(toks)
+    ip = np.zeros(len(rows) + 1, dtype=np.int64)
+    ip[1:] = np.cumsum([toks[r].size for r in rows])
+    qterms = [[int(t) for t in rng.integers(0, V, size=3)] for _ in range(8)]
+    with _engine(dim=256) as a, _engine(dim=256) as b:
+        X = synth.embeddings(n, 256, 32)
+        a.append(X)
+        b.append(X)
+        a.bm25_build_fields(indptr, doc, tf, np.zeros(V, np.int32), dl01)
+        b.text_omit_norms(0, True)
+        b.text_add_rows(0, rows, ip, np.concatenate([toks[r] for r in rows]))
+        b.text_commit([V], n)
+        ia, _, _, _, na = a.text_export()
+        ib, db, tb, _, nb = b.text_export()
+        assert np.array_equal(ia, ib) and np.array_equal(db, doc) and np.array_equal(tb, tf) and np.array_equal(na, nb)
+        assert [x.tolist() for x in a.text_stats()] == [x.tolist() for x in b.text_stats()]
+        ra, sa = a.search_hybrid(None, qterms, 2.0, 0.0, 10)
+        rb_, sb = b.search_hybrid(None, qterms, 2.0, 0.0, 10)
+        assert np.array_equal(ra, rb_) and np.array_equal(sa.view(np.uint32), sb.view(np.uint32))
