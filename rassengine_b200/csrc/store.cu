@@ -92,6 +92,9 @@ __global__ void __launch_bounds__(128) query_prep_kernel(const float* __restrict
     scal->flagged_n = 0;
     scal->max_cand = 0;
     scal->n_certified = 0;
+    // (every scan_umma_kernel launch leaves its tile counter at zero; a search starts from zero whatever happened before)
+    scal->tile_ctr[0] = 0;
+    scal->tile_ctr[1] = 0;
   }
   if (b >= B_pad) return;
   if (b >= B) {
