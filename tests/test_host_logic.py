@@ -385,3 +385,35 @@ def test_store_fhir_docs_entry_point_keeps_the_reference_shape():
     asyncio.run(ix.store_fhir_docs_in_opensearch(structured, chunks, c2, "idx"))       # no embedder: logged, structured stored
     assert len(c2.calls) == 2 and len(c2.calls[1]) == 3
     asyncio.run(ix.store_fhir_docs_in_opensearch(structured, chunks, None, "idx"))
+
+
+def test_text_field_pending_stream_is_sorted_deduplicated_and_incremental():
+    """What TextIndex.sync_device hands to rass_text_add_rows: rows ascending and distinct, the LAST write to a row
+    wins, a row that lost the field travels as an empty token list; and the dictionary blob of the fuzzy scan grows by
+    the new terms only, keyword terms as empty strings."""
+    from rassengine_b200.text import TextField, TextIndex
+    f = TextField()
+    f.set_row_tokens(0, ["a", "b", "a"])
+    f.set_row_tokens(2, ["c"])
+    rows, indptr, terms = f.take_pending()
+    assert rows.tolist() == [0, 2] and indptr.tolist() == [0, 3, 4] and terms.tolist() == [0, 1, 0, 2]
+    assert f.take_pending()[0].size == 0                                   # nothing new
+    f.set_row_tokens(5, ["d"])
+    f.set_row_tokens(2, ["a", "e"])                                        # rewrite of an older row
+    f.set_row_tokens(5, ["b"])                                             # written twice before the sync
+    f.set_row_tokens(0, [])                                                # loses the field
+    f.set_row_tokens(7, [])                                                # never had it: not a change
+    rows, indptr, terms = f.take_pending()
+    assert rows.tolist() == [0, 2, 5] and indptr.tolist() == [0, 0, 2, 3] and terms.tolist() == [0, 4, 1]
+    assert sorted(f.row_terms) == [2, 5]
+    blob, lens = f.encoded_terms()
+    assert bytes(blob) == b"abcde" and lens.tolist() == [1, 1, 1, 1, 1]
+    f.set_row_tokens(9, ["été", "a"])
+    blob, lens = f.encoded_terms()
+    assert bytes(blob) == "abcdeété".encode() and lens.tolist() == [1, 1, 1, 1, 1, 5]
+    ti = TextIndex({"note": "text", "code": "keyword"})
+    ti.set_doc(0, {"note": "Chest pain, chest", "code": "I20.9"}, fresh=True)
+    ti.set_doc(1, {"code": ["I20.9", "R07.4"]}, fresh=True)
+    blob, off = ti.vocab_blob()
+    assert ti.order == ["note", "code"] and blob == b"chestpain" and off.tolist() == [0, 5, 9, 9, 9]
+    assert ti.terms_in_id_order() == ["chest", "pain", "I20.9", "R07.4"]
