@@ -1,9 +1,5 @@
 cd /root/repo
-T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4"
-$T --steps 20 --warmup 5 > gpurun_out/r3i_bench_n4.json 2> gpurun_out/r3i_bench_n4.err; echo "rc=$?"
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r3i_bench_n4.json').read().strip().splitlines()[-1])
-print(round(d['value']), round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']), d['roofline']['frac'], d['parity'].get('ids_equal_cpu_oracle'), d['clocks']['sm_mhz'])
-print('cfg5', {k:d['cfg5'][k] for k in ('qps','ms_per_batch','scan_tflops_per_gpu','frac_of_tensor_peak')}, d['cfg5']['parity'].get('ids_equal_cpu_oracle'))
-PY
+python -m pytest tests -m gpu -x -q > gpurun_out/r3k_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r3k_pytest.log
+python bench.py --workload cfg4 --steps 40 --warmup 5 > gpurun_out/r3k_cfg4.json 2> gpurun_out/r3k_cfg4.err; echo "rc=$?"
+python -c "
+import json; d=json.loads(open('gpurun_out/r3k_cfg4.json').read().strip().splitlines()[-1]); print(round(d['value']), round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value']), 'text', round(d['roofline']['kernels']['bm25_fusion']['ms'],4), d['parity'])"
