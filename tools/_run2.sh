@@ -1,5 +1,5 @@
 cd /root/repo
-python -m pytest tests -m gpu -x -q > gpurun_out/r3k_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r3k_pytest.log
-python bench.py --workload cfg4 --steps 40 --warmup 5 > gpurun_out/r3k_cfg4.json 2> gpurun_out/r3k_cfg4.err; echo "rc=$?"
-python -c "
-import json; d=json.loads(open('gpurun_out/r3k_cfg4.json').read().strip().splitlines()[-1]); print(round(d['value']), round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value']), 'text', round(d['roofline']['kernels']['bm25_fusion']['ms'],4), d['parity'])"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_r2_cfg4_final.csv python bench.py --workload cfg4 --steps 3 --warmup 2 --no-cpu-baseline --no-cpu-parity > gpurun_out/r3l_ncu_l.log 2>&1; echo "launch list rc=$?"
+ncu --set full --import-source on --clock-control none -k regex:hybrid_tile_fast -s 3 -c 1 -o gpurun_out/prof_r2_hyb8 -f python bench.py --workload cfg4 --steps 3 --warmup 1 --no-cpu-parity --no-cpu-baseline > gpurun_out/r3l_ncu_f.log 2>&1; echo "full rc=$?"
+ncu --set full --clock-control none -k regex:finish_kernel -s 4 -c 1 -o gpurun_out/prof_r2_finish -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --no-cpu-parity > gpurun_out/r3l_ncu_g.log 2>&1; echo "finish rc=$?"
+ls -la gpurun_out/prof_r2_hyb8.ncu-rep gpurun_out/prof_r2_finish.ncu-rep gpurun_out/launches_r2_cfg4_final.csv | awk '{print $5,$9}'
