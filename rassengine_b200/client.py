@@ -290,6 +290,15 @@ class _Index:
     def _apply_filter(self, plan: Plan):
         self.engine.set_row_filter_rows(self._filter_rows(plan.filters, plan.host_filters), len(self.sources))
 
+    def _df_of(self, gid: int) -> int:
+        """Document frequency of a global term id, as of the last sync (0 for an unknown id)."""
+        for name in self.text.order:
+            f = self.text.fields[name]
+            lo = self.text.base.get(name, 0)
+            if lo <= gid < lo + f.df.size:
+                return int(f.df[gid - lo])
+        return 0
+
     def _sync_text(self):
         if self.text.dirty and self.engine is not None:
             self.text.sync_device(self.engine, len(self.sources))
@@ -427,7 +436,14 @@ class _Index:
         # filter becomes a device-side pass mask for the tile kernel.
         if has_filter and self.batch_window_s is None and len(eng.devices) == 1:
             frows = self._filter_rows(plan.filters, plan.host_filters)
-            if frows.size <= FILTER_LIST_MAX:
+            # ... unless the lookups would cost more than walking the postings: a fuzzy query string expands to a few
+            # hundred terms, and rows x terms binary searches then lose against the tile kernel over the terms' lists
+            # (RASS_B200_FILTER_ROUTE=list|mask forces one of the two: the A/B switch of the measurement)
+            n_terms = len(ids) if have_text else 0
+            lookups = frows.size * max(n_terms, 1) * 16
+            walk = (sum(self._df_of(t) for t in ids) if have_text else 0) + len(self.sources) // 4
+            route = os.environ.get("RASS_B200_FILTER_ROUTE") or ("list" if lookups <= walk else "mask")
+            if frows.size <= FILTER_LIST_MAX and route == "list":
                 rows, scores = eng.search_hybrid_filtered(q, qterms, w_text, plan.knn_boost, k, [frows],
                                                           qweights=qweights, qflags=qflags)
                 return self._hits([(int(r), float(s)) for r, s in zip(rows[0], scores[0]) if r >= 0][: plan.size])
