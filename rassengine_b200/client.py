@@ -113,6 +113,7 @@ class _Index:
                  if isinstance(spec, dict) and spec.get("type") in ("text", "keyword")}
         types.setdefault(TEXT_FIELD, "text")
         self.text = TextIndex(types, sim_boost)
+        self._global_df = None            # df of every global term id, concatenated (rebuilt after a sync)
         self.n_docs = 0
         self.host_views: dict = {}               # hostquery.FieldView cache (N4 host-side queries)
         self.kw: dict[str, dict[object, list[int]]] = {f: {} for f in FILTER_FIELDS}   # field -> value -> rows
@@ -290,18 +291,20 @@ class _Index:
     def _apply_filter(self, plan: Plan):
         self.engine.set_row_filter_rows(self._filter_rows(plan.filters, plan.host_filters), len(self.sources))
 
-    def _df_of(self, gid: int) -> int:
-        """Document frequency of a global term id, as of the last sync (0 for an unknown id)."""
-        for name in self.text.order:
-            f = self.text.fields[name]
-            lo = self.text.base.get(name, 0)
-            if lo <= gid < lo + f.df.size:
-                return int(f.df[gid - lo])
-        return 0
+    def _postings_of(self, gids) -> int:
+        """Postings the listed global term ids hold together, as of the last sync."""
+        g = self._global_df
+        if g is None or len(g) != sum(f.df.size for f in self.text.fields.values()):
+            g = self._global_df = (np.concatenate([self.text.fields[n].df for n in self.text.order])
+                                   if self.text.order else np.zeros(0, dtype=np.int64))
+        a = np.asarray(gids, dtype=np.int64)
+        a = a[(a >= 0) & (a < g.size)]
+        return int(g[a].sum())
 
     def _sync_text(self):
         if self.text.dirty and self.engine is not None:
             self.text.sync_device(self.engine, len(self.sources))
+            self._global_df = None
             self.engine.set_vocab_raw(*self.text.vocab_blob())
 
     # -- search ------------------------------------------------------------------------------------------
@@ -441,7 +444,7 @@ class _Index:
             # (RASS_B200_FILTER_ROUTE=list|mask forces one of the two: the A/B switch of the measurement)
             n_terms = len(ids) if have_text else 0
             lookups = frows.size * max(n_terms, 1) * 16
-            walk = (sum(self._df_of(t) for t in ids) if have_text else 0) + len(self.sources) // 4
+            walk = (self._postings_of(ids) if have_text else 0) + len(self.sources) // 4
             route = os.environ.get("RASS_B200_FILTER_ROUTE") or ("list" if lookups <= walk else "mask")
             if frows.size <= FILTER_LIST_MAX and route == "list":
                 rows, scores = eng.search_hybrid_filtered(q, qterms, w_text, plan.knn_boost, k, [frows],

@@ -1,6 +1,4 @@
 cd /root/repo
-for r in list mask auto; do
-if [ $r = auto ]; then unset RASS_B200_FILTER_ROUTE; else export RASS_B200_FILTER_ROUTE=$r; fi
-python tools/bench_client.py 300000 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('$r', {k:round(v,3) for k,v in d.items() if k.endswith('_ms')})"
-done
+python -m pytest tests/test_gpu_hybrid.py tests/test_gpu_hostquery.py tests/test_gpu_lifecycle.py tests/test_gpu_text_ingest.py -x -q 2>&1 | tail -3
+python tools/bench_client.py 300000 2>/dev/null | tee gpurun_out/r3m_client.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print({k:round(v,3) for k,v in d.items() if k.endswith('_ms')}, d['text_syncs'])"
