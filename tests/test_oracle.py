@@ -248,3 +248,22 @@ def test_multifield_micro_golden(golden_dir):
         got = multifield.text_total(fields, [(c["query"], [tuple(x) for x in g["text_fields"]], c["w_text"], True),
                                              (c["query"], [tuple(x) for x in g["keyword_fields"]], c["w_keyword"], False)], n)
         assert got.tolist() == c["totals"], c["query"]
+
+
+def test_bm25_reproduces_a_published_explain_output():
+    """The one externally published number the BM25 restatement can be held against without a network: the worked
+    `explain` example of the Elasticsearch 7 reference documentation (Explain API / "similarity" pages; quoted from
+    memory, the pages cannot be fetched here) -- a term with n = 1 of N = 5 documents, freq = 1, dl = 3, avgdl = 5.4,
+    k1 = 1.2, b = 0.75:  idf = ln(1 + (N - n + 0.5)/(n + 0.5)) = 1.3862944,  tf = freq/(freq + k1(1 - b + b dl/avgdl))
+    = 0.5555555,  boost = 2.2,  score = 1.6943598.  The boost of 2.2 is LegacyBM25Similarity's (k1 + 1) (see
+    oracle/SEMANTICS.md): handed to the oracle as the query boost, the same scorer gives the same score.  A weak pin --
+    one posting -- but it is a number this repository did not compute."""
+    docs = [[0, 1, 1], [1] * 6, [1] * 6, [1] * 6, [1] * 6]          # lengths 3, 6, 6, 6, 6: avgdl = 27 / 5 = 5.4
+    idx = bm25.BM25Index.from_token_ids(docs, vocab=2)
+    assert idx.doc_count == 5 and abs(float(idx.avgdl) - 5.4) < 1e-6
+    assert abs(float(idx.idf(0)) - 1.3862944) < 1e-7
+    s = idx.score([0], boost=float(np.float32(1.0) + np.float32(1.2)))
+    assert np.count_nonzero(s) == 1
+    assert abs(float(s[0]) - 1.6943598) < 2e-7 * 1.6943598 + 1e-7
+    tf_part = float(s[0]) / (float(np.float32(2.2)) * float(idx.idf(0)))
+    assert abs(tf_part - 0.5555555) < 1e-6
