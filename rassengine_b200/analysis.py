@@ -116,15 +116,19 @@ _ASCII_CORE = re.compile(r"[A-Za-z0-9]")
 
 
 def _analyze_ascii(text: str) -> list[str]:
-    out: list[str] = []
-    for tok in _ASCII_TOKEN.findall(text):
-        if tok[0] == "_" and not _ASCII_CORE.search(tok):
-            continue
-        if len(tok) <= MAX_TOKEN_LENGTH:
-            out.append(tok.lower())
-        else:
-            _emit(out, tok)
-    return out
+    # lower-casing first does not move a boundary (a letter stays a letter), and it is one C call instead of one per token
+    toks = _ASCII_TOKEN.findall(text.lower())
+    if "_" in text:                                   # a run of underscores alone is not a token
+        toks = [t for t in toks if t[0] != "_" or _ASCII_CORE.search(t)]
+    if len(text) > MAX_TOKEN_LENGTH and any(len(t) > MAX_TOKEN_LENGTH for t in toks):
+        out: list[str] = []
+        for t in toks:
+            if len(t) <= MAX_TOKEN_LENGTH:
+                out.append(t)
+            else:
+                _emit(out, t)
+        return out
+    return toks
 
 
 _LETTER = (ALETTER, HEBREW)

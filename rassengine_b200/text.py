@@ -44,8 +44,12 @@ class TextField:
                 self.pending_ids.append(np.zeros(0, dtype=np.int32))
             return
         v = self.vocab
-        ids = np.fromiter((v.setdefault(t, len(v)) for t in toks), dtype=np.int32, count=len(toks))
-        self._store(row, ids)
+        ids = list(map(v.get, toks))                  # C-speed for the tokens the dictionary knows (nearly all)
+        if None in ids:
+            for i, t in enumerate(toks):
+                if ids[i] is None:
+                    ids[i] = v.setdefault(t, len(v))
+        self._store(row, np.array(ids, dtype=np.int32))
 
     def set_row_ids(self, row: int, ids: np.ndarray):
         """Pre-tokenised input (synthetic corpora): term ids must be < declare_vocab()."""
