@@ -26,11 +26,8 @@ struct VmApi {
   bool ok = false;
 };
 
-const VmApi& vm_api() {
-  static VmApi api;
-  static bool tried = false;
-  if (tried) return api;
-  tried = true;
+VmApi vm_load() {
+  VmApi api;
   auto get = [](const char* name, void** fn) {
     cudaDriverEntryPointQueryResult q;
     return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess &&
@@ -42,6 +39,12 @@ const VmApi& vm_api() {
            get("cuMemSetAccess", (void**)&api.set_access) &&
            get("cuMemGetAllocationGranularity", (void**)&api.granularity);
   if (getenv("RASS_DEBUG_NO_VMM")) api.ok = false;          // A/B and test switch: the cudaMalloc + copy path
+  return api;
+}
+
+// (a function-local static: initialised once, also when the shards of one handle grow from their worker threads)
+const VmApi& vm_api() {
+  static const VmApi api = vm_load();
   return api;
 }
 
